@@ -1,0 +1,291 @@
+// elementwise.cu — bandwidth-bound helpers of the variational path:
+//   bnn_stddev       sigma = 1e-10 + softplus(rho)                (reference core.py:25-27)
+//   bnn_materialize  W_s = mu + sigma * eps(s)                    (reference core.py:44-45)
+//   bnn_bias_grad    reparameterised bias gradient                (autograd of dense.py:46-60)
+//   bnn_im2col / bnn_col2im  conv2d lowering for the sampled GEMM (conv.py:112-119)
+#include "common.cuh"
+
+namespace bnn {
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(int64_t work_items, int per_block, int max_waves = 16) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  int64_t cap = static_cast<int64_t>(sm_count()) * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// ------------------------------------------------------------------ stddev
+__global__ void __launch_bounds__(kThreads) stddev_kernel(const float* __restrict__ rho,
+                                                          float* __restrict__ sigma, int64_t n,
+                                                          bool vec) {
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      const float4 r = ldg_stream4(rho + 4 * i);
+      float4 s;
+      s.x = stddev_exact(r.x); s.y = stddev_exact(r.y); s.z = stddev_exact(r.z); s.w = stddev_exact(r.w);
+      *reinterpret_cast<float4*>(sigma + 4 * i) = s;
+    }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride) sigma[i] = stddev_exact(rho[i]);
+  } else {
+    for (int64_t i = tid; i < n; i += stride) sigma[i] = stddev_exact(rho[i]);
+  }
+}
+
+// ------------------------------------------------------------------ materialize
+// one thread per (sample, Philox group of 4 consecutive elements)
+__global__ void __launch_bounds__(kThreads)
+materialize_kernel(const float* __restrict__ mu, const float* __restrict__ sigma,
+                   const float* __restrict__ eps_in, float* __restrict__ out,
+                   float* __restrict__ eps_out, int64_t numel, int S, uint32_t sample_begin,
+                   bnn_rng rng, bool vec) {
+  const RngKey key = resolve_rng(rng);
+  const int64_t groups = (numel + 3) >> 2;
+  const int64_t total = groups * S;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total; t += stride) {
+    const int s = static_cast<int>(t / groups);
+    const int64_t g = t - static_cast<int64_t>(s) * groups;
+    const int64_t e0 = g << 2;
+    const int64_t so = static_cast<int64_t>(s) * numel;
+    float4 e;
+    if (eps_in != nullptr) {
+      e.x = eps_in[so + e0];
+      e.y = (e0 + 1 < numel) ? eps_in[so + e0 + 1] : 0.f;
+      e.z = (e0 + 2 < numel) ? eps_in[so + e0 + 2] : 0.f;
+      e.w = (e0 + 3 < numel) ? eps_in[so + e0 + 3] : 0.f;
+    } else {
+      e = eps4(key, sample_begin + static_cast<uint32_t>(s), static_cast<uint32_t>(g));
+    }
+    if (vec) {   // numel % 4 == 0 and all bases 16-byte aligned
+      const float4 m = *reinterpret_cast<const float4*>(mu + e0);
+      const float4 sd = *reinterpret_cast<const float4*>(sigma + e0);
+      float4 w;
+      w.x = fmaf(sd.x, e.x, m.x); w.y = fmaf(sd.y, e.y, m.y);
+      w.z = fmaf(sd.z, e.z, m.z); w.w = fmaf(sd.w, e.w, m.w);
+      *reinterpret_cast<float4*>(out + so + e0) = w;
+      if (eps_out != nullptr) *reinterpret_cast<float4*>(eps_out + so + e0) = e;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (e0 + j < numel) {
+          const float ej = pick4(e, j);
+          out[so + e0 + j] = fmaf(sigma[e0 + j], ej, mu[e0 + j]);
+          if (eps_out != nullptr) eps_out[so + e0 + j] = ej;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ bias gradient
+// grid (ceil(N/32), S). Row-major dY (P == 1): lanes along n, warps stride over m.
+__global__ void __launch_bounds__(kThreads)
+bias_grad_rowmajor_kernel(const float* __restrict__ dy, int64_t ld, int64_t sample_stride,
+                          const float* __restrict__ rho_b, const float* __restrict__ eps_b,
+                          float* __restrict__ dmu_b, float* __restrict__ drho_b, int M, int N,
+                          uint32_t sample_begin, bnn_rng rng) {
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  const int s = blockIdx.y;
+  const float* base = dy + static_cast<int64_t>(s) * sample_stride;
+  float acc = 0.f;
+  if (n < N)
+    for (int m = warp; m < M; m += 8) acc += base[static_cast<int64_t>(m) * ld + n];
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && n < N) {
+    float c = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) c += part[w][lane];
+    const RngKey key = resolve_rng(rng);
+    const float e = eps_b != nullptr ? eps_b[static_cast<int64_t>(s) * N + n]
+                                     : eps1(key, sample_begin + s, static_cast<uint64_t>(n));
+    atomicAdd(dmu_b + n, c);
+    atomicAdd(drho_b + n, c * e * sigmoid_fast(rho_b[n]));
+  }
+}
+
+// NCHW dY (P > 1): one block per (n, s); threads stride over m = (b, p), contiguous in p.
+__global__ void __launch_bounds__(kThreads)
+bias_grad_nchw_kernel(const float* __restrict__ dy, int64_t batch_stride, int P,
+                      int64_t sample_stride, const float* __restrict__ rho_b,
+                      const float* __restrict__ eps_b, float* __restrict__ dmu_b,
+                      float* __restrict__ drho_b, int M, int N, uint32_t sample_begin, bnn_rng rng) {
+  __shared__ float part[8];
+  const int n = blockIdx.x, s = blockIdx.y;
+  const float* base = dy + static_cast<int64_t>(s) * sample_stride + static_cast<int64_t>(n) * P;
+  float acc = 0.f;
+  for (int m = threadIdx.x; m < M; m += kThreads) {
+    const int b = m / P, p = m - b * P;
+    acc += base[static_cast<int64_t>(b) * batch_stride + p];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float c = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) c += part[w];
+    const RngKey key = resolve_rng(rng);
+    const float e = eps_b != nullptr ? eps_b[static_cast<int64_t>(s) * N + n]
+                                     : eps1(key, sample_begin + s, static_cast<uint64_t>(n));
+    atomicAdd(dmu_b + n, c);
+    atomicAdd(drho_b + n, c * e * sigmoid_fast(rho_b[n]));
+  }
+}
+
+// ------------------------------------------------------------------ im2col / col2im
+__global__ void __launch_bounds__(kThreads)
+im2col_kernel(const float* __restrict__ x, float* __restrict__ col, bnn_conv2d_geom g) {
+  const int Kg = g.Cg * g.KH * g.KW;
+  const int64_t total = static_cast<int64_t>(g.B) * g.OH * g.OW * Kg;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total; t += stride) {
+    const int k = static_cast<int>(t % Kg);
+    const int64_t m = t / Kg;
+    const int kw = k % g.KW, kh = (k / g.KW) % g.KH, c = k / (g.KW * g.KH);
+    const int ow = static_cast<int>(m % g.OW), oh = static_cast<int>((m / g.OW) % g.OH);
+    const int b = static_cast<int>(m / (static_cast<int64_t>(g.OW) * g.OH));
+    const int ih = oh * g.sh - g.ph + kh * g.dh, iw = ow * g.sw - g.pw + kw * g.dw;
+    float v = 0.f;
+    if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+      v = x[((static_cast<int64_t>(b) * g.C + g.c0 + c) * g.H + ih) * g.W + iw];
+    col[t] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dx, bnn_conv2d_geom g, int accumulate) {
+  const int Kg = g.Cg * g.KH * g.KW;
+  const int64_t total = static_cast<int64_t>(g.B) * g.Cg * g.H * g.W;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total; t += stride) {
+    const int w = static_cast<int>(t % g.W), h = static_cast<int>((t / g.W) % g.H);
+    const int c = static_cast<int>((t / (static_cast<int64_t>(g.W) * g.H)) % g.Cg);
+    const int b = static_cast<int>(t / (static_cast<int64_t>(g.W) * g.H * g.Cg));
+    float acc = 0.f;
+    for (int kh = 0; kh < g.KH; ++kh) {
+      const int hn = h + g.ph - kh * g.dh;
+      if (hn < 0 || hn % g.sh != 0) continue;
+      const int oh = hn / g.sh;
+      if (oh >= g.OH) continue;
+      for (int kw = 0; kw < g.KW; ++kw) {
+        const int wn = w + g.pw - kw * g.dw;
+        if (wn < 0 || wn % g.sw != 0) continue;
+        const int ow = wn / g.sw;
+        if (ow >= g.OW) continue;
+        const int64_t m = (static_cast<int64_t>(b) * g.OH + oh) * g.OW + ow;
+        acc += dcol[m * Kg + (c * g.KH + kh) * g.KW + kw];
+      }
+    }
+    const int64_t o = ((static_cast<int64_t>(b) * g.C + g.c0 + c) * g.H + h) * g.W + w;
+    dx[o] = accumulate ? dx[o] + acc : acc;
+  }
+}
+
+int check_geom(const bnn_conv2d_geom* g) {
+  BNN_REQUIRE(g != nullptr, BNN_ERR_BAD_ARGUMENT, "conv geometry is NULL");
+  BNN_REQUIRE(g->B > 0 && g->C > 0 && g->H > 0 && g->W > 0 && g->Cg > 0 && g->c0 >= 0 &&
+                  g->c0 + g->Cg <= g->C && g->KH > 0 && g->KW > 0 && g->OH > 0 && g->OW > 0 &&
+                  g->sh > 0 && g->sw > 0 && g->dh > 0 && g->dw > 0 && g->ph >= 0 && g->pw >= 0,
+              BNN_ERR_BAD_ARGUMENT, "invalid conv2d geometry");
+  return BNN_OK;
+}
+
+}  // namespace
+}  // namespace bnn
+
+using namespace bnn;
+
+extern "C" {
+
+int bnn_stddev(const float* rho, float* sigma, int64_t numel, void* stream) {
+  BNN_REQUIRE(numel >= 0, BNN_ERR_BAD_ARGUMENT, "numel < 0");
+  if (numel == 0) return BNN_OK;
+  BNN_REQUIRE(rho && sigma, BNN_ERR_BAD_ARGUMENT, "bnn_stddev: NULL pointer");
+  int rc = check_device();
+  if (rc != BNN_OK) return rc;
+  const bool vec = aligned16(rho) && aligned16(sigma);
+  stddev_kernel<<<grid_for(numel, kThreads * 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      rho, sigma, numel, vec);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+int bnn_materialize(const float* mu, const float* sigma, const float* eps_in, float* out,
+                    float* eps_out, int64_t numel, int32_t S, uint32_t sample_begin,
+                    const bnn_rng* rng, void* stream) {
+  BNN_REQUIRE(numel >= 0 && S >= 0, BNN_ERR_BAD_ARGUMENT, "negative size");
+  if (numel == 0 || S == 0) return BNN_OK;
+  BNN_REQUIRE(mu && sigma && out && rng, BNN_ERR_BAD_ARGUMENT, "bnn_materialize: NULL pointer");
+  BNN_REQUIRE(numel <= (int64_t(1) << 34), BNN_ERR_UNSUPPORTED, "tensor larger than 2^34 elements");
+  int rc = check_device();
+  if (rc != BNN_OK) return rc;
+  const bool vec = (numel % 4 == 0) && aligned16(mu) && aligned16(sigma) && aligned16(out) &&
+                   (eps_out == nullptr || aligned16(eps_out));
+  const int64_t items = ((numel + 3) / 4) * S;
+  materialize_kernel<<<grid_for(items, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      mu, sigma, eps_in, out, eps_out, numel, S, sample_begin, *rng, vec);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+int bnn_bias_grad(bnn_view dy, int64_t dy_sample_stride, const float* rho_b, const float* eps_b,
+                  float* dmu_b, float* drho_b, int32_t M, int32_t N, int32_t S,
+                  uint32_t sample_begin, const bnn_rng* rng_b, void* stream) {
+  BNN_REQUIRE(M >= 0 && N >= 0 && S >= 0, BNN_ERR_BAD_ARGUMENT, "negative size");
+  if (M == 0 || N == 0 || S == 0) return BNN_OK;
+  BNN_REQUIRE(dy.base && rho_b && dmu_b && drho_b && rng_b, BNN_ERR_BAD_ARGUMENT, "bnn_bias_grad: NULL pointer");
+  BNN_REQUIRE(dy.P >= 1, BNN_ERR_BAD_ARGUMENT, "view P must be >= 1");
+  BNN_REQUIRE(S <= 65535, BNN_ERR_UNSUPPORTED, "more than 65535 samples per launch");
+  int rc = check_device();
+  if (rc != BNN_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dy.P == 1) {
+    dim3 grid((N + 31) / 32, S);
+    bias_grad_rowmajor_kernel<<<grid, kThreads, 0, st>>>(dy.base, dy.batch_stride, dy_sample_stride,
+                                                        rho_b, eps_b, dmu_b, drho_b, M, N,
+                                                        sample_begin, *rng_b);
+  } else {
+    dim3 grid(N, S);
+    bias_grad_nchw_kernel<<<grid, kThreads, 0, st>>>(dy.base, dy.batch_stride, dy.P,
+                                                    dy_sample_stride, rho_b, eps_b, dmu_b, drho_b,
+                                                    M, N, sample_begin, *rng_b);
+  }
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+int bnn_im2col(const float* x, float* col, const bnn_conv2d_geom* g, void* stream) {
+  int rc = check_geom(g);
+  if (rc != BNN_OK) return rc;
+  BNN_REQUIRE(x && col, BNN_ERR_BAD_ARGUMENT, "bnn_im2col: NULL pointer");
+  rc = check_device();
+  if (rc != BNN_OK) return rc;
+  const int64_t total = static_cast<int64_t>(g->B) * g->OH * g->OW * g->Cg * g->KH * g->KW;
+  im2col_kernel<<<grid_for(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, col, *g);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+int bnn_col2im(const float* dcol, float* dx, const bnn_conv2d_geom* g, int32_t accumulate, void* stream) {
+  int rc = check_geom(g);
+  if (rc != BNN_OK) return rc;
+  BNN_REQUIRE(dcol && dx, BNN_ERR_BAD_ARGUMENT, "bnn_col2im: NULL pointer");
+  rc = check_device();
+  if (rc != BNN_OK) return rc;
+  const int64_t total = static_cast<int64_t>(g->B) * g->Cg * g->H * g->W;
+  col2im_kernel<<<grid_for(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(dcol, dx, *g, accumulate);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+}  // extern "C"

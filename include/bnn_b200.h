@@ -1,0 +1,206 @@
+/*
+ * bnn_b200.h — C ABI of libbnn_b200.so: the B200 (sm_100a) variational hot path of
+ * pytorch_bayesian (Mirko-Nava/BayesianNeuralNetworks).
+ *
+ * The reference has no FFI of its own (it is pure Python on torch ops); each entry point below
+ * replaces the torch-op sequence of one reference call site, cited as file:line relative to the
+ * reference checkout.  All pointers are raw DEVICE pointers to fp32 unless stated otherwise; the
+ * caller owns every buffer (outputs and workspaces included) and passes the CUDA stream to
+ * launch on.  The library never allocates or frees device memory, never synchronises the
+ * stream, keeps no mutable global state besides lazily-set kernel attributes, and has no CPU
+ * fallback.  Every function returns a bnn_status (0 = ok); no C++ exception crosses the boundary.
+ *
+ * Random numbers: eps is a pure function of (seed, step, tensor_id, global sample index,
+ * element index) through Philox4x32-10 + Box-Muller (see bnn_rng), so any partition of the
+ * samples over GPUs or launches regenerates the same stream, and the backward pass regenerates
+ * the forward's eps from the same counters.  When `eps` pointers are non-NULL the kernels read
+ * eps from memory instead (layout [S][numel], the test-only "eps-injected" mode used for parity
+ * against the reference's torch.randn_like tensors).
+ */
+#ifndef BNN_B200_H
+#define BNN_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNN_B200_ABI_VERSION 1
+
+typedef enum bnn_status {
+  BNN_OK = 0,
+  BNN_ERR_BAD_ARGUMENT = 1,   /* null pointer, negative size, inconsistent shapes           */
+  BNN_ERR_MISALIGNED = 2,     /* pointer or leading dimension violates a stated alignment   */
+  BNN_ERR_UNSUPPORTED_ARCH = 3, /* current device is not compute capability 10.x            */
+  BNN_ERR_CUDA = 4,           /* a CUDA runtime call failed; see bnn_last_error_string()    */
+  BNN_ERR_WORKSPACE = 5,      /* workspace too small; query the matching *_workspace_size   */
+  BNN_ERR_UNSUPPORTED = 6     /* valid request the kernels do not implement (stated limits) */
+} bnn_status;
+
+/* Arithmetic mode of the sampled contractions.  TF32: tcgen05 kind::tf32, fp32 accumulate
+ * (2e-3 parity class).  FP32X3: three-term TF32 split (hi*hi + hi*lo + lo*hi), fp32-class
+ * accuracy (1e-5 parity class) on the same tensor-core path. */
+typedef enum bnn_precision {
+  BNN_PREC_TF32 = 0,
+  BNN_PREC_FP32X3 = 1
+} bnn_precision;
+
+/* Philox stream selector.  eps(seed, step, tensor_id, sample, element):
+ *   key     = (seed_lo, seed_hi)
+ *   counter = (element / 4, sample, tensor_id, step_lo) with step_hi folded into key.y
+ * `step_dev` (optional, device pointer to one uint64) is ADDED to `step` inside the kernel, so a
+ * captured CUDA graph can advance the stream without re-capturing. */
+typedef struct bnn_rng {
+  uint64_t seed;
+  uint64_t step;
+  const uint64_t* step_dev;
+  uint32_t tensor_id;
+  uint32_t reserved;
+} bnn_rng;
+
+/* A dense matrix operand seen through an NCHW window: logical element (m, n), m in [0, M),
+ * n in [0, N), lives at  base[(m / P) * batch_stride + n * P + (m % P)].
+ * P = 1, batch_stride = ld  describes an ordinary row-major matrix (Linear activations);
+ * P = OH*OW, batch_stride = C*OH*OW describes a conv feature map with m = (b, oh, ow). */
+typedef struct bnn_view {
+  float* base;
+  int64_t batch_stride;
+  int32_t P;
+  int32_t reserved;
+} bnn_view;
+
+/* ---- library ---- */
+int bnn_abi_version(void);
+const char* bnn_last_error_string(void);           /* thread-local, never NULL */
+int bnn_device_supported(int device);              /* BNN_OK iff compute capability 10.x */
+
+/* sigma = 1e-10 + softplus(rho), softplus beta=1 threshold=20.
+ * Replaces WeightNormal.stddev — pytorch_bayesian/nn/core.py:25-27. */
+int bnn_stddev(const float* rho, float* sigma, int64_t numel, void* stream);
+
+/* out[s][i] = mu[i] + sigma[i] * eps(s0 + s, i) for s in [0, S).
+ * Replaces WeightNormal.sample — pytorch_bayesian/nn/core.py:44-45 (only needed when the caller
+ * wants the sampled tensor in memory: `.sampled`, tests; the contractions never materialise it).
+ * `eps_out` (optional, [S][numel]) receives the eps used.  `eps_in` (optional) injects eps. */
+int bnn_materialize(const float* mu, const float* sigma, const float* eps_in, float* out,
+                    float* eps_out, int64_t numel, int32_t S, uint32_t sample_begin,
+                    const bnn_rng* rng, void* stream);
+
+/* ---- sampled contractions ----
+ * Forward:  Y[s] = A[s] * W_s^T + b_s,  W_s = mu_w + sigma_w * eps_w(s),  b_s likewise.
+ * Replaces NormalLinear.sample/.forward — pytorch_bayesian/nn/dense.py:46-60 — and, with the
+ * im2col matrix as A and an NCHW view as Y, NormalConv2d.forward — pytorch_bayesian/nn/conv.py:
+ * 65-73,112-119 — for all S Monte-Carlo samples of container.py:32-37 in one launch.
+ *   a            [S or 1][M][K] row-major, leading dimension lda (floats); a_sample_stride = 0
+ *                when all samples share the same activations (first Bayesian layer).
+ *   mu_w/sigma_w [N][K] row-major contiguous; mu_b/sigma_b [N] or NULL (no bias).
+ *   eps_w [S][N*K], eps_b [S][N]: optional injected eps (NULL = Philox).
+ *   y            view of [M][N] per sample; y_sample_stride floats between samples.
+ * rng_w / rng_b select the streams of the weight and the bias tensor. */
+int bnn_sampled_gemm_fwd(const float* a, int64_t lda, int64_t a_sample_stride,
+                         const float* mu_w, const float* sigma_w,
+                         const float* mu_b, const float* sigma_b,
+                         const float* eps_w, const float* eps_b,
+                         bnn_view y, int64_t y_sample_stride,
+                         int32_t M, int32_t N, int32_t K, int32_t S, uint32_t sample_begin,
+                         const bnn_rng* rng_w, const bnn_rng* rng_b,
+                         int32_t precision, void* stream);
+
+/* Data gradient: dA[s] = dY[s] * W_s  (W_s regenerated from the same counters).
+ * With a_sample_stride == 0 the S contributions are summed into one dA (shared activations).
+ * Autograd of F.linear / F.conv2d w.r.t. the input at dense.py:60 / conv.py:116-119. */
+int bnn_sampled_gemm_dgrad(bnn_view dy, int64_t dy_sample_stride,
+                           const float* mu_w, const float* sigma_w, const float* eps_w,
+                           float* da, int64_t lda, int64_t a_sample_stride,
+                           int32_t M, int32_t N, int32_t K, int32_t S, uint32_t sample_begin,
+                           const bnn_rng* rng_w, int32_t precision, void* stream);
+
+/* Weight gradient with the reparameterisation chain fused into the epilogue:
+ *   G_s = dY[s]^T * A[s];  dmu_w += sum_s G_s;  drho_w += (sum_s G_s o eps_w(s)) o sigmoid(rho_w)
+ * (autograd of core.py:44-45 + dense.py:60).  dmu_w / drho_w are ACCUMULATED INTO
+ * (atomic adds when the launch splits the reduction), so zero them first for a fresh gradient.
+ * rho_w is the raw scale parameter ([N][K]). */
+int bnn_sampled_gemm_wgrad(bnn_view dy, int64_t dy_sample_stride,
+                           const float* a, int64_t lda, int64_t a_sample_stride,
+                           const float* rho_w, const float* eps_w,
+                           float* dmu_w, float* drho_w,
+                           int32_t M, int32_t N, int32_t K, int32_t S, uint32_t sample_begin,
+                           const bnn_rng* rng_w, int32_t precision, void* stream);
+
+/* Bias gradient: c_s[n] = sum_m dY[s][m][n]; dmu_b += sum_s c_s;
+ * drho_b += (sum_s c_s * eps_b(s, n)) * sigmoid(rho_b[n]).  Accumulates (atomics). */
+int bnn_bias_grad(bnn_view dy, int64_t dy_sample_stride, const float* rho_b, const float* eps_b,
+                  float* dmu_b, float* drho_b, int32_t M, int32_t N, int32_t S,
+                  uint32_t sample_begin, const bnn_rng* rng_b, void* stream);
+
+/* ---- conv2d lowering helpers (NCHW, fp32) ----
+ * col[(b*OH*OW + oh*OW + ow)][(c*KH + kh)*KW + kw] = x[b][c0 + c][oh*sh - ph + kh*dh][...] (0 outside).
+ * c runs over `Cg` channels starting at c0 (one conv group). */
+typedef struct bnn_conv2d_geom {
+  int32_t B, C, H, W;          /* input batch, total channels, height, width */
+  int32_t c0, Cg;              /* first channel and channel count of this group */
+  int32_t KH, KW, OH, OW;
+  int32_t sh, sw, ph, pw, dh, dw;
+} bnn_conv2d_geom;
+int bnn_im2col(const float* x, float* col, const bnn_conv2d_geom* g, void* stream);
+/* dx[b][c0 + c][h][w] (+)= sum over (kh, kw, oh, ow) hitting (h, w) of dcol[...]; gather form, no
+ * atomics; `accumulate` != 0 adds into dx instead of overwriting the group's channels. */
+int bnn_col2im(const float* dcol, float* dx, const bnn_conv2d_geom* g, int32_t accumulate,
+               void* stream);
+
+/* ---- KL divergence, closed form, many tensors per launch ----
+ * For tensor t with posterior N(mu, sigma = 1e-10 + softplus(rho)) and scalar prior N(loc, scale):
+ *   kl_sum[t] = sum_i 0.5*[(sigma/scale)^2 + ((mu-loc)/scale)^2 - 1 - log((sigma/scale)^2)]
+ * Replaces KLDivergence.compute_kl — pytorch_bayesian/nn/loss.py:16-28 — and torch's
+ * _kl_normal_normal (torch/distributions/kl.py:468-471); the caller applies the reference's
+ * mean-of-means / n_batches reduction (loss.py:38) to the per-tensor sums.
+ * Optional gradients (both NULL or both set per tensor), written not accumulated:
+ *   grad_mu = c_t*(mu-loc)/scale^2,  grad_rho = c_t*(sigma/scale^2 - 1/sigma)*sigmoid(rho),
+ *   c_t = grad_coeff[t] * (grad_scale_dev ? *grad_scale_dev : 1).
+ * `kl_sum` may be NULL for a gradient-only pass. */
+typedef struct bnn_kl_tensor {
+  const float* mu;
+  const float* rho;
+  float* grad_mu;      /* optional */
+  float* grad_rho;     /* optional */
+  int64_t numel;
+  float prior_loc;
+  float prior_scale;
+  float grad_coeff;
+  float reserved;
+} bnn_kl_tensor;
+size_t bnn_kl_workspace_size(int32_t n_tensors);
+int bnn_kl(const bnn_kl_tensor* tensors /* HOST array */, int32_t n_tensors,
+           double* kl_sum /* device [n_tensors] or NULL */, const float* grad_scale_dev,
+           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- pruning ----
+ * key_i = log N(0; mu_i, sigma_i) evaluated with the exact op order of torch's Normal.log_prob
+ * (torch/distributions/normal.py:87-102) on softplus(rho)+1e-10; the k largest keys get
+ * mu <- 0, rho <- -30.  Replaces PruneNormal.prune_param — pytorch_bayesian/prune/prune.py:10-17.
+ * Ties at the k-th key are broken towards the lowest element index (torch.topk's tie order is
+ * unspecified; identical masks whenever the k-th key is unique).
+ * All tensors of one call are processed by the same launches.  `mask_out` (optional, uint8
+ * [numel]) receives the selection.  `keys_out` (optional) receives the keys. */
+typedef struct bnn_prune_tensor {
+  float* mu;
+  float* rho;
+  uint8_t* mask_out;   /* optional */
+  float* keys_out;     /* optional */
+  int64_t numel;
+  int64_t k;
+} bnn_prune_tensor;
+size_t bnn_prune_workspace_size(const bnn_prune_tensor* tensors, int32_t n_tensors);
+int bnn_prune(const bnn_prune_tensor* tensors /* HOST array */, int32_t n_tensors,
+              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- self test of the tcgen05 path (one 128xNx32 TF32 tile against a serial fp32 loop run by
+ * the same kernel's thread 0); returns BNN_OK and writes max |err| to *max_err_dev. */
+int bnn_selftest_umma(float* max_err_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNN_B200_H */
