@@ -1,0 +1,336 @@
+"""ctypes binding of libbnn_b200.so (the C ABI in include/bnn_b200.h).
+
+Everything here takes CUDA torch tensors, checks them, and passes raw device pointers plus the
+current CUDA stream across the C boundary.  There is no CPU path: a tensor that is not on a CUDA
+device, or a missing/unsupported library, raises.  Status codes become `BnnError`.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbnn_b200.so")
+
+PREC_TF32 = 0
+PREC_FP32X3 = 1
+
+_c_f32p = ctypes.c_void_p  # raw device pointers travel as integers
+
+
+class BnnError(RuntimeError):
+    def __init__(self, code, where, text):
+        super().__init__(f"{where}: bnn_status {code}: {text}")
+        self.code = code
+
+
+class bnn_rng(ctypes.Structure):
+    _fields_ = [("seed", ctypes.c_uint64), ("step", ctypes.c_uint64),
+                ("step_dev", ctypes.c_void_p), ("elem_offset", ctypes.c_uint64),
+                ("tensor_id", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+class bnn_view(ctypes.Structure):
+    _fields_ = [("base", ctypes.c_void_p), ("batch_stride", ctypes.c_int64),
+                ("P", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class bnn_conv2d_geom(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("B", "C", "H", "W", "c0", "Cg", "KH", "KW", "OH", "OW", "sh", "sw", "ph", "pw", "dh", "dw")]
+
+
+class bnn_kl_tensor(ctypes.Structure):
+    _fields_ = [("mu", ctypes.c_void_p), ("rho", ctypes.c_void_p), ("grad_mu", ctypes.c_void_p),
+                ("grad_rho", ctypes.c_void_p), ("numel", ctypes.c_int64),
+                ("prior_loc", ctypes.c_float), ("prior_scale", ctypes.c_float),
+                ("grad_coeff", ctypes.c_float), ("reserved", ctypes.c_float)]
+
+
+class bnn_prune_tensor(ctypes.Structure):
+    _fields_ = [("mu", ctypes.c_void_p), ("rho", ctypes.c_void_p), ("mask_out", ctypes.c_void_p),
+                ("keys_out", ctypes.c_void_p), ("numel", ctypes.c_int64), ("k", ctypes.c_int64)]
+
+
+_SIGNATURES = {
+    "bnn_abi_version": (ctypes.c_int, []),
+    "bnn_last_error_string": (ctypes.c_char_p, []),
+    "bnn_device_supported": (ctypes.c_int, [ctypes.c_int]),
+    "bnn_stddev": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.c_int64, ctypes.c_void_p]),
+    "bnn_materialize": (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, ctypes.c_int64,
+                                       ctypes.c_int32, ctypes.c_uint32, ctypes.POINTER(bnn_rng),
+                                       ctypes.c_void_p]),
+    "bnn_sampled_gemm_fwd": (ctypes.c_int, [_c_f32p, ctypes.c_int64, ctypes.c_int64, _c_f32p, _c_f32p,
+                                            _c_f32p, _c_f32p, _c_f32p, _c_f32p, bnn_view, ctypes.c_int64,
+                                            ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                            ctypes.c_uint32, ctypes.POINTER(bnn_rng), ctypes.POINTER(bnn_rng),
+                                            ctypes.c_int32, ctypes.c_void_p]),
+    "bnn_sampled_gemm_dgrad": (ctypes.c_int, [bnn_view, ctypes.c_int64, _c_f32p, _c_f32p, _c_f32p, _c_f32p,
+                                              ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                              ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32,
+                                              ctypes.POINTER(bnn_rng), ctypes.c_int32, ctypes.c_void_p]),
+    "bnn_sampled_gemm_wgrad": (ctypes.c_int, [bnn_view, ctypes.c_int64, _c_f32p, ctypes.c_int64, ctypes.c_int64,
+                                              _c_f32p, _c_f32p, _c_f32p, _c_f32p, ctypes.c_int32,
+                                              ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32,
+                                              ctypes.POINTER(bnn_rng), ctypes.c_int32, ctypes.c_void_p]),
+    "bnn_bias_grad": (ctypes.c_int, [bnn_view, ctypes.c_int64, _c_f32p, _c_f32p, _c_f32p, _c_f32p,
+                                     ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32,
+                                     ctypes.POINTER(bnn_rng), ctypes.c_void_p]),
+    "bnn_im2col": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.POINTER(bnn_conv2d_geom), ctypes.c_void_p]),
+    "bnn_col2im": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.POINTER(bnn_conv2d_geom), ctypes.c_int32,
+                                  ctypes.c_void_p]),
+    "bnn_kl_workspace_size": (ctypes.c_size_t, [ctypes.c_int32]),
+    "bnn_kl": (ctypes.c_int, [ctypes.POINTER(bnn_kl_tensor), ctypes.c_int32, ctypes.c_void_p, _c_f32p,
+                              ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "bnn_prune_workspace_size": (ctypes.c_size_t, [ctypes.POINTER(bnn_prune_tensor), ctypes.c_int32]),
+    "bnn_prune": (ctypes.c_int, [ctypes.POINTER(bnn_prune_tensor), ctypes.c_int32, ctypes.c_void_p,
+                                 ctypes.c_size_t, ctypes.c_void_p]),
+    "bnn_selftest_umma": (ctypes.c_int, [_c_f32p, ctypes.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lib_lock = threading.Lock()
+launch_count = 0          # kernels launched through this binding (bench.py reports it)
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        with _lib_lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: build it with `python -m bayesianneuralnetworks_b200._build` "
+                        "(there is no CPU or PyTorch fallback for the variational hot path)")
+                handle = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def _check(code, where):
+    if code != 0:
+        raise BnnError(code, where, lib().bnn_last_error_string().decode("utf-8", "replace"))
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "bayesianneuralnetworks_b200: the variational hot path runs on CUDA (sm_100a) only; got a "
+                f"{t.device} tensor. Move the module and its inputs to a B200 device (no CPU fallback).")
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, name):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def make_rng(seed, step, tensor_id, elem_offset=0, step_dev=None):
+    r = bnn_rng()
+    r.seed = seed & 0xFFFFFFFFFFFFFFFF
+    r.step = step & 0xFFFFFFFFFFFFFFFF
+    r.step_dev = None if step_dev is None else step_dev.data_ptr()
+    r.elem_offset = elem_offset
+    r.tensor_id = tensor_id & 0xFFFFFFFF
+    r.reserved = 0
+    return r
+
+
+def make_view(t_base_ptr, batch_stride, P):
+    v = bnn_view()
+    v.base = t_base_ptr
+    v.batch_stride = batch_stride
+    v.P = P
+    v.reserved = 0
+    return v
+
+
+# ---------------------------------------------------------------------------------------------
+def abi_version():
+    return lib().bnn_abi_version()
+
+
+def device_supported(device=0):
+    return lib().bnn_device_supported(int(device)) == 0
+
+
+def stddev(rho, out=None):
+    require_cuda(rho)
+    rho = _f32c(rho, "rho")
+    if out is None:
+        out = torch.empty_like(rho)
+    with torch.cuda.device(rho.device):
+        _check(lib().bnn_stddev(_ptr(rho), _ptr(out), rho.numel(), _stream()), "bnn_stddev")
+    _count()
+    return out
+
+
+def materialize(mu, sigma, S, sample_begin, rng, eps_in=None, want_eps=False):
+    """[S, *mu.shape] sampled tensors (+ the eps used when want_eps)."""
+    require_cuda(mu, sigma, eps_in)
+    mu, sigma, eps_in = _f32c(mu, "mu"), _f32c(sigma, "sigma"), _f32c(eps_in, "eps_in")
+    out = torch.empty((S,) + tuple(mu.shape), device=mu.device, dtype=torch.float32)
+    eps_out = torch.empty_like(out) if want_eps else None
+    if eps_in is not None and eps_in.numel() != S * mu.numel():
+        raise ValueError("eps_in must hold S * numel values")
+    with torch.cuda.device(mu.device):
+        _check(lib().bnn_materialize(_ptr(mu), _ptr(sigma), _ptr(eps_in), _ptr(out), _ptr(eps_out),
+                                     mu.numel(), S, sample_begin, ctypes.byref(rng), _stream()),
+               "bnn_materialize")
+    _count()
+    return (out, eps_out) if want_eps else out
+
+
+def sampled_gemm_fwd(a, lda, a_sample_stride, mu_w, sigma_w, mu_b, sigma_b, eps_w, eps_b, y_view,
+                     y_sample_stride, M, N, K, S, sample_begin, rng_w, rng_b, precision):
+    with torch.cuda.device(a.device):
+        _check(lib().bnn_sampled_gemm_fwd(_ptr(a), lda, a_sample_stride, _ptr(mu_w), _ptr(sigma_w),
+                                          _ptr(mu_b), _ptr(sigma_b), _ptr(eps_w), _ptr(eps_b), y_view,
+                                          y_sample_stride, M, N, K, S, sample_begin, ctypes.byref(rng_w),
+                                          ctypes.byref(rng_b) if rng_b is not None else None, precision,
+                                          _stream()), "bnn_sampled_gemm_fwd")
+    _count()
+
+
+def sampled_gemm_dgrad(dy_view, dy_sample_stride, mu_w, sigma_w, eps_w, da, lda, a_sample_stride, M, N, K,
+                       S, sample_begin, rng_w, precision):
+    with torch.cuda.device(da.device):
+        _check(lib().bnn_sampled_gemm_dgrad(dy_view, dy_sample_stride, _ptr(mu_w), _ptr(sigma_w), _ptr(eps_w),
+                                            _ptr(da), lda, a_sample_stride, M, N, K, S, sample_begin,
+                                            ctypes.byref(rng_w), precision, _stream()),
+               "bnn_sampled_gemm_dgrad")
+    _count()
+
+
+def sampled_gemm_wgrad(dy_view, dy_sample_stride, a, lda, a_sample_stride, rho_w, eps_w, dmu_w, drho_w, M, N,
+                       K, S, sample_begin, rng_w, precision):
+    with torch.cuda.device(a.device):
+        _check(lib().bnn_sampled_gemm_wgrad(dy_view, dy_sample_stride, _ptr(a), lda, a_sample_stride,
+                                            _ptr(rho_w), _ptr(eps_w), _ptr(dmu_w), _ptr(drho_w), M, N, K, S,
+                                            sample_begin, ctypes.byref(rng_w), precision, _stream()),
+               "bnn_sampled_gemm_wgrad")
+    _count()
+
+
+def bias_grad(dy_view, dy_sample_stride, rho_b, eps_b, dmu_b, drho_b, M, N, S, sample_begin, rng_b):
+    with torch.cuda.device(rho_b.device):
+        _check(lib().bnn_bias_grad(dy_view, dy_sample_stride, _ptr(rho_b), _ptr(eps_b), _ptr(dmu_b),
+                                   _ptr(drho_b), M, N, S, sample_begin, ctypes.byref(rng_b), _stream()),
+               "bnn_bias_grad")
+    _count()
+
+
+def im2col(x, col, geom):
+    with torch.cuda.device(x.device):
+        _check(lib().bnn_im2col(_ptr(x), _ptr(col), ctypes.byref(geom), _stream()), "bnn_im2col")
+    _count()
+
+
+def col2im(dcol, dx, geom, accumulate):
+    with torch.cuda.device(dx.device):
+        _check(lib().bnn_col2im(_ptr(dcol), _ptr(dx), ctypes.byref(geom), 1 if accumulate else 0, _stream()),
+               "bnn_col2im")
+    _count()
+
+
+_kl_ws = {}
+
+
+def _workspace(cache, device, nbytes):
+    ws = cache.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        cache[device] = ws
+    return ws
+
+
+def kl(entries, want_sums=True, grad_scale=None):
+    """entries: list of (mu, rho, grad_mu|None, grad_rho|None, prior_loc, prior_scale, grad_coeff).
+    Returns the per-tensor element sums (float64 device tensor) or None."""
+    n = len(entries)
+    if n == 0:
+        raise ValueError("bnn_kl needs at least one tensor")
+    table = (bnn_kl_tensor * n)()
+    device = entries[0][0].device
+    for i, (mu, rho, gmu, grho, loc, scale, coeff) in enumerate(entries):
+        require_cuda(mu, rho, gmu, grho)
+        _f32c(mu, "mu"), _f32c(rho, "rho"), _f32c(gmu, "grad_mu"), _f32c(grho, "grad_rho")
+        if mu.device != device:
+            raise ValueError("all tensors of one bnn_kl call must live on one device")
+        t = table[i]
+        t.mu, t.rho = mu.data_ptr(), rho.data_ptr()
+        t.grad_mu = None if gmu is None else gmu.data_ptr()
+        t.grad_rho = None if grho is None else grho.data_ptr()
+        t.numel = mu.numel()
+        t.prior_loc, t.prior_scale, t.grad_coeff, t.reserved = loc, scale, coeff, 0.0
+    sums = torch.empty(n, dtype=torch.float64, device=device) if want_sums else None
+    nbytes = lib().bnn_kl_workspace_size(n)
+    ws = _workspace(_kl_ws, device, nbytes + 256)
+    base = (ws.data_ptr() + 255) & ~255
+    with torch.cuda.device(device):
+        _check(lib().bnn_kl(table, n, _ptr(sums), _ptr(grad_scale), ctypes.c_void_p(base), nbytes, _stream()),
+               "bnn_kl")
+    _count((n + 23) // 24)
+    return sums
+
+
+_prune_ws = {}
+
+
+def prune(entries):
+    """entries: list of (mu, rho, k, mask_out|None, keys_out|None); mu/rho are modified in place."""
+    n = len(entries)
+    if n == 0:
+        return
+    table = (bnn_prune_tensor * n)()
+    device = entries[0][0].device
+    for i, (mu, rho, k, mask, keys) in enumerate(entries):
+        require_cuda(mu, rho, mask, keys)
+        _f32c(mu, "mu"), _f32c(rho, "rho"), _f32c(keys, "keys_out")
+        if mask is not None and (mask.dtype not in (torch.uint8, torch.bool) or not mask.is_contiguous()):
+            raise TypeError("mask_out must be a contiguous uint8/bool tensor")
+        t = table[i]
+        t.mu, t.rho = mu.data_ptr(), rho.data_ptr()
+        t.mask_out = None if mask is None else mask.data_ptr()
+        t.keys_out = None if keys is None else keys.data_ptr()
+        t.numel, t.k = mu.numel(), int(k)
+    nbytes = lib().bnn_prune_workspace_size(table, n)
+    ws = _workspace(_prune_ws, device, nbytes + 256)
+    base = (ws.data_ptr() + 255) & ~255
+    with torch.cuda.device(device):
+        _check(lib().bnn_prune(table, n, ctypes.c_void_p(base), nbytes, _stream()), "bnn_prune")
+    _count(9 * ((n + 23) // 24))
+
+
+def selftest_umma(device="cuda"):
+    out = torch.zeros(1, dtype=torch.float32, device=device)
+    with torch.cuda.device(out.device):
+        _check(lib().bnn_selftest_umma(_ptr(out), _stream()), "bnn_selftest_umma")
+    _count()
+    return float(out.item())

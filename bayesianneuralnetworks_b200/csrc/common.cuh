@@ -42,6 +42,7 @@ struct RngKey {        // resolved on the device at kernel entry (adds *step_dev
   uint32_t k0, k1;     // Philox key
   uint32_t tensor_id;  // counter word 2
   uint32_t step_lo;    // counter word 3
+  uint64_t elem_offset;  // added to the element index (slice of a larger tensor)
 };
 
 __device__ __forceinline__ RngKey resolve_rng(const bnn_rng& r) {
@@ -52,6 +53,7 @@ __device__ __forceinline__ RngKey resolve_rng(const bnn_rng& r) {
   k.k1 = static_cast<uint32_t>(r.seed >> 32) ^ static_cast<uint32_t>(step >> 32);
   k.tensor_id = r.tensor_id;
   k.step_lo = static_cast<uint32_t>(step);
+  k.elem_offset = r.elem_offset;
   return k;
 }
 
@@ -83,9 +85,11 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   return make_float2(radius * c, radius * s);
 }
 
-// eps for elements 4*group .. 4*group+3 of (tensor, sample)
+// eps for elements 4*group .. 4*group+3 of (tensor, sample); group counts from the slice start and
+// elem_offset must be a multiple of 4 on this path
 __device__ __forceinline__ float4 eps4(const RngKey& k, uint32_t sample, uint32_t group) {
-  const uint4 r = philox4x32_10(make_uint4(group, sample, k.tensor_id, k.step_lo), k.k0, k.k1);
+  const uint32_t g = group + static_cast<uint32_t>(k.elem_offset >> 2);
+  const uint4 r = philox4x32_10(make_uint4(g, sample, k.tensor_id, k.step_lo), k.k0, k.k1);
   const float2 a = box_muller(r.x, r.y);
   const float2 b = box_muller(r.z, r.w);
   return make_float4(a.x, a.y, b.x, b.y);
@@ -97,7 +101,10 @@ __device__ __forceinline__ float pick4(const float4& v, int j) {
 
 // eps of one element (slow path: one Philox call per element)
 __device__ __forceinline__ float eps1(const RngKey& k, uint32_t sample, uint64_t element) {
-  return pick4(eps4(k, sample, static_cast<uint32_t>(element >> 2)), static_cast<int>(element & 3));
+  const uint64_t e = element + k.elem_offset;
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(e >> 2), sample, k.tensor_id, k.step_lo), k.k0, k.k1);
+  const float2 n = (e & 2) ? box_muller(r.z, r.w) : box_muller(r.x, r.y);
+  return (e & 1) ? n.y : n.x;
 }
 
 // ---------------------------------------------------------------------------------------------

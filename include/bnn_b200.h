@@ -49,13 +49,15 @@ typedef enum bnn_precision {
 
 /* Philox stream selector.  eps(seed, step, tensor_id, sample, element):
  *   key     = (seed_lo, seed_hi)
- *   counter = (element / 4, sample, tensor_id, step_lo) with step_hi folded into key.y
+ *   counter = ((element + elem_offset) / 4, sample, tensor_id, step_lo) with step_hi folded into key.y
  * `step_dev` (optional, device pointer to one uint64) is ADDED to `step` inside the kernel, so a
  * captured CUDA graph can advance the stream without re-capturing. */
 typedef struct bnn_rng {
   uint64_t seed;
   uint64_t step;
   const uint64_t* step_dev;
+  uint64_t elem_offset;   /* added to every element index: lets a launch address a slice (one conv
+                             group) of a tensor and still draw the tensor-global stream */
   uint32_t tensor_id;
   uint32_t reserved;
 } bnn_rng;
