@@ -81,7 +81,7 @@ _SIGNATURES = {
     "bnn_col2im": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.POINTER(bnn_conv2d_geom), ctypes.c_int32,
                                   ctypes.c_void_p]),
     "bnn_kl_workspace_size": (ctypes.c_size_t, [ctypes.c_int32]),
-    "bnn_kl": (ctypes.c_int, [ctypes.POINTER(bnn_kl_tensor), ctypes.c_int32, ctypes.c_void_p, _c_f32p,
+    "bnn_kl": (ctypes.c_int, [ctypes.POINTER(bnn_kl_tensor), ctypes.c_int32, ctypes.c_void_p, _c_f32p, _c_f32p,
                               ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "bnn_prune_workspace_size": (ctypes.c_size_t, [ctypes.POINTER(bnn_prune_tensor), ctypes.c_int32]),
     "bnn_prune": (ctypes.c_int, [ctypes.POINTER(bnn_prune_tensor), ctypes.c_int32, ctypes.c_void_p,
@@ -270,9 +270,10 @@ def _workspace(cache, device, nbytes):
     return ws
 
 
-def kl(entries, want_sums=True, grad_scale=None):
+def kl(entries, want_sums=True, grad_scale=None, want_total=False):
     """entries: list of (mu, rho, grad_mu|None, grad_rho|None, prior_loc, prior_scale, grad_coeff).
-    Returns the per-tensor element sums (float64 device tensor) or None."""
+    Returns the per-tensor element sums (float64 device tensor), or with want_total the 0-dim float32
+    sum_t grad_coeff[t] * kl_sum[t] (both as a tuple when both are requested), or None."""
     n = len(entries)
     if n == 0:
         raise ValueError("bnn_kl needs at least one tensor")
@@ -290,14 +291,17 @@ def kl(entries, want_sums=True, grad_scale=None):
         t.numel = mu.numel()
         t.prior_loc, t.prior_scale, t.grad_coeff, t.reserved = loc, scale, coeff, 0.0
     sums = torch.empty(n, dtype=torch.float64, device=device) if want_sums else None
+    total = torch.empty((), dtype=torch.float32, device=device) if want_total else None
     nbytes = lib().bnn_kl_workspace_size(n)
     ws = _workspace(_kl_ws, device, nbytes + 256)
     base = (ws.data_ptr() + 255) & ~255
     with torch.cuda.device(device):
-        _check(lib().bnn_kl(table, n, _ptr(sums), _ptr(grad_scale), ctypes.c_void_p(base), nbytes, _stream()),
-               "bnn_kl")
+        _check(lib().bnn_kl(table, n, _ptr(sums), _ptr(total), _ptr(grad_scale), ctypes.c_void_p(base), nbytes,
+                            _stream()), "bnn_kl")
     _count((n + 23) // 24)
-    return sums
+    if want_sums and want_total:
+        return sums, total
+    return total if want_total else sums
 
 
 _prune_ws = {}

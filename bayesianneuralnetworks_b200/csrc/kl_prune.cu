@@ -102,15 +102,16 @@ __device__ __forceinline__ double block_sum_double(double v, double* smem8) {
 
 template <bool kGrad>
 __global__ void __launch_bounds__(kThreads)
-kl_kernel(const __grid_constant__ KlTable tab, double* __restrict__ kl_sum,
-          const float* __restrict__ grad_scale_dev, double* __restrict__ partials,
+kl_kernel(const __grid_constant__ KlTable tab, double* __restrict__ kl_sum, float* __restrict__ kl_total,
+          int accumulate_total, const float* __restrict__ grad_scale_dev, double* __restrict__ partials,
           unsigned int* __restrict__ done_counter) {
+  const bool want_sums = kl_sum != nullptr || kl_total != nullptr;
   __shared__ int64_t s_begin[kMaxTensors];
   __shared__ double s_red[kThreads / 32];
   __shared__ bool s_last;
   if (threadIdx.x < tab.n) s_begin[threadIdx.x] = tab.t[threadIdx.x].chunk_begin;
   // every (tensor, block) slot is written exactly once per launch: zero now, overwrite on flush
-  if (kl_sum != nullptr)
+  if (want_sums)
     for (int t = threadIdx.x; t < tab.n; t += kThreads) partials[static_cast<int64_t>(t) * gridDim.x + blockIdx.x] = 0.0;
   __syncthreads();
   const float gscale = (kGrad && grad_scale_dev != nullptr) ? *grad_scale_dev : 1.0f;
@@ -121,7 +122,7 @@ kl_kernel(const __grid_constant__ KlTable tab, double* __restrict__ kl_sum,
   for (int64_t chunk = blockIdx.x; chunk < tab.total_chunks; chunk += gridDim.x) {
     const int t = find_tensor(s_begin, tab.n, chunk);
     if (t != cur) {
-      if (cur >= 0 && kl_sum != nullptr) {
+      if (cur >= 0 && want_sums) {
         const double tot = block_sum_double(acc_d + static_cast<double>(acc), s_red);
         if (threadIdx.x == 0) partials[static_cast<int64_t>(cur) * gridDim.x + blockIdx.x] = tot;
       }
@@ -167,7 +168,7 @@ kl_kernel(const __grid_constant__ KlTable tab, double* __restrict__ kl_sum,
     acc_d += static_cast<double>(acc);
     acc = 0.f;
   }
-  if (kl_sum == nullptr) return;
+  if (!want_sums) return;
   if (cur >= 0) {
     const double tot = block_sum_double(acc_d, s_red);
     if (threadIdx.x == 0) partials[static_cast<int64_t>(cur) * gridDim.x + blockIdx.x] = tot;
@@ -182,14 +183,22 @@ kl_kernel(const __grid_constant__ KlTable tab, double* __restrict__ kl_sum,
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  double weighted = 0.0;
   for (int t = 0; t < tab.n; ++t) {
     double v = 0.0;
     for (unsigned int b = threadIdx.x; b < gridDim.x; b += kThreads)
       v += __ldcg(partials + static_cast<int64_t>(t) * gridDim.x + b);
     const double tot = block_sum_double(v, s_red);
-    if (threadIdx.x == 0) kl_sum[t] = tot;
+    if (threadIdx.x == 0) {
+      if (kl_sum != nullptr) kl_sum[t] = tot;
+      weighted += static_cast<double>(tab.t[t].coeff) * tot;
+    }
   }
-  if (threadIdx.x == 0) *done_counter = 0u;   // ready for the next launch on this stream
+  if (threadIdx.x == 0) {
+    if (kl_total != nullptr)
+      *kl_total = static_cast<float>((accumulate_total ? static_cast<double>(*kl_total) : 0.0) + weighted);
+    *done_counter = 0u;   // ready for the next launch on this stream
+  }
 }
 
 int kl_grid(bool grad, int64_t total_chunks) {
@@ -483,7 +492,7 @@ size_t bnn_kl_workspace_size(int32_t n_tensors) {
   return static_cast<size_t>(kMaxTensors) * kMaxGrid * sizeof(double) + 256;
 }
 
-int bnn_kl(const bnn_kl_tensor* tensors, int32_t n_tensors, double* kl_sum,
+int bnn_kl(const bnn_kl_tensor* tensors, int32_t n_tensors, double* kl_sum, float* kl_total,
            const float* grad_scale_dev, void* workspace, size_t workspace_bytes, void* stream) {
   BNN_REQUIRE(n_tensors >= 0, BNN_ERR_BAD_ARGUMENT, "n_tensors < 0");
   if (n_tensors == 0) return BNN_OK;
@@ -513,7 +522,10 @@ int bnn_kl(const bnn_kl_tensor* tensors, int32_t n_tensors, double* kl_sum,
     for (int i = 0; i < n_tensors; ++i)
       BNN_REQUIRE(tensors[i].grad_mu != nullptr || tensors[i].numel == 0, BNN_ERR_BAD_ARGUMENT,
                   "bnn_kl: gradients requested for some tensors but not tensor %d", i);
-  BNN_REQUIRE(kl_sum != nullptr || any_grad, BNN_ERR_BAD_ARGUMENT, "bnn_kl: nothing to compute");
+  BNN_REQUIRE(kl_sum != nullptr || kl_total != nullptr || any_grad, BNN_ERR_BAD_ARGUMENT,
+              "bnn_kl: nothing to compute");
+  const bool want_sums = kl_sum != nullptr || kl_total != nullptr;
+  bool total_started = false;
 
   for (int first = 0; first < n_tensors; first += kMaxTensors) {
     const int n = (n_tensors - first < kMaxTensors) ? n_tensors - first : kMaxTensors;
@@ -541,14 +553,17 @@ int bnn_kl(const bnn_kl_tensor* tensors, int32_t n_tensors, double* kl_sum,
       if (out) BNN_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double) * n, st));
       continue;
     }
-    if (out) BNN_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    if (want_sums) BNN_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
     const int grid = kl_grid(any_grad, chunks);
+    const int acc = total_started ? 1 : 0;
     if (any_grad)
-      kl_kernel<true><<<grid, kThreads, 0, st>>>(tab, out, grad_scale_dev, partials, counter);
+      kl_kernel<true><<<grid, kThreads, 0, st>>>(tab, out, kl_total, acc, grad_scale_dev, partials, counter);
     else
-      kl_kernel<false><<<grid, kThreads, 0, st>>>(tab, out, grad_scale_dev, partials, counter);
+      kl_kernel<false><<<grid, kThreads, 0, st>>>(tab, out, kl_total, acc, grad_scale_dev, partials, counter);
     BNN_CUDA_OK(cudaGetLastError());
+    total_started = true;
   }
+  if (kl_total != nullptr && !total_started) BNN_CUDA_OK(cudaMemsetAsync(kl_total, 0, sizeof(float), st));
   return BNN_OK;
 }
 

@@ -1,0 +1,270 @@
+"""torch.autograd glue around the C ABI: each Function forwards to the CUDA library on the current
+stream and implements the closed-form backward of SURVEY §3.2 with the fused kernels (eps is
+regenerated from the Philox counters, never stored).  No CPU path: non-CUDA tensors raise.
+"""
+import torch
+
+from . import _C
+
+
+class DrawSpec:
+    """Which eps a launch uses: Philox (seed, tensor_id, [sample_begin, sample_begin+S)) or an
+    injected tensor [S, numel] (tests)."""
+    __slots__ = ("seed", "tensor_id", "sample_begin", "step", "eps")
+
+    def __init__(self, seed, tensor_id, draw_begin, eps=None):
+        self.seed = seed
+        self.tensor_id = tensor_id
+        self.sample_begin = draw_begin & 0xFFFFFFFF
+        self.step = draw_begin >> 32
+        self.eps = eps
+
+    def rng(self, elem_offset=0):
+        return _C.make_rng(self.seed, self.step, self.tensor_id, elem_offset=elem_offset)
+
+
+def _check_f32_cuda(name, t):
+    if t is None:
+        return
+    _C.require_cuda(t)
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: the variational hot path computes in float32, got {t.dtype}")
+
+
+def _eps_slice(spec, S, numel, lo=None, hi=None):
+    """Injected eps as a contiguous [S, n] block (optionally the [lo, hi) slice of every sample)."""
+    if spec is None or spec.eps is None:
+        return None
+    e = spec.eps.reshape(S, numel)
+    if lo is not None:
+        e = e[:, lo:hi]
+    return e.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+class SampledLinear(torch.autograd.Function):
+    """y[s] = x[s] W_s^T + b_s for S Monte-Carlo samples in one launch (dense.py:46-60).
+
+    x: [R, K] with R = S*M rows (sample-major) or, when `shared`, [M, K] used by every sample.
+    Returns [S*M, N]."""
+
+    @staticmethod
+    def forward(ctx, x, mu_w, rho_w, mu_b, rho_b, S, shared, spec_w, spec_b, precision):
+        for n, t in (("input", x), ("weight.mean", mu_w), ("weight.scale", rho_w), ("bias.mean", mu_b),
+                     ("bias.scale", rho_b)):
+            _check_f32_cuda(n, t)
+        x = x.contiguous()
+        N, K = mu_w.shape
+        if x.dim() != 2 or x.shape[1] != K:
+            raise RuntimeError(f"sampled linear: input {tuple(x.shape)} does not match in_features {K}")
+        rows = x.shape[0]
+        M = rows if shared else rows // S
+        if not shared and M * S != rows:
+            raise RuntimeError(f"sampled linear: {rows} rows are not divisible by {S} Monte-Carlo samples")
+        mu_w_c, rho_w_c = mu_w.contiguous(), rho_w.contiguous()
+        sigma_w = _C.stddev(rho_w_c)
+        has_bias = mu_b is not None
+        sigma_b = _C.stddev(rho_b.contiguous()) if has_bias else None
+        y = torch.empty((S * M, N), device=x.device, dtype=torch.float32)
+        _C.sampled_gemm_fwd(x, K, 0 if shared else M * K, mu_w_c, sigma_w,
+                            mu_b.contiguous() if has_bias else None, sigma_b,
+                            _eps_slice(spec_w, S, N * K), _eps_slice(spec_b, S, N) if has_bias else None,
+                            _C.make_view(y.data_ptr(), N, 1), M * N, M, N, K, S, spec_w.sample_begin,
+                            spec_w.rng(), spec_b.rng() if has_bias else None, precision)
+        ctx.save_for_backward(x, mu_w_c, rho_w_c, sigma_w, rho_b)
+        ctx.meta = (S, shared, spec_w, spec_b, precision, M, N, K)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mu_w, rho_w, sigma_w, rho_b = ctx.saved_tensors
+        S, shared, spec_w, spec_b, precision, M, N, K = ctx.meta
+        dy = dy.contiguous()
+        dy_view = _C.make_view(dy.data_ptr(), N, 1)
+        eps_w = _eps_slice(spec_w, S, N * K)
+        a_stride = 0 if shared else M * K
+        dx = dmu_w = drho_w = dmu_b = drho_b = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _C.sampled_gemm_dgrad(dy_view, M * N, mu_w, sigma_w, eps_w, dx, K, a_stride, M, N, K, S,
+                                  spec_w.sample_begin, spec_w.rng(), precision)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            grads = torch.zeros((2, N, K), device=x.device, dtype=torch.float32)
+            dmu_w, drho_w = grads[0], grads[1]
+            _C.sampled_gemm_wgrad(dy_view, M * N, x, K, a_stride, rho_w, eps_w, dmu_w, drho_w, M, N, K, S,
+                                  spec_w.sample_begin, spec_w.rng(), precision)
+        if rho_b is not None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
+            bg = torch.zeros((2, N), device=x.device, dtype=torch.float32)
+            dmu_b, drho_b = bg[0], bg[1]
+            _C.bias_grad(dy_view, M * N, rho_b.contiguous(), _eps_slice(spec_b, S, N), dmu_b, drho_b, M, N, S,
+                         spec_b.sample_begin, spec_b.rng())
+        return dx, dmu_w, drho_w, dmu_b, drho_b, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+def _conv_out(size, k, s, p, d):
+    return (size + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+class SampledConv2d(torch.autograd.Function):
+    """y[s] = conv2d(x[s], W_s, b_s) for S samples (conv.py:65-73,112-119): im2col lowering of the
+    activations per group, then the sampled GEMM writing straight into the NCHW output.
+
+    x: [S*B, C, H, W] (sample-major) or, when `shared`, [B, C, H, W].  Returns [S*B, Cout, OH, OW]."""
+
+    @staticmethod
+    def forward(ctx, x, mu_w, rho_w, mu_b, rho_b, S, shared, spec_w, spec_b, precision, stride, padding,
+                dilation, groups):
+        for n, t in (("input", x), ("weight.mean", mu_w), ("weight.scale", rho_w), ("bias.mean", mu_b),
+                     ("bias.scale", rho_b)):
+            _check_f32_cuda(n, t)
+        x = x.contiguous()
+        Cout, Cg, KH, KW = mu_w.shape
+        if x.dim() != 4 or x.shape[1] != Cg * groups:
+            raise RuntimeError(f"sampled conv2d: input {tuple(x.shape)} does not match weight {tuple(mu_w.shape)} "
+                               f"with groups={groups}")
+        rows, C, H, W = x.shape
+        B = rows if shared else rows // S
+        if not shared and B * S != rows:
+            raise RuntimeError(f"sampled conv2d: batch {rows} is not divisible by {S} Monte-Carlo samples")
+        OH = _conv_out(H, KH, stride[0], padding[0], dilation[0])
+        OW = _conv_out(W, KW, stride[1], padding[1], dilation[1])
+        if OH <= 0 or OW <= 0:
+            raise RuntimeError("sampled conv2d: empty output")
+        geo = (B, C, H, W, Cout, Cg, KH, KW, OH, OW, tuple(stride), tuple(padding), tuple(dilation), groups)
+        mu_w_c, rho_w_c = mu_w.contiguous(), rho_w.contiguous()
+        sigma_w = _C.stddev(rho_w_c)
+        has_bias = mu_b is not None
+        mu_b_c = mu_b.contiguous() if has_bias else None
+        sigma_b = _C.stddev(rho_b.contiguous()) if has_bias else None
+        y = torch.empty((S * B, Cout, OH, OW), device=x.device, dtype=torch.float32)
+        Ng, Kg, P = Cout // groups, Cg * KH * KW, OH * OW
+        M = B * P
+        col = torch.empty((rows * P, Kg), device=x.device, dtype=torch.float32)
+        for g in range(groups):
+            _C.im2col(x, col, SampledConv2d._geom(rows, geo, g))
+            lo, hi = g * Ng * Kg, (g + 1) * Ng * Kg
+            view = _C.make_view(y.data_ptr() + 4 * g * Ng * P, Cout * P, P)
+            _C.sampled_gemm_fwd(col, Kg, 0 if shared else M * Kg, mu_w_c.view(-1)[lo:hi], sigma_w.view(-1)[lo:hi],
+                                mu_b_c[g * Ng:(g + 1) * Ng] if has_bias else None,
+                                sigma_b[g * Ng:(g + 1) * Ng] if has_bias else None,
+                                _eps_slice(spec_w, S, Cout * Kg, lo, hi),
+                                _eps_slice(spec_b, S, Cout, g * Ng, (g + 1) * Ng) if has_bias else None,
+                                view, B * Cout * P, M, Ng, Kg, S, spec_w.sample_begin, spec_w.rng(lo),
+                                spec_b.rng(g * Ng) if has_bias else None, precision)
+        ctx.save_for_backward(x, mu_w_c, rho_w_c, sigma_w, rho_b)
+        ctx.meta = (S, shared, spec_w, spec_b, precision, geo)
+        return y
+
+    @staticmethod
+    def _geom(batch, geo, g):
+        B, C, H, W, Cout, Cg, KH, KW, OH, OW, stride, padding, dilation, groups = geo
+        return _C.bnn_conv2d_geom(batch, C, H, W, g * Cg, Cg, KH, KW, OH, OW, stride[0], stride[1],
+                                  padding[0], padding[1], dilation[0], dilation[1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mu_w, rho_w, sigma_w, rho_b = ctx.saved_tensors
+        S, shared, spec_w, spec_b, precision, geo = ctx.meta
+        B, C, H, W, Cout, Cg, KH, KW, OH, OW, stride, padding, dilation, groups = geo
+        dy = dy.contiguous()
+        rows = x.shape[0]
+        Ng, Kg, P = Cout // groups, Cg * KH * KW, OH * OW
+        M = B * P
+        a_stride = 0 if shared else M * Kg
+        need_x = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        need_b = rho_b is not None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
+        dx = torch.empty_like(x) if need_x else None
+        grads = torch.zeros((2,) + tuple(mu_w.shape), device=x.device, dtype=torch.float32) if need_w else None
+        bg = torch.zeros((2, Cout), device=x.device, dtype=torch.float32) if need_b else None
+        col = torch.empty((rows * P, Kg), device=x.device, dtype=torch.float32) if need_w else None
+        dcol = torch.empty((rows * P, Kg), device=x.device, dtype=torch.float32) if need_x else None
+        for g in range(groups):
+            lo, hi = g * Ng * Kg, (g + 1) * Ng * Kg
+            dy_view = _C.make_view(dy.data_ptr() + 4 * g * Ng * P, Cout * P, P)
+            eps_w = _eps_slice(spec_w, S, Cout * Kg, lo, hi)
+            geom = SampledConv2d._geom(rows, geo, g)
+            if need_x:
+                _C.sampled_gemm_dgrad(dy_view, B * Cout * P, mu_w.view(-1)[lo:hi], sigma_w.view(-1)[lo:hi], eps_w,
+                                      dcol, Kg, a_stride, M, Ng, Kg, S, spec_w.sample_begin, spec_w.rng(lo),
+                                      precision)
+                _C.col2im(dcol, dx, geom, False)
+            if need_w:
+                _C.im2col(x, col, geom)
+                _C.sampled_gemm_wgrad(dy_view, B * Cout * P, col, Kg, a_stride, rho_w.view(-1)[lo:hi], eps_w,
+                                      grads[0].view(-1)[lo:hi], grads[1].view(-1)[lo:hi], M, Ng, Kg, S,
+                                      spec_w.sample_begin, spec_w.rng(lo), precision)
+            if need_b:
+                _C.bias_grad(dy_view, B * Cout * P, rho_b.contiguous()[g * Ng:(g + 1) * Ng],
+                             _eps_slice(spec_b, S, Cout, g * Ng, (g + 1) * Ng), bg[0][g * Ng:(g + 1) * Ng],
+                             bg[1][g * Ng:(g + 1) * Ng], M, Ng, S, spec_b.sample_begin, spec_b.rng(g * Ng))
+        return (dx, grads[0] if need_w else None, grads[1] if need_w else None,
+                bg[0] if need_b else None, bg[1] if need_b else None) + (None,) * 9
+
+
+# ------------------------------------------------------------------------------------------------
+class Materialize(torch.autograd.Function):
+    """W_s = mean + stddev * eps_s for s in [0, S) as a tensor [S, *shape] (core.py:44-45); used by
+    `.sampled` and by layers without a fused contraction (NormalConv3d)."""
+
+    @staticmethod
+    def forward(ctx, mu, rho, S, spec):
+        _check_f32_cuda("mean", mu)
+        _check_f32_cuda("scale", rho)
+        mu_c, rho_c = mu.contiguous(), rho.contiguous()
+        sigma = _C.stddev(rho_c)
+        out = _C.materialize(mu_c, sigma, S, spec.sample_begin, spec.rng(), eps_in=_eps_slice(spec, S, mu.numel()))
+        ctx.save_for_backward(rho_c)
+        ctx.meta = (S, spec)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (rho,) = ctx.saved_tensors
+        S, spec = ctx.meta
+        if spec.eps is not None:
+            eps = spec.eps.reshape((S,) + tuple(rho.shape))
+        else:
+            zero, one = torch.zeros_like(rho), torch.ones_like(rho)
+            eps = _C.materialize(zero, one, S, spec.sample_begin, spec.rng())
+        dmu = g.sum(0)
+        drho = (g * eps).sum(0) * torch.sigmoid(rho)
+        return dmu, drho, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+class KLSum(torch.autograd.Function):
+    """sum_t coeff_t * sum_i KL(N(mu_ti, sigma_ti) || N(loc_t, scale_t)) over many tensors in one
+    bandwidth-bound launch (loss.py:16-38 with coeff_t = 1 / (numel_t * n_tensors * n_batches)).
+    Backward is one more pass that writes coeff_t * dKL/d(mu, rho) scaled by the upstream gradient
+    (read on the device, no host sync)."""
+
+    @staticmethod
+    def forward(ctx, priors, coeffs, *params):
+        n = len(params) // 2
+        entries = []
+        for t in range(n):
+            mu, rho = params[2 * t], params[2 * t + 1]
+            _check_f32_cuda("mean", mu)
+            _check_f32_cuda("scale", rho)
+            entries.append((mu.contiguous(), rho.contiguous(), None, None, priors[t][0], priors[t][1], coeffs[t]))
+        total = _C.kl(entries, want_sums=False, want_total=True)
+        ctx.save_for_backward(*[e[i] for e in entries for i in (0, 1)])
+        ctx.meta = (priors, coeffs)
+        return total
+
+    @staticmethod
+    def backward(ctx, g):
+        priors, coeffs = ctx.meta
+        saved = ctx.saved_tensors
+        n = len(saved) // 2
+        scale = g.detach().to(torch.float32).reshape(1).contiguous()
+        entries, grads = [], []
+        for t in range(n):
+            mu, rho = saved[2 * t], saved[2 * t + 1]
+            gm, gr = torch.empty_like(mu), torch.empty_like(rho)
+            grads += [gm, gr]
+            entries.append((mu, rho, gm, gr, priors[t][0], priors[t][1], coeffs[t]))
+        _C.kl(entries, want_sums=False, want_total=False, grad_scale=scale)
+        return (None, None) + tuple(grads)

@@ -1,0 +1,12 @@
+"""Source-compatible surface of pytorch_bayesian.nn for the variational hot path
+(pytorch_bayesian/nn/__init__.py:7-35; classes outside SURVEY §8's scope are not provided)."""
+from .container import BayesianModule, BayesianNetworkModule, register_rowwise_module
+from .variational import WeightNormal
+from .layers import (BayesianLinear, NormalLinear, BayesianConvNd, NormalConvNd, NormalConv1d, NormalConv2d,
+                     NormalConv3d)
+from .loss import KLDivergence, Entropy
+
+__all__ = [
+    'BayesianModule', 'BayesianNetworkModule', 'WeightNormal', 'BayesianLinear', 'NormalLinear',
+    'BayesianConvNd', 'NormalConvNd', 'NormalConv1d', 'NormalConv2d', 'NormalConv3d', 'KLDivergence', 'Entropy',
+]

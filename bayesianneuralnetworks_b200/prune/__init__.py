@@ -1,0 +1,4 @@
+"""pytorch_bayesian.prune: PruneNormal (mirror of pytorch_bayesian/prune/prune.py:5-22)."""
+from .prune import PruneNormal
+
+__all__ = ['PruneNormal']

@@ -1,0 +1,133 @@
+"""Process-wide knobs of the variational hot path that the reference does not have (additive,
+module-level; no constructor signature changes — SURVEY §8b):
+
+  manual_seed(seed)        key of the in-kernel Philox stream (default 0x5EED)
+  set_precision(mode)      'fp32' (three-term TF32 split, 1e-5 parity class; default) or 'tf32'
+  set_mc_batching(mode)    'auto' | 'always' | 'never': fold the S Monte-Carlo passes of
+                           BayesianNetworkModule.forward (container.py:32-37) into one launch per layer
+  set_sample_partition(rank, world)   this process evaluates MC samples s with s % world == rank ... see below
+  injected_eps({weight: eps})         test-only: feed recorded torch.randn_like draws to the kernels
+
+Every variational tensor (WeightNormal) owns a Philox stream (tensor_id) and a draw counter; eps
+is a pure function of (seed, tensor_id, draw index, element), so the backward pass, `.sampled`
+and any partition of the draws over GPUs regenerate identical numbers.
+"""
+import contextlib
+import itertools
+import threading
+
+from . import _C
+
+_state = {
+    "seed": 0x5EED,
+    "precision": _C.PREC_FP32X3,
+    "mc_batching": "auto",
+}
+_tensor_ids = itertools.count(1)
+_tls = threading.local()
+
+
+def manual_seed(seed):
+    """Seed of the Philox stream shared by every variational tensor of this process."""
+    _state["seed"] = int(seed) & 0xFFFFFFFFFFFFFFFF
+
+
+def seed():
+    return _state["seed"]
+
+
+def set_precision(mode):
+    modes = {"fp32": _C.PREC_FP32X3, "tf32": _C.PREC_TF32}
+    if mode not in modes:
+        raise ValueError(f"precision must be one of {sorted(modes)}, got {mode!r}")
+    _state["precision"] = modes[mode]
+
+
+def precision():
+    return _state["precision"]
+
+
+def precision_name():
+    return "fp32" if _state["precision"] == _C.PREC_FP32X3 else "tf32"
+
+
+def set_mc_batching(mode):
+    if mode not in ("auto", "always", "never"):
+        raise ValueError("mc batching mode must be 'auto', 'always' or 'never'")
+    _state["mc_batching"] = mode
+
+
+def mc_batching():
+    return _state["mc_batching"]
+
+
+def next_tensor_id():
+    return next(_tensor_ids)
+
+
+# ---------------------------------------------------------------------------------------------
+# Monte-Carlo batch context: set by BayesianNetworkModule.forward while it runs `_forward` ONCE for
+# all S samples.  Activations enter with B rows (shared by all samples); the first Bayesian layer
+# expands them to S*B rows (sample-major), later layers see S independent row blocks.
+# ---------------------------------------------------------------------------------------------
+class MCContext:
+    def __init__(self, samples, rows, sample_offset=0, total_samples=None):
+        self.samples = samples            # samples evaluated by this process in this pass
+        self.rows = rows                  # leading dimension of the un-expanded input
+        self.expanded = False
+        self.sample_offset = sample_offset            # first global sample index of this process
+        self.total_samples = total_samples or samples  # draws consumed per pass by every process
+
+
+def current_mc():
+    return getattr(_tls, "mc", None)
+
+
+@contextlib.contextmanager
+def mc_batch(ctx):
+    prev = getattr(_tls, "mc", None)
+    _tls.mc = ctx
+    try:
+        yield ctx
+    finally:
+        _tls.mc = prev
+
+
+# ---------------------------------------------------------------------------------------------
+# sample partition across processes: rank r of R evaluates the contiguous block of
+# global sample indices [r*S/R, (r+1)*S/R) of every pass; all ranks advance every draw counter by
+# the global S, so the union over ranks reproduces the single-process stream.
+# ---------------------------------------------------------------------------------------------
+_partition = {"rank": 0, "world": 1}
+
+
+def set_sample_partition(rank, world):
+    if not (0 <= rank < world):
+        raise ValueError("need 0 <= rank < world")
+    _partition["rank"], _partition["world"] = int(rank), int(world)
+
+
+def sample_partition():
+    return _partition["rank"], _partition["world"]
+
+
+# ---------------------------------------------------------------------------------------------
+# eps injection (parity tests against the reference's recorded torch.randn_like draws)
+# ---------------------------------------------------------------------------------------------
+def injected_for(weight):
+    table = getattr(_tls, "eps", None)
+    if table is None:
+        return None
+    return table.get(id(weight))
+
+
+@contextlib.contextmanager
+def injected_eps(mapping):
+    """mapping: {WeightNormal instance: eps tensor [S, *shape]} consumed by the next forward (and its
+    backward).  Test-only: the kernels read eps from memory instead of generating it."""
+    prev = getattr(_tls, "eps", None)
+    _tls.eps = {id(k): v for k, v in mapping.items()}
+    try:
+        yield
+    finally:
+        _tls.eps = prev

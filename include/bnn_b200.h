@@ -161,7 +161,7 @@ int bnn_col2im(const float* dcol, float* dx, const bnn_conv2d_geom* g, int32_t a
  * Optional gradients (both NULL or both set per tensor), written not accumulated:
  *   grad_mu = c_t*(mu-loc)/scale^2,  grad_rho = c_t*(sigma/scale^2 - 1/sigma)*sigmoid(rho),
  *   c_t = grad_coeff[t] * (grad_scale_dev ? *grad_scale_dev : 1).
- * `kl_sum` may be NULL for a gradient-only pass. */
+ * `kl_sum` and `kl_total` may both be NULL for a gradient-only pass. */
 typedef struct bnn_kl_tensor {
   const float* mu;
   const float* rho;
@@ -175,8 +175,11 @@ typedef struct bnn_kl_tensor {
 } bnn_kl_tensor;
 size_t bnn_kl_workspace_size(int32_t n_tensors);
 int bnn_kl(const bnn_kl_tensor* tensors /* HOST array */, int32_t n_tensors,
-           double* kl_sum /* device [n_tensors] or NULL */, const float* grad_scale_dev,
-           void* workspace, size_t workspace_bytes, void* stream);
+           double* kl_sum /* device [n_tensors] or NULL */,
+           float* kl_total /* device scalar or NULL: sum_t grad_coeff[t] * kl_sum[t], i.e. the
+                              reference's mean-of-means / n_batches when grad_coeff[t] =
+                              1 / (numel_t * n_tensors * n_batches) (loss.py:28,38) */,
+           const float* grad_scale_dev, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- pruning ----
  * key_i = log N(0; mu_i, sigma_i) evaluated with the exact op order of torch's Normal.log_prob

@@ -1,0 +1,171 @@
+"""CPU tests of the host-side mirror of the reference interface: traversal semantics (reference
+tests/test_utils.py), containers (tests/test_nn/test_container.py), constructor contracts, state_dict
+layout, the Monte-Carlo batching plan, draw bookkeeping — and that the C-ABI library loads and exports
+every symbol include/bnn_b200.h declares.  No kernel is launched."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import bayesianneuralnetworks_b200 as bnn
+from bayesianneuralnetworks_b200 import _C, runtime
+from bayesianneuralnetworks_b200.nn import (BayesianModule, BayesianNetworkModule, NormalConv1d, NormalConv2d,
+                                            NormalConv3d, NormalLinear, WeightNormal)
+from bayesianneuralnetworks_b200.utils import _item_or_list, _pair, _single, _triple, apply_wb, traverse
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class Net(BayesianNetworkModule):
+    def __init__(self, seq, samples=1):
+        super().__init__(1, 1, samples)
+        self.layers = seq
+
+    def _forward(self, x):
+        return self.layers(x)
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_header_symbols_are_exported_by_the_library():
+    header = open(os.path.join(ROOT, "include", "bnn_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(bnn_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert os.path.exists(_C.LIB_PATH), "libbnn_b200.so missing: run `python -m bayesianneuralnetworks_b200._build`"
+    lib = ctypes.CDLL(_C.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/bnn_b200.h but not exported"
+    assert declared == set(_C.EXPORTED_SYMBOLS), "ctypes binding and header disagree"
+    assert _C.lib().bnn_abi_version() == 1
+    assert isinstance(_C.lib().bnn_last_error_string(), bytes)
+
+
+def test_binding_struct_sizes_match_the_header():
+    assert ctypes.sizeof(_C.bnn_rng) == 40
+    assert ctypes.sizeof(_C.bnn_view) == 24
+    assert ctypes.sizeof(_C.bnn_conv2d_geom) == 64
+    assert ctypes.sizeof(_C.bnn_kl_tensor) == 56
+    assert ctypes.sizeof(_C.bnn_prune_tensor) == 48
+
+
+def test_hot_path_rejects_cpu_tensors():
+    layer = NormalLinear(3, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        layer(torch.zeros(1, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        layer.weight.sampled
+    with pytest.raises(RuntimeError, match="CUDA"):
+        bnn.prune.PruneNormal()(Net(torch.nn.Sequential(layer)), 0.5)
+
+
+# ------------------------------------------------------------------------------------------------ utils
+def test_item_or_list_and_ntuples():
+    """reference tests/test_utils.py:6-24."""
+    assert _item_or_list([1]) == 1 and _item_or_list([1, 2]) == [1, 2] and _item_or_list([]) == []
+    assert _single(3) == (3,) and _pair(3) == (3, 3) and _triple(3) == (3, 3, 3)
+    assert _pair((1, 2)) == (1, 2) and _pair([1, 2, 3]) == [1, 2, 3]      # iterables pass through unchecked
+
+
+def test_apply_wb_semantics():
+    """reference tests/test_utils.py:27-50."""
+    m = NormalLinear(3, 3)
+    assert apply_wb(m, lambda p: p.shape) == [(3, 3), (3,)]
+    assert apply_wb(m, lambda p: None) is None
+    assert apply_wb(m, lambda p, type: type, pass_type=True) == ['w', 'b']
+    assert apply_wb(m, lambda p, module: module, pass_module=True) == [m, m]
+    assert apply_wb(NormalLinear(3, 3, False), lambda p, type: type, pass_type=True) == ['w']
+    assert apply_wb(m, lambda p, a, b=0: a + b, 1, b=2) == [3, 3]
+
+
+def test_traverse_semantics():
+    """reference tests/test_utils.py:53-65 and utils.py:50-67."""
+    a, b = NormalLinear(3, 3), NormalConv2d(3, 4, 3)
+    assert traverse(torch.nn.Linear(3, 3), lambda m: [1]) is None
+    assert traverse(a, lambda m: [m]) == [a]
+    assert traverse(a, lambda m: m) is None                      # non-list results are dropped
+    seq = torch.nn.Sequential(a, torch.nn.ReLU(), torch.nn.Sequential(b), torch.nn.ModuleList([a]))
+    assert traverse(seq, lambda m: [m]) == [a, b, a]             # registration order, nested containers
+    assert traverse(torch.nn.Sequential(torch.nn.ReLU()), lambda m: [m]) is None
+
+    class Block(torch.nn.Module):                                # not a traversed container type
+        def __init__(self):
+            super().__init__()
+            self.inner = NormalLinear(3, 3)
+    assert traverse(torch.nn.Sequential(Block()), lambda m: [m]) is None
+    net = Net(torch.nn.Sequential(a, b))
+    assert net.traverse(lambda m: [type(m).__name__]) == ['NormalLinear', 'NormalConv2d']
+
+
+# ------------------------------------------------------------------------------------------------ containers / ctors
+def test_containers():
+    """reference tests/test_nn/test_container.py:16-33."""
+    p, bp = torch.distributions.Normal(0, 1), torch.distributions.Normal(0, 2)
+    m = BayesianModule(3, 4, p)
+    assert (m.in_channels, m.out_channels, m.weight_prior, m.bias_prior) == (3, 4, p, p)
+    assert BayesianModule(3, 4, p, bp).bias_prior is bp
+    n = BayesianNetworkModule(3, 4, samples=7)
+    assert (n.in_channels, n.out_channels, n.samples) == (3, 4, 7)
+    with pytest.raises(NotImplementedError):
+        n(torch.zeros(1, 3))
+
+
+def test_constructor_signatures_and_state_dict_layout():
+    lin = NormalLinear(3, 4, True, torch.distributions.Normal(0, 1))
+    assert lin.weight.shape == (4, 3) and lin.bias.shape == (4,)
+    assert float(lin.weight_prior.scale) == 1.0 and lin.bias_prior is lin.weight_prior
+    quirk = NormalLinear(3, 3, torch.distributions.Normal(0, 1))      # reference tests/conftest.py:91 passes the
+    assert quirk.bias is not None and float(quirk.weight_prior.scale) == pytest.approx(0.1)   # prior as `bias`
+    c1, c2, c3 = NormalConv1d(4, 6, 3, groups=2), NormalConv2d(4, 6, 3, 2, 1, 1, 2, False), NormalConv3d(2, 2, (1, 2, 3))
+    assert c1.weight.shape == (6, 2, 3) and c1.kernel_size == (3,) and c1.stride == (1,)
+    assert c2.weight.shape == (6, 2, 3, 3) and c2.bias is None and c2.stride == (2, 2) and c2.groups == 2
+    assert c3.weight.shape == (2, 2, 1, 2, 3) and c3.padding == (0, 0, 0) and not c3.transposed
+    with pytest.raises(ValueError):
+        NormalConv2d(3, 4, 3, groups=2)
+    net = Net(torch.nn.Sequential(torch.nn.Conv2d(1, 2, 3), c2, lin))
+    assert sorted(net.state_dict().keys()) == sorted([
+        'layers.0.weight', 'layers.0.bias', 'layers.1.weight.mean', 'layers.1.weight.scale',
+        'layers.2.weight.mean', 'layers.2.weight.scale', 'layers.2.bias.mean', 'layers.2.bias.scale'])
+    # reference initialisation (dense.py:34-44): scale ~ N(-2, 0.15), |mean| <= 1/sqrt(fan_in)
+    big = NormalLinear(400, 300)
+    assert abs(float(big.weight.scale.mean()) + 2.0) < 0.01 and abs(float(big.weight.scale.std()) - 0.15) < 0.01
+    assert float(big.weight.mean.abs().max()) <= 1 / 20 + 1e-6 and float(big.bias.mean.abs().max()) <= 1 / 20 + 1e-6
+
+
+def test_draw_bookkeeping_and_partition_arithmetic():
+    w = WeightNormal(3, 3)
+    d0 = w._draw
+    assert d0 == 1                               # the constructor's sample() (core.py:15)
+    w.sample()
+    assert w._last == (d0, 1) and w._draw == d0 + 1
+    begin = w.advance(4, offset=8, total=16)     # rank 2 of 4, 4 samples each
+    assert begin == d0 + 1 + 8 and w._last == (begin, 4) and w._draw == d0 + 17
+    spec = w.draw_spec((1 << 32) + 5, 2)
+    assert spec.sample_begin == 5 and spec.step == 1 and spec.tensor_id == w._tensor_id
+    assert WeightNormal(2)._tensor_id != w._tensor_id
+    with pytest.raises(ValueError):
+        bnn.set_sample_partition(2, 2)
+    with pytest.raises(ValueError):
+        bnn.set_precision("bf16")
+
+
+def test_mc_batching_plan():
+    ok = Net(torch.nn.Sequential(torch.nn.Conv2d(1, 2, 3), torch.nn.BatchNorm2d(2), torch.nn.ELU(),
+                                 NormalConv2d(2, 2, 3), torch.nn.Flatten(), NormalLinear(8, 3),
+                                 torch.nn.Softmax(dim=-1)), samples=4)
+    foldable, bns = ok._mc_plan()
+    assert foldable and len(bns) == 1
+    ok.eval()
+    assert ok._mc_plan() == (True, [])
+    assert not Net(torch.nn.Sequential(torch.nn.Linear(3, 3)))._mc_plan()[0]             # nothing Bayesian
+    assert not Net(torch.nn.Sequential(NormalLinear(3, 3), torch.nn.Softmax(dim=0)))._mc_plan()[0]
+    assert not Net(torch.nn.Sequential(torch.nn.Dropout(0.5), NormalLinear(3, 3)))._mc_plan()[0]
+
+    class Custom(torch.nn.Module):
+        def forward(self, x):
+            return x.view(x.size(0), -1)
+    assert not Net(torch.nn.Sequential(Custom(), NormalLinear(3, 3)))._mc_plan()[0]
+    bnn.nn.register_rowwise_module(Custom)
+    assert Net(torch.nn.Sequential(Custom(), NormalLinear(3, 3)))._mc_plan()[0]
+    assert not Net(torch.nn.Sequential(NormalConv3d(1, 1, 1)))._mc_plan()[0]              # no fused 3-d path

@@ -1,0 +1,441 @@
+"""GPU parity tests of the module API (the source-compatible mirror of pytorch_bayesian.nn / .prune)
+against golden vectors produced by the reference itself (tests/golden/make_golden.py) and against
+the CPU oracle.  eps recorded from the reference's torch.randn_like draws is injected into the CUDA
+path; tolerances: 1e-5 relative in 'fp32' mode, 2e-3 in 'tf32' (BASELINE.json north_star).
+The structure follows the reference's own tests (tests/test_nn/*.py, tests/test_prune.py), run on
+the device because the hot path has no CPU implementation.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import bayesianneuralnetworks_b200 as bnn
+from bayesianneuralnetworks_b200.nn import (BayesianConvNd, BayesianLinear, BayesianNetworkModule, KLDivergence,
+                                            NormalConv1d, NormalConv2d, NormalConv3d, NormalConvNd, NormalLinear,
+                                            WeightNormal)
+from bayesianneuralnetworks_b200.prune import PruneNormal
+from oracle import variational_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = {"fp32": 1e-5, "tf32": 2e-3}
+
+
+def rel_err(got, ref):
+    ref = torch.as_tensor(ref).double()
+    scale = ref.abs().max().clamp_min(1e-30)
+    return float((got.detach().double().cpu() - ref).abs().max() / scale)
+
+
+@pytest.fixture(autouse=True)
+def _defaults():
+    bnn.set_precision("fp32")
+    bnn.set_mc_batching("auto")
+    bnn.set_sample_partition(0, 1)
+    bnn.manual_seed(0x5EED)
+    yield
+    bnn.set_precision("fp32")
+    bnn.set_mc_batching("auto")
+
+
+class Net(BayesianNetworkModule):
+    def __init__(self, seq, samples=1):
+        super().__init__(1, 1, samples)
+        self.layers = seq
+
+    def _forward(self, x):
+        return self.layers(x)
+
+
+def load_weight(w, mean, scale):
+    with torch.no_grad():
+        w.mean.copy_(torch.from_numpy(mean))
+        w.scale.copy_(torch.from_numpy(scale))
+
+
+# ------------------------------------------------------------------------------------------------ golden: layers
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_linear_matches_reference_golden(prec):
+    z = np.load(os.path.join(GOLD, "linear_case.npz"))
+    bnn.set_precision(prec)
+    layer = NormalLinear(20, 7)
+    load_weight(layer.weight, z["w_mean"], z["w_scale"])
+    load_weight(layer.bias, z["b_mean"], z["b_scale"])
+    layer.cuda()
+    x = torch.from_numpy(z["x"]).cuda().requires_grad_(True)
+    dy = torch.from_numpy(z["dy"]).cuda()
+    ys = []
+    for s in range(3):          # the reference's loop: one pass per MC sample, W drawn before b
+        with bnn.injected_eps({layer.weight: torch.from_numpy(z["eps_w"][s:s + 1]),
+                               layer.bias: torch.from_numpy(z["eps_b"][s:s + 1])}):
+            ys.append(layer(x))
+    for s in range(3):
+        assert rel_err(ys[s], z["y"][s]) < TOL[prec]
+    kl = KLDivergence(number_of_batches=int(z["n_batches"]))(Net(torch.nn.Sequential(layer)))
+    assert float(kl) == pytest.approx(float(z["kl"]), rel=1e-5)
+    loss = sum((y * dy[s]).sum() for s, y in enumerate(ys)) + kl
+    loss.backward()
+    assert rel_err(layer.weight.mean.grad, z["g_w_mean"]) < TOL[prec]
+    assert rel_err(layer.weight.scale.grad, z["g_w_scale"]) < TOL[prec]
+    assert rel_err(layer.bias.mean.grad, z["g_b_mean"]) < TOL[prec]
+    assert rel_err(layer.bias.scale.grad, z["g_b_scale"]) < TOL[prec]
+    assert rel_err(x.grad, z["g_x"]) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("name", ["ref_cfg_a", "ref_cfg_b", "strided_grouped", "c2_shape"])
+def test_conv2d_matches_reference_golden(name, prec):
+    z = np.load(os.path.join(GOLD, f"conv_case_{name}.npz"))
+    cin, cout, k, stride, padding, dilation, groups, bias = [int(v) for v in z["cfg"]]
+    bnn.set_precision(prec)
+    layer = NormalConv2d(cin, cout, k, stride, padding, dilation, groups, bool(bias))
+    load_weight(layer.weight, z["w_mean"], z["w_scale"])
+    if bias:
+        load_weight(layer.bias, z["b_mean"], z["b_scale"])
+    layer.cuda()
+    x = torch.from_numpy(z["x"]).cuda().requires_grad_(True)
+    dy = torch.from_numpy(z["dy"]).cuda()
+    ys = []
+    for s in range(2):
+        inj = {layer.weight: torch.from_numpy(z["eps_w"][s:s + 1])}
+        if bias:
+            inj[layer.bias] = torch.from_numpy(z["eps_b"][s:s + 1])
+        with bnn.injected_eps(inj):
+            ys.append(layer(x))
+    for s in range(2):
+        assert ys[s].shape == z["y"][s].shape
+        assert rel_err(ys[s], z["y"][s]) < TOL[prec]
+    kl = KLDivergence(number_of_batches=int(z["n_batches"]))(Net(torch.nn.Sequential(layer)))
+    assert float(kl) == pytest.approx(float(z["kl"]), rel=1e-5)
+    (sum((y * dy[s]).sum() for s, y in enumerate(ys)) + kl).backward()
+    assert rel_err(layer.weight.mean.grad, z["g_w_mean"]) < TOL[prec]
+    assert rel_err(layer.weight.scale.grad, z["g_w_scale"]) < TOL[prec]
+    if bias:
+        assert rel_err(layer.bias.mean.grad, z["g_b_mean"]) < TOL[prec]
+        assert rel_err(layer.bias.scale.grad, z["g_b_scale"]) < TOL[prec]
+    assert rel_err(x.grad, z["g_x"]) < TOL[prec]
+
+
+def build_model_case(z, samples=3):
+    seq = torch.nn.Sequential(
+        torch.nn.Conv2d(1, 8, 3, padding=1, stride=2), torch.nn.ELU(),
+        NormalConv2d(8, 8, 3, padding=1, stride=2), torch.nn.ELU(),
+        torch.nn.Flatten(), NormalLinear(8 * 3 * 3, 10), torch.nn.Softmax(dim=-1))
+    net = Net(seq, samples)
+    sd = {k[len("param."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param.")}
+    net.load_state_dict(sd)          # the reference's state_dict keys load unchanged
+    return net.cuda()
+
+
+@pytest.mark.parametrize("batching", ["auto", "never"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_network_elbo_step_matches_reference_golden(prec, batching):
+    """examples/MNIST/train.py:57-63 on a small network: S=3 predictions, KL, loss and every gradient."""
+    z = np.load(os.path.join(GOLD, "model_case.npz"))
+    bnn.set_precision(prec)
+    bnn.set_mc_batching(batching)
+    net = build_model_case(z)
+    conv, lin = net.layers[2], net.layers[5]
+    x = torch.from_numpy(z["x"]).cuda()
+    y = torch.from_numpy(z["y"]).cuda()
+    eps = {conv.weight: z["eps.conv_w"], conv.bias: z["eps.conv_b"], lin.weight: z["eps.lin_w"],
+           lin.bias: z["eps.lin_b"]}
+    if batching == "auto":
+        with bnn.injected_eps({k: torch.from_numpy(v) for k, v in eps.items()}):
+            preds = net(x)
+    else:
+        preds = []
+        for s in range(3):
+            with bnn.injected_eps({k: torch.from_numpy(v[s:s + 1]) for k, v in eps.items()}):
+                preds.append(net(x, samples=1))
+    assert isinstance(preds, list) and len(preds) == 3
+    for s in range(3):
+        assert rel_err(preds[s], z["preds"][s]) < TOL[prec]
+    kl = KLDivergence(number_of_batches=int(z["n_batches"]))(net)
+    likelihood = torch.stack([F.cross_entropy(p, y) for p in preds]).mean()
+    loss = likelihood + kl
+    assert float(kl) == pytest.approx(float(z["kl"]), rel=1e-5)
+    assert float(loss) == pytest.approx(float(z["loss"]), rel=TOL[prec])
+    loss.backward()
+    for name, p in net.named_parameters():
+        assert rel_err(p.grad, z["grad." + name]) < TOL[prec] * 2, name
+
+
+def test_checkpoint_kl_golden():
+    """KLDivergence(1) on the Bayesian layers of examples/MNIST/mnist_pretrained.pth = 0.20435977."""
+    z = np.load(os.path.join(GOLD, "mnist_ckpt_bayes_layers.npz"))
+    gold = json.load(open(os.path.join(GOLD, "golden_values.json")))["mnist"]
+    conv, lin = NormalConv2d(64, 64, 3, padding=1, stride=2), NormalLinear(576, 10)
+    load_weight(conv.weight, z["conv_w_mean"], z["conv_w_scale"])
+    load_weight(conv.bias, z["conv_b_mean"], z["conv_b_scale"])
+    load_weight(lin.weight, z["lin_w_mean"], z["lin_w_scale"])
+    load_weight(lin.bias, z["lin_b_mean"], z["lin_b_scale"])
+    net = Net(torch.nn.Sequential(conv, torch.nn.Flatten(), lin)).cuda()
+    assert float(KLDivergence(1)(net)) == pytest.approx(gold["kl_n_batches_1"], rel=5e-6)
+    # and PruneNormal through the module API reproduces the reference's masks (bit-exact fingerprints)
+    import hashlib
+    PruneNormal()(net, torch.tensor(0.75))
+    for w, h, c in zip((conv.weight, conv.bias, lin.weight, lin.bias), gold["prune"]["0.75"]["sha1_12"],
+                       gold["prune"]["0.75"]["counts"]):
+        mask = (w.scale == -30)
+        assert int(mask.sum()) == c
+        assert bool((w.mean[mask] == 0).all())
+        assert hashlib.sha1(mask.cpu().numpy().tobytes()).hexdigest()[:12] == h
+
+
+# ------------------------------------------------------------------------------------------------ API contract
+def test_weight_normal_contract():
+    """reference tests/test_nn/test_core.py:14-39."""
+    for shape in [(3,), (3, 4), (2, 3, 4, 5)]:
+        w = WeightNormal(*shape).cuda()
+        assert isinstance(w.mean, torch.nn.Parameter) and isinstance(w.scale, torch.nn.Parameter)
+        assert w.mean.shape == shape and w.scale.shape == shape
+        assert w.shape == shape and w.size() == shape and w.size(0) == shape[0]
+        assert w.device == w.mean.device and w.requires_grad
+        assert isinstance(w.dist, torch.distributions.Normal)
+        torch.nn.init.constant_(w.mean, 0)
+        torch.nn.init.constant_(w.scale, -100)
+        assert bool((w.stddev > 0).all())
+        assert torch.equal(w.stddev ** 2, w.variance)
+        w.sample()
+        assert isinstance(w.sampled, torch.Tensor) and w.sampled.shape == shape
+        assert torch.allclose(w.sampled, torch.zeros(shape, device="cuda"), atol=1e-5, rtol=1e-5)
+
+
+def test_weight_normal_sample_statistics_and_determinism():
+    w = WeightNormal(512, 256).cuda()
+    with torch.no_grad():
+        w.mean.uniform_(-1, 1)
+        w.scale.normal_(-2.0, 0.15)
+    w.sample()
+    a, b = w.sampled, w.sampled
+    assert torch.equal(a, b)                       # same draw until sample() is called again
+    w.sample()
+    c = w.sampled
+    assert not torch.equal(a, c)
+    draws = w.materialize(w._draw, 64)              # 64 further draws of the stream
+    zscore = (draws - w.mean) / w.stddev
+    assert abs(float(zscore.mean())) < 5 / np.sqrt(zscore.numel())
+    assert abs(float(zscore.var()) - 1) < 5 * np.sqrt(2 / zscore.numel())
+    per_elem_mean = zscore.mean(0)                 # each element over 64 draws: N(0, 1/64)
+    assert abs(float(per_elem_mean.var()) * 64 - 1) < 0.05
+
+
+def test_sampled_is_differentiable():
+    w = WeightNormal(8, 5).cuda()
+    with torch.no_grad():
+        w.mean.normal_()
+        w.scale.normal_(-1.0, 0.3)
+    w.sample()
+    s = w.sampled
+    g = torch.randn_like(s)
+    (s * g).sum().backward()
+    eps = ((s - w.mean) / w.stddev).detach()
+    assert torch.allclose(w.mean.grad, g, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(w.scale.grad, g * eps * torch.sigmoid(w.scale), rtol=1e-4, atol=1e-5)
+
+
+def test_bayesian_linear_and_conv_shapes():
+    """reference tests/test_nn/test_dense.py:23-35 and test_conv.py:22-43."""
+    for i, o, bias in [(3, 4, True), (5, 2, False)]:
+        m = BayesianLinear(i, o, bias, WeightNormal, torch.distributions.Normal(0, 1))
+        assert m.weight.shape == (o, i)
+        assert (m.bias.shape == (o,)) if bias else (m.bias is None)
+    m = BayesianConvNd(4, 6, (3, 3), (1, 1), (0, 0), (1, 1), False, 2, True, WeightNormal,
+                       torch.distributions.Normal(0, 1))
+    assert m.weight.shape == (6, 2, 3, 3) and m.bias.shape == (6,)
+    assert (m.kernel_size, m.stride, m.padding, m.dilation, m.transposed, m.groups) == \
+        ((3, 3), (1, 1), (0, 0), (1, 1), False, 2)
+    t = BayesianConvNd(4, 6, (3,), (1,), (0,), (1,), True, 2, False, WeightNormal, None)
+    assert t.weight.shape == (4, 3, 3) and t.bias is None
+    with pytest.raises(ValueError):
+        BayesianConvNd(3, 4, (3,), (1,), (0,), (1,), False, 2, True, WeightNormal, None)
+    with pytest.raises(ValueError):
+        BayesianConvNd(4, 3, (3,), (1,), (0,), (1,), False, 2, True, WeightNormal, None)
+
+
+@pytest.mark.parametrize("i,o,bias", [(3, 3, True), (5, 4, False), (576, 10, True)])
+def test_normal_linear_known_answer(i, o, bias):
+    """reference tests/test_nn/test_dense.py:38-70: W = 1, b = 3, sigma = 1e-10, x = ones -> i (+3)."""
+    layer = NormalLinear(i, o, bias).cuda()
+    assert torch.distributions.kl_divergence(layer.weight_prior, torch.distributions.Normal(0, .1)) < 1e-8
+    assert isinstance(layer.sampled, tuple) and len(layer.sampled) == 2
+    assert isinstance(layer.sampled[0], torch.Tensor)
+    assert (isinstance(layer.sampled[1], torch.Tensor)) if bias else (layer.sampled[1] is None)
+    with torch.no_grad():
+        layer.weight.mean.fill_(1), layer.weight.scale.fill_(-100)
+        if bias:
+            layer.bias.mean.fill_(3), layer.bias.scale.fill_(-100)
+    x = torch.ones(o, i, device="cuda")
+    want = torch.full((o, o), float(i + (3 if bias else 0)), device="cuda")
+    assert torch.allclose(layer(x), want, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(layer(x, sample=False), want, atol=1e-5, rtol=1e-5)
+
+
+CONV_CFG = [(1, 1, 1, 1, 1, 1, 1), (3, 4, 3, 1, 1, 1, 1), (4, 6, 3, 2, 1, 2, 2)]
+
+
+@pytest.mark.parametrize("cfg", CONV_CFG)
+@pytest.mark.parametrize("bias", [True, False])
+@pytest.mark.parametrize("nd", [1, 2, 3])
+def test_normal_conv_known_answer(nd, cfg, bias):
+    """reference tests/test_nn/test_conv.py:71-146: ones weights (+3 bias) against F.convNd."""
+    i, o, k, s, p, d, g = cfg
+    cls = {1: NormalConv1d, 2: NormalConv2d, 3: NormalConv3d}[nd]
+    conv = {1: F.conv1d, 2: F.conv2d, 3: F.conv3d}[nd]
+    layer = cls(i, o, k, s, p, d, g, bias).cuda()
+    assert isinstance(layer.sampled, tuple) and len(layer.sampled) == 2
+    assert (isinstance(layer.sampled[1], torch.Tensor)) if bias else (layer.sampled[1] is None)
+    with torch.no_grad():
+        layer.weight.mean.fill_(1), layer.weight.scale.fill_(-100)
+        if bias:
+            layer.bias.mean.fill_(3), layer.bias.scale.fill_(-100)
+    x = torch.rand((2, i) + (10,) * nd, device="cuda")
+    want = conv(x, torch.ones_like(layer.weight.mean), None, s, p, d, g) + (3 if bias else 0)
+    got = layer(x)
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
+
+
+def test_forward_sample_false_reuses_draw():
+    layer = NormalLinear(32, 16).cuda()
+    x = torch.randn(8, 32, device="cuda")
+    a = layer(x)
+    b = layer(x, sample=False)
+    c = layer(x)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    w, bias = layer.sampled
+    assert torch.allclose(c, F.linear(x, w, bias), atol=1e-5, rtol=1e-5)   # .sampled is the draw forward used
+
+
+def test_kl_divergence_contract():
+    """reference tests/test_nn/test_loss.py:23-34."""
+    with pytest.raises(ValueError):
+        KLDivergence()(Net(torch.nn.Sequential(torch.nn.Linear(3, 3))).cuda())
+    for layer in (NormalLinear(3, 3), NormalLinear(3, 4, False), NormalConv2d(3, 4, 3)):
+        out = KLDivergence(number_of_batches=2)(Net(torch.nn.Sequential(layer)).cuda())
+        assert isinstance(out, torch.Tensor) and out.dim() == 0 and float(out) > 0
+    # invisible to traverse: a Bayesian layer nested in a plain Module (utils.py:51-52)
+    class Block(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.inner = NormalLinear(3, 3)
+    with pytest.raises(ValueError):
+        KLDivergence()(Net(torch.nn.Sequential(Block())).cuda())
+
+
+def test_kl_matches_torch_distributions_on_device():
+    layers = [NormalLinear(40, 30, prior=torch.distributions.Normal(0.1, 0.5)), NormalConv2d(3, 8, 3)]
+    net = Net(torch.nn.Sequential(*layers)).cuda()
+    got = KLDivergence(number_of_batches=3)(net)
+    per = []
+    for l in layers:
+        for w, prior in ((l.weight, l.weight_prior), (l.bias, l.bias_prior)):
+            per.append(torch.distributions.kl_divergence(
+                w.dist, torch.distributions.Normal(prior.loc.cuda(), prior.scale.cuda())).mean())
+    want = torch.stack(per).mean() / 3
+    assert float(got) == pytest.approx(float(want), rel=1e-5)
+    got.backward()
+    g1 = [p.grad.clone() for p in net.parameters()]
+    net.zero_grad()
+    want.backward()
+    for a, p in zip(g1, net.parameters()):
+        assert rel_err(a, p.grad.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("p", [0.0, 0.25, 0.5, torch.tensor(0.75), 1.0])
+def test_prune_normal_fraction(p):
+    """reference tests/test_prune.py:7-24 (fraction of changed means), plus scale == -30 on the selected."""
+    torch.manual_seed(0)
+    net = Net(torch.nn.Sequential(NormalConv2d(3, 8, 3), torch.nn.Flatten(), NormalLinear(8, 5))).cuda()
+    before = [w.mean.detach().clone() for w in (net.layers[0].weight, net.layers[0].bias, net.layers[2].weight,
+                                                net.layers[2].bias)]
+    PruneNormal()(net, p)
+    after = [net.layers[0].weight, net.layers[0].bias, net.layers[2].weight, net.layers[2].bias]
+    for b, w in zip(before, after):
+        k = int(p * b.numel())
+        changed = (w.mean != b)
+        assert int(changed.sum()) == k
+        assert int((w.scale == -30).sum()) == k
+        assert bool((w.mean[changed] == 0).all())
+
+
+# ------------------------------------------------------------------------------------------------ MC batching
+def make_bn_net(samples):
+    torch.manual_seed(3)
+    seq = torch.nn.Sequential(
+        torch.nn.Conv2d(1, 6, 3, padding=1), torch.nn.BatchNorm2d(6), torch.nn.ELU(),
+        NormalConv2d(6, 6, 3, padding=1, stride=2), torch.nn.ELU(), torch.nn.Flatten(),
+        NormalLinear(6 * 4 * 4, 5), torch.nn.Softmax(dim=-1))
+    return Net(seq, samples).cuda()
+
+
+def test_batched_forward_equals_loop_and_batchnorm_statistics():
+    x = torch.rand(7, 1, 8, 8, device="cuda")
+    nets = []
+    for mode in ("auto", "never"):
+        bnn.set_mc_batching(mode)
+        net = make_bn_net(4)
+        preds = net(x)
+        assert isinstance(preds, list) and len(preds) == 4 and preds[0].shape == (7, 5)
+        loss = torch.stack([p.square().sum() for p in preds]).mean()
+        loss.backward()
+        nets.append((net, preds))
+    (a, pa), (b, pb) = nets
+    for s in range(4):
+        assert torch.allclose(pa[s], pb[s], rtol=1e-5, atol=1e-6)     # same Philox draws either way
+    for (n1, p1), (n2, p2) in zip(a.named_parameters(), b.named_parameters()):
+        assert rel_err(p1.grad, p2.grad.cpu()) < 2e-5, n1
+    bn_a, bn_b = a.layers[1], b.layers[1]
+    assert int(bn_a.num_batches_tracked) == int(bn_b.num_batches_tracked) == 4
+    assert torch.allclose(bn_a.running_mean, bn_b.running_mean, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(bn_a.running_var, bn_b.running_var, rtol=1e-4, atol=1e-6)
+
+
+def test_single_sample_returns_tensor_and_samples_kwarg():
+    net = make_bn_net(1)
+    x = torch.rand(3, 1, 8, 8, device="cuda")
+    assert isinstance(net(x), torch.Tensor)                # utils.py:10-11
+    out = net(x, samples=5)
+    assert isinstance(out, list) and len(out) == 5
+    assert not torch.equal(out[0], out[1])
+
+
+def test_batchnorm_after_bayesian_layer_falls_back_to_loop():
+    torch.manual_seed(4)
+    seq = torch.nn.Sequential(NormalLinear(6, 6), torch.nn.BatchNorm1d(6), NormalLinear(6, 3))
+    net = Net(seq, 3).cuda()
+    out = net(torch.rand(5, 6, device="cuda"))
+    assert isinstance(out, list) and len(out) == 3 and out[0].shape == (5, 3)
+    assert int(net.layers[1].num_batches_tracked) == 3
+    assert net._mc_plan()[0] is False
+
+
+def test_sample_partition_reproduces_single_process_stream():
+    """rank r of R evaluates global samples [r*S/R, (r+1)*S/R); the union is the 1-GPU result."""
+    x = torch.rand(4, 1, 8, 8, device="cuda")
+    net = make_bn_net(4).eval()
+    state = [(w, w._draw) for w in net.modules() if isinstance(w, WeightNormal)]
+    with torch.no_grad():
+        full = net(x)
+        parts = []
+        for rank in range(2):
+            for w, d in state:
+                w._draw = d
+            bnn.set_sample_partition(rank, 2)
+            parts += net(x)
+        bnn.set_sample_partition(0, 1)
+    for s in range(4):
+        assert torch.equal(full[s], parts[s])
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    layer = NormalLinear(4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        layer(torch.zeros(2, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        KLDivergence()(Net(torch.nn.Sequential(layer)))
