@@ -120,6 +120,42 @@ def _check(code, where):
         raise BnnError(code, where, lib().bnn_last_error_string().decode("utf-8", "replace"))
 
 
+_timing = None            # list of (name, start event, stop event) while kernel timing is on
+
+
+def set_kernel_timing(on):
+    """Bracket every library call with CUDA events on the launching stream (bench.py's live per-kernel times)."""
+    global _timing
+    _timing = [] if on else None
+
+
+def kernel_timing_summary(steps=1):
+    """{entry point: {ms_per_step, launches_per_step}} of the calls recorded since set_kernel_timing(True)."""
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in _timing or []:
+        d = out.setdefault(name, {"ms_per_step": 0.0, "launches_per_step": 0})
+        d["ms_per_step"] += e0.elapsed_time(e1)
+        d["launches_per_step"] += 1
+    for d in out.values():
+        d["ms_per_step"] /= steps
+        d["launches_per_step"] /= steps
+    return out
+
+
+def _call(name, *args):
+    fn = getattr(lib(), name)
+    if _timing is None:
+        rc = fn(*args)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _timing.append((name, e0, e1))
+    _check(rc, name)
+
+
 def _count(n=1):
     global launch_count
     launch_count += n
@@ -186,7 +222,7 @@ def stddev(rho, out=None):
     if out is None:
         out = torch.empty_like(rho)
     with torch.cuda.device(rho.device):
-        _check(lib().bnn_stddev(_ptr(rho), _ptr(out), rho.numel(), _stream()), "bnn_stddev")
+        _call("bnn_stddev", _ptr(rho), _ptr(out), rho.numel(), _stream())
     _count()
     return out
 
@@ -200,9 +236,8 @@ def materialize(mu, sigma, S, sample_begin, rng, eps_in=None, want_eps=False):
     if eps_in is not None and eps_in.numel() != S * mu.numel():
         raise ValueError("eps_in must hold S * numel values")
     with torch.cuda.device(mu.device):
-        _check(lib().bnn_materialize(_ptr(mu), _ptr(sigma), _ptr(eps_in), _ptr(out), _ptr(eps_out),
-                                     mu.numel(), S, sample_begin, ctypes.byref(rng), _stream()),
-               "bnn_materialize")
+        _call("bnn_materialize", _ptr(mu), _ptr(sigma), _ptr(eps_in), _ptr(out), _ptr(eps_out),
+                                     mu.numel(), S, sample_begin, ctypes.byref(rng), _stream())
     _count()
     return (out, eps_out) if want_eps else out
 
@@ -210,52 +245,48 @@ def materialize(mu, sigma, S, sample_begin, rng, eps_in=None, want_eps=False):
 def sampled_gemm_fwd(a, lda, a_sample_stride, mu_w, sigma_w, mu_b, sigma_b, eps_w, eps_b, y_view,
                      y_sample_stride, M, N, K, S, sample_begin, rng_w, rng_b, precision):
     with torch.cuda.device(a.device):
-        _check(lib().bnn_sampled_gemm_fwd(_ptr(a), lda, a_sample_stride, _ptr(mu_w), _ptr(sigma_w),
+        _call("bnn_sampled_gemm_fwd", _ptr(a), lda, a_sample_stride, _ptr(mu_w), _ptr(sigma_w),
                                           _ptr(mu_b), _ptr(sigma_b), _ptr(eps_w), _ptr(eps_b), y_view,
                                           y_sample_stride, M, N, K, S, sample_begin, ctypes.byref(rng_w),
                                           ctypes.byref(rng_b) if rng_b is not None else None, precision,
-                                          _stream()), "bnn_sampled_gemm_fwd")
+                                          _stream())
     _count()
 
 
 def sampled_gemm_dgrad(dy_view, dy_sample_stride, mu_w, sigma_w, eps_w, da, lda, a_sample_stride, M, N, K,
                        S, sample_begin, rng_w, precision):
     with torch.cuda.device(da.device):
-        _check(lib().bnn_sampled_gemm_dgrad(dy_view, dy_sample_stride, _ptr(mu_w), _ptr(sigma_w), _ptr(eps_w),
+        _call("bnn_sampled_gemm_dgrad", dy_view, dy_sample_stride, _ptr(mu_w), _ptr(sigma_w), _ptr(eps_w),
                                             _ptr(da), lda, a_sample_stride, M, N, K, S, sample_begin,
-                                            ctypes.byref(rng_w), precision, _stream()),
-               "bnn_sampled_gemm_dgrad")
+                                            ctypes.byref(rng_w), precision, _stream())
     _count()
 
 
 def sampled_gemm_wgrad(dy_view, dy_sample_stride, a, lda, a_sample_stride, rho_w, eps_w, dmu_w, drho_w, M, N,
                        K, S, sample_begin, rng_w, precision):
     with torch.cuda.device(a.device):
-        _check(lib().bnn_sampled_gemm_wgrad(dy_view, dy_sample_stride, _ptr(a), lda, a_sample_stride,
+        _call("bnn_sampled_gemm_wgrad", dy_view, dy_sample_stride, _ptr(a), lda, a_sample_stride,
                                             _ptr(rho_w), _ptr(eps_w), _ptr(dmu_w), _ptr(drho_w), M, N, K, S,
-                                            sample_begin, ctypes.byref(rng_w), precision, _stream()),
-               "bnn_sampled_gemm_wgrad")
+                                            sample_begin, ctypes.byref(rng_w), precision, _stream())
     _count()
 
 
 def bias_grad(dy_view, dy_sample_stride, rho_b, eps_b, dmu_b, drho_b, M, N, S, sample_begin, rng_b):
     with torch.cuda.device(rho_b.device):
-        _check(lib().bnn_bias_grad(dy_view, dy_sample_stride, _ptr(rho_b), _ptr(eps_b), _ptr(dmu_b),
-                                   _ptr(drho_b), M, N, S, sample_begin, ctypes.byref(rng_b), _stream()),
-               "bnn_bias_grad")
+        _call("bnn_bias_grad", dy_view, dy_sample_stride, _ptr(rho_b), _ptr(eps_b), _ptr(dmu_b),
+                                   _ptr(drho_b), M, N, S, sample_begin, ctypes.byref(rng_b), _stream())
     _count()
 
 
 def im2col(x, col, geom):
     with torch.cuda.device(x.device):
-        _check(lib().bnn_im2col(_ptr(x), _ptr(col), ctypes.byref(geom), _stream()), "bnn_im2col")
+        _call("bnn_im2col", _ptr(x), _ptr(col), ctypes.byref(geom), _stream())
     _count()
 
 
 def col2im(dcol, dx, geom, accumulate):
     with torch.cuda.device(dx.device):
-        _check(lib().bnn_col2im(_ptr(dcol), _ptr(dx), ctypes.byref(geom), 1 if accumulate else 0, _stream()),
-               "bnn_col2im")
+        _call("bnn_col2im", _ptr(dcol), _ptr(dx), ctypes.byref(geom), 1 if accumulate else 0, _stream())
     _count()
 
 
@@ -296,8 +327,8 @@ def kl(entries, want_sums=True, grad_scale=None, want_total=False):
     ws = _workspace(_kl_ws, device, nbytes + 256)
     base = (ws.data_ptr() + 255) & ~255
     with torch.cuda.device(device):
-        _check(lib().bnn_kl(table, n, _ptr(sums), _ptr(total), _ptr(grad_scale), ctypes.c_void_p(base), nbytes,
-                            _stream()), "bnn_kl")
+        _call("bnn_kl", table, n, _ptr(sums), _ptr(total), _ptr(grad_scale), ctypes.c_void_p(base), nbytes,
+                            _stream())
     _count((n + 23) // 24)
     if want_sums and want_total:
         return sums, total
@@ -328,13 +359,13 @@ def prune(entries):
     ws = _workspace(_prune_ws, device, nbytes + 256)
     base = (ws.data_ptr() + 255) & ~255
     with torch.cuda.device(device):
-        _check(lib().bnn_prune(table, n, ctypes.c_void_p(base), nbytes, _stream()), "bnn_prune")
+        _call("bnn_prune", table, n, ctypes.c_void_p(base), nbytes, _stream())
     _count(9 * ((n + 23) // 24))
 
 
 def selftest_umma(device="cuda"):
     out = torch.zeros(1, dtype=torch.float32, device=device)
     with torch.cuda.device(out.device):
-        _check(lib().bnn_selftest_umma(_ptr(out), _stream()), "bnn_selftest_umma")
+        _call("bnn_selftest_umma", _ptr(out), _stream())
     _count()
     return float(out.item())

@@ -1,0 +1,478 @@
+#!/usr/bin/env python
+"""bench.py — ELBO training throughput of the variational hot path on B200 (driver contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c4]
+
+Metric (BASELINE.json): ELBO train samples*MC/sec = B*S*N / step time, where one step is the body
+of the reference's training loop, examples/MNIST/train.py:55-65: zero_grad -> model(x) (S Monte-Carlo
+predictions) -> KLDivergence(model) -> mean cross-entropy over the S predictions -> backward ->
+[gradient all-reduce] -> Adam step.  Default workload = BASELINE.json configs[1] ("c2"): the
+examples/MNIST/model.py topology (what the FashionMNIST topology is with NormalConv2d/NormalLinear,
+SURVEY §0-4), 28x28 inputs, batch 256 per GPU, S=8.  Synthetic data, reference initialisation.
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM; `e2e`: the same step fed from
+pinned host memory with the loss read back every step; `roofline`: the dominant hot-path kernel timed
+live with CUDA events; `cpu_baseline`: the oracle's restatement of the reference step on the host
+cores (bounded sample); `kl_prune`: the bandwidth-bound KL / prune sweeps (C5 shape, bounded size).
+`--impl reference` times the reference's CPU path (oracle port) on the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BATCHES = 469          # ceil(60000 / 128), examples/MNIST/train.py:38 (any constant)
+WORKLOADS = {
+    "c2": dict(name="C2 examples/MNIST BCNN topology (NormalConv2d 64x64x3x3 s2 + NormalLinear 576x10), 28x28",
+               batch=256, samples=8),
+    "c4": dict(name="C4 wide Bayesian MLP 4x NormalLinear(4096,4096)", batch=1024, samples=32),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------ models
+def build_model(workload, samples):
+    import bayesianneuralnetworks_b200 as bnn
+    from torch.nn import BatchNorm2d, Conv2d, ELU, Flatten, Sequential, Softmax
+
+    class Net(bnn.nn.BayesianNetworkModule):
+        def __init__(self, layers, cin, cout):
+            super().__init__(cin, cout, samples)
+            self.layers = layers
+
+        def _forward(self, x):
+            return self.layers(x)
+
+    if workload == "c2":        # examples/MNIST/model.py:20-33
+        layers = Sequential(Conv2d(1, 32, 5, padding=2, stride=2), BatchNorm2d(32), ELU(),
+                            Conv2d(32, 32, 3, padding=1, stride=1), ELU(),
+                            Conv2d(32, 64, 3, padding=0, stride=2), ELU(),
+                            bnn.nn.NormalConv2d(64, 64, 3, padding=1, stride=2), ELU(), Flatten(),
+                            bnn.nn.NormalLinear(576, 10), Softmax(dim=-1))
+        return Net(layers, 1, 10)
+    layers = Sequential(bnn.nn.NormalLinear(4096, 4096), ELU(), bnn.nn.NormalLinear(4096, 4096), ELU(),
+                        bnn.nn.NormalLinear(4096, 4096), ELU(), bnn.nn.NormalLinear(4096, 4096), Softmax(dim=-1))
+    return Net(layers, 4096, 4096)
+
+
+def synthetic_batch(workload, batch, gen):
+    if workload == "c2":
+        return torch.rand(batch, 1, 28, 28, generator=gen), torch.randint(0, 10, (batch,), generator=gen)
+    return torch.randn(batch, 4096, generator=gen), torch.randint(0, 4096, (batch,), generator=gen)
+
+
+def hot_flops_per_step(workload, batch, samples):
+    """Algorithmic flops of the hot-path contractions per step: fwd 2MNK, bwd 4MNK (2MNK for a
+    first layer without dX)."""
+    if workload == "c2":
+        conv = 2 * 9 * 64 * 576         # per sample*MC row, forward
+        lin = 2 * 10 * 576
+        return batch * samples * 3 * (conv + lin)
+    return batch * samples * (4 * 6 - 2) * 4096 * 4096
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ the step
+class Trainer:
+    """The reference training-loop body (train.py:55-65) on this repo's public API."""
+
+    def __init__(self, workload, device, world, samples):
+        import bayesianneuralnetworks_b200 as bnn
+        self.bnn = bnn
+        torch.manual_seed(0)
+        self.model = build_model(workload, samples).to(device)
+        self.kld = bnn.nn.KLDivergence(number_of_batches=N_BATCHES)
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-3)
+        self.world = world
+        self.params = [p for p in self.model.parameters()]
+        self.flat = None
+
+    def step(self, x, y):
+        self.opt.zero_grad(set_to_none=True)
+        preds = self.model(x)
+        divergence = self.kld(self.model)
+        likelihood = torch.stack([F.cross_entropy(p, y) for p in preds]).mean()
+        loss = likelihood + divergence
+        loss.backward()
+        if self.world > 1:      # data parallel: one all-reduce (avg) of the flat gradient buffer
+            import torch.distributed as dist
+            grads = [p.grad for p in self.params]
+            flat = torch._utils._flatten_dense_tensors(grads)
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                g.copy_(f)
+        self.opt.step()
+        return loss
+
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    from bayesianneuralnetworks_b200 import _C
+    import bayesianneuralnetworks_b200 as bnn
+    _C.lib()                          # fails loudly when the CUDA library is missing
+    wl = WORKLOADS[args.workload]
+    B, S = wl["batch"], wl["samples"]
+    bnn.set_precision("tf32" if args.workload == "c4" else "fp32")
+    trainer = Trainer(args.workload, device, world, S)
+    gen = torch.Generator().manual_seed(1 + rank)
+    n_host = 8
+    host = [tuple(t.pin_memory() for t in synthetic_batch(args.workload, B, gen)) for _ in range(n_host)]
+    dev = [(x.to(device), y.to(device)) for x, y in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, feed_from_host):
+        """K steps, each bracketed by CUDA events on the current stream; L2 flushed (untimed) between steps."""
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps)]
+        barrier()
+        t0 = time.perf_counter()
+        last = None
+        for i in range(n_steps):
+            flush.zero_()
+            starts[i].record()
+            if feed_from_host:
+                hx, hy = host[i % n_host]
+                x, y = hx.to(device, non_blocking=True), hy.to(device, non_blocking=True)
+            else:
+                x, y = dev[i % n_host]
+            loss = trainer.step(x, y)
+            if feed_from_host:
+                last = loss.item()            # device -> host read of the step's result, every step
+            stops[i].record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
+        return ms / 1e3, wall, last
+
+    for i in range(max(args.warmup, 3)):
+        trainer.step(*dev[i % n_host])
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = _C.launch_count
+    dev_s, dev_wall, _ = timed(args.steps, False)
+    launches = _C.launch_count - launches0
+    e2e_s, e2e_wall, last_loss = timed(args.steps, True)
+    clock_info = clocks.stop()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        import torch.distributed as dist
+        t = torch.tensor([v], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    dev_s, e2e_s = max_over_ranks(dev_s), max_over_ranks(e2e_s)
+    units = B * S * world * args.steps
+    pk = peaks()
+
+    # ---- roofline of the dominant hot-path kernel, timed live with CUDA events on the launching stream
+    _C.set_kernel_timing(True)
+    n_prof = min(args.steps, 10)
+    for i in range(n_prof):
+        flush.zero_()
+        trainer.step(*dev[i % n_host])
+    per_kernel = _C.kernel_timing_summary(n_prof)
+    _C.set_kernel_timing(False)
+    roof = roofline(args.workload, B, S, per_kernel, pk)
+
+    out = None
+    if rank == 0:
+        x0, y0 = host[0]
+        out = {
+            "metric": "ELBO train samples*MC/sec", "value": units / dev_s, "unit": "samples*MC/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32" if args.workload == "c4" else "fp32 (3xTF32 split on tcgen05)",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "batch_per_gpu": B, "mc_samples": S, "global_batch": B * world,
+                       "parallelism": f"dp{world}" if world > 1 else "single", "n_batches": N_BATCHES,
+                       "optimizer": "Adam", "l2": "flushed between steps (256 MiB write, untimed); each step "
+                       "timed with its own CUDA event pair", "step": "zero_grad+forward(S)+KL+CE+backward+Adam"},
+            "e2e": {"value": units / e2e_s, "unit": "samples*MC/s",
+                    "h2d_bytes_per_step": x0.numel() * x0.element_size() + y0.numel() * y0.element_size(),
+                    "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * e2e_s / args.steps, "last_loss": last_loss},
+            "gpu_launches": launches,
+            "wall_s": {"device_resident": dev_wall, "e2e": e2e_wall},
+            "clocks": clock_info,
+            "roofline": roof,
+            "hot_path": {"algorithmic_tflops_per_s": hot_flops_per_step(args.workload, B, S) * world /
+                         (dev_s / args.steps) / 1e12, "kernels_ms_per_step": per_kernel},
+            "peaks": pk,
+        }
+    if rank == 0 and world == 1 and not args.no_extras:
+        out["kl_prune"] = bench_kl_prune(device, pk)
+        out["cpu_baseline"] = cpu_baseline(args.workload, bounded_seconds=20.0)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def roofline(workload, B, S, per_kernel, pk):
+    """Dominant hot-path kernel = the libbnn_b200 entry point with the largest time share of the step."""
+    if not per_kernel:
+        return None
+    name = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
+    contractions = {"bnn_sampled_gemm_fwd": 1, "bnn_sampled_gemm_dgrad": 1, "bnn_sampled_gemm_wgrad": 1}
+    k = per_kernel[name]
+    if name in contractions:
+        # flops of ALL launches of this entry point per step / their summed duration
+        if workload == "c2":
+            per_row = 2 * 9 * 64 * 576 + 2 * 10 * 576
+        else:
+            per_row = (3 if name == "bnn_sampled_gemm_dgrad" else 4) * 2 * 4096 * 4096
+        flops = B * S * per_row
+        achieved = flops / (k["ms_per_step"] * 1e-3) / 1e12
+        peak = pk["bf16_sustained"] / 2.0        # TF32 dense = half the bf16 rate on this tensor pipe
+        return {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "launches_per_step": k["launches_per_step"],
+                "avg_launch_us": 1e3 * k["ms_per_step"] / k["launches_per_step"],
+                "peak_note": "TF32 dense peak taken as half of the measured sustained bf16 cuBLAS rate "
+                             f"({pk['source']}); fp32 mode issues 3 TF32 MMAs per product"}
+    return {"kernel": name, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
+            "traffic": None, "launches_per_step": k["launches_per_step"],
+            "avg_launch_us": 1e3 * k["ms_per_step"] / k["launches_per_step"]}
+
+
+def bench_kl_prune(device, pk, pairs=1 << 28):
+    """KL forward, KL forward+grad and prune over `pairs` (mu, rho) pairs in 16 tensors of 4096x4096 (the C5
+    layout, BASELINE.json configs[4], at a quarter of its size so the default run stays short); working set
+    2 GiB >> L2.  Algorithmic bytes: KL fwd 8 B/pair, fwd+grad 16 B/pair, prune 8 + 8p B/pair."""
+    from bayesianneuralnetworks_b200 import _C
+    n_t = pairs // (4096 * 4096)
+    gen = torch.Generator(device=device).manual_seed(5)
+    mus = [(torch.rand(4096, 4096, device=device, generator=gen) * 2 - 1) / 64 for _ in range(n_t)]
+    rhos = [torch.randn(4096, 4096, device=device, generator=gen) * 0.15 - 2.0 for _ in range(n_t)]
+    gm = [torch.empty_like(m) for m in mus]
+    gr = [torch.empty_like(m) for m in mus]
+    fwd = [(m, r, None, None, 0.0, 0.1, 1.0) for m, r in zip(mus, rhos)]
+    both = [(m, r, a, b, 0.0, 0.1, 1.0) for m, r, a, b in zip(mus, rhos, gm, gr)]
+
+    def time_it(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best * 1e-3
+
+    res = {"pairs": pairs, "tensors": n_t, "l2": "working set 2 GiB, larger than L2"}
+    t = time_it(lambda: _C.kl(fwd))
+    res["kl_fwd"] = {"GBps": 8 * pairs / t / 1e9, "frac_of_measured_hbm": 8 * pairs / t / 1e9 / pk["hbm"], "ms": t * 1e3}
+    t = time_it(lambda: _C.kl(both))
+    res["kl_fwd_grad"] = {"GBps": 16 * pairs / t / 1e9, "frac_of_measured_hbm": 16 * pairs / t / 1e9 / pk["hbm"],
+                          "ms": t * 1e3}
+    p = 0.75
+    k = int(p * 4096 * 4096)
+    del gm, gr
+    saved = [(m.clone(), r.clone()) for m, r in zip(mus, rhos)]
+
+    def prune_once():
+        _C.prune([(m, r, k, None, None) for m, r in zip(mus, rhos)])
+    prune_once()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        for (m, r), (sm, sr) in zip(zip(mus, rhos), saved):
+            m.copy_(sm), r.copy_(sr)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        prune_once()
+        b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b) * 1e-3)
+    bytes_alg = (8 + 8 * p) * pairs
+    res["prune_p0.75"] = {"GBps": bytes_alg / best / 1e9, "frac_of_measured_hbm": bytes_alg / best / 1e9 / pk["hbm"],
+                          "ms": best * 1e3}
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def oracle_step_fn(workload, B, S):
+    """The reference step restated on CPU tensors by oracle/variational_oracle.py (ElboStepOracle)."""
+    from oracle import variational_oracle as orc
+    torch.manual_seed(0)
+    model = build_model(workload, S)      # used only as a container of identically initialised parameters
+    stages, cur = [], []
+    for m in model.layers:
+        kind = type(m).__name__
+        if kind in ("NormalConv2d", "NormalLinear"):
+            if cur:
+                stages.append(('torch', torch.nn.Sequential(*cur)))
+                cur = []
+            ps = [m.weight.mean, m.weight.scale, m.bias.mean, m.bias.scale]
+            loc, scale = float(m.weight_prior.loc), float(m.weight_prior.scale)
+            if kind == "NormalLinear":
+                stages.append(('linear', *ps, loc, scale))
+            else:
+                stages.append(('conv2d', *ps, loc, scale, m.stride, m.padding, m.dilation, m.groups))
+        else:
+            cur.append(m)
+    if cur:
+        stages.append(('torch', torch.nn.Sequential(*cur)))
+    step = orc.ElboStepOracle(stages, S, N_BATCHES)
+    opt = torch.optim.Adam(step.parameters(), lr=1e-3)
+    gen = torch.Generator().manual_seed(1)
+    x, y = synthetic_batch(workload, B, gen)
+
+    def run():
+        opt.zero_grad()
+        loss, _ = step.loss(x, y)
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return run
+
+
+def cpu_baseline(workload, bounded_seconds):
+    wl = WORKLOADS[workload]
+    B, S = wl["batch"], wl["samples"]
+    sample = "full step (B=%d, S=%d)" % (B, S)
+    if workload == "c4":            # a full C4 step is ~12 TFLOP on the CPU: time a 1-sample slice
+        S, sample = 1, "one MC sample of the step (B=1024, S=1 of 32), scaled by samples*MC"
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run = oracle_step_fn(workload, B, S)
+    run()
+    t0, n = time.perf_counter(), 0
+    while n < 3 or (time.perf_counter() - t0 < bounded_seconds and n < 200):
+        run()
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"value": B * S / dt, "unit": "samples*MC/s", "cores": cores, "kind": "port",
+            "sample": f"{sample}, {n} steps, torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads",
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle port: the reference is
+    Python on torch ops and cannot be vendored) on the host cores, same config / metric / unit."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    B, S = wl["batch"], wl["samples"]
+    sample = f"full step (B={B}, S={S})"
+    if args.workload == "c4":
+        S, sample = 1, "one MC sample of the step (S=1 of 32)"
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run = oracle_step_fn(args.workload, B, S)
+    steps, warmup = min(args.steps, 20), min(max(args.warmup, 1), 3)
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    value = B * S / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "ELBO train samples*MC/sec", "value": value, "unit": "samples*MC/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": wl["name"], "batch_per_gpu": B, "mc_samples": S, "n_batches": N_BATCHES,
+                   "optimizer": "Adam", "step": "zero_grad+forward(S)+KL+CE+backward+Adam"},
+        "cpu_baseline": {"value": value, "unit": "samples*MC/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample}, {steps} steps, torch {torch.__version__} CPU fp32, "
+                                   f"{torch.get_num_threads()} threads"},
+        "e2e": {"value": value, "unit": "samples*MC/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true", help="skip the kl_prune and cpu_baseline legs (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

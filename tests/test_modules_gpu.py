@@ -376,10 +376,12 @@ def make_bn_net(samples):
 
 def test_batched_forward_equals_loop_and_batchnorm_statistics():
     x = torch.rand(7, 1, 8, 8, device="cuda")
+    import copy
     nets = []
+    proto = make_bn_net(4)
     for mode in ("auto", "never"):
         bnn.set_mc_batching(mode)
-        net = make_bn_net(4)
+        net = copy.deepcopy(proto)       # same parameters, same Philox stream ids and draw counters
         preds = net(x)
         assert isinstance(preds, list) and len(preds) == 4 and preds[0].shape == (7, 5)
         loss = torch.stack([p.square().sum() for p in preds]).mean()
