@@ -150,13 +150,9 @@ class Trainer:
         likelihood = torch.stack([F.cross_entropy(p, y) for p in preds]).mean()
         loss = likelihood + divergence
         loss.backward()
-        if self.world > 1:      # data parallel: one all-reduce (avg) of the flat gradient buffer
-            import torch.distributed as dist
-            grads = [p.grad for p in self.params]
-            flat = torch._utils._flatten_dense_tensors(grads)
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                g.copy_(f)
+        if self.world > 1:      # data parallel: ONE all-reduce (avg) of the flat gradient buffer
+            from bayesianneuralnetworks_b200 import parallel
+            parallel.allreduce_gradients(self.params)
         self.opt.step()
         return loss
 
