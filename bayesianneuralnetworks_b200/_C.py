@@ -50,7 +50,8 @@ class bnn_kl_tensor(ctypes.Structure):
 
 class bnn_prune_tensor(ctypes.Structure):
     _fields_ = [("mu", ctypes.c_void_p), ("rho", ctypes.c_void_p), ("mask_out", ctypes.c_void_p),
-                ("keys_out", ctypes.c_void_p), ("numel", ctypes.c_int64), ("k", ctypes.c_int64)]
+                ("keys_out", ctypes.c_void_p), ("numel", ctypes.c_int64), ("k", ctypes.c_int64),
+                ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 _SIGNATURES = {
@@ -338,8 +339,12 @@ def kl(entries, want_sums=True, grad_scale=None, want_total=False):
 _prune_ws = {}
 
 
-def prune(entries):
-    """entries: list of (mu, rho, k, mask_out|None, keys_out|None); mu/rho are modified in place."""
+PRUNE_GENERAL = 1
+
+
+def prune(entries, flags=0):
+    """entries: list of (mu, rho, k, mask_out|None, keys_out|None); mu/rho are modified in place.
+    flags=PRUNE_GENERAL forces the general radix-select path for every tensor."""
     n = len(entries)
     if n == 0:
         return
@@ -355,12 +360,13 @@ def prune(entries):
         t.mask_out = None if mask is None else mask.data_ptr()
         t.keys_out = None if keys is None else keys.data_ptr()
         t.numel, t.k = mu.numel(), int(k)
+        t.flags, t.reserved = flags, 0
     nbytes = lib().bnn_prune_workspace_size(table, n)
     ws = _workspace(_prune_ws, device, nbytes + 256)
     base = (ws.data_ptr() + 255) & ~255
     with torch.cuda.device(device):
         _call("bnn_prune", table, n, ctypes.c_void_p(base), nbytes, _stream())
-    _count(9 * ((n + 23) // 24))
+    _count(13 * ((n + 23) // 24))
 
 
 def selftest_umma(device="cuda"):

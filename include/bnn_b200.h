@@ -188,7 +188,11 @@ int bnn_kl(const bnn_kl_tensor* tensors /* HOST array */, int32_t n_tensors,
  * Ties at the k-th key are broken towards the lowest element index (torch.topk's tie order is
  * unspecified; identical masks whenever the k-th key is unique).
  * All tensors of one call are processed by the same launches.  `mask_out` (optional, uint8
- * [numel]) receives the selection.  `keys_out` (optional) receives the keys. */
+ * [numel]) receives the selection.  `keys_out` (optional) receives the keys.
+ * Two exact implementations are chosen per tensor on the device: a sampled two-sweep path (bracket
+ * the k-th key from a sample, compact the few candidates, resolve exactly, apply) and the general
+ * three-pass radix select over a key workspace, which also catches every case the first declines. */
+#define BNN_PRUNE_GENERAL 1u   /* flags: force the general radix-select path (tests; implied by keys_out) */
 typedef struct bnn_prune_tensor {
   float* mu;
   float* rho;
@@ -196,6 +200,8 @@ typedef struct bnn_prune_tensor {
   float* keys_out;     /* optional */
   int64_t numel;
   int64_t k;
+  uint32_t flags;
+  uint32_t reserved;
 } bnn_prune_tensor;
 size_t bnn_prune_workspace_size(const bnn_prune_tensor* tensors, int32_t n_tensors);
 int bnn_prune(const bnn_prune_tensor* tensors /* HOST array */, int32_t n_tensors,

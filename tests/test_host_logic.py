@@ -47,7 +47,7 @@ def test_binding_struct_sizes_match_the_header():
     assert ctypes.sizeof(_C.bnn_view) == 24
     assert ctypes.sizeof(_C.bnn_conv2d_geom) == 64
     assert ctypes.sizeof(_C.bnn_kl_tensor) == 56
-    assert ctypes.sizeof(_C.bnn_prune_tensor) == 48
+    assert ctypes.sizeof(_C.bnn_prune_tensor) == 56
 
 
 def test_hot_path_rejects_cpu_tensors():

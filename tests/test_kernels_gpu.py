@@ -186,6 +186,50 @@ def test_prune_bit_exact(C, shape, p):
     # in-place update: mean <- 0, scale <- -30 on the selected, untouched elsewhere
     em, er = orc.prune_apply(mu.clone(), rho.clone(), cpu_mask)
     assert torch.equal(dmu.cpu(), em) and torch.equal(drho.cpu(), er)
+    # the request above asked for keys_out (general path); the default (sampled) path gives the same
+    dmu2, drho2 = mu.cuda(), rho.cuda()
+    mask2 = torch.empty(shape, dtype=torch.uint8, device="cuda")
+    C.prune([(dmu2, drho2, k, mask2, None)])
+    assert torch.equal(mask2, mask) and torch.equal(dmu2, dmu) and torch.equal(drho2, drho)
+
+
+@pytest.mark.parametrize("numel,p", [(333000, 0.3), (333000, 0.75), (1 << 20, 0.9), (1 << 20, 0.999), (70001, 0.5),
+                                     (200000, 1e-5), (200000, 0.99999)])
+def test_prune_sampled_path_equals_general_path(C, numel, p):
+    """The sampled two-sweep path and the general radix-select path are both exact: identical masks, and
+    identical to the stable descending sort of torch's keys on the device."""
+    g = torch.Generator().manual_seed(12)
+    mu, rho = init_params((numel,), g, fan_in=400)
+    k = max(1, orc.prune_count(p, numel)) if p < 0.5 else min(numel - 1, orc.prune_count(p, numel))
+    ref = orc.prune_mask_from_keys(torch_keys_same_device(mu.cuda(), rho.cuda()), k)
+    outs = []
+    for flags in (0, C.PRUNE_GENERAL):
+        dmu, drho = mu.cuda(), rho.cuda()
+        mask = torch.empty(numel, dtype=torch.uint8, device="cuda")
+        C.prune([(dmu, drho, k, mask, None)], flags=flags)
+        assert int(mask.sum()) == k
+        assert torch.equal(mask.bool(), ref)
+        outs.append((dmu, drho))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert bool((outs[0][0][ref] == 0).all()) and bool((outs[0][1][ref] == -30).all())
+    assert torch.equal(outs[0][0][~ref].cpu(), mu[~ref.cpu()])
+
+
+@pytest.mark.parametrize("classes", [1, 2, 3])
+def test_prune_large_tie_classes(C, classes):
+    """Huge tie classes on a tensor large enough for the sampled path: the bracket collapses onto one key
+    (candidate-heavy resolve, index bound) or overflows the candidate buffer (device-side fallback)."""
+    n = 300000
+    base_mu = torch.tensor([0.0, 0.5, 1.0][:classes]).repeat(n // classes)
+    base_rho = torch.full((base_mu.numel(),), -2.0)
+    keys = torch_keys_same_device(base_mu.cuda(), base_rho.cuda())
+    for k in sorted({1, n // classes - 1, n // classes, min(n // classes + 1, base_mu.numel()), n // 2,
+                     base_mu.numel() - 1}):
+        mu, rho = base_mu.clone().cuda(), base_rho.clone().cuda()
+        mask = torch.empty(base_mu.numel(), dtype=torch.uint8, device="cuda")
+        C.prune([(mu, rho, k, mask, None)])
+        assert int(mask.sum()) == k
+        assert torch.equal(mask.bool(), orc.prune_mask_from_keys(keys, k))
 
 
 def test_prune_ties_lowest_index_first(C):
