@@ -88,6 +88,7 @@ _SIGNATURES = {
     "bnn_prune": (ctypes.c_int, [ctypes.POINTER(bnn_prune_tensor), ctypes.c_int32, ctypes.c_void_p,
                                  ctypes.c_size_t, ctypes.c_void_p]),
     "bnn_selftest_umma": (ctypes.c_int, [_c_f32p, ctypes.c_void_p]),
+    "bnn_selftest_umma_mn": (ctypes.c_int, [_c_f32p, ctypes.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -369,9 +370,9 @@ def prune(entries, flags=0):
     _count(13 * ((n + 23) // 24))
 
 
-def selftest_umma(device="cuda"):
+def selftest_umma(device="cuda", mn_major=False):
     out = torch.zeros(1, dtype=torch.float32, device=device)
     with torch.cuda.device(out.device):
-        _call("bnn_selftest_umma", _ptr(out), _stream())
+        _call("bnn_selftest_umma_mn" if mn_major else "bnn_selftest_umma", _ptr(out), _stream())
     _count()
     return float(out.item())

@@ -1,0 +1,666 @@
+// sampled_gemm_tma.cu — TMA-fed TF32 variants of the sample-and-contract kernels for aligned row-major
+// operands (the large-shape path: BASELINE config C4 and the im2col matrices of the conv layers).
+//
+//   forward / data gradient   activations (or dY) arrive by TMA (cp.async.bulk.tensor, 128B swizzle, TF32
+//                             conversion done by the copy engine) into a ring of 16 KiB tile slots; the eight
+//                             producer warps do nothing but generate W_s = mu + sigma * eps_s (Philox) into a
+//                             second ring; one thread issues tcgen05.mma; four warps drain TMEM.
+//                             The data gradient stores the generated weight tile in the MN-major canonical
+//                             layout, i.e. in W's natural [n][k] orientation (vector stores, no transpose).
+//   weight gradient           BOTH operands (dY^T and A^T) are MN-major tiles loaded by TMA — no thread touches
+//                             operand data; the four epilogue warps regenerate eps per sample and keep the
+//                             running sums of G_s and G_s o eps_s in TMEM (as in sampled_gemm.cu).
+// Eligibility (else the caller uses sampled_gemm.cu): TF32 precision, row-major operands (view P == 1 for
+// everything that is READ), 16-byte aligned bases and leading dimensions, contiguous samples.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <mutex>
+
+#include "contract.cuh"
+
+namespace bnn {
+namespace contract {
+namespace {
+
+constexpr int kASlots = 8;                   // activation tile ring (16 KiB each)
+constexpr int kWSlots = 4;                   // generated weight tile ring
+constexpr int kTmaWarp = 13;
+constexpr int kThreadsTma = 14 * 32;
+constexpr uint32_t kMnLbo = 4096, kMnSbo = 512;    // MN-major 128 x 32 tile: 4 groups of 32 MN, 8 atoms of 4 K-rows
+constexpr uint32_t kMnKStep = 2 * kMnSbo;            // one UMMA K-step (8 TF32) = two 4-row atoms
+
+// ---------------------------------------------------------------------------------------------- tensor maps
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  });
+  return fn;
+}
+
+// fp32 matrix [samples][rows][cols] (row stride ld, sample stride ss floats) -> 3-d map with a box of
+// 32 columns x box_rows rows, 128B swizzle, TF32 conversion, zero fill outside [cols) x [rows) x [samples)
+int make_map(CUtensorMap* map, const float* base, int64_t cols, int64_t rows, int64_t samples, int64_t ld, int64_t ss,
+             int box_rows, bool mn_major = false) {
+  EncodeFn fn = encode_fn();
+  if (fn == nullptr) return kNotEligible;
+  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows),
+                              static_cast<cuuint64_t>(samples)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4u,
+                                 static_cast<cuuint64_t>(samples > 1 ? ss : ld * rows) * 4u};
+  const cuuint32_t box[3] = {32u, static_cast<cuuint32_t>(box_rows), 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return kNotEligible;
+  return BNN_OK;
+}
+
+bool tma_ok(const void* base, int64_t ld, int64_t ss) {
+  return aligned16(base) && ld % 4 == 0 && ss % 4 == 0 && ld > 0;
+}
+
+// ---------------------------------------------------------------------------------------------- forward / dgrad
+struct TmaContractParams {
+  CUtensorMap map_l;        // fwd: activations [S or 1][M][K]; dgrad: dY [S][M][N]
+  View out;                 // fwd: y view; dgrad: da as a row-major view
+  int64_t out_sample_stride;
+  const float* mu_w;
+  const float* sigma_w;
+  const float* eps_w;
+  const float* mu_b;
+  const float* sigma_b;
+  const float* eps_b;
+  int M, N, K, S;
+  uint32_t sample_begin;
+  bnn_rng rng_w, rng_b;
+  int shared_l;             // all samples read sample 0 of the L operand (shared activations)
+  int sum_samples;          // dgrad with shared activations: one output, summed over the samples
+  int vec_out;
+};
+
+struct TmaPipe {
+  uint64_t* full_a;      // [kASlots] TMA transaction barriers
+  uint64_t* empty_a;     // [kASlots] tcgen05.commit
+  uint64_t* full_w;      // [kWSlots] 256 producer arrivals
+  uint64_t* empty_w;     // [kWSlots] tcgen05.commit
+  uint64_t* accum_full;  // [2]
+  uint64_t* accum_empty; // [2]
+  uint32_t* tmem_slot;
+  float* aux;
+  uint32_t ring_a, ring_w;
+};
+
+__device__ __forceinline__ TmaPipe carve_tma(uint8_t* smem_raw) {
+  TmaPipe p;
+  p.full_a = reinterpret_cast<uint64_t*>(smem_raw);
+  p.empty_a = p.full_a + kASlots;
+  p.full_w = p.empty_a + kASlots;
+  p.empty_w = p.full_w + kWSlots;
+  p.accum_full = p.empty_w + kWSlots;
+  p.accum_empty = p.accum_full + 2;
+  p.tmem_slot = reinterpret_cast<uint32_t*>(p.accum_empty + 2);
+  p.aux = reinterpret_cast<float*>(smem_raw + 512);
+  const uint32_t base = smem_u32(smem_raw) + kSmemAux;
+  p.ring_a = (base + 1023u) & ~1023u;
+  p.ring_w = p.ring_a + kASlots * kTileBytes;
+  return p;
+}
+
+// W_s tile, K-major (rows n, columns k) — forward
+__device__ __forceinline__ void gen_w_kmajor(uint32_t tile, const float* __restrict__ mu, const float* __restrict__ sigma,
+                                             const EpsSrc& eps, int n0, int N, int k0, int K, int tid) {
+  float4 m[4], s[4];
+  int64_t idx[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int item = it * kProducerThreads + tid;
+    const int n = n0 + (item >> 3), k = k0 + ((item & 7) << 2);
+    idx[it] = -1;
+    if (n < N && k < K) {
+      idx[it] = static_cast<int64_t>(n) * K + k;
+      m[it] = __ldg(reinterpret_cast<const float4*>(mu + idx[it]));
+      s[it] = __ldg(reinterpret_cast<const float4*>(sigma + idx[it]));
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int item = it * kProducerThreads + tid;
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx[it] >= 0) {
+      const float4 e = eps_vec4(eps, idx[it]);
+      w.x = fmaf(s[it].x, e.x, m[it].x);
+      w.y = fmaf(s[it].y, e.y, m[it].y);
+      w.z = fmaf(s[it].z, e.z, m[it].z);
+      w.w = fmaf(s[it].w, e.w, m[it].w);
+    }
+    sts128(tile + tile_offset(item >> 3, item & 7), to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+  }
+}
+
+// W_s tile, MN-major (MN = k: 128 columns of W, K-rows = n: 32 rows of W) — data gradient.  W is read and
+// generated in its natural orientation; each float4 of a row lands as one 16-byte chunk of the 128-byte row.
+__device__ __forceinline__ void gen_w_mnmajor(uint32_t tile, const float* __restrict__ mu, const float* __restrict__ sigma,
+                                              const EpsSrc& eps, int n0, int N, int k0, int K, int tid) {
+  float4 m[4], s[4];
+  int64_t idx[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int item = it * kProducerThreads + tid;
+    const int n = n0 + (item >> 5), k = k0 + ((item & 31) << 2);
+    idx[it] = -1;
+    if (n < N && k < K) {
+      idx[it] = static_cast<int64_t>(n) * K + k;
+      m[it] = __ldg(reinterpret_cast<const float4*>(mu + idx[it]));
+      s[it] = __ldg(reinterpret_cast<const float4*>(sigma + idx[it]));
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int item = it * kProducerThreads + tid;
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx[it] >= 0) {
+      const float4 e = eps_vec4(eps, idx[it]);
+      w.x = fmaf(s[it].x, e.x, m[it].x);
+      w.y = fmaf(s[it].y, e.y, m[it].y);
+      w.z = fmaf(s[it].z, e.z, m[it].z);
+      w.w = fmaf(s[it].w, e.w, m[it].w);
+    }
+    const int nl = item >> 5, kq = item & 31;                       // K-row, float4 index along MN
+    sts128(tile + tile_offset_mn(kq << 2, nl, kMnLbo, kMnSbo), to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+  }
+}
+
+template <int MB, bool kDgrad>
+__global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __grid_constant__ TmaContractParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr uint32_t kTmemCols = tmem_cols_pow2(MB * 128);
+  const TmaPipe pipe = carve_tma(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kASlots; ++i) { mbar_init(pipe.full_a + i, 1); mbar_init(pipe.empty_a + i, 1); }
+    for (int i = 0; i < kWSlots; ++i) { mbar_init(pipe.full_w + i, kProducerThreads); mbar_init(pipe.empty_w + i, 1); }
+    mbar_init(pipe.accum_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == kTmaWarp && lane == 0) tma_prefetch_desc(&p.map_l);
+  if (warp == kMmaWarp) tmem_alloc(pipe.tmem_slot, kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(pipe.tmem_slot);
+
+  const int col0 = blockIdx.x * 128;                   // output columns (n for fwd, k for dgrad)
+  const int row0 = blockIdx.y * (MB * 128);            // output rows (m)
+  const int n_cols = kDgrad ? p.K : p.N;
+  const int n_red = kDgrad ? p.N : p.K;
+  const int s_begin = p.sum_samples ? 0 : blockIdx.z;
+  const int s_end = p.sum_samples ? p.S : blockIdx.z + 1;
+  const int red_blocks = (n_red + kBK - 1) / kBK;
+  int mb_used = (p.M - row0 + 127) / 128;
+  if (mb_used > MB) mb_used = MB;
+
+  if (warp < kProducerWarps) {
+    // ------------------------------------------------------------------ weight generators
+    const int tid = threadIdx.x;
+    const RngKey key = resolve_rng(p.rng_w);
+    int it = 0;
+    for (int s = s_begin; s < s_end; ++s) {
+      EpsSrc eps;
+      eps.inj = p.eps_w ? p.eps_w + static_cast<int64_t>(s) * p.N * p.K : nullptr;
+      eps.key = key;
+      eps.sample = p.sample_begin + s;
+      for (int rb = 0; rb < red_blocks; ++rb, ++it) {
+        const int slot = it % kWSlots;
+        mbar_wait(pipe.empty_w + slot, ((it / kWSlots) & 1) ^ 1);
+        const uint32_t tile = pipe.ring_w + slot * kTileBytes;
+        if (!kDgrad)
+          gen_w_kmajor(tile, p.mu_w, p.sigma_w, eps, col0, p.N, rb * kBK, p.K, tid);
+        else
+          gen_w_mnmajor(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, col0, p.K, tid);
+        fence_proxy_async_smem();
+        mbar_arrive(pipe.full_w + slot);
+      }
+    }
+  } else if (warp == kTmaWarp) {
+    // ------------------------------------------------------------------ TMA issuer
+    if (lane == 0) {
+      int cnt = 0;
+      for (int s = s_begin; s < s_end; ++s) {
+        const int smp = p.shared_l ? 0 : s;
+        for (int rb = 0; rb < red_blocks; ++rb) {
+          for (int mb = 0; mb < mb_used; ++mb, ++cnt) {
+            const int slot = cnt % kASlots;
+            mbar_wait(pipe.empty_a + slot, ((cnt / kASlots) & 1) ^ 1);
+            mbar_arrive_expect_tx(pipe.full_a + slot, kTileBytes);
+            tma_load_3d(pipe.ring_a + slot * kTileBytes, &p.map_l, rb * kBK, row0 + mb * 128, smp, pipe.full_a + slot);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, mma_n(n_cols - col0), false, kDgrad);
+      int it = 0, cnt = 0;
+      for (int s = s_begin; s < s_end; ++s) {
+        for (int rb = 0; rb < red_blocks; ++rb, ++it) {
+          const int wslot = it % kWSlots;
+          mbar_wait(pipe.full_w + wslot, (it / kWSlots) & 1);
+          const uint32_t wt = pipe.ring_w + wslot * kTileBytes;
+          for (int mb = 0; mb < mb_used; ++mb, ++cnt) {
+            const int aslot = cnt % kASlots;
+            mbar_wait(pipe.full_a + aslot, (cnt / kASlots) & 1);
+            tc_fence_after_sync();
+            const uint32_t at = pipe.ring_a + aslot * kTileBytes;
+#pragma unroll
+            for (int ks = 0; ks < kBK / 8; ++ks) {
+              const uint64_t da = make_smem_desc(at + ks * 32);
+              const uint64_t db = kDgrad ? make_smem_desc_mn(wt + ks * kMnKStep, kMnLbo, kMnSbo) : make_smem_desc(wt + ks * 32);
+              mma_tf32(tmem + mb * 128, da, db, idesc, it > 0 || ks > 0);
+            }
+            mma_commit(pipe.empty_a + aslot);
+          }
+          mma_commit(pipe.empty_w + wslot);
+        }
+      }
+      mma_commit(pipe.accum_full);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int et = threadIdx.x - kEpiWarp0 * 32;   // 0..127
+    const int quad = warp & 3;
+    if (!kDgrad) {
+      float b = 0.f;
+      const int n = col0 + et;
+      if (p.mu_b != nullptr && n < p.N) {
+        const int s = blockIdx.z;
+        const float e = p.eps_b ? __ldg(p.eps_b + static_cast<int64_t>(s) * p.N + n)
+                                : eps1(resolve_rng(p.rng_b), p.sample_begin + s, static_cast<uint64_t>(n));
+        b = fmaf(__ldg(p.sigma_b + n), e, __ldg(p.mu_b + n));
+      }
+      pipe.aux[et] = b;
+      named_bar_sync(kEpiBarrier, kEpiThreads);
+    }
+    mbar_wait(pipe.accum_full, 0);
+    tc_fence_after_sync();
+    View out = p.out;
+    out.base += (p.sum_samples ? 0 : static_cast<int64_t>(blockIdx.z) * p.out_sample_stride);
+    const int cols_here = n_cols - col0 < 128 ? n_cols - col0 : 128;
+    for (int mb = 0; mb < mb_used; ++mb) {
+      const int m = row0 + mb * 128 + quad * 32 + lane;
+      for (int c = 0; c * 16 < cols_here; ++c) {
+        float v[16];
+        tmem_ld16(tmem + (static_cast<uint32_t>(quad * 32) << 16) + mb * 128 + c * 16, v);
+        if (!kDgrad) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += pipe.aux[c * 16 + j];
+        }
+        if (m < p.M) store_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+constexpr size_t kContractSmem = kSmemAux + 1024 + static_cast<size_t>(kASlots + kWSlots) * kTileBytes;
+
+template <int MB, bool kDgrad>
+int launch_tma_contract(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    BNN_CUDA_OK(cudaFuncSetAttribute(contract_tma_kernel<MB, kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(kContractSmem)));
+    attr_set = true;
+  }
+  contract_tma_kernel<MB, kDgrad><<<grid, kThreadsTma, kContractSmem, st>>>(p);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+template <bool kDgrad>
+int dispatch_tma_contract(const TmaContractParams& p, int n_cols, cudaStream_t st) {
+  const int m_blocks = (p.M + 127) / 128;
+  const int gx = (n_cols + 127) / 128, gz = p.sum_samples ? 1 : p.S;
+  if (m_blocks >= 4) return launch_tma_contract<4, kDgrad>(p, dim3(gx, (m_blocks + 3) / 4, gz), st);
+  if (m_blocks >= 2) return launch_tma_contract<2, kDgrad>(p, dim3(gx, (m_blocks + 1) / 2, gz), st);
+  return launch_tma_contract<1, kDgrad>(p, dim3(gx, m_blocks, gz), st);
+}
+
+// ---------------------------------------------------------------------------------------------- weight gradient
+// CTA (k-tile, n-tile, sample group).  Stage = dY^T tile (MN = n) + A^T tile (MN = k), each 4 TMA boxes of
+// 32 MN x 32 K-rows (m).  TMEM columns: [0,128) G0 | [128,256) sum G | [256,384) sum G o eps | [384,512) G1.
+constexpr int kWgStages = 6;
+constexpr int kWgThreads = 6 * 32;           // warp 0 TMA, warp 1 MMA (+TMEM owner), warps 2-5 epilogue
+constexpr size_t kWgradSmem = kSmemAux + 1024 + static_cast<size_t>(kWgStages) * 2 * kTileBytes;
+
+struct TmaWgradParams {
+  CUtensorMap map_dy;       // dY [S][M][N], box 32 x 32
+  CUtensorMap map_a;        // A  [S or 1][M][K], box 32 x 32
+  const float* rho_w;
+  const float* eps_w;
+  float* dmu_w;
+  float* drho_w;
+  int M, N, K, S;
+  uint32_t sample_begin;
+  bnn_rng rng_w;
+  int shared_a;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_constant__ TmaWgradParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t kColG0 = 0, kColMu = 128, kColRho = 256, kColG1 = 384;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + kWgStages;
+  uint64_t* accum_full = empty + kWgStages;
+  uint64_t* accum_empty = accum_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_empty + 2);
+  const uint32_t ring = (smem_u32(smem_raw) + kSmemAux + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(accum_full + i, 1); mbar_init(accum_empty + i, kEpiThreads); }
+    fence_mbar_init();
+    tma_prefetch_desc(&p.map_dy);
+    tma_prefetch_desc(&p.map_a);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int k0 = blockIdx.x * 128;
+  const int n0 = blockIdx.y * 128;
+  const int groups = gridDim.z;
+  const int per = (p.S + groups - 1) / groups;
+  const int s_begin = blockIdx.z * per;
+  const int s_end = s_begin + per < p.S ? s_begin + per : p.S;
+  const int m_blocks = (p.M + kBK - 1) / kBK;
+
+  if (s_begin < s_end) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int it = 0;
+        for (int s = s_begin; s < s_end; ++s) {
+          const int sa = p.shared_a ? 0 : s;
+          for (int mb = 0; mb < m_blocks; ++mb, ++it) {
+            const int stage = it % kWgStages;
+            mbar_wait(empty + stage, ((it / kWgStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(full + stage, 2 * kTileBytes);
+            const uint32_t base = ring + stage * 2 * kTileBytes;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              tma_load_3d(base + g * kMnLbo, &p.map_dy, n0 + g * 32, mb * kBK, s, full + stage);
+              tma_load_3d(base + kTileBytes + g * kMnLbo, &p.map_a, k0 + g * 32, mb * kBK, sa, full + stage);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_tf32(128, mma_n(p.K - k0), true, true);
+        int it = 0;
+        for (int s = s_begin, i = 0; s < s_end; ++s, ++i) {
+          const int buf = i & 1;
+          mbar_wait(accum_empty + buf, ((i >> 1) & 1) ^ 1);
+          tc_fence_after_sync();
+          const uint32_t d = tmem + (buf ? kColG1 : kColG0);
+          for (int mb = 0; mb < m_blocks; ++mb, ++it) {
+            const int stage = it % kWgStages;
+            mbar_wait(full + stage, (it / kWgStages) & 1);
+            tc_fence_after_sync();
+            const uint32_t base = ring + stage * 2 * kTileBytes;
+#pragma unroll
+            for (int ks = 0; ks < kBK / 8; ++ks)
+              mma_tf32(d, make_smem_desc_mn(base + ks * kMnKStep, kMnLbo, kMnSbo),
+                       make_smem_desc_mn(base + kTileBytes + ks * kMnKStep, kMnLbo, kMnSbo), idesc, mb > 0 || ks > 0);
+            mma_commit(empty + stage);
+          }
+          mma_commit(accum_full + buf);
+        }
+      }
+      __syncwarp();
+    } else {
+      const int quad = warp & 3;
+      const int n = n0 + quad * 32 + lane;
+      const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+      const RngKey key = resolve_rng(p.rng_w);
+      const int cols_here = p.K - k0 < 128 ? p.K - k0 : 128;
+      for (int s = s_begin, i = 0; s < s_end; ++s, ++i) {
+        const int buf = i & 1;
+        const bool first = (s == s_begin), last = (s + 1 == s_end);
+        EpsSrc eps;
+        eps.inj = p.eps_w ? p.eps_w + static_cast<int64_t>(s) * p.N * p.K : nullptr;
+        eps.key = key;
+        eps.sample = p.sample_begin + s;
+        mbar_wait(accum_full + buf, (i >> 1) & 1);
+        tc_fence_after_sync();
+        for (int c = 0; c * 16 < cols_here; ++c) {
+          float g[16], dm[16], dr[16];
+          tmem_ld16(lane_addr + (buf ? kColG1 : kColG0) + c * 16, g);
+          if (!first) {
+            tmem_ld16(lane_addr + kColMu + c * 16, dm);
+            tmem_ld16(lane_addr + kColRho + c * 16, dr);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dm[j] = dr[j] = 0.f;
+          }
+          const int k = k0 + c * 16;
+          if (n < p.N) {
+            const int64_t row = static_cast<int64_t>(n) * p.K;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (k + q * 4 < p.K) {
+                const float4 e = eps_vec4(eps, row + k + q * 4);
+                dm[q * 4 + 0] += g[q * 4 + 0]; dr[q * 4 + 0] = fmaf(g[q * 4 + 0], e.x, dr[q * 4 + 0]);
+                dm[q * 4 + 1] += g[q * 4 + 1]; dr[q * 4 + 1] = fmaf(g[q * 4 + 1], e.y, dr[q * 4 + 1]);
+                dm[q * 4 + 2] += g[q * 4 + 2]; dr[q * 4 + 2] = fmaf(g[q * 4 + 2], e.z, dr[q * 4 + 2]);
+                dm[q * 4 + 3] += g[q * 4 + 3]; dr[q * 4 + 3] = fmaf(g[q * 4 + 3], e.w, dr[q * 4 + 3]);
+              }
+            }
+          }
+          if (!last) {
+            tmem_st16(lane_addr + kColMu + c * 16, dm);
+            tmem_st16(lane_addr + kColRho + c * 16, dr);
+          } else if (n < p.N) {
+            const int64_t row = static_cast<int64_t>(n) * p.K;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (k + q * 4 < p.K) {
+                const int64_t i0 = row + k + q * 4;
+                const float4 r = __ldg(reinterpret_cast<const float4*>(p.rho_w + i0));
+                red_add4(p.dmu_w + i0, dm[q * 4], dm[q * 4 + 1], dm[q * 4 + 2], dm[q * 4 + 3]);
+                red_add4(p.drho_w + i0, dr[q * 4] * sigmoid_fast(r.x), dr[q * 4 + 1] * sigmoid_fast(r.y),
+                         dr[q * 4 + 2] * sigmoid_fast(r.z), dr[q * 4 + 3] * sigmoid_fast(r.w));
+              }
+            }
+          }
+        }
+        tc_fence_before_sync();
+        mbar_arrive(accum_empty + buf);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- self test
+// MN-major operand tiles: D(128 x 64) = A^T-tile(MN-major, 128 x 32) * B^T-tile(MN-major, 64 x 32)^T against a
+// serial fp32 loop over the TF32-rounded values.
+__device__ __forceinline__ float st_a(int r, int c) {
+  return __uint_as_float(to_tf32(0.01f * static_cast<float>((r * 7 + c * 13) % 97) - 0.4f));
+}
+__device__ __forceinline__ float st_b(int r, int c) {
+  return __uint_as_float(to_tf32(0.02f * static_cast<float>((r * 5 + c * 3) % 89) - 0.7f));
+}
+__global__ void __launch_bounds__(128, 1) selftest_mn_kernel(float* max_err, int variant) {
+  __shared__ __align__(1024) uint8_t tiles[2 * kTileBytes];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ float red[4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t ta = smem_u32(tiles), tb = ta + kTileBytes;
+  const bool a_mn = variant & 1, b_mn = variant & 2;
+  const uint32_t lbo = kMnLbo, sbo = kMnSbo;
+  for (int i = tid; i < 128 * 32; i += 128) {
+    const int mn = i & 127, k = i >> 7;
+    const uint32_t va = __float_as_uint(st_a(mn, k)), vb = __float_as_uint(mn < 64 ? st_b(mn, k) : 0.f);
+    if (a_mn) sts32(ta + tile_offset_mn(mn, k, lbo, sbo), va);
+    else sts32(ta + tile_offset(mn, k >> 2) + ((k & 3) << 2), va);
+    if (b_mn) sts32(tb + tile_offset_mn(mn, k, lbo, sbo), vb);
+    else sts32(tb + tile_offset(mn, k >> 2) + ((k & 3) << 2), vb);
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&slot, 64);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&slot);
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_tf32(128, 64, a_mn, b_mn);
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t da = a_mn ? make_smem_desc_mn(ta + ks * kMnKStep, lbo, sbo) : make_smem_desc(ta + ks * 32);
+      const uint64_t db = b_mn ? make_smem_desc_mn(tb + ks * kMnKStep, lbo, sbo) : make_smem_desc(tb + ks * 32);
+      mma_tf32(tmem, da, db, idesc, ks > 0);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after_sync();
+  float err = (ta & 1023u) ? 1e30f : 0.f;
+  for (int c = 0; c < 4; ++c) {
+    float v[16];
+    tmem_ld16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c * 16, v);
+    for (int j = 0; j < 16; ++j) {
+      float ref = 0.f;
+      for (int k = 0; k < 32; ++k) ref = fmaf(st_a(tid, k), st_b(c * 16 + j, k), ref);
+      err = fmaxf(err, fabsf(ref - v[j]));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
+  if (lane == 0) red[warp] = err;
+  tc_fence_before_sync();
+  __syncthreads();
+  if (tid == 0) *max_err = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, 64);
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- host entry points
+int tma_fwd(const float* a, int64_t lda, int64_t a_sample_stride, const float* mu_w, const float* sigma_w,
+            const float* mu_b, const float* sigma_b, const float* eps_w, const float* eps_b, bnn_view y,
+            int64_t y_sample_stride, int M, int N, int K, int S, uint32_t sample_begin, const bnn_rng* rng_w,
+            const bnn_rng* rng_b, cudaStream_t st) {
+  const bool shared = a_sample_stride == 0;
+  if (!tma_ok(a, lda, a_sample_stride) || K % 4 != 0 || rng_w->elem_offset % 4 != 0 || !aligned16(mu_w) ||
+      !aligned16(sigma_w) || (eps_w != nullptr && !aligned16(eps_w)))
+    return kNotEligible;
+  TmaContractParams p{};
+  int rc = make_map(&p.map_l, a, K, M, shared ? 1 : S, lda, a_sample_stride, 128);
+  if (rc != BNN_OK) return rc;
+  p.out.base = y.base; p.out.bs = y.batch_stride; p.out.P = y.P; p.out_sample_stride = y_sample_stride;
+  p.mu_w = mu_w; p.sigma_w = sigma_w; p.eps_w = eps_w; p.mu_b = mu_b; p.sigma_b = sigma_b; p.eps_b = eps_b;
+  p.M = M; p.N = N; p.K = K; p.S = S; p.sample_begin = sample_begin;
+  p.rng_w = *rng_w; p.rng_b = rng_b ? *rng_b : *rng_w;
+  p.shared_l = shared ? 1 : 0;
+  p.sum_samples = 0;
+  p.vec_out = (y.P == 1) && (y.batch_stride % 4 == 0) && (y_sample_stride % 4 == 0) && aligned16(y.base);
+  return dispatch_tma_contract<false>(p, N, st);
+}
+
+int tma_dgrad(bnn_view dy, int64_t dy_sample_stride, const float* mu_w, const float* sigma_w, const float* eps_w,
+              float* da, int64_t lda, int64_t a_sample_stride, int M, int N, int K, int S, uint32_t sample_begin,
+              const bnn_rng* rng_w, cudaStream_t st) {
+  if (dy.P != 1 || !tma_ok(dy.base, dy.batch_stride, dy_sample_stride) || K % 4 != 0 || rng_w->elem_offset % 4 != 0 ||
+      !aligned16(mu_w) || !aligned16(sigma_w) || (eps_w != nullptr && !aligned16(eps_w)))
+    return kNotEligible;
+  TmaContractParams p{};
+  int rc = make_map(&p.map_l, dy.base, N, M, S, dy.batch_stride, dy_sample_stride, 128);
+  if (rc != BNN_OK) return rc;
+  p.out.base = da; p.out.bs = lda; p.out.P = 1; p.out_sample_stride = a_sample_stride;
+  p.mu_w = mu_w; p.sigma_w = sigma_w; p.eps_w = eps_w;
+  p.M = M; p.N = N; p.K = K; p.S = S; p.sample_begin = sample_begin;
+  p.rng_w = *rng_w; p.rng_b = *rng_w;
+  p.shared_l = 0;
+  p.sum_samples = (a_sample_stride == 0) ? 1 : 0;
+  p.vec_out = (lda % 4 == 0) && (a_sample_stride % 4 == 0) && aligned16(da);
+  return dispatch_tma_contract<true>(p, K, st);
+}
+
+int tma_wgrad(bnn_view dy, int64_t dy_sample_stride, const float* a, int64_t lda, int64_t a_sample_stride,
+              const float* rho_w, const float* eps_w, float* dmu_w, float* drho_w, int M, int N, int K, int S,
+              uint32_t sample_begin, const bnn_rng* rng_w, cudaStream_t st) {
+  const bool shared = a_sample_stride == 0;
+  if (dy.P != 1 || !tma_ok(dy.base, dy.batch_stride, dy_sample_stride) || !tma_ok(a, lda, a_sample_stride) ||
+      K % 4 != 0 || rng_w->elem_offset % 4 != 0 || !aligned16(rho_w) || !aligned16(dmu_w) || !aligned16(drho_w) ||
+      (eps_w != nullptr && !aligned16(eps_w)))
+    return kNotEligible;
+  TmaWgradParams p{};
+  int rc = make_map(&p.map_dy, dy.base, N, M, S, dy.batch_stride, dy_sample_stride, 32, true);
+  if (rc != BNN_OK) return rc;
+  rc = make_map(&p.map_a, a, K, M, shared ? 1 : S, lda, a_sample_stride, 32, true);
+  if (rc != BNN_OK) return rc;
+  p.rho_w = rho_w; p.eps_w = eps_w; p.dmu_w = dmu_w; p.drho_w = drho_w;
+  p.M = M; p.N = N; p.K = K; p.S = S; p.sample_begin = sample_begin;
+  p.rng_w = *rng_w;
+  p.shared_a = shared ? 1 : 0;
+  const int tiles = ((N + 127) / 128) * ((K + 127) / 128);
+  int groups = (2 * sm_count() + tiles - 1) / tiles;
+  if (groups > S) groups = S;
+  if (groups < 1) groups = 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BNN_CUDA_OK(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(kWgradSmem)));
+    attr_set = true;
+  }
+  wgrad_tma_kernel<<<dim3((K + 127) / 128, (N + 127) / 128, groups), kWgThreads, kWgradSmem, st>>>(p);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+int tma_selftest(float* max_err_dev, cudaStream_t st) {
+  const char* v = getenv("BNN_SELFTEST_VARIANT");      // debugging aid: operand-layout variants of the self test
+  selftest_mn_kernel<<<1, 128, 0, st>>>(max_err_dev, v ? atoi(v) : 3);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+}  // namespace contract
+}  // namespace bnn

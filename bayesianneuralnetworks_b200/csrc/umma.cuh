@@ -137,10 +137,49 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (uint64_t(1) << 16) |
          (uint64_t(kAtomBytes >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M x N tile
-__device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
+// kind::tf32, fp32 accumulate, M x N tile; a_mn / b_mn select MN-major (transposed) operand tiles
+__device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+// MN-major operand tile of fp32/TF32 data.  For 32-bit MN-major operands the only swizzled layout tcgen05 accepts is
+// SWIZZLE_128B_BASE32B (CuTe: Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> o (32 MN x 4 K) : (1, 32)): 32 consecutive MN
+// elements form a 128-byte row, 4 K-rows form a 512-byte swizzle atom in which the 32-BYTE chunk c32 of K-row r sits
+// at r*128 + ((c32 ^ r) * 32); the next 4 K-rows follow at SBO, the next 32 MN elements at LBO.  It is what TMA
+// writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  One UMMA K-step (8 TF32) = two atoms.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32) | (uint64_t(1) << 46) | (uint64_t(1) << 61);
+}
+// byte offset of element (mn, k) inside an MN-major tile with the given LBO / SBO
+__device__ __forceinline__ uint32_t tile_offset_mn(int mn, int k, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const int r = k & 3;
+  return static_cast<uint32_t>(mn >> 5) * lbo_bytes + static_cast<uint32_t>(k >> 2) * sbo_bytes +
+         static_cast<uint32_t>(r * kRowBytes) + static_cast<uint32_t>(((((mn & 31) >> 3) ^ r) << 5) + ((mn & 7) << 2));
+}
+
+// ---- TMA (cp.async.bulk.tensor) -----------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+// 3-d tile load: coordinates (c0 = innermost element, c1 = row, c2 = sample); out-of-bounds elements are zero
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// 2-d tile load: coordinates (c0 = innermost element index, c1 = row index); completes on `bar` (tx bytes)
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, one K-step of 8 TF32 elements; issued by ONE thread
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,

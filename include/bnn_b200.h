@@ -210,6 +210,8 @@ int bnn_prune(const bnn_prune_tensor* tensors /* HOST array */, int32_t n_tensor
 /* ---- self test of the tcgen05 path (one 128xNx32 TF32 tile against a serial fp32 loop run by
  * the same kernel's thread 0); returns BNN_OK and writes max |err| to *max_err_dev. */
 int bnn_selftest_umma(float* max_err_dev, void* stream);
+/* same for MN-major (transposed) operand tiles, the layout the data- and weight-gradient kernels use */
+int bnn_selftest_umma_mn(float* max_err_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,8 @@ def test_abi_version_and_umma_selftest(C):
     assert C.abi_version() == 1
     err = C.selftest_umma()
     assert err < 1e-4, f"tcgen05 tile self test: max |err| = {err}"
+    err = C.selftest_umma(mn_major=True)
+    assert err < 1e-4, f"tcgen05 MN-major tile self test: max |err| = {err}"
 
 
 def test_stddev_matches_oracle(C):
