@@ -25,8 +25,15 @@ namespace {
 
 constexpr int kASlots = 8;                   // activation tile ring (16 KiB each)
 constexpr int kWSlots = 4;                   // generated weight tile ring
-constexpr int kTmaWarp = 13;
-constexpr int kThreadsTma = 14 * 32;
+// warp roles of the forward / data-gradient kernel: 16 weight generators (the Philox chains are latency bound:
+// four warps per scheduler hide them), MMA issuer, four epilogue warps (TMEM lane quarter = warp % 4), TMA issuer
+constexpr int kGenWarps = 16;
+constexpr int kGenThreads = kGenWarps * 32;
+constexpr int kGenItems = 1024 / kGenThreads;       // float4 items of a 128 x 32 tile per generator thread
+constexpr int kMmaWarpT = kGenWarps;
+constexpr int kEpiWarp0T = kGenWarps + 1;
+constexpr int kTmaWarp = kGenWarps + 5;
+constexpr int kThreadsTma = (kGenWarps + 6) * 32;
 constexpr uint32_t kMnLbo = 4096, kMnSbo = 512;    // MN-major 128 x 32 tile: 4 groups of 32 MN, 8 atoms of 4 K-rows
 constexpr uint32_t kMnKStep = 2 * kMnSbo;            // one UMMA K-step (8 TF32) = two 4-row atoms
 
@@ -123,11 +130,11 @@ __device__ __forceinline__ TmaPipe carve_tma(uint8_t* smem_raw) {
 // W_s tile, K-major (rows n, columns k) — forward
 __device__ __forceinline__ void gen_w_kmajor(uint32_t tile, const float* __restrict__ mu, const float* __restrict__ sigma,
                                              const EpsSrc& eps, int n0, int N, int k0, int K, int tid) {
-  float4 m[4], s[4];
-  int64_t idx[4];
+  float4 m[kGenItems], s[kGenItems];
+  int64_t idx[kGenItems];
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int item = it * kProducerThreads + tid;
+  for (int it = 0; it < kGenItems; ++it) {
+    const int item = it * kGenThreads + tid;
     const int n = n0 + (item >> 3), k = k0 + ((item & 7) << 2);
     idx[it] = -1;
     if (n < N && k < K) {
@@ -137,8 +144,8 @@ __device__ __forceinline__ void gen_w_kmajor(uint32_t tile, const float* __restr
     }
   }
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int item = it * kProducerThreads + tid;
+  for (int it = 0; it < kGenItems; ++it) {
+    const int item = it * kGenThreads + tid;
     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
     if (idx[it] >= 0) {
       const float4 e = eps_vec4(eps, idx[it]);
@@ -155,11 +162,11 @@ __device__ __forceinline__ void gen_w_kmajor(uint32_t tile, const float* __restr
 // generated in its natural orientation; each float4 of a row lands as one 16-byte chunk of the 128-byte row.
 __device__ __forceinline__ void gen_w_mnmajor(uint32_t tile, const float* __restrict__ mu, const float* __restrict__ sigma,
                                               const EpsSrc& eps, int n0, int N, int k0, int K, int tid) {
-  float4 m[4], s[4];
-  int64_t idx[4];
+  float4 m[kGenItems], s[kGenItems];
+  int64_t idx[kGenItems];
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int item = it * kProducerThreads + tid;
+  for (int it = 0; it < kGenItems; ++it) {
+    const int item = it * kGenThreads + tid;
     const int n = n0 + (item >> 5), k = k0 + ((item & 31) << 2);
     idx[it] = -1;
     if (n < N && k < K) {
@@ -169,8 +176,8 @@ __device__ __forceinline__ void gen_w_mnmajor(uint32_t tile, const float* __rest
     }
   }
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int item = it * kProducerThreads + tid;
+  for (int it = 0; it < kGenItems; ++it) {
+    const int item = it * kGenThreads + tid;
     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
     if (idx[it] >= 0) {
       const float4 e = eps_vec4(eps, idx[it]);
@@ -192,12 +199,12 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kASlots; ++i) { mbar_init(pipe.full_a + i, 1); mbar_init(pipe.empty_a + i, 1); }
-    for (int i = 0; i < kWSlots; ++i) { mbar_init(pipe.full_w + i, kProducerThreads); mbar_init(pipe.empty_w + i, 1); }
+    for (int i = 0; i < kWSlots; ++i) { mbar_init(pipe.full_w + i, kGenThreads); mbar_init(pipe.empty_w + i, 1); }
     mbar_init(pipe.accum_full, 1);
     fence_mbar_init();
   }
   if (warp == kTmaWarp && lane == 0) tma_prefetch_desc(&p.map_l);
-  if (warp == kMmaWarp) tmem_alloc(pipe.tmem_slot, kTmemCols);
+  if (warp == kMmaWarpT) tmem_alloc(pipe.tmem_slot, kTmemCols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
   int mb_used = (p.M - row0 + 127) / 128;
   if (mb_used > MB) mb_used = MB;
 
-  if (warp < kProducerWarps) {
+  if (warp < kGenWarps) {
     // ------------------------------------------------------------------ weight generators
     const int tid = threadIdx.x;
     const RngKey key = resolve_rng(p.rng_w);
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
       }
     }
     __syncwarp();
-  } else if (warp == kMmaWarp) {
+  } else if (warp == kMmaWarpT) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(128, mma_n(n_cols - col0), false, kDgrad);
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue
-    const int et = threadIdx.x - kEpiWarp0 * 32;   // 0..127
+    const int et = threadIdx.x - kEpiWarp0T * 32;   // 0..127
     const int quad = warp & 3;
     if (!kDgrad) {
       float b = 0.f;
@@ -317,7 +324,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kMmaWarpT) {
     tc_fence_after_sync();
     tmem_dealloc(tmem, kTmemCols);
   }
@@ -365,6 +372,8 @@ struct TmaWgradParams {
   uint32_t sample_begin;
   bnn_rng rng_w;
   int shared_a;
+  int n_chunks;             // the M reduction of every sample is cut into n_chunks pieces of chunk_blocks k-blocks:
+  int chunk_blocks;         // a work unit = (sample, chunk); (sum_chunks G) o eps = sum_chunks (G o eps), so units are independent
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_constant__ TmaWgradParams p) {
@@ -394,18 +403,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
   const int k0 = blockIdx.x * 128;
   const int n0 = blockIdx.y * 128;
   const int groups = gridDim.z;
-  const int per = (p.S + groups - 1) / groups;
-  const int s_begin = blockIdx.z * per;
-  const int s_end = s_begin + per < p.S ? s_begin + per : p.S;
-  const int m_blocks = (p.M + kBK - 1) / kBK;
+  const int units = p.S * p.n_chunks;
+  const int per = (units + groups - 1) / groups;
+  const int s_begin = blockIdx.z * per;                          // work units [s_begin, s_end)
+  const int s_end = s_begin + per < units ? s_begin + per : units;
+  const int m_total = (p.M + kBK - 1) / kBK;
+  auto unit_blocks = [&](int u, int* mb0) {                      // k-block range of unit u
+    const int c = u % p.n_chunks;
+    *mb0 = c * p.chunk_blocks;
+    const int left = m_total - *mb0;
+    return left < p.chunk_blocks ? left : p.chunk_blocks;
+  };
 
   if (s_begin < s_end) {
     if (warp == 0) {
       if (lane == 0) {
         int it = 0;
-        for (int s = s_begin; s < s_end; ++s) {
+        for (int u = s_begin; u < s_end; ++u) {
+          const int s = u / p.n_chunks;
           const int sa = p.shared_a ? 0 : s;
-          for (int mb = 0; mb < m_blocks; ++mb, ++it) {
+          int mb0;
+          const int m_blocks = unit_blocks(u, &mb0);
+          for (int mb = mb0; mb < mb0 + m_blocks; ++mb, ++it) {
             const int stage = it % kWgStages;
             mbar_wait(empty + stage, ((it / kWgStages) & 1) ^ 1);
             mbar_arrive_expect_tx(full + stage, 2 * kTileBytes);
@@ -423,11 +442,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
       if (lane == 0) {
         const uint32_t idesc = make_idesc_tf32(128, mma_n(p.K - k0), true, true);
         int it = 0;
-        for (int s = s_begin, i = 0; s < s_end; ++s, ++i) {
+        for (int u = s_begin, i = 0; u < s_end; ++u, ++i) {
           const int buf = i & 1;
           mbar_wait(accum_empty + buf, ((i >> 1) & 1) ^ 1);
           tc_fence_after_sync();
           const uint32_t d = tmem + (buf ? kColG1 : kColG0);
+          int mb0;
+          const int m_blocks = unit_blocks(u, &mb0);
           for (int mb = 0; mb < m_blocks; ++mb, ++it) {
             const int stage = it % kWgStages;
             mbar_wait(full + stage, (it / kWgStages) & 1);
@@ -449,9 +470,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
       const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
       const RngKey key = resolve_rng(p.rng_w);
       const int cols_here = p.K - k0 < 128 ? p.K - k0 : 128;
-      for (int s = s_begin, i = 0; s < s_end; ++s, ++i) {
+      for (int u = s_begin, i = 0; u < s_end; ++u, ++i) {
+        const int s = u / p.n_chunks;
         const int buf = i & 1;
-        const bool first = (s == s_begin), last = (s + 1 == s_end);
+        const bool first = (u == s_begin), last = (u + 1 == s_end);
         EpsSrc eps;
         eps.inj = p.eps_w ? p.eps_w + static_cast<int64_t>(s) * p.N * p.K : nullptr;
         eps.key = key;
@@ -641,9 +663,19 @@ int tma_wgrad(bnn_view dy, int64_t dy_sample_stride, const float* a, int64_t lda
   p.rng_w = *rng_w;
   p.shared_a = shared ? 1 : 0;
   const int tiles = ((N + 127) / 128) * ((K + 127) / 128);
-  int groups = (2 * sm_count() + tiles - 1) / tiles;
-  if (groups > S) groups = S;
-  if (groups < 1) groups = 1;
+  const int m_total = (M + kBK - 1) / kBK;
+  int want = (2 * sm_count() + tiles - 1) / tiles;        // CTAs per output tile that fill the machine twice
+  if (want < 1) want = 1;
+  int n_chunks = 1;
+  if (want > S) {                                         // few samples / tiles: also split the M reduction
+    n_chunks = (want + S - 1) / S;
+    const int max_chunks = (m_total + 7) / 8;             // keep >= 8 k-blocks per unit (epilogue cost per unit)
+    if (n_chunks > max_chunks) n_chunks = max_chunks;
+    if (n_chunks < 1) n_chunks = 1;
+  }
+  p.chunk_blocks = (m_total + n_chunks - 1) / n_chunks;
+  p.n_chunks = (m_total + p.chunk_blocks - 1) / p.chunk_blocks;
+  int groups = want < S * p.n_chunks ? want : S * p.n_chunks;
   static bool attr_set = false;
   if (!attr_set) {
     BNN_CUDA_OK(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -9,18 +9,20 @@ from . import _C
 
 class DrawSpec:
     """Which eps a launch uses: Philox (seed, tensor_id, [sample_begin, sample_begin+S)) or an
-    injected tensor [S, numel] (tests)."""
-    __slots__ = ("seed", "tensor_id", "sample_begin", "step", "eps")
+    injected tensor [S, numel] (tests).  `step_dev` (optional int64[1] device tensor) is added to the
+    Philox step word inside the kernels (CUDA-graph replays, runtime.graph_safe_rng)."""
+    __slots__ = ("seed", "tensor_id", "sample_begin", "step", "eps", "step_dev")
 
-    def __init__(self, seed, tensor_id, draw_begin, eps=None):
+    def __init__(self, seed, tensor_id, draw_begin, eps=None, step_dev=None):
         self.seed = seed
         self.tensor_id = tensor_id
         self.sample_begin = draw_begin & 0xFFFFFFFF
         self.step = draw_begin >> 32
         self.eps = eps
+        self.step_dev = step_dev
 
     def rng(self, elem_offset=0):
-        return _C.make_rng(self.seed, self.step, self.tensor_id, elem_offset=elem_offset)
+        return _C.make_rng(self.seed, self.step, self.tensor_id, elem_offset=elem_offset, step_dev=self.step_dev)
 
 
 def _check_f32_cuda(name, t):
@@ -172,6 +174,11 @@ class SampledConv2d(torch.autograd.Function):
         Ng, Kg, P = Cout // groups, Cg * KH * KW, OH * OW
         M = B * P
         a_stride = 0 if shared else M * Kg
+        # TF32: hand dY to the kernels as a row-major [S*B*P, Cout] matrix (one strided copy), which makes the
+        # TMA-fed data- and weight-gradient kernels eligible; fp32 mode reads the NCHW tensor in place.
+        rowmajor_dy = precision == _C.PREC_TF32 and P > 1 and Cout % 4 == 0 and Ng % 4 == 0
+        if rowmajor_dy:
+            dy_rows = dy.view(S * B, Cout, P).transpose(1, 2).contiguous()
         need_x = ctx.needs_input_grad[0]
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         need_b = rho_b is not None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
@@ -182,21 +189,24 @@ class SampledConv2d(torch.autograd.Function):
         dcol = torch.empty((rows * P, Kg), device=x.device, dtype=torch.float32) if need_x else None
         for g in range(groups):
             lo, hi = g * Ng * Kg, (g + 1) * Ng * Kg
-            dy_view = _C.make_view(dy.data_ptr() + 4 * g * Ng * P, Cout * P, P)
+            if rowmajor_dy:
+                dy_view, dy_ss = _C.make_view(dy_rows.data_ptr() + 4 * g * Ng, Cout, 1), M * Cout
+            else:
+                dy_view, dy_ss = _C.make_view(dy.data_ptr() + 4 * g * Ng * P, Cout * P, P), B * Cout * P
             eps_w = _eps_slice(spec_w, S, Cout * Kg, lo, hi)
             geom = SampledConv2d._geom(rows, geo, g)
             if need_x:
-                _C.sampled_gemm_dgrad(dy_view, B * Cout * P, mu_w.view(-1)[lo:hi], sigma_w.view(-1)[lo:hi], eps_w,
+                _C.sampled_gemm_dgrad(dy_view, dy_ss, mu_w.view(-1)[lo:hi], sigma_w.view(-1)[lo:hi], eps_w,
                                       dcol, Kg, a_stride, M, Ng, Kg, S, spec_w.sample_begin, spec_w.rng(lo),
                                       precision)
                 _C.col2im(dcol, dx, geom, False)
             if need_w:
                 _C.im2col(x, col, geom)
-                _C.sampled_gemm_wgrad(dy_view, B * Cout * P, col, Kg, a_stride, rho_w.view(-1)[lo:hi], eps_w,
+                _C.sampled_gemm_wgrad(dy_view, dy_ss, col, Kg, a_stride, rho_w.view(-1)[lo:hi], eps_w,
                                       grads[0].view(-1)[lo:hi], grads[1].view(-1)[lo:hi], M, Ng, Kg, S,
                                       spec_w.sample_begin, spec_w.rng(lo), precision)
             if need_b:
-                _C.bias_grad(dy_view, B * Cout * P, rho_b.contiguous()[g * Ng:(g + 1) * Ng],
+                _C.bias_grad(dy_view, dy_ss, rho_b.contiguous()[g * Ng:(g + 1) * Ng],
                              _eps_slice(spec_b, S, Cout, g * Ng, (g + 1) * Ng), bg[0][g * Ng:(g + 1) * Ng],
                              bg[1][g * Ng:(g + 1) * Ng], M, Ng, S, spec_b.sample_begin, spec_b.rng(g * Ng))
         return (dx, grads[0] if need_w else None, grads[1] if need_w else None,

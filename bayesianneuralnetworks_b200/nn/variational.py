@@ -72,7 +72,8 @@ class WeightNormal(Module):
                 raise ValueError(f"injected eps must have shape [{count}, {tuple(self.mean.shape)}], got "
                                  f"{tuple(eps.shape)}")
             eps = eps.to(device=self.mean.device, dtype=torch.float32).contiguous()
-        return DrawSpec(runtime.seed(), self._tensor_id, begin, eps)
+        return DrawSpec(runtime.seed(), self._tensor_id, begin, eps, runtime.step_counter(self.mean.device)
+                        if self.mean.is_cuda else None)
 
     def sample(self):
         """core.py:44-45 — draws a fresh eps (by advancing the counter)."""

@@ -66,6 +66,44 @@ def next_tensor_id():
 
 
 # ---------------------------------------------------------------------------------------------
+# Device-side step counter: lets a captured CUDA graph draw fresh eps on every replay.  The draw
+# indices a launch uses are host integers baked into the captured kernel arguments; with the device
+# counter enabled every kernel ADDS the value of one uint64 in device memory to the Philox `step`
+# word (bnn_rng.step_dev), and `advance_rng_step()` — one tiny in-graph add — moves all streams on.
+# Call it at the START of each training step so forward, backward and `.sampled` agree.
+# ---------------------------------------------------------------------------------------------
+_device_step = {"enabled": False, "counters": {}}
+
+
+def graph_safe_rng(enabled=True):
+    _device_step["enabled"] = bool(enabled)
+
+
+def step_counter(device):
+    """The device step counter of `device` (int64[1] tensor) or None when graph-safe RNG is off."""
+    if not _device_step["enabled"]:
+        return None
+    import torch
+    key = torch.device(device)
+    if key.index is None:
+        key = torch.device(key.type, torch.cuda.current_device())
+    c = _device_step["counters"].get(key)
+    if c is None:
+        c = torch.zeros(1, dtype=torch.int64, device=key)
+        _device_step["counters"][key] = c
+    return c
+
+
+def advance_rng_step(device=None):
+    """Advance every Philox stream on `device` by one step (graph-capturable: a single in-place add)."""
+    import torch
+    c = step_counter(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    if c is None:
+        raise RuntimeError("advance_rng_step() needs graph_safe_rng(True)")
+    c.add_(1)
+
+
+# ---------------------------------------------------------------------------------------------
 # Monte-Carlo batch context: set by BayesianNetworkModule.forward while it runs `_forward` ONCE for
 # all S samples.  Activations enter with B rows (shared by all samples); the first Bayesian layer
 # expands them to S*B rows (sample-major), later layers see S independent row blocks.

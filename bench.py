@@ -130,20 +130,28 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ the step
 class Trainer:
-    """The reference training-loop body (train.py:55-65) on this repo's public API."""
+    """The reference training-loop body (train.py:55-65) on this repo's public API.  With `graph=True` the whole
+    step (RNG advance, zero_grad, S-sample forward, KL, CE, backward, gradient all-reduce, Adam) is captured
+    once into a CUDA graph and replayed: the Philox streams advance through a device-side step counter
+    (bnn.graph_safe_rng), so every replay draws fresh eps."""
 
-    def __init__(self, workload, device, world, samples):
+    def __init__(self, workload, device, world, samples, graph):
         import bayesianneuralnetworks_b200 as bnn
         self.bnn = bnn
         torch.manual_seed(0)
+        bnn.graph_safe_rng(graph)
         self.model = build_model(workload, samples).to(device)
         self.kld = bnn.nn.KLDivergence(number_of_batches=N_BATCHES)
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-3)
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-3, capturable=graph)
         self.world = world
         self.params = [p for p in self.model.parameters()]
-        self.flat = None
+        self.graph = None
+        self.use_graph = graph
+        self.launches_per_step = None
 
-    def step(self, x, y):
+    def _body(self, x, y):
+        if self.use_graph:
+            self.bnn.advance_rng_step(x.device)
         self.opt.zero_grad(set_to_none=True)
         preds = self.model(x)
         divergence = self.kld(self.model)
@@ -155,6 +163,32 @@ class Trainer:
             parallel.allreduce_gradients(self.params)
         self.opt.step()
         return loss
+
+    def capture(self, x, y):
+        """Warm up eagerly on a side stream, then capture one step on static input buffers."""
+        from bayesianneuralnetworks_b200 import _C
+        self.sx, self.sy = x.clone(), y.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._body(self.sx, self.sy)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        before = _C.launch_count
+        with torch.cuda.graph(graph):
+            self.static_loss = self._body(self.sx, self.sy)
+        self.launches_per_step = _C.launch_count - before
+        self.graph = graph
+
+    def step(self, x, y):
+        if self.graph is None:
+            return self._body(x, y)
+        self.sx.copy_(x, non_blocking=True)
+        self.sy.copy_(y, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss
 
 
 def run_b200(args):
@@ -174,8 +208,8 @@ def run_b200(args):
     _C.lib()                          # fails loudly when the CUDA library is missing
     wl = WORKLOADS[args.workload]
     B, S = wl["batch"], wl["samples"]
-    bnn.set_precision("tf32" if args.workload == "c4" else "fp32")
-    trainer = Trainer(args.workload, device, world, S)
+    bnn.set_precision(args.precision)
+    trainer = Trainer(args.workload, device, world, S, graph=not args.no_graph)
     gen = torch.Generator().manual_seed(1 + rank)
     n_host = 8
     host = [tuple(t.pin_memory() for t in synthetic_batch(args.workload, B, gen)) for _ in range(n_host)]
@@ -212,6 +246,16 @@ def run_b200(args):
         ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
         return ms / 1e3, wall, last
 
+    graph_note = "eager launches"
+    if trainer.use_graph:
+        try:
+            trainer.capture(*dev[0])
+            graph_note = "whole step captured in one CUDA graph (device-side Philox step counter), replayed per step"
+        except Exception as exc:      # noqa: BLE001 — fall back to eager launches, say so in the result
+            sys.stderr.write(f"CUDA graph capture failed ({exc!r}); running eagerly\n")
+            trainer.graph, trainer.use_graph = None, False
+            bnn.graph_safe_rng(False)
+            graph_note = f"eager launches (graph capture failed: {type(exc).__name__})"
     for i in range(max(args.warmup, 3)):
         trainer.step(*dev[i % n_host])
     clocks = ClockSampler(local)
@@ -219,6 +263,8 @@ def run_b200(args):
     launches0 = _C.launch_count
     dev_s, dev_wall, _ = timed(args.steps, False)
     launches = _C.launch_count - launches0
+    if trainer.graph is not None:
+        launches = trainer.launches_per_step * args.steps      # replays launch the captured kernels
     e2e_s, e2e_wall, last_loss = timed(args.steps, True)
     clock_info = clocks.stop()
 
@@ -239,7 +285,7 @@ def run_b200(args):
     n_prof = min(args.steps, 10)
     for i in range(n_prof):
         flush.zero_()
-        trainer.step(*dev[i % n_host])
+        trainer._body(*dev[i % n_host])          # eager launches so that every library call can be bracketed
     per_kernel = _C.kernel_timing_summary(n_prof)
     _C.set_kernel_timing(False)
     roof = roofline(args.workload, B, S, per_kernel, pk)
@@ -251,11 +297,12 @@ def run_b200(args):
             "metric": "ELBO train samples*MC/sec", "value": units / dev_s, "unit": "samples*MC/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32" if args.workload == "c4" else "fp32 (3xTF32 split on tcgen05)",
+            "vs_baseline": None,
+            "dtype": "tf32" if args.precision == "tf32" else "fp32 (3xTF32 split on tcgen05)",
             "data": "synthetic",
             "config": {"workload": wl["name"], "batch_per_gpu": B, "mc_samples": S, "global_batch": B * world,
                        "parallelism": f"dp{world}" if world > 1 else "single", "n_batches": N_BATCHES,
-                       "optimizer": "Adam", "l2": "flushed between steps (256 MiB write, untimed); each step "
+                       "optimizer": "Adam", "launch": graph_note, "l2": "flushed between steps (256 MiB write, untimed); each step "
                        "timed with its own CUDA event pair", "step": "zero_grad+forward(S)+KL+CE+backward+Adam"},
             "e2e": {"value": units / e2e_s, "unit": "samples*MC/s",
                     "h2d_bytes_per_step": x0.numel() * x0.element_size() + y0.numel() * y0.element_size(),
@@ -462,6 +509,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
+                    help="hot-path contraction mode: tf32 (2e-3 parity class) or fp32 = 3xTF32 split (1e-5 class)")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the kl_prune and cpu_baseline legs (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
