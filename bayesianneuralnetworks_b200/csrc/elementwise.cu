@@ -96,9 +96,23 @@ bias_grad_rowmajor_kernel(const float* __restrict__ dy, int64_t ld, int64_t samp
   const int n = blockIdx.x * 32 + lane;
   const int s = blockIdx.y;
   const float* base = dy + static_cast<int64_t>(s) * sample_stride;
+  // blockIdx.z splits the rows: the chain c * eps * sigmoid(rho) is linear in c, so partial sums add up
+  const int rows_per = (M + gridDim.z - 1) / gridDim.z;
+  const int m_begin = blockIdx.z * rows_per;
+  const int m_end = m_begin + rows_per < M ? m_begin + rows_per : M;
   float acc = 0.f;
-  if (n < N)
-    for (int m = warp; m < M; m += 8) acc += base[static_cast<int64_t>(m) * ld + n];
+  if (n < N) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent loads in flight per thread
+    int m = m_begin + warp;
+    for (; m + 24 < m_end; m += 32) {
+      a0 += base[static_cast<int64_t>(m) * ld + n];
+      a1 += base[static_cast<int64_t>(m + 8) * ld + n];
+      a2 += base[static_cast<int64_t>(m + 16) * ld + n];
+      a3 += base[static_cast<int64_t>(m + 24) * ld + n];
+    }
+    for (; m < m_end; m += 8) a0 += base[static_cast<int64_t>(m) * ld + n];
+    acc = (a0 + a1) + (a2 + a3);
+  }
   part[warp][lane] = acc;
   __syncthreads();
   if (warp == 0 && n < N) {
@@ -250,7 +264,12 @@ int bnn_bias_grad(bnn_view dy, int64_t dy_sample_stride, const float* rho_b, con
   if (rc != BNN_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dy.P == 1) {
-    dim3 grid((N + 31) / 32, S);
+    const int col_blocks = (N + 31) / 32;
+    int chunks = (2 * sm_count() + col_blocks * S - 1) / (col_blocks * S);     // fill the machine about twice
+    const int max_chunks = (M + 63) / 64;                                      // at least 64 rows per block
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    dim3 grid(col_blocks, S, chunks);
     bias_grad_rowmajor_kernel<<<grid, kThreads, 0, st>>>(dy.base, dy.batch_stride, dy_sample_stride,
                                                         rho_b, eps_b, dmu_b, drho_b, M, N,
                                                         sample_begin, *rng_b);

@@ -81,24 +81,29 @@ class SampledLinear(torch.autograd.Function):
     def backward(ctx, dy):
         x, mu_w, rho_w, sigma_w, rho_b = ctx.saved_tensors
         S, shared, spec_w, spec_b, precision, M, N, K = ctx.meta
+        ldy = N
+        if precision == _C.PREC_TF32 and N % 4 != 0:
+            # the TMA-fed kernels need a 16-byte row pitch: pad the (narrow) gradient rows, e.g. a 10-class head
+            ldy = (N + 3) // 4 * 4
+            dy = torch.nn.functional.pad(dy, (0, ldy - N))
         dy = dy.contiguous()
-        dy_view = _C.make_view(dy.data_ptr(), N, 1)
+        dy_view = _C.make_view(dy.data_ptr(), ldy, 1)
         eps_w = _eps_slice(spec_w, S, N * K)
         a_stride = 0 if shared else M * K
         dx = dmu_w = drho_w = dmu_b = drho_b = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            _C.sampled_gemm_dgrad(dy_view, M * N, mu_w, sigma_w, eps_w, dx, K, a_stride, M, N, K, S,
+            _C.sampled_gemm_dgrad(dy_view, M * ldy, mu_w, sigma_w, eps_w, dx, K, a_stride, M, N, K, S,
                                   spec_w.sample_begin, spec_w.rng(), precision)
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             grads = torch.zeros((2, N, K), device=x.device, dtype=torch.float32)
             dmu_w, drho_w = grads[0], grads[1]
-            _C.sampled_gemm_wgrad(dy_view, M * N, x, K, a_stride, rho_w, eps_w, dmu_w, drho_w, M, N, K, S,
+            _C.sampled_gemm_wgrad(dy_view, M * ldy, x, K, a_stride, rho_w, eps_w, dmu_w, drho_w, M, N, K, S,
                                   spec_w.sample_begin, spec_w.rng(), precision)
         if rho_b is not None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
             bg = torch.zeros((2, N), device=x.device, dtype=torch.float32)
             dmu_b, drho_b = bg[0], bg[1]
-            _C.bias_grad(dy_view, M * N, rho_b.contiguous(), _eps_slice(spec_b, S, N), dmu_b, drho_b, M, N, S,
+            _C.bias_grad(dy_view, M * ldy, rho_b.contiguous(), _eps_slice(spec_b, S, N), dmu_b, drho_b, M, N, S,
                          spec_b.sample_begin, spec_b.rng())
         return dx, dmu_w, drho_w, dmu_b, drho_b, None, None, None, None, None
 

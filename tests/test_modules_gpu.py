@@ -464,8 +464,10 @@ def test_graph_safe_rng_fresh_eps_per_replay_and_consistent_backward():
         assert torch.equal(y0, y0_again) and not torch.equal(y0, y1)
         w, b = layer.sampled                  # materialised with the current counter value
         assert torch.allclose(y1, F.linear(x, w, b), atol=1e-5, rtol=1e-5)
-        # captured forward + backward
-        sx = x.clone().requires_grad_(True)
+        # captured forward + backward (static input, gradients of the parameters).  A fresh layer: autograd ties a
+        # parameter's gradient accumulation to the stream of its first use, which must not be the legacy stream.
+        layer = NormalLinear(64, 32).cuda()
+        sx = x.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -475,22 +477,24 @@ def test_graph_safe_rng_fresh_eps_per_replay_and_consistent_backward():
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         layer.zero_grad(set_to_none=True)
-        sx.grad = None
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             bnn.advance_rng_step()
             out = layer(sx)
             out.square().sum().backward()
-        outs, grads = [], []
+        outs = []
         for _ in range(3):
             g.replay()
             torch.cuda.synchronize()
-            outs.append(out.clone())
+            outs.append(out.detach().clone())
             w, b = layer.sampled
-            # the weights this replay used: out = x W^T + b, dL/dx = 2 out W
-            assert torch.allclose(out, F.linear(sx.detach(), w, b), atol=1e-4, rtol=1e-4)
-            assert torch.allclose(sx.grad, 2 * out.detach() @ w, atol=1e-3, rtol=1e-3)
-            grads.append(layer.weight.mean.grad.clone())
+            # the weights this replay used: out = x W^T + b; dL/dmean = 2 out^T x; dL/dscale = dL/dmean * eps * sigmoid
+            assert torch.allclose(out, F.linear(sx, w, b), atol=1e-4, rtol=1e-4)
+            gw = 2 * out.detach().t() @ sx
+            assert torch.allclose(layer.weight.mean.grad, gw, atol=1e-3, rtol=1e-3)
+            eps = (w - layer.weight.mean) / layer.weight.stddev
+            assert torch.allclose(layer.weight.scale.grad, gw * eps * torch.sigmoid(layer.weight.scale), atol=2e-3,
+                                  rtol=2e-3)
         assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
     finally:
         bnn.graph_safe_rng(False)
