@@ -29,6 +29,7 @@ import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = "WARN"        # NCCL's version banner goes to stdout; this program prints ONE JSON line there
 
 N_BATCHES = 469          # ceil(60000 / 128), examples/MNIST/train.py:38 (any constant)
 WORKLOADS = {
@@ -146,28 +147,53 @@ class Trainer:
         self.world = world
         self.params = [p for p in self.model.parameters()]
         self.graph = None
+        self.graph_opt = None
+        self.flat = None
         self.use_graph = graph
         self.launches_per_step = None
 
-    def _body(self, x, y):
+    def _forward_backward(self, x, y):
         if self.use_graph:
             self.bnn.advance_rng_step(x.device)
-        self.opt.zero_grad(set_to_none=True)
+        if self.flat is not None:
+            self.flat.zero_()                 # gradients are views of one flat buffer (static addresses)
+        else:
+            self.opt.zero_grad(set_to_none=True)
         preds = self.model(x)
         divergence = self.kld(self.model)
         likelihood = torch.stack([F.cross_entropy(p, y) for p in preds]).mean()
         loss = likelihood + divergence
         loss.backward()
-        if self.world > 1:      # data parallel: ONE all-reduce (avg) of the flat gradient buffer
+        return loss
+
+    def _allreduce(self):
+        """Data parallel: ONE all-reduce (avg) of the flat gradient buffer."""
+        import torch.distributed as dist
+        if self.flat is not None:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        else:
             from bayesianneuralnetworks_b200 import parallel
             parallel.allreduce_gradients(self.params)
+
+    def _body(self, x, y):
+        loss = self._forward_backward(x, y)
+        if self.world > 1:
+            self._allreduce()
         self.opt.step()
         return loss
 
     def capture(self, x, y):
-        """Warm up eagerly on a side stream, then capture one step on static input buffers."""
+        """Warm up eagerly on a side stream, then capture the step on static input buffers.  One GPU: one graph.
+        Several GPUs: forward+backward and the optimizer step are two graphs with the NCCL all-reduce of the flat
+        gradient buffer launched eagerly between them (collectives stay outside the captured region)."""
         from bayesianneuralnetworks_b200 import _C
         self.sx, self.sy = x.clone(), y.clone()
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, device=x.device, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -175,12 +201,17 @@ class Trainer:
                 self._body(self.sx, self.sy)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
         before = _C.launch_count
-        with torch.cuda.graph(graph):
-            self.static_loss = self._body(self.sx, self.sy)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._forward_backward(self.sx, self.sy)
+            if self.world == 1:
+                self.opt.step()
+        if self.world > 1:
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt):
+                self.opt.step()
         self.launches_per_step = _C.launch_count - before
-        self.graph = graph
 
     def step(self, x, y):
         if self.graph is None:
@@ -188,6 +219,9 @@ class Trainer:
         self.sx.copy_(x, non_blocking=True)
         self.sy.copy_(y, non_blocking=True)
         self.graph.replay()
+        if self.world > 1:
+            self._allreduce()
+            self.graph_opt.replay()
         return self.static_loss
 
 
@@ -250,10 +284,12 @@ def run_b200(args):
     if trainer.use_graph:
         try:
             trainer.capture(*dev[0])
-            graph_note = "whole step captured in one CUDA graph (device-side Philox step counter), replayed per step"
+            graph_note = ("whole step captured in one CUDA graph (device-side Philox step counter), replayed per step"
+                          if world == 1 else "forward+backward and optimizer captured as two CUDA graphs, the NCCL "
+                          "all-reduce of the flat gradient buffer launched eagerly between them")
         except Exception as exc:      # noqa: BLE001 — fall back to eager launches, say so in the result
             sys.stderr.write(f"CUDA graph capture failed ({exc!r}); running eagerly\n")
-            trainer.graph, trainer.use_graph = None, False
+            trainer.graph, trainer.graph_opt, trainer.use_graph = None, None, False
             bnn.graph_safe_rng(False)
             graph_note = f"eager launches (graph capture failed: {type(exc).__name__})"
     for i in range(max(args.warmup, 3)):
