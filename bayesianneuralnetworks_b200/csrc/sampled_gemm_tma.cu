@@ -21,15 +21,27 @@
 
 namespace bnn {
 namespace contract {
+#ifdef BNN_PROFILE_WAITS
+// profiling builds: cycles spent waiting, summed over CTAs: [0] kernel, [1] MMA on full_w, [2] MMA on full_a,
+// [3] generator warp 0 on empty_w, [4] TMA thread on empty_a, [5] CTAs
+__device__ unsigned long long g_wait_cycles[8];
+#define BNN_T0() const long long _t0 = clock64()
+#define BNN_ACC(var) var += clock64() - _t0
+#else
+#define BNN_T0()
+#define BNN_ACC(var)
+#endif
 namespace {
 
 constexpr int kASlots = 8;                   // activation tile ring (16 KiB each)
-constexpr int kWSlots = 4;                   // generated weight tile ring
+constexpr int kWSlots = 4;                   // generated weight tile ring (the k-block bookkeeping assumes 4)
 // warp roles of the forward / data-gradient kernel: 16 weight generators (the Philox chains are latency bound:
 // four warps per scheduler hide them), MMA issuer, four epilogue warps (TMEM lane quarter = warp % 4), TMA issuer
 constexpr int kGenWarps = 16;
 constexpr int kGenThreads = kGenWarps * 32;
-constexpr int kGenItems = 1024 / kGenThreads;       // float4 items of a 128 x 32 tile per generator thread
+constexpr int kGenGroups = 4;                       // generator groups: group j produces the k-blocks it % 4 == j into
+constexpr int kGroupWarps = kGenWarps / kGenGroups; // weight slot j, so four tiles are in flight at different phases
+constexpr int kGroupThreads = kGroupWarps * 32;     // (one tile's latency — loads, Philox chain — is hidden by the others)
 constexpr int kMmaWarpT = kGenWarps;
 constexpr int kEpiWarp0T = kGenWarps + 1;
 constexpr int kTmaWarp = kGenWarps + 5;
@@ -97,6 +109,7 @@ struct TmaContractParams {
   int shared_l;             // all samples read sample 0 of the L operand (shared activations)
   int sum_samples;          // dgrad with shared activations: one output, summed over the samples
   int vec_out;
+  int exp_flags;            // profiling builds: 1 = skip weight generation, 2 = skip TMA loads, 4 = skip MMA issue
 };
 
 struct TmaPipe {
@@ -127,79 +140,69 @@ __device__ __forceinline__ TmaPipe carve_tma(uint8_t* smem_raw) {
   return p;
 }
 
-// W_s tile, K-major (rows n, columns k) — forward
-__device__ __forceinline__ void gen_w_kmajor(uint32_t tile, const float* __restrict__ mu, const float* __restrict__ sigma,
-                                             const EpsSrc& eps, int n0, int N, int k0, int K, int tid) {
-  float4 m[kGenItems], s[kGenItems];
-  int64_t idx[kGenItems];
+// W_s = mu + sigma * eps_s for a (kRows x 32) piece of the weight matrix, written as an operand tile by ONE generator
+// group (kGroupThreads threads, four float4 per thread and trip: all loads first, then the Philox chains).
+//   kMnMajor = false: K-major tile, tile rows = n (kRows of them), columns = k          (forward)
+//   kMnMajor = true : MN-major tile, K-rows = n (32), MN = k (kRows of them)            (data gradient)
+template <int kRows, bool kMnMajor>
+__device__ __forceinline__ void gen_w_tile(uint32_t tile, const float* __restrict__ mu, const float* __restrict__ sigma,
+                                           const EpsSrc& eps, int n0, int N, int k0, int K, int tid) {
+  constexpr int kItems = kRows * 8;                       // float4 items
+  constexpr int kTrips = kItems / (4 * kGroupThreads);
+  static_assert(kItems % (4 * kGroupThreads) == 0, "tile does not divide over the generator group");
+#pragma unroll 1
+  for (int trip = 0; trip < kTrips; ++trip) {
+    float4 m[4], sg[4];
+    int64_t idx[4];
 #pragma unroll
-  for (int it = 0; it < kGenItems; ++it) {
-    const int item = it * kGenThreads + tid;
-    const int n = n0 + (item >> 3), k = k0 + ((item & 7) << 2);
-    idx[it] = -1;
-    if (n < N && k < K) {
-      idx[it] = static_cast<int64_t>(n) * K + k;
-      m[it] = __ldg(reinterpret_cast<const float4*>(mu + idx[it]));
-      s[it] = __ldg(reinterpret_cast<const float4*>(sigma + idx[it]));
+    for (int u = 0; u < 4; ++u) {
+      const int item = (trip * 4 + u) * kGroupThreads + tid;
+      int n, k;
+      if (!kMnMajor) { n = n0 + (item >> 3); k = k0 + ((item & 7) << 2); }
+      else { n = n0 + item / (kRows / 4); k = k0 + ((item % (kRows / 4)) << 2); }
+      idx[u] = -1;
+      if (n < N && k < K) {
+        idx[u] = static_cast<int64_t>(n) * K + k;
+        m[u] = __ldg(reinterpret_cast<const float4*>(mu + idx[u]));
+        sg[u] = __ldg(reinterpret_cast<const float4*>(sigma + idx[u]));
+      }
     }
-  }
 #pragma unroll
-  for (int it = 0; it < kGenItems; ++it) {
-    const int item = it * kGenThreads + tid;
-    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (idx[it] >= 0) {
-      const float4 e = eps_vec4(eps, idx[it]);
-      w.x = fmaf(s[it].x, e.x, m[it].x);
-      w.y = fmaf(s[it].y, e.y, m[it].y);
-      w.z = fmaf(s[it].z, e.z, m[it].z);
-      w.w = fmaf(s[it].w, e.w, m[it].w);
+    for (int u = 0; u < 4; ++u) {
+      const int item = (trip * 4 + u) * kGroupThreads + tid;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx[u] >= 0) {
+        const float4 e = eps_vec4(eps, idx[u]);
+        w.x = fmaf(sg[u].x, e.x, m[u].x);
+        w.y = fmaf(sg[u].y, e.y, m[u].y);
+        w.z = fmaf(sg[u].z, e.z, m[u].z);
+        w.w = fmaf(sg[u].w, e.w, m[u].w);
+      }
+      uint32_t off;
+      if (!kMnMajor) off = tile_offset(item >> 3, item & 7);
+      else off = tile_offset_mn((item % (kRows / 4)) << 2, item / (kRows / 4), kMnLbo, kMnSbo);
+      sts128(tile + off, to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
     }
-    sts128(tile + tile_offset(item >> 3, item & 7), to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
-  }
-}
-
-// W_s tile, MN-major (MN = k: 128 columns of W, K-rows = n: 32 rows of W) — data gradient.  W is read and
-// generated in its natural orientation; each float4 of a row lands as one 16-byte chunk of the 128-byte row.
-__device__ __forceinline__ void gen_w_mnmajor(uint32_t tile, const float* __restrict__ mu, const float* __restrict__ sigma,
-                                              const EpsSrc& eps, int n0, int N, int k0, int K, int tid) {
-  float4 m[kGenItems], s[kGenItems];
-  int64_t idx[kGenItems];
-#pragma unroll
-  for (int it = 0; it < kGenItems; ++it) {
-    const int item = it * kGenThreads + tid;
-    const int n = n0 + (item >> 5), k = k0 + ((item & 31) << 2);
-    idx[it] = -1;
-    if (n < N && k < K) {
-      idx[it] = static_cast<int64_t>(n) * K + k;
-      m[it] = __ldg(reinterpret_cast<const float4*>(mu + idx[it]));
-      s[it] = __ldg(reinterpret_cast<const float4*>(sigma + idx[it]));
-    }
-  }
-#pragma unroll
-  for (int it = 0; it < kGenItems; ++it) {
-    const int item = it * kGenThreads + tid;
-    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (idx[it] >= 0) {
-      const float4 e = eps_vec4(eps, idx[it]);
-      w.x = fmaf(s[it].x, e.x, m[it].x);
-      w.y = fmaf(s[it].y, e.y, m[it].y);
-      w.z = fmaf(s[it].z, e.z, m[it].z);
-      w.w = fmaf(s[it].w, e.w, m[it].w);
-    }
-    const int nl = item >> 5, kq = item & 31;                       // K-row, float4 index along MN
-    sts128(tile + tile_offset_mn(kq << 2, nl, kMnLbo, kMnSbo), to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
   }
 }
 
 template <int MB, bool kDgrad>
 __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __grid_constant__ TmaContractParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  long long w_kernel = 0, w_mma_w = 0, w_mma_a = 0, w_gen = 0, w_tma = 0;
+  (void)w_kernel; (void)w_mma_w; (void)w_mma_a; (void)w_gen; (void)w_tma;
+#ifdef BNN_PROFILE_WAITS
+  const long long t_kernel0 = clock64();
+#endif
   constexpr uint32_t kTmemCols = tmem_cols_pow2(MB * 128);
   const TmaPipe pipe = carve_tma(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kASlots; ++i) { mbar_init(pipe.full_a + i, 1); mbar_init(pipe.empty_a + i, 1); }
-    for (int i = 0; i < kWSlots; ++i) { mbar_init(pipe.full_w + i, kGenThreads); mbar_init(pipe.empty_w + i, 1); }
+    // full_a[g]: the MB activation tiles of k-block group g (two groups of MB slots); full_w[j]: generated weight
+    // tile j (one arrival per generator warp); empty_w[j] = "k-block consumed": ONE tcgen05.commit per k-block frees
+    // weight slot j for the generators and, two k-blocks later, activation group j & 1 for the TMA thread
+    for (int i = 0; i < 2; ++i) mbar_init(pipe.full_a + i, 1);
+    for (int i = 0; i < kWSlots; ++i) { mbar_init(pipe.full_w + i, kGroupWarps); mbar_init(pipe.empty_w + i, 1); }
     mbar_init(pipe.accum_full, 1);
     fence_mbar_init();
   }
@@ -221,40 +224,44 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
   if (mb_used > MB) mb_used = MB;
 
   if (warp < kGenWarps) {
-    // ------------------------------------------------------------------ weight generators
-    const int tid = threadIdx.x;
+    // ------------------------------------------------------------------ weight generators (four groups, slot = group)
+    const int group = warp / kGroupWarps, tid = threadIdx.x - group * kGroupThreads;
     const RngKey key = resolve_rng(p.rng_w);
-    int it = 0;
-    for (int s = s_begin; s < s_end; ++s) {
+    const int total = red_blocks * (s_end - s_begin);
+    for (int it = group; it < total; it += kGenGroups) {
+      const int s = s_begin + it / red_blocks, rb = it - (it / red_blocks) * red_blocks;
       EpsSrc eps;
       eps.inj = p.eps_w ? p.eps_w + static_cast<int64_t>(s) * p.N * p.K : nullptr;
       eps.key = key;
       eps.sample = p.sample_begin + s;
-      for (int rb = 0; rb < red_blocks; ++rb, ++it) {
-        const int slot = it % kWSlots;
-        mbar_wait(pipe.empty_w + slot, ((it / kWSlots) & 1) ^ 1);
-        const uint32_t tile = pipe.ring_w + slot * kTileBytes;
-        if (!kDgrad)
-          gen_w_kmajor(tile, p.mu_w, p.sigma_w, eps, col0, p.N, rb * kBK, p.K, tid);
-        else
-          gen_w_mnmajor(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, col0, p.K, tid);
-        fence_proxy_async_smem();
-        mbar_arrive(pipe.full_w + slot);
-      }
+      { BNN_T0(); mbar_wait(pipe.empty_w + group, ((it >> 2) & 1) ^ 1); BNN_ACC(w_gen); }
+      const uint32_t tile = pipe.ring_w + group * kTileBytes;
+#ifdef BNN_PROFILE_WAITS
+      if (p.exp_flags & 1) { /* skip */ } else
+#endif
+      if (!kDgrad)
+        gen_w_tile<128, false>(tile, p.mu_w, p.sigma_w, eps, col0, p.N, rb * kBK, p.K, tid);
+      else
+        gen_w_tile<128, true>(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, col0, p.K, tid);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pipe.full_w + group);
     }
   } else if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA issuer
     if (lane == 0) {
-      int cnt = 0;
+      int it = 0;
       for (int s = s_begin; s < s_end; ++s) {
         const int smp = p.shared_l ? 0 : s;
-        for (int rb = 0; rb < red_blocks; ++rb) {
-          for (int mb = 0; mb < mb_used; ++mb, ++cnt) {
-            const int slot = cnt % kASlots;
-            mbar_wait(pipe.empty_a + slot, ((cnt / kASlots) & 1) ^ 1);
-            mbar_arrive_expect_tx(pipe.full_a + slot, kTileBytes);
-            tma_load_3d(pipe.ring_a + slot * kTileBytes, &p.map_l, rb * kBK, row0 + mb * 128, smp, pipe.full_a + slot);
-          }
+        for (int rb = 0; rb < red_blocks; ++rb, ++it) {
+          const int g = it & 1;
+          if (it >= 2) { BNN_T0(); mbar_wait(pipe.empty_w + ((it - 2) & 3), ((it - 2) >> 2) & 1); BNN_ACC(w_tma); }
+#ifdef BNN_PROFILE_WAITS
+          if (p.exp_flags & 2) { mbar_arrive(pipe.full_a + g); continue; }
+#endif
+          mbar_arrive_expect_tx(pipe.full_a + g, mb_used * kTileBytes);
+          for (int mb = 0; mb < mb_used; ++mb)
+            tma_load_3d(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, rb * kBK, row0 + mb * 128, smp, pipe.full_a + g);
         }
       }
     }
@@ -263,26 +270,27 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(128, mma_n(n_cols - col0), false, kDgrad);
-      int it = 0, cnt = 0;
+      const uint64_t desc_a0 = make_smem_desc(pipe.ring_a);
+      const uint64_t desc_w0 = kDgrad ? make_smem_desc_mn(pipe.ring_w, kMnLbo, kMnSbo) : make_smem_desc(pipe.ring_w);
+      int it = 0;
       for (int s = s_begin; s < s_end; ++s) {
         for (int rb = 0; rb < red_blocks; ++rb, ++it) {
-          const int wslot = it % kWSlots;
-          mbar_wait(pipe.full_w + wslot, (it / kWSlots) & 1);
-          const uint32_t wt = pipe.ring_w + wslot * kTileBytes;
-          for (int mb = 0; mb < mb_used; ++mb, ++cnt) {
-            const int aslot = cnt % kASlots;
-            mbar_wait(pipe.full_a + aslot, (cnt / kASlots) & 1);
-            tc_fence_after_sync();
-            const uint32_t at = pipe.ring_a + aslot * kTileBytes;
+          const int wslot = it & 3, g = it & 1;
+          { BNN_T0(); mbar_wait(pipe.full_w + wslot, (it >> 2) & 1); BNN_ACC(w_mma_w); }
+          { BNN_T0(); mbar_wait(pipe.full_a + g, (it >> 1) & 1); BNN_ACC(w_mma_a); }
+          tc_fence_after_sync();
+          const uint64_t da0 = desc_advance(desc_a0, static_cast<uint32_t>(g * MB) * (kTileBytes >> 4));
+          const uint64_t db0 = desc_advance(desc_w0, static_cast<uint32_t>(wslot) * (kTileBytes >> 4));
+#ifdef BNN_PROFILE_WAITS
+          if (!(p.exp_flags & 4))
+#endif
+          for (int mb = 0; mb < mb_used; ++mb) {
 #pragma unroll
-            for (int ks = 0; ks < kBK / 8; ++ks) {
-              const uint64_t da = make_smem_desc(at + ks * 32);
-              const uint64_t db = kDgrad ? make_smem_desc_mn(wt + ks * kMnKStep, kMnLbo, kMnSbo) : make_smem_desc(wt + ks * 32);
-              mma_tf32(tmem + mb * 128, da, db, idesc, it > 0 || ks > 0);
-            }
-            mma_commit(pipe.empty_a + aslot);
+            for (int ks = 0; ks < kBK / 8; ++ks)
+              mma_tf32(tmem + mb * 128, desc_advance(da0, mb * (kTileBytes >> 4) + ks * 2),
+                       desc_advance(db0, ks * ((kDgrad ? kMnKStep : 32u) >> 4)), idesc, it > 0 || ks > 0);
           }
-          mma_commit(pipe.empty_w + wslot);
+          mma_commit(pipe.empty_w + wslot);           // the one commit of this k-block
         }
       }
       mma_commit(pipe.accum_full);
@@ -322,6 +330,16 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
       }
     }
   }
+#ifdef BNN_PROFILE_WAITS
+  {
+    const int w_ = threadIdx.x >> 5, l_ = threadIdx.x & 31;
+    if (l_ == 0) {
+      if (w_ == 0) { atomicAdd(&g_wait_cycles[3], (unsigned long long)w_gen); atomicAdd(&g_wait_cycles[0], (unsigned long long)(clock64() - t_kernel0)); atomicAdd(&g_wait_cycles[5], 1ull); }
+      if (w_mma_w | w_mma_a) { atomicAdd(&g_wait_cycles[1], (unsigned long long)w_mma_w); atomicAdd(&g_wait_cycles[2], (unsigned long long)w_mma_a); }
+      if (w_tma) atomicAdd(&g_wait_cycles[4], (unsigned long long)w_tma);
+    }
+  }
+#endif
   tc_fence_before_sync();
   __syncthreads();
   if (warp == kMmaWarpT) {
@@ -345,10 +363,237 @@ int launch_tma_contract(const TmaContractParams& p, dim3 grid, cudaStream_t st) 
   return BNN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- CTA-pair forward / dgrad
+// Same contraction, two SMs per tile (cta_group::2): the pair computes 2 x MB x 128 output rows against ONE 128-column
+// weight tile of which each CTA generates only its half (64 n-rows forward / 64 k-columns dgrad) — half the Philox work
+// per SM and per MMA cycle.  Each CTA loads its own activation tiles by TMA (transaction bytes land on the LEADER's
+// barrier), the generator warps of the peer arrive on the leader's barrier through the cluster address space, the
+// leader's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256) and frees the slots of BOTH CTAs with
+// multicast commits.  Epilogue: every CTA drains its own TMEM.
+constexpr int kPairWSlots = 4;               // 8 KiB half-tiles (the k-block bookkeeping assumes 4)
+constexpr int kHalfTileBytes = kTileBytes / 2;
+constexpr size_t kPairSmem = kSmemAux + 1024 + static_cast<size_t>(kASlots) * kTileBytes + kPairWSlots * kHalfTileBytes;
+
+struct PairPipe {
+  uint64_t* full_a;      // [kASlots]      leader: 1 arrival (expect_tx) + bytes of both CTAs' tiles
+  uint64_t* empty_a;     // [kASlots]      both:   multicast tcgen05.commit
+  uint64_t* full_w;      // [kPairWSlots]  leader: one arrival per generator warp of both CTAs
+  uint64_t* empty_w;     // [kPairWSlots]  both:   multicast tcgen05.commit
+  uint64_t* accum_full;  // both
+  uint32_t* tmem_slot;
+  float* aux;
+  uint32_t ring_a, ring_w;
+};
+
+__device__ __forceinline__ PairPipe carve_pair(uint8_t* smem_raw) {
+  PairPipe p;
+  p.full_a = reinterpret_cast<uint64_t*>(smem_raw);
+  p.empty_a = p.full_a + kASlots;
+  p.full_w = p.empty_a + kASlots;
+  p.empty_w = p.full_w + kPairWSlots;
+  p.accum_full = p.empty_w + kPairWSlots;
+  p.tmem_slot = reinterpret_cast<uint32_t*>(p.accum_full + 2);
+  p.aux = reinterpret_cast<float*>(smem_raw + 512);
+  const uint32_t base = smem_u32(smem_raw) + kSmemAux;
+  p.ring_a = (base + 1023u) & ~1023u;
+  p.ring_w = p.ring_a + kASlots * kTileBytes;
+  return p;
+}
+
+template <int MB, bool kDgrad>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTma, 1)
+contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  long long w_kernel = 0, w_mma_w = 0, w_mma_a = 0, w_gen = 0, w_tma = 0;
+  (void)w_kernel; (void)w_mma_w; (void)w_mma_a; (void)w_gen; (void)w_tma;
+#ifdef BNN_PROFILE_WAITS
+  const long long t_kernel0 = clock64();
+#endif
+  constexpr uint32_t kTmemCols = tmem_cols_pow2(MB * 128);
+  const PairPipe pipe = carve_pair(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  if (threadIdx.x == 0) {
+    // leader: full_a[g] = activation tiles of k-block group g of BOTH CTAs (1 arrival + bytes), full_w[j] = both halves of
+    // weight tile j (one arrival per generator warp of both CTAs); both CTAs: empty_w[j] = "k-block consumed", ONE
+    // multicast tcgen05.commit per k-block (frees weight slot j, and activation group j & 1 two k-blocks later)
+    for (int i = 0; i < 2; ++i) mbar_init(pipe.full_a + i, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(pipe.full_w + i, 2 * kGroupWarps); mbar_init(pipe.empty_w + i, 1); }
+    mbar_init(pipe.accum_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == kTmaWarp && lane == 0) tma_prefetch_desc(&p.map_l);
+  if (warp == kMmaWarpT) tmem_alloc_pair(pipe.tmem_slot, kTmemCols);
+  tc_fence_before_sync();
+  cluster_sync_all();                                // barriers of both CTAs initialised before any remote arrive
+  tc_fence_after_sync();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(pipe.tmem_slot);
+
+  const int col0 = blockIdx.y * 128;                   // output columns of the PAIR (n for fwd, k for dgrad)
+  const int row0 = blockIdx.x * (MB * 128);            // output rows of THIS CTA (the pair is adjacent in x)
+  const int n_cols = kDgrad ? p.K : p.N;
+  const int n_red = kDgrad ? p.N : p.K;
+  const int s_begin = p.sum_samples ? 0 : blockIdx.z;
+  const int s_end = p.sum_samples ? p.S : blockIdx.z + 1;
+  const int red_blocks = (n_red + kBK - 1) / kBK;
+  // both CTAs walk the same number of M-blocks (the leader holds the lower rows, so its count is the larger one);
+  // tiles beyond M are zero-filled by TMA and never stored
+  const int lead_row0 = (blockIdx.x & ~1u) * (MB * 128);
+  int mb_pair = (p.M - lead_row0 + 127) / 128;
+  if (mb_pair > MB) mb_pair = MB;
+
+  if (warp < kGenWarps) {
+    // ------------------------------------------------------------------ weight generators (half tile per CTA, four groups)
+    const int group = warp / kGroupWarps, tid = threadIdx.x - group * kGroupThreads;
+    const RngKey key = resolve_rng(p.rng_w);
+    const int half0 = col0 + static_cast<int>(rank) * 64;
+    const int total = red_blocks * (s_end - s_begin);
+    const uint32_t lead_full_w = mapa_u32(smem_u32(pipe.full_w + group), 0);
+    for (int it = group; it < total; it += kGenGroups) {
+      const int s = s_begin + it / red_blocks, rb = it - (it / red_blocks) * red_blocks;
+      EpsSrc eps;
+      eps.inj = p.eps_w ? p.eps_w + static_cast<int64_t>(s) * p.N * p.K : nullptr;
+      eps.key = key;
+      eps.sample = p.sample_begin + s;
+      { BNN_T0(); mbar_wait(pipe.empty_w + group, ((it >> 2) & 1) ^ 1); BNN_ACC(w_gen); }
+      const uint32_t tile = pipe.ring_w + group * kHalfTileBytes;
+      if (!kDgrad)
+        gen_w_tile<64, false>(tile, p.mu_w, p.sigma_w, eps, half0, p.N, rb * kBK, p.K, tid);
+      else
+        gen_w_tile<64, true>(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, half0, p.K, tid);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_full_w);
+    }
+  } else if (warp == kTmaWarp) {
+    // ------------------------------------------------------------------ TMA issuer (own rows; bytes counted by the leader)
+    if (lane == 0) {
+      int it = 0;
+      const uint32_t lead_full_a = mapa_u32(smem_u32(pipe.full_a), 0);
+      for (int s = s_begin; s < s_end; ++s) {
+        const int smp = p.shared_l ? 0 : s;
+        for (int rb = 0; rb < red_blocks; ++rb, ++it) {
+          const int g = it & 1;
+          if (it >= 2) { BNN_T0(); mbar_wait(pipe.empty_w + ((it - 2) & 3), ((it - 2) >> 2) & 1); BNN_ACC(w_tma); }
+          if (rank == 0) mbar_arrive_expect_tx(pipe.full_a + g, 2 * mb_pair * kTileBytes);
+          for (int mb = 0; mb < mb_pair; ++mb)
+            tma_load_3d_pair(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, rb * kBK, row0 + mb * 128, smp,
+                             lead_full_a + g * 8);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarpT) {
+    // ------------------------------------------------------------------ MMA issuer (leader only)
+    if (rank == 0 && lane == 0) {
+      // N = 128 always: each CTA contributes its 64-row half of the weight tile (zero rows beyond the matrix edge)
+      const uint32_t idesc = make_idesc_tf32(256, 128, false, kDgrad);
+      const uint64_t desc_a0 = make_smem_desc(pipe.ring_a);
+      const uint64_t desc_w0 = kDgrad ? make_smem_desc_mn(pipe.ring_w, kMnLbo, kMnSbo) : make_smem_desc(pipe.ring_w);
+      int it = 0;
+      for (int s = s_begin; s < s_end; ++s) {
+        for (int rb = 0; rb < red_blocks; ++rb, ++it) {
+          const int wslot = it & 3, g = it & 1;
+          { BNN_T0(); mbar_wait_cluster(pipe.full_w + wslot, (it >> 2) & 1); BNN_ACC(w_mma_w); }
+          { BNN_T0(); mbar_wait_cluster(pipe.full_a + g, (it >> 1) & 1); BNN_ACC(w_mma_a); }
+          tc_fence_after_sync();
+          const uint64_t da0 = desc_advance(desc_a0, static_cast<uint32_t>(g * MB) * (kTileBytes >> 4));
+          const uint64_t db0 = desc_advance(desc_w0, static_cast<uint32_t>(wslot) * (kHalfTileBytes >> 4));
+          for (int mb = 0; mb < mb_pair; ++mb) {
+#pragma unroll
+            for (int ks = 0; ks < kBK / 8; ++ks)
+              mma_tf32_pair(tmem + mb * 128, desc_advance(da0, mb * (kTileBytes >> 4) + ks * 2),
+                            desc_advance(db0, ks * ((kDgrad ? kMnKStep : 32u) >> 4)), idesc, it > 0 || ks > 0);
+          }
+          mma_commit_pair(pipe.empty_w + wslot, 3);   // the one (multicast) commit of this k-block
+        }
+      }
+      mma_commit_pair(pipe.accum_full, 3);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (own TMEM, own rows)
+    const int et = threadIdx.x - kEpiWarp0T * 32;   // 0..127
+    const int quad = warp & 3;
+    if (!kDgrad) {
+      float b = 0.f;
+      const int n = col0 + et;
+      if (p.mu_b != nullptr && n < p.N) {
+        const int s = blockIdx.z;
+        const float e = p.eps_b ? __ldg(p.eps_b + static_cast<int64_t>(s) * p.N + n)
+                                : eps1(resolve_rng(p.rng_b), p.sample_begin + s, static_cast<uint64_t>(n));
+        b = fmaf(__ldg(p.sigma_b + n), e, __ldg(p.mu_b + n));
+      }
+      pipe.aux[et] = b;
+      named_bar_sync(kEpiBarrier, kEpiThreads);
+    }
+    mbar_wait(pipe.accum_full, 0);
+    tc_fence_after_sync();
+    View out = p.out;
+    out.base += (p.sum_samples ? 0 : static_cast<int64_t>(blockIdx.z) * p.out_sample_stride);
+    const int cols_here = n_cols - col0 < 128 ? n_cols - col0 : 128;
+    for (int mb = 0; mb < mb_pair; ++mb) {
+      const int m = row0 + mb * 128 + quad * 32 + lane;
+      if (row0 + mb * 128 >= p.M) break;               // uniform per CTA
+      for (int c = 0; c * 16 < cols_here; ++c) {
+        float v[16];
+        tmem_ld16(tmem + (static_cast<uint32_t>(quad * 32) << 16) + mb * 128 + c * 16, v);
+        if (!kDgrad) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += pipe.aux[c * 16 + j];
+        }
+        if (m < p.M) store_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+      }
+    }
+  }
+#ifdef BNN_PROFILE_WAITS
+  {
+    const int w_ = threadIdx.x >> 5, l_ = threadIdx.x & 31;
+    if (l_ == 0) {
+      if (w_ == 0) { atomicAdd(&g_wait_cycles[3], (unsigned long long)w_gen); atomicAdd(&g_wait_cycles[0], (unsigned long long)(clock64() - t_kernel0)); atomicAdd(&g_wait_cycles[5], 1ull); }
+      if (w_mma_w | w_mma_a) { atomicAdd(&g_wait_cycles[1], (unsigned long long)w_mma_w); atomicAdd(&g_wait_cycles[2], (unsigned long long)w_mma_a); }
+      if (w_tma) atomicAdd(&g_wait_cycles[4], (unsigned long long)w_tma);
+    }
+  }
+#endif
+  tc_fence_before_sync();
+  cluster_sync_all();                                // nobody leaves while the partner may still signal or read
+  if (warp == kMmaWarpT) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair(tmem, kTmemCols);
+  }
+}
+
+template <int MB, bool kDgrad>
+int launch_pair_contract(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    BNN_CUDA_OK(cudaFuncSetAttribute(contract_pair_kernel<MB, kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(kPairSmem)));
+    attr_set = true;
+  }
+  contract_pair_kernel<MB, kDgrad><<<grid, kThreadsTma, kPairSmem, st>>>(p);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BNN_DISABLE_CTA_PAIRS");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <bool kDgrad>
 int dispatch_tma_contract(const TmaContractParams& p, int n_cols, cudaStream_t st) {
   const int m_blocks = (p.M + 127) / 128;
   const int gx = (n_cols + 127) / 128, gz = p.sum_samples ? 1 : p.S;
+  if (m_blocks > 4 && pair_enabled()) {      // two CTAs (one cluster) per 1024 rows: each generates half of the weight tile
+    const int pairs = (m_blocks + 7) / 8;
+    return launch_pair_contract<4, kDgrad>(p, dim3(2 * pairs, gx, gz), st);
+  }
   if (m_blocks >= 4) return launch_tma_contract<4, kDgrad>(p, dim3(gx, (m_blocks + 3) / 4, gz), st);
   if (m_blocks >= 2) return launch_tma_contract<2, kDgrad>(p, dim3(gx, (m_blocks + 1) / 2, gz), st);
   return launch_tma_contract<1, kDgrad>(p, dim3(gx, m_blocks, gz), st);
@@ -357,9 +602,12 @@ int dispatch_tma_contract(const TmaContractParams& p, int n_cols, cudaStream_t s
 // ---------------------------------------------------------------------------------------------- weight gradient
 // CTA (k-tile, n-tile, sample group).  Stage = dY^T tile (MN = n) + A^T tile (MN = k), each 4 TMA boxes of
 // 32 MN x 32 K-rows (m).  TMEM columns: [0,128) G0 | [128,256) sum G | [256,384) sum G o eps | [384,512) G1.
-constexpr int kWgStages = 6;
+constexpr int kWgStages = 3;                 // stages of 64 contraction rows: 8 MMAs per barrier wait / tcgen05.commit
+constexpr int kWgRows = 64;                  // contraction rows (m) per stage
+constexpr int kWgOperandBytes = 4 * kWgRows * kRowBytes;      // 4 MN groups x 64 K-rows x 128 B = 32 KiB per operand
+constexpr uint32_t kWgLbo = kWgRows * kRowBytes;              // next 32 MN elements: 8 KiB further
 constexpr int kWgThreads = 6 * 32;           // warp 0 TMA, warp 1 MMA (+TMEM owner), warps 2-5 epilogue
-constexpr size_t kWgradSmem = kSmemAux + 1024 + static_cast<size_t>(kWgStages) * 2 * kTileBytes;
+constexpr size_t kWgradSmem = kSmemAux + 1024 + static_cast<size_t>(kWgStages) * 2 * kWgOperandBytes;
 
 struct TmaWgradParams {
   CUtensorMap map_dy;       // dY [S][M][N], box 32 x 32
@@ -407,7 +655,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
   const int per = (units + groups - 1) / groups;
   const int s_begin = blockIdx.z * per;                          // work units [s_begin, s_end)
   const int s_end = s_begin + per < units ? s_begin + per : units;
-  const int m_total = (p.M + kBK - 1) / kBK;
+  const int m_total = (p.M + kWgRows - 1) / kWgRows;        // stages of 64 rows
   auto unit_blocks = [&](int u, int* mb0) {                      // k-block range of unit u
     const int c = u % p.n_chunks;
     *mb0 = c * p.chunk_blocks;
@@ -427,12 +675,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
           for (int mb = mb0; mb < mb0 + m_blocks; ++mb, ++it) {
             const int stage = it % kWgStages;
             mbar_wait(empty + stage, ((it / kWgStages) & 1) ^ 1);
-            mbar_arrive_expect_tx(full + stage, 2 * kTileBytes);
-            const uint32_t base = ring + stage * 2 * kTileBytes;
+            mbar_arrive_expect_tx(full + stage, 2 * kWgOperandBytes);
+            const uint32_t base = ring + stage * 2 * kWgOperandBytes;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              tma_load_3d(base + g * kMnLbo, &p.map_dy, n0 + g * 32, mb * kBK, s, full + stage);
-              tma_load_3d(base + kTileBytes + g * kMnLbo, &p.map_a, k0 + g * 32, mb * kBK, sa, full + stage);
+              tma_load_3d(base + g * kWgLbo, &p.map_dy, n0 + g * 32, mb * kWgRows, s, full + stage);
+              tma_load_3d(base + kWgOperandBytes + g * kWgLbo, &p.map_a, k0 + g * 32, mb * kWgRows, sa, full + stage);
             }
           }
         }
@@ -441,6 +689,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
     } else if (warp == 1) {
       if (lane == 0) {
         const uint32_t idesc = make_idesc_tf32(128, mma_n(p.K - k0), true, true);
+        const uint64_t desc_dy0 = make_smem_desc_mn(ring, kWgLbo, kMnSbo);
+        const uint64_t desc_a0 = make_smem_desc_mn(ring + kWgOperandBytes, kWgLbo, kMnSbo);
         int it = 0;
         for (int u = s_begin, i = 0; u < s_end; ++u, ++i) {
           const int buf = i & 1;
@@ -453,11 +703,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
             const int stage = it % kWgStages;
             mbar_wait(full + stage, (it / kWgStages) & 1);
             tc_fence_after_sync();
-            const uint32_t base = ring + stage * 2 * kTileBytes;
+            const uint64_t da0 = desc_advance(desc_dy0, static_cast<uint32_t>(stage) * (2 * kWgOperandBytes >> 4));
+            const uint64_t db0 = desc_advance(desc_a0, static_cast<uint32_t>(stage) * (2 * kWgOperandBytes >> 4));
 #pragma unroll
-            for (int ks = 0; ks < kBK / 8; ++ks)
-              mma_tf32(d, make_smem_desc_mn(base + ks * kMnKStep, kMnLbo, kMnSbo),
-                       make_smem_desc_mn(base + kTileBytes + ks * kMnKStep, kMnLbo, kMnSbo), idesc, mb > 0 || ks > 0);
+            for (int ks = 0; ks < kWgRows / 8; ++ks)
+              mma_tf32(d, desc_advance(da0, ks * (kMnKStep >> 4)), desc_advance(db0, ks * (kMnKStep >> 4)), idesc,
+                       mb > 0 || ks > 0);
             mma_commit(empty + stage);
           }
           mma_commit(accum_full + buf);
@@ -622,6 +873,7 @@ int tma_fwd(const float* a, int64_t lda, int64_t a_sample_stride, const float* m
   p.rng_w = *rng_w; p.rng_b = rng_b ? *rng_b : *rng_w;
   p.shared_l = shared ? 1 : 0;
   p.sum_samples = 0;
+  { const char* e = getenv("BNN_EXP_FLAGS"); p.exp_flags = e ? atoi(e) : 0; }
   p.vec_out = (y.P == 1) && (y.batch_stride % 4 == 0) && (y_sample_stride % 4 == 0) && aligned16(y.base);
   return dispatch_tma_contract<false>(p, N, st);
 }
@@ -654,22 +906,22 @@ int tma_wgrad(bnn_view dy, int64_t dy_sample_stride, const float* a, int64_t lda
       (eps_w != nullptr && !aligned16(eps_w)))
     return kNotEligible;
   TmaWgradParams p{};
-  int rc = make_map(&p.map_dy, dy.base, N, M, S, dy.batch_stride, dy_sample_stride, 32, true);
+  int rc = make_map(&p.map_dy, dy.base, N, M, S, dy.batch_stride, dy_sample_stride, kWgRows, true);
   if (rc != BNN_OK) return rc;
-  rc = make_map(&p.map_a, a, K, M, shared ? 1 : S, lda, a_sample_stride, 32, true);
+  rc = make_map(&p.map_a, a, K, M, shared ? 1 : S, lda, a_sample_stride, kWgRows, true);
   if (rc != BNN_OK) return rc;
   p.rho_w = rho_w; p.eps_w = eps_w; p.dmu_w = dmu_w; p.drho_w = drho_w;
   p.M = M; p.N = N; p.K = K; p.S = S; p.sample_begin = sample_begin;
   p.rng_w = *rng_w;
   p.shared_a = shared ? 1 : 0;
   const int tiles = ((N + 127) / 128) * ((K + 127) / 128);
-  const int m_total = (M + kBK - 1) / kBK;
+  const int m_total = (M + kWgRows - 1) / kWgRows;         // 64-row stages
   int want = (2 * sm_count() + tiles - 1) / tiles;        // CTAs per output tile that fill the machine twice
   if (want < 1) want = 1;
   int n_chunks = 1;
   if (want > S) {                                         // few samples / tiles: also split the M reduction
     n_chunks = (want + S - 1) / S;
-    const int max_chunks = (m_total + 7) / 8;             // keep >= 8 k-blocks per unit (epilogue cost per unit)
+    const int max_chunks = (m_total + 3) / 4;             // keep >= 4 stages (256 rows) per unit (epilogue cost per unit)
     if (n_chunks > max_chunks) n_chunks = max_chunks;
     if (n_chunks < 1) n_chunks = 1;
   }
@@ -685,6 +937,20 @@ int tma_wgrad(bnn_view dy, int64_t dy_sample_stride, const float* a, int64_t lda
   wgrad_tma_kernel<<<dim3((K + 127) / 128, (N + 127) / 128, groups), kWgThreads, kWgradSmem, st>>>(p);
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
+}
+
+int tma_wait_counters(unsigned long long* out8, int reset) {
+#ifdef BNN_PROFILE_WAITS
+  BNN_CUDA_OK(cudaMemcpyFromSymbol(out8, g_wait_cycles, 8 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    BNN_CUDA_OK(cudaMemcpyToSymbol(g_wait_cycles, z, sizeof(z)));
+  }
+  return BNN_OK;
+#else
+  (void)out8; (void)reset;
+  return kNotEligible;
+#endif
 }
 
 int tma_selftest(float* max_err_dev, cudaStream_t st) {

@@ -307,6 +307,8 @@ GEMM_SHAPES = [
     (256, 130, 100, 2, False),      # N just over one tile
     (640, 64, 96, 2, False),        # M blocks > 4
     (5, 3, 7, 2, False),            # tiny, unaligned K (scalar paths)
+    (1024, 256, 128, 2, False),     # > 512 rows per sample: CTA-pair (cta_group::2) kernels in TF32 mode
+    (700, 136, 96, 3, True),        # CTA pair with a ragged second CTA, shared activations (dgrad sums the samples)
 ]
 
 
