@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — ELBO training throughput of the variational hot path on B200 (driver contract).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4]
 
 Metric (BASELINE.json): ELBO train samples*MC/sec = B*S*N / step time, where one step is the body
 of the reference's training loop, examples/MNIST/train.py:55-65: zero_grad -> model(x) (S Monte-Carlo
@@ -35,6 +35,9 @@ N_BATCHES = 469          # ceil(60000 / 128), examples/MNIST/train.py:38 (any co
 WORKLOADS = {
     "c2": dict(name="C2 examples/MNIST BCNN topology (NormalConv2d 64x64x3x3 s2 + NormalLinear 576x10), 28x28",
                batch=256, samples=8),
+    "c3": dict(name="C3 examples/CIFAR10 BCNN topology (NormalConv2d 128x128x3x3 on 4x4 maps; the full-covariance "
+                    "MultivariateNormalLinear head, out of the hot path, replaced by NormalLinear(128,10)), 32x32x3",
+               batch=512, samples=16),
     "c4": dict(name="C4 wide Bayesian MLP 4x NormalLinear(4096,4096)", batch=1024, samples=32),
 }
 
@@ -68,6 +71,15 @@ def build_model(workload, samples):
                             bnn.nn.NormalConv2d(64, 64, 3, padding=1, stride=2), ELU(), Flatten(),
                             bnn.nn.NormalLinear(576, 10), Softmax(dim=-1))
         return Net(layers, 1, 10)
+    if workload == "c3":        # examples/CIFAR10/model.py:20-39
+        from torch.nn import Linear
+        layers = Sequential(Conv2d(3, 64, 5, padding=2, stride=2), BatchNorm2d(64), ELU(),
+                            Conv2d(64, 128, 5, padding=2, stride=2), ELU(),
+                            Conv2d(128, 128, 5, padding=2, stride=2), ELU(),
+                            Conv2d(128, 128, 3, padding=1), ELU(), Conv2d(128, 128, 3, padding=1), ELU(),
+                            bnn.nn.NormalConv2d(128, 128, 3, padding=1), ELU(), Flatten(),
+                            Linear(2048, 128), ELU(), bnn.nn.NormalLinear(128, 10), Softmax(dim=-1))
+        return Net(layers, 3, 10)
     layers = Sequential(bnn.nn.NormalLinear(4096, 4096), ELU(), bnn.nn.NormalLinear(4096, 4096), ELU(),
                         bnn.nn.NormalLinear(4096, 4096), ELU(), bnn.nn.NormalLinear(4096, 4096), Softmax(dim=-1))
     return Net(layers, 4096, 4096)
@@ -76,6 +88,8 @@ def build_model(workload, samples):
 def synthetic_batch(workload, batch, gen):
     if workload == "c2":
         return torch.rand(batch, 1, 28, 28, generator=gen), torch.randint(0, 10, (batch,), generator=gen)
+    if workload == "c3":
+        return torch.rand(batch, 3, 32, 32, generator=gen), torch.randint(0, 10, (batch,), generator=gen)
     return torch.randn(batch, 4096, generator=gen), torch.randint(0, 4096, (batch,), generator=gen)
 
 
@@ -86,6 +100,8 @@ def hot_flops_per_step(workload, batch, samples):
         conv = 2 * 9 * 64 * 576         # per sample*MC row, forward
         lin = 2 * 10 * 576
         return batch * samples * 3 * (conv + lin)
+    if workload == "c3":
+        return batch * samples * 3 * (2 * 16 * 128 * 1152 + 2 * 10 * 128)
     return batch * samples * (4 * 6 - 2) * 4096 * 4096
 
 
@@ -362,24 +378,38 @@ def run_b200(args):
         print(json.dumps(out))
 
 
+def measured_traffic(workload, name):
+    """DRAM bytes per launch of `name` from the committed `ncu --set full` capture (profiles/ncu_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path)).get(workload, {}).get(name, {}).get("bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 def roofline(workload, B, S, per_kernel, pk):
-    """Dominant hot-path kernel = the libbnn_b200 entry point with the largest time share of the step."""
+    """Dominant hot-path kernel = the libbnn_b200 CONTRACTION entry point with the largest time share of the step
+    (the path's bound is the tensor pipe; the bandwidth-bound helpers are listed in hot_path.kernels_ms_per_step)."""
     if not per_kernel:
         return None
-    name = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
+    gemms = {k: v for k, v in per_kernel.items() if k.startswith("bnn_sampled_gemm")}
+    name = max(gemms or per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
     contractions = {"bnn_sampled_gemm_fwd": 1, "bnn_sampled_gemm_dgrad": 1, "bnn_sampled_gemm_wgrad": 1}
     k = per_kernel[name]
     if name in contractions:
         # flops of ALL launches of this entry point per step / their summed duration
         if workload == "c2":
             per_row = 2 * 9 * 64 * 576 + 2 * 10 * 576
+        elif workload == "c3":
+            per_row = 2 * 16 * 128 * 1152 + 2 * 10 * 128
         else:
             per_row = (3 if name == "bnn_sampled_gemm_dgrad" else 4) * 2 * 4096 * 4096
         flops = B * S * per_row
         achieved = flops / (k["ms_per_step"] * 1e-3) / 1e12
         peak = pk["bf16_sustained"] / 2.0        # TF32 dense = half the bf16 rate on this tensor pipe
         return {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "launches_per_step": k["launches_per_step"],
+                "frac": achieved / peak, "traffic": measured_traffic(workload, name),
+                "launches_per_step": k["launches_per_step"],
                 "avg_launch_us": 1e3 * k["ms_per_step"] / k["launches_per_step"],
                 "peak_note": "TF32 dense peak taken as half of the measured sustained bf16 cuBLAS rate "
                              f"({pk['source']}); fp32 mode issues 3 TF32 MMAs per product"}
