@@ -4,9 +4,12 @@ from .container import BayesianModule, BayesianNetworkModule, register_rowwise_m
 from .variational import WeightNormal
 from .layers import (BayesianLinear, NormalLinear, BayesianConvNd, NormalConvNd, NormalConv1d, NormalConv2d,
                      NormalConv3d)
+from .flipout import (FlipoutNormalLinear, FlipOutNormalConvNd, FlipOutNormalConv1d, FlipOutNormalConv2d,
+                      FlipOutNormalConv3d)
 from .loss import KLDivergence, Entropy
 
 __all__ = [
     'BayesianModule', 'BayesianNetworkModule', 'WeightNormal', 'BayesianLinear', 'NormalLinear',
-    'BayesianConvNd', 'NormalConvNd', 'NormalConv1d', 'NormalConv2d', 'NormalConv3d', 'KLDivergence', 'Entropy',
+    'BayesianConvNd', 'NormalConvNd', 'NormalConv1d', 'NormalConv2d', 'NormalConv3d', 'FlipoutNormalLinear',
+    'FlipOutNormalConvNd', 'FlipOutNormalConv1d', 'FlipOutNormalConv2d', 'FlipOutNormalConv3d', 'KLDivergence', 'Entropy',
 ]

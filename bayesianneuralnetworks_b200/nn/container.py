@@ -72,7 +72,7 @@ class BayesianNetworkModule(Module):
         for m in self.modules():
             if m is self or isinstance(m, (WeightNormal, torch.nn.Sequential, torch.nn.ModuleList, torch.nn.ModuleDict)):
                 continue
-            if isinstance(m, _FusedBayesianLayer):
+            if isinstance(m, _FusedBayesianLayer) and m._fused:
                 n_bayes += 1
             elif isinstance(m, _BATCHNORM):
                 if m.training and m.track_running_stats:

@@ -1,0 +1,101 @@
+"""Flipout layers (Wen et al. 2018) — SURVEY §8(f) rank 1: `FlipoutNormalLinear` (pytorch_bayesian/nn/dense.py:63-83)
+and `FlipOutNormalConvNd/1d/2d/3d` (conv.py:145-251).
+
+Not on the `mu + softplus(rho) * eps` path: the perturbation is sigma itself with random sign flips,
+    y = op(x, mean) + op(x * S, stddev) * R,        R, S in {-1, +1},
+i.e. two contractions with UNSAMPLED weights, so these layers are torch composites (cuBLAS / cuDNN).  Their
+variational tensor is a WeightNormal, hence KLDivergence and PruneNormal treat them like every other Bayesian layer
+(the fused KL / prune kernels).  Reference quirks kept: no bias; the Linear signs are per feature and shared by the
+whole batch (dense.py:71-75), the conv signs are per example (conv.py:154-161).
+"""
+import torch
+import torch.nn.functional as F
+from torch.distributions.normal import Normal
+
+from ..utils.traversal import _pair, _single, _triple
+from .layers import NormalConvNd, NormalLinear
+
+
+def _signs(*shape, device):
+    return (torch.rand(*shape, device=device) - .5).sign()
+
+
+class FlipoutNormalLinear(NormalLinear):
+    _fused = False        # evaluated by torch ops: not part of the batched Monte-Carlo launch
+
+    def __init__(self, in_features, out_features, prior=Normal(0, .1)):
+        super(FlipoutNormalLinear, self).__init__(in_features, out_features, False, prior)
+
+    def sample(self):
+        self.R = _signs(self.weight.size(0), device=self.weight.device)
+        self.S = _signs(self.weight.size(1), device=self.weight.device)
+
+    @property
+    def sampled(self):
+        return (self.R, self.S)
+
+    def forward(self, x, sample=True):
+        if sample:
+            self.sample()
+        perturbation = (x * self.S).matmul(self.weight.stddev.t()) * self.R
+        return F.linear(x, self.weight.mean, perturbation)       # dense.py:81-83: the perturbation rides in as the bias
+
+
+class FlipOutNormalConvNd(NormalConvNd):
+    _op = None            # set by the dimensional subclasses
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation, transposed, groups, prior):
+        super(FlipOutNormalConvNd, self).__init__(in_channels, out_channels, _single(kernel_size), stride, padding,
+                                                  dilation, transposed, groups, False, prior)
+
+    def sample(self, batch_size=1, additional_dims=()):
+        self.R = _signs(batch_size, self.weight.size(0), *additional_dims, device=self.weight.device)
+        self.S = _signs(batch_size, self.weight.size(1), *additional_dims, device=self.weight.device)
+
+    @property
+    def sampled(self):
+        return (self.R, self.S)
+
+    def _flipout(self, x, nd, sample):
+        if sample:
+            self.sample(x.size(0), (1,) * nd)
+        op = type(self)._op
+        args = (self.stride, self.padding, self.dilation, self.groups)
+        out = op(x, self.weight.mean, self.bias, *args)
+        return out + op(x * self.S.expand_as(x), self.weight.stddev, self.bias, *args) * self.R.expand_as(out)
+
+
+class FlipOutNormalConv1d(FlipOutNormalConvNd):
+    _op = staticmethod(F.conv1d)
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 prior=Normal(0, .1)):
+        super(FlipOutNormalConv1d, self).__init__(in_channels, out_channels, _single(kernel_size), _single(stride),
+                                                  _single(padding), _single(dilation), False, groups, prior)
+
+    def forward(self, x, sample=True):
+        return self._flipout(x, 1, sample)
+
+
+class FlipOutNormalConv2d(FlipOutNormalConvNd):
+    _op = staticmethod(F.conv2d)
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 prior=Normal(0, .1)):
+        super(FlipOutNormalConv2d, self).__init__(in_channels, out_channels, _pair(kernel_size), _pair(stride),
+                                                  _pair(padding), _pair(dilation), False, groups, prior)
+
+    def forward(self, x, sample=True):
+        return self._flipout(x, 2, sample)
+
+
+class FlipOutNormalConv3d(FlipOutNormalConvNd):
+    _op = staticmethod(F.conv3d)
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 prior=Normal(0, .1)):
+        super(FlipOutNormalConv3d, self).__init__(in_channels, out_channels, _triple(kernel_size), _triple(stride),
+                                                  _triple(padding), _triple(dilation), False, groups, prior)
+
+    def forward(self, x, sample=True):
+        return self._flipout(x, 3, sample)

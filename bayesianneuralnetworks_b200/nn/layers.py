@@ -33,6 +33,7 @@ def _init_normal_posterior(layer):
 
 class _FusedBayesianLayer:
     """Mixin of the layers whose forward is one fused launch over all Monte-Carlo samples."""
+    _fused = True         # subclasses evaluated by torch ops (Flipout) switch this off
 
     def _mc_shape(self, x):
         """(S, shared, sample offset, draws to reserve) for this call from the MC context."""

@@ -9,6 +9,7 @@ can be injected into the CUDA path.
 Outputs
   linear_case.npz   NormalLinear(20, 7): S=3 outputs, KL, gradients of sum(y*dy)+KL
   conv_case_*.npz   NormalConv2d configs incl. the reference's own test configs, stride/dilation/groups
+  flipout_case.npz  FlipoutNormalLinear / FlipOutNormalConv2d outputs and gradients for recorded sign tensors
   model_case.npz    small BayesianNetworkModule (Conv2d+ELU trunk, NormalConv2d, NormalLinear, Softmax):
                     S=3 ELBO loss (examples/MNIST/train.py:57-63) and all gradients
   mnist_ckpt_bayes_layers.npz  mean/scale of the Bayesian layers of examples/MNIST/mnist_pretrained.pth
@@ -156,6 +157,30 @@ def model_case():
     np.savez(os.path.join(HERE, "model_case.npz"), **out)
 
 
+def flipout_case():
+    """Flipout layers (dense.py:63-83, conv.py:145-221): outputs and gradients for recorded sign tensors R, S."""
+    from pytorch_bayesian.nn import FlipoutNormalLinear, FlipOutNormalConv2d
+    torch.manual_seed(300)
+    lin = FlipoutNormalLinear(12, 5)
+    x = torch.randn(6, 12)
+    y = lin(x)
+    dy = torch.randn_like(y)
+    kl = KLDivergence(number_of_batches=3)(_wrap(lin))
+    ((y * dy).sum() + kl).backward()
+    conv = FlipOutNormalConv2d(3, 4, 3, 2, 1)
+    xc = torch.randn(5, 3, 8, 8)
+    yc = conv(xc)
+    dyc = torch.randn_like(yc)
+    (yc * dyc).sum().backward()
+    np.savez(os.path.join(HERE, "flipout_case.npz"),
+             lin_x=np32(x), lin_dy=np32(dy), lin_w_mean=np32(lin.weight.mean), lin_w_scale=np32(lin.weight.scale),
+             lin_R=np32(lin.R), lin_S=np32(lin.S), lin_y=np32(y), lin_kl=np32(kl),
+             lin_g_mean=np32(lin.weight.mean.grad), lin_g_scale=np32(lin.weight.scale.grad),
+             conv_x=np32(xc), conv_dy=np32(dyc), conv_w_mean=np32(conv.weight.mean), conv_w_scale=np32(conv.weight.scale),
+             conv_R=np32(conv.R), conv_S=np32(conv.S), conv_y=np32(yc),
+             conv_g_mean=np32(conv.weight.mean.grad), conv_g_scale=np32(conv.weight.scale.grad))
+
+
 def checkpoint_fixtures():
     sys.path.insert(0, os.path.join(REF, "examples", "MNIST"))
     from model import BCNN  # examples/MNIST/model.py
@@ -192,5 +217,6 @@ if __name__ == "__main__":
     conv_case("strided_grouped", 8, 6, 3, 2, 0, 2, 2, False, (9, 7), 203)
     conv_case("c2_shape", 64, 64, 3, 2, 1, 1, 1, True, (6, 6), 204)      # examples/MNIST/model.py:28
     model_case()
+    flipout_case()
     checkpoint_fixtures()
     print("golden vectors written to", HERE)
