@@ -261,8 +261,6 @@ int bnn_kl(const bnn_kl_tensor* tensors, int32_t n_tensors, double* kl_sum, floa
               bnn_kl_workspace_size(n_tensors));
   BNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, BNN_ERR_MISALIGNED,
               "bnn_kl: workspace must be 256-byte aligned");
-  int rc = check_device();
-  if (rc != BNN_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
   double* partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
@@ -285,6 +283,8 @@ int bnn_kl(const bnn_kl_tensor* tensors, int32_t n_tensors, double* kl_sum, floa
               "bnn_kl: nothing to compute");
   const bool want_sums = kl_sum != nullptr || kl_total != nullptr;
   bool total_started = false;
+  int rc = check_device();          // arguments are validated first: bad calls fail the same way on any machine
+  if (rc != BNN_OK) return rc;
 
   for (int first = 0; first < n_tensors; first += kMaxTensors) {
     const int n = (n_tensors - first < kMaxTensors) ? n_tensors - first : kMaxTensors;

@@ -259,8 +259,13 @@ def run_b200(args):
     wl = WORKLOADS[args.workload]
     B, S = wl["batch"], wl["samples"]
     bnn.set_precision(args.precision)
+    sample_parallel = args.parallel == "sample" and world > 1
+    if sample_parallel:          # rank r evaluates the global MC samples [r*S/R, (r+1)*S/R) of the SAME batch
+        if S % world != 0:
+            raise SystemExit(f"{S} MC samples do not split over {world} ranks")
+        bnn.set_sample_partition(rank, world)
     trainer = Trainer(args.workload, device, world, S, graph=not args.no_graph)
-    gen = torch.Generator().manual_seed(1 + rank)
+    gen = torch.Generator().manual_seed(1 if sample_parallel else 1 + rank)
     n_host = 8
     host = [tuple(t.pin_memory() for t in synthetic_batch(args.workload, B, gen)) for _ in range(n_host)]
     dev = [(x.to(device), y.to(device)) for x, y in host]
@@ -329,7 +334,7 @@ def run_b200(args):
         return float(t)
 
     dev_s, e2e_s = max_over_ranks(dev_s), max_over_ranks(e2e_s)
-    units = B * S * world * args.steps
+    units = B * S * (1 if sample_parallel else world) * args.steps
     pk = peaks()
 
     # ---- roofline of the dominant hot-path kernel, timed live with CUDA events on the launching stream
@@ -348,12 +353,15 @@ def run_b200(args):
         out = {
             "metric": "ELBO train samples*MC/sec", "value": units / dev_s, "unit": "samples*MC/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+            "scaling": "strong" if sample_parallel else "weak",
             "vs_baseline": None,
             "dtype": "tf32" if args.precision == "tf32" else "fp32 (3xTF32 split on tcgen05)",
             "data": "synthetic",
-            "config": {"workload": wl["name"], "batch_per_gpu": B, "mc_samples": S, "global_batch": B * world,
-                       "parallelism": f"dp{world}" if world > 1 else "single", "n_batches": N_BATCHES,
+            "config": {"workload": wl["name"], "batch_per_gpu": B, "mc_samples": S,
+                       "global_batch": B if sample_parallel else B * world,
+                       "parallelism": (f"sp{world} (MC samples sharded, {S // world} per GPU)" if sample_parallel
+                                       else f"dp{world}") if world > 1 else "single", "n_batches": N_BATCHES,
                        "optimizer": "Adam", "launch": graph_note, "l2": "flushed between steps (256 MiB write, untimed); each step "
                        "timed with its own CUDA event pair", "step": "zero_grad+forward(S)+KL+CE+backward+Adam"},
             "e2e": {"value": units / e2e_s, "unit": "samples*MC/s",
@@ -363,7 +371,7 @@ def run_b200(args):
             "wall_s": {"device_resident": dev_wall, "e2e": e2e_wall},
             "clocks": clock_info,
             "roofline": roof,
-            "hot_path": {"algorithmic_tflops_per_s": hot_flops_per_step(args.workload, B, S) * world /
+            "hot_path": {"algorithmic_tflops_per_s": hot_flops_per_step(args.workload, B, S) * (1 if sample_parallel else world) /
                          (dev_s / args.steps) / 1e12, "kernels_ms_per_step": per_kernel},
             "peaks": pk,
         }
@@ -577,6 +585,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
                     help="hot-path contraction mode: tf32 (2e-3 parity class) or fp32 = 3xTF32 split (1e-5 class)")
+    ap.add_argument("--parallel", default="data", choices=["data", "sample"],
+                    help="N > 1: shard the batch (weak scaling, default) or the MC samples of one batch (strong scaling)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the kl_prune and cpu_baseline legs (profiling runs)")
     args = ap.parse_args()

@@ -169,3 +169,45 @@ def test_mc_batching_plan():
     bnn.nn.register_rowwise_module(Custom)
     assert Net(torch.nn.Sequential(Custom(), NormalLinear(3, 3)))._mc_plan()[0]
     assert not Net(torch.nn.Sequential(NormalConv3d(1, 1, 1)))._mc_plan()[0]              # no fused 3-d path
+
+
+# ------------------------------------------------------------------------------------------------ C ABI error behaviour
+def test_c_abi_rejects_bad_arguments_without_a_gpu():
+    """Argument validation happens before any device work: status codes and the thread-local message (no GPU needed)."""
+    lib = _C.lib()
+    null = ctypes.c_void_p(None)
+    one = ctypes.c_void_p(16)               # never dereferenced on these paths
+
+    def msg():
+        return lib.bnn_last_error_string().decode()
+
+    assert lib.bnn_stddev(null, null, 8, null) == 1 and "NULL" in msg()
+    assert lib.bnn_stddev(null, null, -1, null) == 1
+    assert lib.bnn_stddev(null, null, 0, null) == 0                       # empty input is fine
+    assert lib.bnn_kl(None, -1, null, null, null, null, 0, null) == 1
+    assert lib.bnn_kl(None, 0, null, null, null, null, 0, null) == 0
+    table = (_C.bnn_kl_tensor * 1)()
+    table[0].mu, table[0].rho, table[0].numel, table[0].prior_scale = 16, 16, 4, 1.0
+    assert lib.bnn_kl(table, 1, one, null, null, null, 0, null) == 5 and "workspace" in msg()      # BNN_ERR_WORKSPACE
+    need = lib.bnn_kl_workspace_size(1)
+    assert lib.bnn_kl(table, 1, one, null, null, ctypes.c_void_p(8), need, null) == 2              # BNN_ERR_MISALIGNED
+    table[0].prior_scale = 0.0
+    assert lib.bnn_kl(table, 1, one, null, null, ctypes.c_void_p(256), need, null) == 1 and "scale" in msg()
+    pt = (_C.bnn_prune_tensor * 1)()
+    pt[0].mu, pt[0].rho, pt[0].numel, pt[0].k = 16, 16, 10, 11
+    ws = lib.bnn_prune_workspace_size(pt, 1)
+    assert ws > 0
+    assert lib.bnn_prune(pt, 1, ctypes.c_void_p(256), ws, null) == 1 and "k" in msg()
+    rng = _C.make_rng(1, 0, 0)
+    view = _C.make_view(16, 8, 1)
+    # unknown precision, negative size, bias with only one of (mu_b, sigma_b)
+    assert lib.bnn_sampled_gemm_fwd(one, 8, 0, one, one, null, null, null, null, view, 0, 4, 4, 8, 1, 0,
+                                    ctypes.byref(rng), None, 7, null) == 1 and "precision" in msg()
+    assert lib.bnn_sampled_gemm_fwd(one, 8, 0, one, one, null, null, null, null, view, 0, -4, 4, 8, 1, 0,
+                                    ctypes.byref(rng), None, 0, null) == 1
+    assert lib.bnn_sampled_gemm_fwd(one, 8, 0, one, one, one, null, null, null, view, 0, 4, 4, 8, 1, 0,
+                                    ctypes.byref(rng), None, 0, null) == 1 and "bias" in msg()
+    assert lib.bnn_sampled_gemm_fwd(one, 8, 0, one, one, null, null, null, null, view, 0, 4, 4, 8, 70000, 0,
+                                    ctypes.byref(rng), None, 0, null) == 6                          # BNN_ERR_UNSUPPORTED
+    geom = _C.bnn_conv2d_geom(1, 4, 8, 8, 2, 4, 3, 3, 6, 6, 1, 1, 0, 0, 1, 1)                       # c0 + Cg > C
+    assert lib.bnn_im2col(one, one, ctypes.byref(geom), null) == 1 and "geometry" in msg()
