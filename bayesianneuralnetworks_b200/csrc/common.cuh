@@ -36,6 +36,16 @@ int sm_count();                             // multiprocessor count of the curre
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------------------------------------
+// single-MUFU approximations (flush-to-zero forms: no denormal range fix-ups around the MUFU op; every use below
+// keeps its arguments in the normal range or is indifferent to a flushed result)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_ftz(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_ftz(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float exp_fast(float x) { return ex2_ftz(x * 1.4426950408889634f); }
+__device__ __forceinline__ float log_fast(float x) { return lg2_ftz(x) * 0.6931471805599453f; }
+
+// ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11) keyed by (seed, step, tensor, sample, element/4)
 // ---------------------------------------------------------------------------------------------
 struct RngKey {        // resolved on the device at kernel entry (adds *step_dev when given)
@@ -75,14 +85,15 @@ __device__ __forceinline__ float u01(uint32_t r) {
   return fmaf(static_cast<float>(r), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
 }
 
-// Box-Muller on a pair of words: (radius*cos, radius*sin)
+// Box-Muller on a pair of words: (radius*cos, radius*sin); u1 in [2^-33, 1] is a normal number, the angle in (-pi, pi]
+// is where sin/cos.approx are most accurate
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   const float u1 = u01(a), u2 = u01(b);
-  float radius;                                        // sqrt.approx: one MUFU op instead of the IEEE sequence
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(radius) : "f"(-2.0f * __logf(u1)));
-  float s, c;
-  // angle in (-pi, pi]: the range where sin/cos.approx are most accurate
-  __sincosf(fmaf(u2, 6.283185307179586f, -3.141592653589793f), &s, &c);
+  float radius, s, c;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(radius) : "f"(lg2_ftz(u1) * -1.3862943611198906f));   // sqrt(-2 ln u1)
+  const float angle = fmaf(u2, 6.283185307179586f, -3.141592653589793f);
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(angle));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(angle));
   return make_float2(radius * c, radius * s);
 }
 

@@ -68,22 +68,22 @@ __device__ __forceinline__ KlTerm kl_element_slow(float mu, float rho, float loc
 template <bool kGrad>
 __device__ __forceinline__ KlTerm kl_element_fast(float mu, float rho, float loc, float inv_scale,
                                                   float log_scale, float coeff) {
-  const float e = __expf(rho);
-  const float z = __fdividef(e, 2.0f + e);
+  const float e = exp_fast(rho);                       // flushed to 0 below rho ~ -87: sigma = 1e-10, as in fp32 torch
+  const float z = e * rcp_ftz(2.0f + e);
   const float z2 = z * z;
   float p = fmaf(z2, 0.1111111111f, 0.1428571429f);
   p = fmaf(z2, p, 0.2f);
   p = fmaf(z2, p, 0.3333333333f);
   p = fmaf(z2, p, 1.0f);
-  const float sigma = fmaf(2.0f * z, p, 1e-10f);
+  const float sigma = fmaf(2.0f * z, p, 1e-10f);       // >= 1e-10: normal range for rcp / lg2
   const float r = sigma * inv_scale;
   const float d = (mu - loc) * inv_scale;
   KlTerm out;
-  out.kl = fmaf(0.5f, fmaf(r, r, fmaf(d, d, -1.0f)), log_scale) - __logf(sigma);
+  out.kl = fmaf(0.5f, fmaf(r, r, fmaf(d, d, -1.0f)), log_scale) - log_fast(sigma);
   if (kGrad) {
-    const float sig = __fdividef(e, 1.0f + e);
+    const float sig = e * rcp_ftz(1.0f + e);
     out.gmu = coeff * d * inv_scale;
-    out.grho = coeff * (r * inv_scale - __fdividef(1.0f, sigma)) * sig;
+    out.grho = coeff * (r * inv_scale - rcp_ftz(sigma)) * sig;
   } else {
     out.gmu = 0.f;
     out.grho = 0.f;

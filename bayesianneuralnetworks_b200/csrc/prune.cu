@@ -61,8 +61,8 @@ struct FastKey { float key, margin; };
 __device__ __forceinline__ FastKey prune_key_fast(float mu, float rho) {
   float sp;
   if (rho <= -1.3862944f) {
-    const float e = __expf(rho);
-    const float z = __fdividef(e, 2.0f + e);
+    const float e = exp_fast(rho);
+    const float z = e * rcp_ftz(2.0f + e);
     const float z2 = z * z;
     float p = fmaf(z2, 0.1111111111f, 0.1428571429f);
     p = fmaf(z2, p, 0.2f);
@@ -73,9 +73,10 @@ __device__ __forceinline__ FastKey prune_key_fast(float mu, float rho) {
     sp = softplus_exact(rho);
   }
   const float sigma = 1e-10f + sp;
-  const float q = mu * mu * __fdividef(0.5f, sigma * sigma);
+  const float t = mu * rcp_ftz(sigma);
+  const float q = 0.5f * t * t;
   FastKey k;
-  k.key = -q - __logf(sigma) - 0.9189385332046727f;
+  k.key = -q - log_fast(sigma) - 0.9189385332046727f;
   k.margin = fmaf(2e-5f, q, 2e-5f);
   return k;
 }
@@ -268,11 +269,34 @@ __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __g
   }
 }
 
-// fast classification of one element against the bracket: 2 = above hi, 0 = below lo, 1 = needs the exact key
-__device__ __forceinline__ int classify_fast(float mu, float rho, float lo_f, float hi_f) {
+// Fast classification of one element against the bracket: 2 = above hi, 0 = below lo, 1 = needs the exact key.
+// With Q = (mu / sigma)^2 = 2q and a = -log(sigma):  key = -Q/2 + a - c.  The fast value is within
+// margin = 2e-5 * q + 2e-5 of the exact key (see prune_key_fast), so
+//   key - margin > hi  <=>  fma(Q, -(1 + 2e-5)/2, a) > hi + c + 2e-5 =: hi_t
+//   key + margin < lo  <=>  fma(Q, -(1 - 2e-5)/2, a) < lo + c - 2e-5 =: lo_t
+// Branch-free for rho <= ln(1/4) (series softplus); 4 MUFU + ~16 FP32 operations per element.
+__device__ __forceinline__ int classify_fast_small_rho(float mu, float rho, float lo_t, float hi_t) {
+  const float e = exp_fast(rho);                       // flushed to 0 below rho ~ -87: sigma = 1e-10, as in fp32 torch
+  const float z = e * rcp_ftz(2.0f + e);
+  const float z2 = z * z;
+  float p = fmaf(z2, 0.1111111111f, 0.1428571429f);
+  p = fmaf(z2, p, 0.2f);
+  p = fmaf(z2, p, 0.3333333333f);
+  p = fmaf(z2, p, 1.0f);
+  const float sigma = fmaf(2.0f * z, p, 1e-10f);       // >= 1e-10: normal range for rcp / lg2
+  const float t = mu * rcp_ftz(sigma);
+  const float Q = t * t;
+  const float a = lg2_ftz(sigma) * -0.6931471805599453f;
+  const bool above = fmaf(Q, -0.50001f, a) > hi_t;
+  const bool below = fmaf(Q, -0.49999f, a) < lo_t;
+  return above ? 2 : (below ? 0 : 1);
+}
+__device__ __forceinline__ int classify_fast(float mu, float rho, float lo_t, float hi_t) {
+  if (rho <= -1.3862944f) return classify_fast_small_rho(mu, rho, lo_t, hi_t);
   const FastKey f = prune_key_fast(mu, rho);
-  if (f.key - f.margin > hi_f) return 2;          // hi_f = +inf when the bracket is open above
-  if (f.key + f.margin < lo_f) return 0;          // lo_f = -inf when open below
+  // same thresholds, general form: key - margin > hi  <=>  key + c - margin + 2e-5 > hi_t
+  if (f.key + 0.9189385332046727f - f.margin + 2e-5f > hi_t) return 2;
+  if (f.key + 0.9189385332046727f + f.margin - 2e-5f < lo_t) return 0;
   return 1;
 }
 
@@ -291,6 +315,7 @@ __global__ void __launch_bounds__(kThreads) prune_partition_kernel(const __grid_
   bool active = false;
   uint32_t lo = 0, hi = 0;
   float lo_f = 0.f, hi_f = 0.f;
+  int hshift = 0;
   unsigned int gt = 0;
   auto flush = [&]() {
     // block-wide (uniform) — adds this block's count of "above" elements of tensor `cur`
@@ -314,8 +339,12 @@ __global__ void __launch_bounds__(kThreads) prune_partition_kernel(const __grid_
       const PruneState st = *d0.state;
       active = !st.general && d0.k > 0 && d0.k < d0.numel;
       lo = st.lo; hi = st.hi;
-      lo_f = lo == 0u ? -INFINITY : unorder_key(lo);
-      hi_f = hi == 0xffffffffu ? INFINITY : unorder_key(hi);
+      // thresholds of classify_fast (open brackets: +-inf) and the digit shift of the candidates' first-level histogram
+      lo_f = lo == 0u ? -INFINITY : unorder_key(lo) + 0.9189385332046727f - 2e-5f;
+      hi_f = hi == 0xffffffffu ? INFINITY : unorder_key(hi) + 0.9189385332046727f + 2e-5f;
+      const uint32_t range = hi - lo;
+      const int bits = range == 0u ? 0 : 32 - __clz(range);
+      hshift = bits > 11 ? bits - 11 : 0;
     }
     if (!active) continue;
     const PruneDesc& d = tab.t[t];
@@ -336,11 +365,20 @@ __global__ void __launch_bounds__(kThreads) prune_partition_kernel(const __grid_
       for (int j = 0; j < kVecPerThread; ++j) {
         const float mm[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
         const float rr[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
+        if (fmaxf(fmaxf(rr[0], rr[1]), fmaxf(rr[2], rr[3])) <= -1.3862944f) {      // one branch per 4 elements
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c = classify_fast(mm[q], rr[q], lo_f, hi_f);
-          gt += (c == 2);
-          undecided |= (c == 1 ? 1u : 0u) << (j * 4 + q);
+          for (int q = 0; q < 4; ++q) {
+            const int c = classify_fast_small_rho(mm[q], rr[q], lo_f, hi_f);
+            gt += (c == 2);
+            undecided |= (c == 1 ? 1u : 0u) << (j * 4 + q);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = classify_fast(mm[q], rr[q], lo_f, hi_f);
+            gt += (c == 2);
+            undecided |= (c == 1 ? 1u : 0u) << (j * 4 + q);
+          }
         }
       }
     } else {
@@ -389,6 +427,10 @@ __global__ void __launch_bounds__(kThreads) prune_partition_kernel(const __grid_
         idx = static_cast<uint32_t>(i);
         ok = order_key(prune_key(d.mu[i], d.rho[i]));
         c = ok > hi ? 2 : (ok >= lo ? 1 : 0);
+        if (c == 1) {      // first-level histogram of the candidates (digits relative to lo), read by the resolve kernel
+          const uint32_t bin = (ok - lo) >> hshift;
+          atomicAdd(d.hist + (bin < static_cast<uint32_t>(kBins) ? bin : static_cast<uint32_t>(kBins - 1)), 1u);
+        }
       }
       gt += (c == 2);
       const unsigned int bal = __ballot_sync(0xffffffffu, c == 1);
@@ -438,7 +480,7 @@ __device__ uint32_t cand_select(const uint32_t* cand, uint32_t n, int field, uin
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const uint32_t i = i0 + u * blockDim.x + threadIdx.x;
-      e[u] = i < n ? __ldcg(reinterpret_cast<const uint2*>(cand) + i) : make_uint2(0u, 0u);
+      e[u] = i < n ? reinterpret_cast<const uint2*>(cand)[i] : make_uint2(0u, 0u);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -483,7 +525,7 @@ __device__ uint32_t cand_select(const uint32_t* cand, uint32_t n, int field, uin
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const uint32_t i = i0 + u * blockDim.x + threadIdx.x;
-        e[u] = i < n ? __ldcg(reinterpret_cast<const uint2*>(cand) + i) : make_uint2(0u, 0u);
+        e[u] = i < n ? reinterpret_cast<const uint2*>(cand)[i] : make_uint2(0u, 0u);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -537,28 +579,90 @@ __device__ uint32_t cand_select(const uint32_t* cand, uint32_t n, int field, uin
   return prefix + mn;
 }
 
-// 3. one block per tensor: exact threshold among the candidates
+// 3. one block per tensor: exact threshold among the candidates.  The partition sweep left a 2048-bin histogram of the
+// candidates; the bin holding the wanted rank is found from it, its members (a few hundred) are filtered into shared
+// memory in ONE pass over the candidate list, and the exact select runs there.  A bin with more members than the
+// shared list holds (massive ties) takes the multi-pass select over the whole list instead.
+constexpr uint32_t kResolveList = 4096;      // (key, index) pairs in shared memory
+
 __global__ void __launch_bounds__(kResolveThreads) prune_resolve_kernel(const __grid_constant__ PruneTable tab) {
   __shared__ uint32_t s_hist[kBins];
   __shared__ uint32_t s_bcast[4];
+  __shared__ uint32_t s_list[2 * kResolveList];
+  __shared__ unsigned int s_count;
   const PruneDesc& d = tab.t[blockIdx.x];
   PruneState st = *d.state;
   if (st.general || d.k <= 0 || d.k >= d.numel) return;
   const uint64_t k = static_cast<uint64_t>(d.k);
-  bool ok = st.n_cand <= d.cand_cap && st.count_gt < k && k <= st.count_gt + st.n_cand;
+  const bool ok = st.n_cand <= d.cand_cap && st.count_gt < k && k <= st.count_gt + st.n_cand;
+  for (int b = threadIdx.x; b < kBins; b += blockDim.x) {
+    s_hist[b] = d.hist[b];
+    d.hist[b] = 0;                                   // clean for the general path / the next call
+  }
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
   if (ok) {
     const uint64_t rank = k - st.count_gt - 1;                  // 0-based, descending, among the candidates
+    const uint32_t range = st.hi - st.lo;
+    const int bits = range == 0u ? 0 : 32 - __clz(range);
+    const int hshift = bits > 11 ? bits - 11 : 0;
+    if (threadIdx.x < 32) {
+      uint32_t bin;
+      uint64_t before;
+      warp_find_bin(s_hist, true, rank, &bin, &before);
+      if (threadIdx.x == 0) { s_bcast[0] = bin; s_bcast[1] = static_cast<uint32_t>(before); s_bcast[2] = s_hist[bin]; }
+    }
+    __syncthreads();
+    const uint32_t bin = s_bcast[0], before_bins = s_bcast[1], in_bin = s_bcast[2];
+    __syncthreads();
     uint64_t above = 0;
-    uint32_t eq = 0;
-    const uint32_t T = cand_select(d.keys, st.n_cand, 0, 0u, rank, s_hist, s_bcast, &above, &eq);
-    const uint64_t take_eq = rank - above + 1;                  // how many of the key == T entries are taken
-    st.T = T;
-    st.take_all_eq = take_eq >= eq ? 1u : 0u;
-    st.idx_bound = 0xffffffffu;
-    if (!st.take_all_eq) {
-      uint64_t b2 = 0;
-      uint32_t e2 = 0;
-      st.idx_bound = cand_select(d.keys, st.n_cand, 1, T, take_eq - 1, s_hist, s_bcast, &b2, &e2);
+    uint32_t eq = 0, T = 0;
+    const bool small = in_bin <= kResolveList;
+    if (small) {
+      // one pass: members of the bin -> shared list
+      for (uint32_t i0 = 0; i0 < st.n_cand; i0 += 8u * blockDim.x) {
+        uint2 e[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+          e[u] = i < st.n_cand ? reinterpret_cast<const uint2*>(d.keys)[i] : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t i = i0 + u * blockDim.x + threadIdx.x;
+          if (i >= st.n_cand) continue;
+          uint32_t b = (e[u].x - st.lo) >> hshift;
+          b = b < static_cast<uint32_t>(kBins) ? b : static_cast<uint32_t>(kBins - 1);
+          if (b == bin) {
+            const unsigned int slot = atomicAdd(&s_count, 1u);
+            if (slot < kResolveList) { s_list[2 * slot] = e[u].x; s_list[2 * slot + 1] = e[u].y; }
+          }
+        }
+      }
+      __syncthreads();
+      const uint32_t n_list = s_count < kResolveList ? s_count : kResolveList;
+      T = cand_select(s_list, n_list, 0, 0u, rank - before_bins, s_hist, s_bcast, &above, &eq);
+      above += before_bins;
+      const uint64_t take_eq = rank - above + 1;
+      st.T = T;
+      st.take_all_eq = take_eq >= eq ? 1u : 0u;
+      st.idx_bound = 0xffffffffu;
+      if (!st.take_all_eq) {
+        uint64_t b2 = 0;
+        uint32_t e2 = 0;
+        st.idx_bound = cand_select(s_list, n_list, 1, T, take_eq - 1, s_hist, s_bcast, &b2, &e2);
+      }
+    } else {
+      T = cand_select(d.keys, st.n_cand, 0, 0u, rank, s_hist, s_bcast, &above, &eq);
+      const uint64_t take_eq = rank - above + 1;                // how many of the key == T entries are taken
+      st.T = T;
+      st.take_all_eq = take_eq >= eq ? 1u : 0u;
+      st.idx_bound = 0xffffffffu;
+      if (!st.take_all_eq) {
+        uint64_t b2 = 0;
+        uint32_t e2 = 0;
+        st.idx_bound = cand_select(d.keys, st.n_cand, 1, T, take_eq - 1, s_hist, s_bcast, &b2, &e2);
+      }
     }
   } else {
     st.general = 1u;
