@@ -606,7 +606,9 @@ constexpr int kWgStages = 3;                 // stages of 64 contraction rows: 8
 constexpr int kWgRows = 64;                  // contraction rows (m) per stage
 constexpr int kWgOperandBytes = 4 * kWgRows * kRowBytes;      // 4 MN groups x 64 K-rows x 128 B = 32 KiB per operand
 constexpr uint32_t kWgLbo = kWgRows * kRowBytes;              // next 32 MN elements: 8 KiB further
-constexpr int kWgThreads = 6 * 32;           // warp 0 TMA, warp 1 MMA (+TMEM owner), warps 2-5 epilogue
+constexpr int kWgEpiWarps = 12;              // three warps per TMEM lane quarter share the 8 column chunks of a tile:
+constexpr int kWgThreads = (2 + kWgEpiWarps) * 32;   // regenerating eps for 128 x 128 per sample is the long pole
+                                             // warp 0 TMA, warp 1 MMA (+TMEM owner), warps 2.. epilogue
 constexpr size_t kWgradSmem = kSmemAux + 1024 + static_cast<size_t>(kWgStages) * 2 * kWgOperandBytes;
 
 struct TmaWgradParams {
@@ -637,7 +639,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(accum_full + i, 1); mbar_init(accum_empty + i, kEpiThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(accum_full + i, 1); mbar_init(accum_empty + i, kWgEpiWarps); }
     fence_mbar_init();
     tma_prefetch_desc(&p.map_dy);
     tma_prefetch_desc(&p.map_a);
@@ -716,7 +718,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
       }
       __syncwarp();
     } else {
-      const int quad = warp & 3;
+      const int quad = warp & 3;                    // TMEM lane quarter this warp may access
+      const int sub = (warp - 2) >> 2;              // which third of the column chunks it handles
       const int n = n0 + quad * 32 + lane;
       const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
       const RngKey key = resolve_rng(p.rng_w);
@@ -731,7 +734,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
         eps.sample = p.sample_begin + s;
         mbar_wait(accum_full + buf, (i >> 1) & 1);
         tc_fence_after_sync();
-        for (int c = 0; c * 16 < cols_here; ++c) {
+        for (int c = sub; c * 16 < cols_here; c += kWgEpiWarps / 4) {
           float g[16], dm[16], dr[16];
           tmem_ld16(lane_addr + (buf ? kColG1 : kColG0) + c * 16, g);
           if (!first) {
@@ -773,7 +776,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
           }
         }
         tc_fence_before_sync();
-        mbar_arrive(accum_empty + buf);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accum_empty + buf);
       }
     }
   }
