@@ -590,12 +590,17 @@ template <bool kDgrad>
 int dispatch_tma_contract(const TmaContractParams& p, int n_cols, cudaStream_t st) {
   const int m_blocks = (p.M + 127) / 128;
   const int gx = (n_cols + 127) / 128, gz = p.sum_samples ? 1 : p.S;
-  if (m_blocks > 4 && pair_enabled()) {      // two CTAs (one cluster) per 1024 rows: each generates half of the weight tile
+  const int sms = sm_count();
+  auto ctas = [&](int mb) { return static_cast<int64_t>(gx) * ((m_blocks + mb - 1) / mb) * gz; };
+  // Rows per CTA: as many 128-row blocks as possible share one generated weight tile (4, doubled by the CTA pair) —
+  // but never at the price of leaving SMs idle: small problems take fewer blocks per CTA so that the k-loop of each
+  // CTA is short and every SM has one.
+  if (m_blocks > 4 && pair_enabled() && ctas(8) * 2 >= sms) {     // two CTAs (one cluster) per 1024 rows
     const int pairs = (m_blocks + 7) / 8;
     return launch_pair_contract<4, kDgrad>(p, dim3(2 * pairs, gx, gz), st);
   }
-  if (m_blocks >= 4) return launch_tma_contract<4, kDgrad>(p, dim3(gx, (m_blocks + 3) / 4, gz), st);
-  if (m_blocks >= 2) return launch_tma_contract<2, kDgrad>(p, dim3(gx, (m_blocks + 1) / 2, gz), st);
+  if (m_blocks >= 4 && ctas(4) >= sms) return launch_tma_contract<4, kDgrad>(p, dim3(gx, (m_blocks + 3) / 4, gz), st);
+  if (m_blocks >= 2 && ctas(2) >= sms) return launch_tma_contract<2, kDgrad>(p, dim3(gx, (m_blocks + 1) / 2, gz), st);
   return launch_tma_contract<1, kDgrad>(p, dim3(gx, m_blocks, gz), st);
 }
 
