@@ -1,17 +1,22 @@
-// sampled_gemm_tma.cu — TMA-fed TF32 variants of the sample-and-contract kernels for aligned row-major
-// operands (the large-shape path: BASELINE config C4 and the im2col matrices of the conv layers).
+// sampled_gemm_tma.cu — TMA-fed TF32 variants of the sample-and-contract kernels for aligned row-major operands (the
+// large-shape path: BASELINE config C4 and the im2col matrices of the conv layers).
 //
-//   forward / data gradient   activations (or dY) arrive by TMA (cp.async.bulk.tensor, 128B swizzle, TF32
-//                             conversion done by the copy engine) into a ring of 16 KiB tile slots; the eight
-//                             producer warps do nothing but generate W_s = mu + sigma * eps_s (Philox) into a
-//                             second ring; one thread issues tcgen05.mma; four warps drain TMEM.
-//                             The data gradient stores the generated weight tile in the MN-major canonical
-//                             layout, i.e. in W's natural [n][k] orientation (vector stores, no transpose).
+//   forward / data gradient   Activations (or dY) arrive by TMA (cp.async.bulk.tensor.3d, 128B swizzle, TF32 conversion in
+//     contract_tma_kernel     the copy engine): the MB tiles of a k-block land in one of two slot groups on one
+//     contract_pair_kernel    transaction barrier.  Sixteen generator warps in four groups do nothing but produce
+//                             W_s = mu + sigma * eps_s (Philox) — group j owns weight slot j and the k-blocks
+//                             it % 4 == j, so four tiles are in flight.  One thread issues tcgen05.mma and ONE
+//                             tcgen05.commit per k-block ("k-block consumed": frees the weight slot and, two k-blocks
+//                             later, the activation group).  Four warps drain TMEM.  The data gradient stores the
+//                             generated tile in the MN-major canonical layout, i.e. in W's natural [n][k] orientation.
+//                             The pair kernel runs the same protocol over a cluster of two CTAs (cta_group::2): each
+//                             generates half of the weight tile, the leader issues M = 256 MMAs and multicast commits.
 //   weight gradient           BOTH operands (dY^T and A^T) are MN-major tiles loaded by TMA — no thread touches
-//                             operand data; the four epilogue warps regenerate eps per sample and keep the
-//                             running sums of G_s and G_s o eps_s in TMEM (as in sampled_gemm.cu).
-// Eligibility (else the caller uses sampled_gemm.cu): TF32 precision, row-major operands (view P == 1 for
-// everything that is READ), 16-byte aligned bases and leading dimensions, contiguous samples.
+//     wgrad_tma_kernel        operand data; twelve epilogue warps regenerate eps per work unit and keep the running
+//                             sums of G_s and G_s o eps_s in TMEM.
+// Eligibility (else the caller uses sampled_gemm.cu): TF32 precision, row-major operands (view P == 1 for everything
+// that is READ), 16-byte aligned bases and leading dimensions.
+// Profiling builds (-DBNN_PROFILE_WAITS) add wait-cycle counters and elimination switches (BNN_EXP_FLAGS).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -23,7 +28,7 @@ namespace bnn {
 namespace contract {
 #ifdef BNN_PROFILE_WAITS
 // profiling builds: cycles spent waiting, summed over CTAs: [0] kernel, [1] MMA on full_w, [2] MMA on full_a,
-// [3] generator warp 0 on empty_w, [4] TMA thread on empty_a, [5] CTAs
+// [3] generator warp 0 on empty_w, [4] TMA thread on the consumed barrier, [5] CTAs
 __device__ unsigned long long g_wait_cycles[8];
 #define BNN_T0() const long long _t0 = clock64()
 #define BNN_ACC(var) var += clock64() - _t0
@@ -33,12 +38,11 @@ __device__ unsigned long long g_wait_cycles[8];
 #endif
 namespace {
 
-constexpr int kASlots = 8;                   // activation tile ring (16 KiB each)
+constexpr int kASlots = 8;                   // activation tile slots (16 KiB each): two k-block groups of up to 4 tiles
 constexpr int kWSlots = 4;                   // generated weight tile ring (the k-block bookkeeping assumes 4)
 // warp roles of the forward / data-gradient kernel: 16 weight generators (the Philox chains are latency bound:
 // four warps per scheduler hide them), MMA issuer, four epilogue warps (TMEM lane quarter = warp % 4), TMA issuer
 constexpr int kGenWarps = 16;
-constexpr int kGenThreads = kGenWarps * 32;
 constexpr int kGenGroups = 4;                       // generator groups: group j produces the k-blocks it % 4 == j into
 constexpr int kGroupWarps = kGenWarps / kGenGroups; // weight slot j, so four tiles are in flight at different phases
 constexpr int kGroupThreads = kGroupWarps * 32;     // (one tile's latency — loads, Philox chain — is hidden by the others)
@@ -113,26 +117,22 @@ struct TmaContractParams {
 };
 
 struct TmaPipe {
-  uint64_t* full_a;      // [kASlots] TMA transaction barriers
-  uint64_t* empty_a;     // [kASlots] tcgen05.commit
-  uint64_t* full_w;      // [kWSlots] 256 producer arrivals
-  uint64_t* empty_w;     // [kWSlots] tcgen05.commit
-  uint64_t* accum_full;  // [2]
-  uint64_t* accum_empty; // [2]
+  uint64_t* full_a;      // [2]        TMA transaction barriers: the MB activation tiles of one k-block group
+  uint64_t* full_w;      // [kWSlots]  one arrival per warp of the generator group that owns the slot
+  uint64_t* empty_w;     // [kWSlots]  "k-block consumed": one tcgen05.commit per k-block
+  uint64_t* accum_full;  // accumulators complete
   uint32_t* tmem_slot;
-  float* aux;
+  float* aux;            // 128 floats: the sampled bias row of this CTA's columns
   uint32_t ring_a, ring_w;
 };
 
 __device__ __forceinline__ TmaPipe carve_tma(uint8_t* smem_raw) {
   TmaPipe p;
   p.full_a = reinterpret_cast<uint64_t*>(smem_raw);
-  p.empty_a = p.full_a + kASlots;
-  p.full_w = p.empty_a + kASlots;
+  p.full_w = p.full_a + 2;
   p.empty_w = p.full_w + kWSlots;
   p.accum_full = p.empty_w + kWSlots;
-  p.accum_empty = p.accum_full + 2;
-  p.tmem_slot = reinterpret_cast<uint32_t*>(p.accum_empty + 2);
+  p.tmem_slot = reinterpret_cast<uint32_t*>(p.accum_full + 1);
   p.aux = reinterpret_cast<float*>(smem_raw + 512);
   const uint32_t base = smem_u32(smem_raw) + kSmemAux;
   p.ring_a = (base + 1023u) & ~1023u;
@@ -375,11 +375,10 @@ constexpr int kHalfTileBytes = kTileBytes / 2;
 constexpr size_t kPairSmem = kSmemAux + 1024 + static_cast<size_t>(kASlots) * kTileBytes + kPairWSlots * kHalfTileBytes;
 
 struct PairPipe {
-  uint64_t* full_a;      // [kASlots]      leader: 1 arrival (expect_tx) + bytes of both CTAs' tiles
-  uint64_t* empty_a;     // [kASlots]      both:   multicast tcgen05.commit
-  uint64_t* full_w;      // [kPairWSlots]  leader: one arrival per generator warp of both CTAs
-  uint64_t* empty_w;     // [kPairWSlots]  both:   multicast tcgen05.commit
-  uint64_t* accum_full;  // both
+  uint64_t* full_a;      // [2]  leader: 1 arrival (expect_tx) + the bytes of both CTAs' tiles of one k-block group
+  uint64_t* full_w;      // [4]  leader: one arrival per warp of the owning generator group of both CTAs
+  uint64_t* empty_w;     // [4]  both CTAs: "k-block consumed", one multicast tcgen05.commit per k-block
+  uint64_t* accum_full;  // both CTAs
   uint32_t* tmem_slot;
   float* aux;
   uint32_t ring_a, ring_w;
@@ -388,11 +387,10 @@ struct PairPipe {
 __device__ __forceinline__ PairPipe carve_pair(uint8_t* smem_raw) {
   PairPipe p;
   p.full_a = reinterpret_cast<uint64_t*>(smem_raw);
-  p.empty_a = p.full_a + kASlots;
-  p.full_w = p.empty_a + kASlots;
+  p.full_w = p.full_a + 2;
   p.empty_w = p.full_w + kPairWSlots;
   p.accum_full = p.empty_w + kPairWSlots;
-  p.tmem_slot = reinterpret_cast<uint32_t*>(p.accum_full + 2);
+  p.tmem_slot = reinterpret_cast<uint32_t*>(p.accum_full + 1);
   p.aux = reinterpret_cast<float*>(smem_raw + 512);
   const uint32_t base = smem_u32(smem_raw) + kSmemAux;
   p.ring_a = (base + 1023u) & ~1023u;
