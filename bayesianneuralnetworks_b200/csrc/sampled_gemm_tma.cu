@@ -629,6 +629,11 @@ struct TmaWgradParams {
   int chunk_blocks;         // a work unit = (sample, chunk); (sum_chunks G) o eps = sum_chunks (G o eps), so units are independent
 };
 
+// kPair: the same kernel over a cluster of two CTAs (launched with cluster dimension (2,1,1)): the pair owns two adjacent
+// n-tiles and ONE k-tile, tcgen05.mma.cta_group::2 computes 256 (n) x 128 (k) per instruction, and each CTA loads its own
+// dY^T tile but only HALF of the shared A^T tile (48 instead of 64 KiB per stage and CTA: the kernel is paced by operand
+// delivery).  TMA bytes and the epilogue's buffer releases land on the leader's barriers; commits are multicast.
+template <bool kPair>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_constant__ TmaWgradParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr uint32_t kTmemCols = 512;
@@ -642,19 +647,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(accum_full + i, 1); mbar_init(accum_empty + i, kWgEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(accum_full + i, 1); mbar_init(accum_empty + i, (kPair ? 2 : 1) * kWgEpiWarps); }
     fence_mbar_init();
     tma_prefetch_desc(&p.map_dy);
     tma_prefetch_desc(&p.map_a);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 1) { if (kPair) tmem_alloc_pair(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols); }
   tc_fence_before_sync();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;      // 0 = leader
 
-  const int k0 = blockIdx.x * 128;
-  const int n0 = blockIdx.y * 128;
+  const int n0 = blockIdx.x * 128;                          // this CTA's rows of dmu / drho (pairs are adjacent in x)
+  const int k0 = blockIdx.y * 128;
   const int groups = gridDim.z;
   const int units = p.S * p.n_chunks;
   const int per = (units + groups - 1) / groups;
@@ -680,43 +686,60 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
           for (int mb = mb0; mb < mb0 + m_blocks; ++mb, ++it) {
             const int stage = it % kWgStages;
             mbar_wait(empty + stage, ((it / kWgStages) & 1) ^ 1);
-            mbar_arrive_expect_tx(full + stage, 2 * kWgOperandBytes);
             const uint32_t base = ring + stage * 2 * kWgOperandBytes;
+            if (!kPair) {
+              mbar_arrive_expect_tx(full + stage, 2 * kWgOperandBytes);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              tma_load_3d(base + g * kWgLbo, &p.map_dy, n0 + g * 32, mb * kWgRows, s, full + stage);
-              tma_load_3d(base + kWgOperandBytes + g * kWgLbo, &p.map_a, k0 + g * 32, mb * kWgRows, sa, full + stage);
+              for (int g = 0; g < 4; ++g) {
+                tma_load_3d(base + g * kWgLbo, &p.map_dy, n0 + g * 32, mb * kWgRows, s, full + stage);
+                tma_load_3d(base + kWgOperandBytes + g * kWgLbo, &p.map_a, k0 + g * 32, mb * kWgRows, sa, full + stage);
+              }
+            } else {
+              const uint32_t lead_full = mapa_u32(smem_u32(full + stage), 0);
+              if (rank == 0) mbar_arrive_expect_tx(full + stage, 2 * (kWgOperandBytes + kWgOperandBytes / 2));
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                tma_load_3d_pair(base + g * kWgLbo, &p.map_dy, n0 + g * 32, mb * kWgRows, s, lead_full);
+#pragma unroll
+              for (int g = 0; g < 2; ++g)       // this CTA's half (64 columns) of the shared A^T tile
+                tma_load_3d_pair(base + kWgOperandBytes + g * kWgLbo, &p.map_a, k0 + static_cast<int>(rank) * 64 + g * 32,
+                                 mb * kWgRows, sa, lead_full);
             }
           }
         }
       }
       __syncwarp();
     } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = make_idesc_tf32(128, mma_n(p.K - k0), true, true);
+      if (lane == 0 && rank == 0) {
+        const uint32_t idesc = kPair ? make_idesc_tf32(256, 128, true, true) : make_idesc_tf32(128, mma_n(p.K - k0), true, true);
         const uint64_t desc_dy0 = make_smem_desc_mn(ring, kWgLbo, kMnSbo);
         const uint64_t desc_a0 = make_smem_desc_mn(ring + kWgOperandBytes, kWgLbo, kMnSbo);
         int it = 0;
         for (int u = s_begin, i = 0; u < s_end; ++u, ++i) {
           const int buf = i & 1;
-          mbar_wait(accum_empty + buf, ((i >> 1) & 1) ^ 1);
+          if (kPair) mbar_wait_cluster(accum_empty + buf, ((i >> 1) & 1) ^ 1); else mbar_wait(accum_empty + buf, ((i >> 1) & 1) ^ 1);
           tc_fence_after_sync();
           const uint32_t d = tmem + (buf ? kColG1 : kColG0);
           int mb0;
           const int m_blocks = unit_blocks(u, &mb0);
           for (int mb = 0; mb < m_blocks; ++mb, ++it) {
             const int stage = it % kWgStages;
-            mbar_wait(full + stage, (it / kWgStages) & 1);
+            if (kPair) mbar_wait_cluster(full + stage, (it / kWgStages) & 1); else mbar_wait(full + stage, (it / kWgStages) & 1);
             tc_fence_after_sync();
             const uint64_t da0 = desc_advance(desc_dy0, static_cast<uint32_t>(stage) * (2 * kWgOperandBytes >> 4));
             const uint64_t db0 = desc_advance(desc_a0, static_cast<uint32_t>(stage) * (2 * kWgOperandBytes >> 4));
 #pragma unroll
-            for (int ks = 0; ks < kWgRows / 8; ++ks)
-              mma_tf32(d, desc_advance(da0, ks * (kMnKStep >> 4)), desc_advance(db0, ks * (kMnKStep >> 4)), idesc,
-                       mb > 0 || ks > 0);
-            mma_commit(empty + stage);
+            for (int ks = 0; ks < kWgRows / 8; ++ks) {
+              if (kPair)
+                mma_tf32_pair(d, desc_advance(da0, ks * (kMnKStep >> 4)), desc_advance(db0, ks * (kMnKStep >> 4)), idesc,
+                              mb > 0 || ks > 0);
+              else
+                mma_tf32(d, desc_advance(da0, ks * (kMnKStep >> 4)), desc_advance(db0, ks * (kMnKStep >> 4)), idesc,
+                         mb > 0 || ks > 0);
+            }
+            if (kPair) mma_commit_pair(empty + stage, 3); else mma_commit(empty + stage);
           }
-          mma_commit(accum_full + buf);
+          if (kPair) mma_commit_pair(accum_full + buf, 3); else mma_commit(accum_full + buf);
         }
       }
       __syncwarp();
@@ -780,15 +803,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
         }
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(accum_empty + buf);
+        if (lane == 0) {
+          if (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(accum_empty + buf), 0)); else mbar_arrive(accum_empty + buf);
+        }
       }
     }
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem, kTmemCols);
+    if (kPair) tmem_dealloc_pair(tmem, kTmemCols); else tmem_dealloc(tmem, kTmemCols);
   }
 }
 
@@ -937,11 +962,29 @@ int tma_wgrad(bnn_view dy, int64_t dy_sample_stride, const float* a, int64_t lda
   int groups = want < S * p.n_chunks ? want : S * p.n_chunks;
   static bool attr_set = false;
   if (!attr_set) {
-    BNN_CUDA_OK(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    BNN_CUDA_OK(cudaFuncSetAttribute(wgrad_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(kWgradSmem)));
+    BNN_CUDA_OK(cudaFuncSetAttribute(wgrad_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(kWgradSmem)));
     attr_set = true;
   }
-  wgrad_tma_kernel<<<dim3((K + 127) / 128, (N + 127) / 128, groups), kWgThreads, kWgradSmem, st>>>(p);
+  const int n_tiles = (N + 127) / 128, k_tiles = (K + 127) / 128;
+  if (n_tiles >= 2 && pair_enabled() && static_cast<int64_t>(tiles) * groups >= 2 * sm_count()) {
+    // CTA pairs over adjacent n-tiles (large problems: the kernel is paced by operand delivery, a pair halves the A^T traffic)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((n_tiles + 1) / 2 * 2, k_tiles, groups);
+    cfg.blockDim = dim3(kWgThreads);
+    cfg.dynamicSmemBytes = kWgradSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    BNN_CUDA_OK(cudaLaunchKernelEx(&cfg, wgrad_tma_kernel<true>, p));
+  } else {
+    wgrad_tma_kernel<false><<<dim3(n_tiles, k_tiles, groups), kWgThreads, kWgradSmem, st>>>(p);
+  }
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
 }
