@@ -107,18 +107,21 @@ def hot_flops_per_step(workload, batch, samples):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions (B200_PROFILING.md recipe).  The sampler
+    runs from before the warm-up (nvidia-smi needs ~100 ms to deliver its first line) and every line is stamped on
+    arrival; `stop()` reports the samples that fall inside the marked windows — or, for a window shorter than the
+    sampling period, the samples nearest to it."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.windows = index, [], None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -126,23 +129,33 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        rows = [(t, r) for t, r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in rows if any(a - 0.05 <= t <= b + 0.05 for a, b in self.windows)]
+        note = "inside the timed regions"
+        if not inside and rows and self.windows:
+            mid = sum(a + b for a, b in self.windows) / (2 * len(self.windows))
+            inside = [r for _, r in sorted(rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+            note = "nearest to the timed regions (shorter than the sampling period)"
+        sm = sorted(float(r[1]) for r in inside)
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [float(r[2]) for r in inside if r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in inside if r[3].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None, "window": note}
 
 
 # ------------------------------------------------------------------------------------------------ the step
@@ -302,6 +315,8 @@ def run_b200(args):
         ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
         return ms / 1e3, wall, last
 
+    clocks = ClockSampler(local)
+    clocks.start()
     graph_note = "eager launches"
     if trainer.use_graph:
         try:
@@ -316,15 +331,17 @@ def run_b200(args):
             graph_note = f"eager launches (graph capture failed: {type(exc).__name__})"
     for i in range(max(args.warmup, 3)):
         trainer.step(*dev[i % n_host])
-    clocks = ClockSampler(local)
-    clocks.start()
     launches0 = _C.launch_count
+    t_a = time.time()
     dev_s, dev_wall, _ = timed(args.steps, False)
+    clocks.mark(t_a, time.time())
     launches = _C.launch_count - launches0
     if trainer.graph is not None:
         launches = trainer.launches_per_step * args.steps      # replays launch the captured kernels
     timed(2, True)                                    # untimed: first-touch of the staging allocations of the host-fed path
+    t_a = time.time()
     e2e_s, e2e_wall, last_loss = timed(args.steps, True)
+    clocks.mark(t_a, time.time())
     clock_info = clocks.stop()
 
     def max_over_ranks(v):
