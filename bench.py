@@ -217,6 +217,10 @@ class Trainer:
         Several GPUs: forward+backward and the optimizer step are two graphs with the NCCL all-reduce of the flat
         gradient buffer launched eagerly between them (collectives stay outside the captured region)."""
         from bayesianneuralnetworks_b200 import _C
+        # warm-up runs on a side stream, capture on the capture stream: the gradient accumulators legitimately see two
+        # streams (neither is the legacy default stream), so silence torch's advisory about it
+        if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         self.sx, self.sy = x.clone(), y.clone()
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, device=x.device, dtype=torch.float32)
@@ -394,8 +398,11 @@ def run_b200(args):
                          (dev_s / args.steps) / 1e12, "kernels_ms_per_step": per_kernel},
             "peaks": pk,
         }
+    if not args.no_extras:
+        kl_prune = bench_kl_prune(device, pk, world=world)          # every rank sweeps its shard of the tensors
+        if rank == 0:
+            out["kl_prune"] = kl_prune
     if rank == 0 and world == 1 and not args.no_extras:
-        out["kl_prune"] = bench_kl_prune(device, pk)
         out["cpu_baseline"] = cpu_baseline(args.workload, bounded_seconds=20.0)
     if world > 1:
         import torch.distributed as dist
@@ -445,10 +452,13 @@ def roofline(workload, B, S, per_kernel, pk):
             "avg_launch_us": 1e3 * k["ms_per_step"] / k["launches_per_step"]}
 
 
-def bench_kl_prune(device, pk, pairs=1 << 28):
-    """KL forward, KL forward+grad and prune over `pairs` (mu, rho) pairs in 16 tensors of 4096x4096 (the C5
-    layout, BASELINE.json configs[4], at a quarter of its size so the default run stays short); working set
-    2 GiB >> L2.  Algorithmic bytes: KL fwd 8 B/pair, fwd+grad 16 B/pair, prune 8 + 8p B/pair."""
+def bench_kl_prune(device, pk, pairs=1 << 28, world=1):
+    """KL forward, KL forward+grad and prune over `pairs` (mu, rho) pairs PER GPU in 16 tensors of 4096x4096 (the C5
+    layout, BASELINE.json configs[4]: 64 tensors sharded round-robin over the GPUs — at N=8 this is C5 at full size,
+    at N=1 a quarter of it so the default run stays short); working set 2 GiB per GPU >> L2.  Algorithmic bytes
+    (SURVEY §8d): KL fwd 8 B/pair, fwd+grad 16 B/pair, prune 8 + 8p B/pair.  With several GPUs the KL legs include the
+    one scalar all-reduce of the sharded sum, prune needs no exchange; times are the max over ranks and
+    GB/s the aggregate."""
     from bayesianneuralnetworks_b200 import _C
     n_t = pairs // (4096 * 4096)
     gen = torch.Generator(device=device).manual_seed(5)
@@ -458,6 +468,21 @@ def bench_kl_prune(device, pk, pairs=1 << 28):
     gr = [torch.empty_like(m) for m in mus]
     fwd = [(m, r, None, None, 0.0, 0.1, 1.0) for m, r in zip(mus, rhos)]
     both = [(m, r, a, b, 0.0, 0.1, 1.0) for m, r, a, b in zip(mus, rhos, gm, gr)]
+
+    def over_ranks(seconds):
+        if world == 1:
+            return seconds
+        import torch.distributed as dist
+        t = torch.tensor([seconds], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def kl_leg(entries):
+        sums = _C.kl(entries)
+        if world > 1:                       # tensor-sharded KL: one small all-reduce
+            import torch.distributed as dist
+            total = sums.sum()
+            dist.all_reduce(total)
 
     def time_it(fn, reps=5):
         fn()
@@ -470,14 +495,15 @@ def bench_kl_prune(device, pk, pairs=1 << 28):
             b.record()
             torch.cuda.synchronize()
             best = min(best, a.elapsed_time(b))
-        return best * 1e-3
+        return over_ranks(best * 1e-3)
 
-    res = {"pairs": pairs, "tensors": n_t, "l2": "working set 2 GiB, larger than L2"}
-    t = time_it(lambda: _C.kl(fwd))
-    res["kl_fwd"] = {"GBps": 8 * pairs / t / 1e9, "frac_of_measured_hbm": 8 * pairs / t / 1e9 / pk["hbm"], "ms": t * 1e3}
-    t = time_it(lambda: _C.kl(both))
-    res["kl_fwd_grad"] = {"GBps": 16 * pairs / t / 1e9, "frac_of_measured_hbm": 16 * pairs / t / 1e9 / pk["hbm"],
-                          "ms": t * 1e3}
+    def entry(bytes_per_pair, t):
+        gbps = bytes_per_pair * pairs * world / t / 1e9
+        return {"GBps": gbps, "frac_of_measured_hbm": gbps / (pk["hbm"] * world), "ms": t * 1e3}
+
+    res = {"pairs_per_gpu": pairs, "tensors_per_gpu": n_t, "n_gpus": world, "l2": "working set 2 GiB per GPU, larger than L2"}
+    res["kl_fwd"] = entry(8, time_it(lambda: kl_leg(fwd)))
+    res["kl_fwd_grad"] = entry(16, time_it(lambda: kl_leg(both)))
     p = 0.75
     k = int(p * 4096 * 4096)
     del gm, gr
@@ -498,9 +524,7 @@ def bench_kl_prune(device, pk, pairs=1 << 28):
         b.record()
         torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b) * 1e-3)
-    bytes_alg = (8 + 8 * p) * pairs
-    res["prune_p0.75"] = {"GBps": bytes_alg / best / 1e9, "frac_of_measured_hbm": bytes_alg / best / 1e9 / pk["hbm"],
-                          "ms": best * 1e3}
+    res["prune_p0.75"] = entry(8 + 8 * p, over_ranks(best))
     return res
 
 
