@@ -498,3 +498,68 @@ def test_graph_safe_rng_fresh_eps_per_replay_and_consistent_backward():
         assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
     finally:
         bnn.graph_safe_rng(False)
+
+
+# ------------------------------------------------------------------------------------------------ example flow
+class _ExampleFlatten(torch.nn.Module):
+    """The user-defined Flatten of the reference's examples (examples/MNIST/model.py:6-12)."""
+
+    def forward(self, x):
+        return x.view(x.size(0), -1)
+
+
+def _example_bcnn(samples):
+    """examples/MNIST/model.py:15-36 at a reduced width (same layer types and order)."""
+    from torch.nn import BatchNorm2d, Conv2d, ELU, Softmax
+    seq = torch.nn.Sequential(
+        Conv2d(1, 8, 5, padding=2, stride=2), BatchNorm2d(8), ELU(), Conv2d(8, 8, 3, padding=1), ELU(),
+        Conv2d(8, 16, 3, padding=0, stride=2), ELU(), NormalConv2d(16, 16, 3, padding=1, stride=2), ELU(),
+        _ExampleFlatten(), NormalLinear(16 * 3 * 3, 10), Softmax(dim=-1))
+    return Net(seq, samples)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_example_training_loop_learns_and_prunes(prec):
+    """The body of examples/MNIST/train.py:53-65 and examples/MNIST/prune.py:47-50 on synthetic, separable data:
+    the ELBO goes down, accuracy goes up, pruning keeps the fractions — with the user-defined Flatten first on the
+    reference loop, then (after register_rowwise_module) on the batched Monte-Carlo forward."""
+    from bayesianneuralnetworks_b200.nn import container
+    if _ExampleFlatten in container._ROWWISE:               # registered by an earlier parametrisation of this test
+        container._ROWWISE.remove(_ExampleFlatten)
+    bnn.set_precision(prec)
+    torch.manual_seed(0)
+    model = _example_bcnn(4).cuda()
+    assert model._mc_plan()[0] is False                    # unknown user module -> the reference loop
+    protos = torch.rand(10, 1, 28, 28, device="cuda")
+    y = torch.arange(64, device="cuda") % 10
+    x = (protos[y] + 0.1 * torch.randn(64, 1, 28, 28, device="cuda")).clamp(0, 1)
+    kld = KLDivergence(number_of_batches=100)
+    opt = torch.optim.Adam(model.parameters(), lr=3e-3)
+
+    def step():
+        opt.zero_grad()
+        preds = model(x)
+        loss = torch.stack([F.cross_entropy(p, y) for p in preds]).mean() + kld(model)
+        loss.backward()
+        opt.step()
+        acc = (torch.stack(preds).mean(0).argmax(-1) == y).float().mean()
+        return float(loss), float(acc)
+
+    first = step()
+    for _ in range(10):
+        step()
+    bnn.nn.register_rowwise_module(_ExampleFlatten)        # now eligible for the batched forward
+    assert model._mc_plan()[0] is True
+    for _ in range(60):
+        last = step()
+    assert last[0] < first[0] - 0.1 and last[1] > 0.5, (first, last)
+    sd = model.state_dict()
+    assert "layers.7.weight.mean" in sd and "layers.10.bias.scale" in sd
+    for p in torch.linspace(.75, 1, 3):                     # examples/MNIST/prune.py:49-50 (p is a 0-dim tensor)
+        PruneNormal()(model, p)
+        w = model.layers[7].weight
+        assert int((w.scale == -30).sum()) == int(p * w.mean.numel())
+    model.eval()
+    with torch.no_grad():
+        out = model(x)
+    assert len(out) == 4 and torch.isfinite(out[0]).all()
