@@ -6,10 +6,12 @@ from .layers import (BayesianLinear, NormalLinear, BayesianConvNd, NormalConvNd,
                      NormalConv3d)
 from .flipout import (FlipoutNormalLinear, FlipOutNormalConvNd, FlipOutNormalConv1d, FlipOutNormalConv2d,
                       FlipOutNormalConv3d)
+from .mvn import WeightMultivariateNormal, MultivariateNormalLinear
 from .loss import KLDivergence, Entropy
 
 __all__ = [
     'BayesianModule', 'BayesianNetworkModule', 'WeightNormal', 'BayesianLinear', 'NormalLinear',
     'BayesianConvNd', 'NormalConvNd', 'NormalConv1d', 'NormalConv2d', 'NormalConv3d', 'FlipoutNormalLinear',
-    'FlipOutNormalConvNd', 'FlipOutNormalConv1d', 'FlipOutNormalConv2d', 'FlipOutNormalConv3d', 'KLDivergence', 'Entropy',
+    'FlipOutNormalConvNd', 'FlipOutNormalConv1d', 'FlipOutNormalConv2d', 'FlipOutNormalConv3d', 'WeightMultivariateNormal',
+    'MultivariateNormalLinear', 'KLDivergence', 'Entropy',
 ]

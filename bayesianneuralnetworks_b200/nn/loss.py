@@ -10,8 +10,12 @@ import warnings
 import torch
 from torch.nn import Module
 
+from torch.distributions import MultivariateNormal
+from torch.distributions.kl import kl_divergence
+
 from ..functional import KLSum
 from ..utils.traversal import apply_wb
+from .mvn import WeightMultivariateNormal
 from .variational import WeightNormal
 
 
@@ -29,21 +33,34 @@ class KLDivergence(Module):
         self.n_batches = number_of_batches
 
     def compute_kl(self, param, module, type):
-        """loss.py:16-28 — here it only gathers (tensor, prior); the arithmetic happens in one launch."""
+        """loss.py:16-28 — factorised Gaussians are only gathered here as (tensor, prior) and reduced by one launch;
+        the full-covariance tensors of MultivariateNormalLinear (loss.py:24-26, out of the hot path) go through
+        torch.distributions and come back as their mean KL."""
+        prior = module.weight_prior if type == 'w' else module.bias_prior
+        if isinstance(param, WeightMultivariateNormal):
+            prior = MultivariateNormal(prior.mean.to(param.device), scale_tril=prior.scale_tril.to(param.device))
+            return kl_divergence(param.dist, prior).mean()
         if not isinstance(param, WeightNormal):
             raise NotImplementedError(f"KLDivergence: unsupported variational tensor {param.__class__.__name__}")
-        prior = module.weight_prior if type == 'w' else module.bias_prior
         return (param, _scalar_prior(prior, f"{module.__class__.__name__}.{'weight' if type == 'w' else 'bias'}"))
 
     def forward(self, model):
         found = model.traverse(lambda m: apply_wb(m, self.compute_kl, pass_module=True, pass_type=True))
         if found is None:
             raise ValueError('KLDivergence was not able to find BayasianModules')    # loss.py:34-36
-        n = len(found)
-        priors = [p for _, p in found]
-        coeffs = [1.0 / (w.mean.numel() * n * self.n_batches) for w, _ in found]
-        flat = [t for w, _ in found for t in (w.mean, w.scale)]
-        return KLSum.apply(priors, coeffs, *flat)
+        n = len(found)                          # loss.py:38: mean over ALL listed tensors, / n_batches
+        fused = [f for f in found if isinstance(f, tuple)]
+        other = [f for f in found if not isinstance(f, tuple)]
+        total = None
+        if fused:
+            priors = [p for _, p in fused]
+            coeffs = [1.0 / (w.mean.numel() * n * self.n_batches) for w, _ in fused]
+            flat = [t for w, _ in fused for t in (w.mean, w.scale)]
+            total = KLSum.apply(priors, coeffs, *flat)
+        if other:
+            rest = torch.stack(other).sum() / (n * self.n_batches)
+            total = rest if total is None else total + rest
+        return total
 
 
 class Entropy(Module):

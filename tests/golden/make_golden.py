@@ -10,6 +10,7 @@ Outputs
   linear_case.npz   NormalLinear(20, 7): S=3 outputs, KL, gradients of sum(y*dy)+KL
   conv_case_*.npz   NormalConv2d configs incl. the reference's own test configs, stride/dilation/groups
   flipout_case.npz  FlipoutNormalLinear / FlipOutNormalConv2d outputs and gradients for recorded sign tensors
+  mvn_case.npz      MultivariateNormalLinear output for recorded uniform draws; KLDivergence of a mixed model
   model_case.npz    small BayesianNetworkModule (Conv2d+ELU trunk, NormalConv2d, NormalLinear, Softmax):
                     S=3 ELBO loss (examples/MNIST/train.py:57-63) and all gradients
   mnist_ckpt_bayes_layers.npz  mean/scale of the Bayesian layers of examples/MNIST/mnist_pretrained.pth
@@ -181,6 +182,33 @@ def flipout_case():
              conv_g_mean=np32(conv.weight.mean.grad), conv_g_scale=np32(conv.weight.scale.grad))
 
 
+def mvn_case():
+    """MultivariateNormalLinear (dense.py:86-138, core.py:48-92) with recorded torch.rand_like draws (uniform noise),
+    alone and next to a NormalLinear in KLDivergence (loss.py:24-28,38)."""
+    from pytorch_bayesian.nn import MultivariateNormalLinear
+    torch.manual_seed(400)
+    mvn = MultivariateNormalLinear(6, 4)
+    lin = NormalLinear(5, 6)
+    draws = []
+    real = torch.rand_like
+    def rec(t, *a, **k):
+        e = real(t, *a, **k)
+        draws.append(e.detach().clone())
+        return e
+    torch.rand_like = rec
+    x = torch.randn(3, 6)
+    y = mvn(x)
+    torch.rand_like = real
+    net = _Net(torch.nn.Sequential(lin, mvn))
+    kl = KLDivergence(number_of_batches=2)(net)
+    kl.backward()
+    np.savez(os.path.join(HERE, "mvn_case.npz"), x=np32(x), y=np32(y), u_w=np32(draws[0]), u_b=np32(draws[1]),
+             w_mean=np32(mvn.weight.mean), w_scale=np32(mvn.weight.scale), b_mean=np32(mvn.bias.mean),
+             b_scale=np32(mvn.bias.scale), lin_w_mean=np32(lin.weight.mean), lin_w_scale=np32(lin.weight.scale),
+             lin_b_mean=np32(lin.bias.mean), lin_b_scale=np32(lin.bias.scale), kl=np32(kl),
+             g_w_scale=np32(mvn.weight.scale.grad), g_lin_w_mean=np32(lin.weight.mean.grad))
+
+
 def checkpoint_fixtures():
     sys.path.insert(0, os.path.join(REF, "examples", "MNIST"))
     from model import BCNN  # examples/MNIST/model.py
@@ -218,5 +246,6 @@ if __name__ == "__main__":
     conv_case("c2_shape", 64, 64, 3, 2, 1, 1, 1, True, (6, 6), 204)      # examples/MNIST/model.py:28
     model_case()
     flipout_case()
+    mvn_case()
     checkpoint_fixtures()
     print("golden vectors written to", HERE)

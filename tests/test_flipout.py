@@ -79,3 +79,47 @@ def test_flipout_on_gpu_with_fused_kl():
     kl.backward()
     assert torch.allclose(lin.weight.mean.grad.cpu(), T(z["lin_g_mean"]), rtol=2e-3, atol=2e-3)
     assert torch.allclose(lin.weight.scale.grad.cpu(), T(z["lin_g_scale"]), rtol=2e-3, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------------ full covariance (f-4)
+def _load_mvn_case(device):
+    from bayesianneuralnetworks_b200.nn import MultivariateNormalLinear
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "mvn_case.npz"))
+    mvn, lin = MultivariateNormalLinear(6, 4), NormalLinear(5, 6)
+    with torch.no_grad():
+        mvn.weight.mean.copy_(T(z["w_mean"])), mvn.weight.scale.copy_(T(z["w_scale"]))
+        mvn.bias.mean.copy_(T(z["b_mean"])), mvn.bias.scale.copy_(T(z["b_scale"]))
+        lin.weight.mean.copy_(T(z["lin_w_mean"])), lin.weight.scale.copy_(T(z["lin_w_scale"]))
+        lin.bias.mean.copy_(T(z["lin_b_mean"])), lin.bias.scale.copy_(T(z["lin_b_scale"]))
+    return z, mvn.to(device), lin.to(device)
+
+
+def test_multivariate_normal_linear_matches_reference_vectors_cpu():
+    """Reference quirks included: uniform noise, elementwise sqrt of the triangular matrix (core.py:68-69,91)."""
+    from bayesianneuralnetworks_b200.nn import MultivariateNormalLinear, WeightMultivariateNormal
+    z, mvn, _ = _load_mvn_case("cpu")
+    assert isinstance(mvn.weight, WeightMultivariateNormal) and mvn.weight.shape == (4, 6) and mvn.weight.scale.shape == (4, 6, 6)
+    assert isinstance(mvn.sampled, tuple) and len(mvn.sampled) == 2
+    draws = iter([T(z["u_w"]), T(z["u_b"])])
+    real = torch.rand_like
+    torch.rand_like = lambda t, *a, **k: next(draws)
+    try:
+        y = mvn(T(z["x"]))
+    finally:
+        torch.rand_like = real
+    assert torch.allclose(y, T(z["y"]), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(mvn(T(z["x"]), sample=False), T(z["y"]), rtol=1e-6, atol=1e-6)
+    fresh = MultivariateNormalLinear(5, 3, False)
+    assert fresh.bias is None and bool((fresh.weight.scale[:, 0, 1:] == -100).all())        # dense.py:106-109
+
+
+@pytest.mark.gpu
+def test_kl_of_mixed_model_with_full_covariance_layer_on_gpu():
+    """loss.py:24-28,38: the MVN tensors go through torch.distributions, the factorised ones through the fused kernel;
+    the mean is taken over all four listed tensors."""
+    z, mvn, lin = _load_mvn_case("cuda")
+    kl = KLDivergence(number_of_batches=2)(Net(torch.nn.Sequential(lin, mvn)))
+    assert float(kl) == pytest.approx(float(z["kl"]), rel=1e-5)
+    kl.backward()
+    assert torch.allclose(mvn.weight.scale.grad.cpu(), T(z["g_w_scale"]), rtol=1e-4, atol=1e-7)
+    assert torch.allclose(lin.weight.mean.grad.cpu(), T(z["g_lin_w_mean"]), rtol=1e-4, atol=1e-7)
