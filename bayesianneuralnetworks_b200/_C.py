@@ -367,7 +367,7 @@ def prune(entries, flags=0):
     base = (ws.data_ptr() + 255) & ~255
     with torch.cuda.device(device):
         _call("bnn_prune", table, n, ctypes.c_void_p(base), nbytes, _stream())
-    _count(13 * ((n + 23) // 24))
+    _count(14 * ((n + 23) // 24))
 
 
 def selftest_umma(device="cuda", mn_major=False):

@@ -4,16 +4,21 @@
 // key_i = log N(0; mu_i, sigma_i), the k largest get mu <- 0, rho <- -30; ties at the k-th key go to the
 // lowest element index.  Two implementations behind one entry point, chosen per tensor ON THE DEVICE:
 //
-//  * sampled path (default; ~2 reads of (mu, rho), no key workspace traffic):
-//      1. sample      exact keys of <= 32768 strided elements -> two order statistics (lo, hi) that bracket the
-//                     k-th key with ~6 sigma of the sampling distribution
-//      2. partition   one sweep: cheap fast-math key with a rigorous error margin classifies each element as
-//                     above / below the bracket; only elements inside (or within the margin of) the bracket get
-//                     the exact key; they are compacted as (key, index) candidates, the rest is counted
-//      3. resolve     exact radix select among the candidates (a few % of the tensor): threshold T, number of
-//                     ties to take, and the index bound for them
-//      4. apply       second sweep: fast key against T (exact key only within the margin), vector stores
-//    Any surprise — bracket missed, candidate buffer overflow, >= 2^32 elements — flags the tensor for
+//  * sampled path (default; two reads of (mu, rho), one write, no key workspace traffic).  Every element gets a cheap
+//    CERTIFIED INTERVAL for its key (fast math + a rigorous error margin), expressed in grid coordinates y: a 2048-bin
+//    grid laid over a bracket of the k-th key.
+//      1. sample    exact keys of <= 32768 strided elements -> two order statistics that bracket the k-th key with
+//                   ~6 sigma of the sampling distribution -> the grid
+//      2. bin       sweep 1 (read only): elements whose interval lies above / below the grid are counted, the others
+//                   (~3 %) enter two histograms: bin of the interval's lower end, bin of its upper end
+//      3. bracket   from the two histograms: bins j_lo <= j_hi that PROVABLY enclose the k-th key, the exact number of
+//                   elements above them (all pruned) and of elements that overlap them (~1000 per tensor: deferred)
+//      4. apply     sweep 2: same interval arithmetic; above -> pruned (vector stores), below -> kept, overlapping ->
+//                   (index, mu, rho) appended to a short list
+//      5. finish    exact keys (torch op order) of the deferred elements, exact select of the missing k - |above|
+//                   among them (ties -> lowest index), scattered writes
+//    Nothing is modified before step 3 has proven the bracket and sized the list; any surprise — bracket missed,
+//    massive ties, >= 2^32 elements — flags the tensor for
 //  * the general path (exact 3-pass radix select over a stored key workspace + per-chunk tie ranking),
 //    which also serves BNN_PRUNE_GENERAL and keys_out requests.  Its kernels return at once for tensors
 //    that the sampled path has finished.
@@ -23,14 +28,17 @@
 namespace bnn {
 namespace {
 
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
 constexpr int kThreads = 256;
 constexpr int kVecPerThread = 4;
 constexpr int kChunk = kThreads * 4 * kVecPerThread;           // 4096 elements
 constexpr int kMaxTensors = 24;
 constexpr int kBins = 2048;
 constexpr int kSample = 32768;                                 // sampled keys per tensor (128 KiB of smem)
-constexpr int kSmallTensor = 65536;                            // at or below: every element is a candidate
+constexpr int kSmallTensor = 65536;                            // at or below: every element is deferred to the exact select
 constexpr int kResolveThreads = 1024;
+constexpr int kUnit = 512;                                     // elements one warp handles per pass (8 units per chunk)
 
 // ordered key: unsigned order == float order (larger float -> larger uint)
 __device__ __forceinline__ uint32_t order_key(float f) {
@@ -54,33 +62,6 @@ __device__ __forceinline__ float prune_key(float mu, float rho) {
   return __fsub_rn(a, 0.9189385332046727f);
 }
 
-// Fast-math key and a bound on |fast - exact|.  sigma carries <= ~3e-6 relative error (ex2.approx with the
-// argument scaling, approximate division, series), so q = mu^2 / (2 sigma^2) is within ~7e-6 relative and
-// log(sigma) within ~4e-6 absolute; the margin 2e-5 * |q| + 2e-5 covers both with room to spare.
-struct FastKey { float key, margin; };
-__device__ __forceinline__ FastKey prune_key_fast(float mu, float rho) {
-  float sp;
-  if (rho <= -1.3862944f) {
-    const float e = exp_fast(rho);
-    const float z = e * rcp_ftz(2.0f + e);
-    const float z2 = z * z;
-    float p = fmaf(z2, 0.1111111111f, 0.1428571429f);
-    p = fmaf(z2, p, 0.2f);
-    p = fmaf(z2, p, 0.3333333333f);
-    p = fmaf(z2, p, 1.0f);
-    sp = 2.0f * z * p;
-  } else {
-    sp = softplus_exact(rho);
-  }
-  const float sigma = 1e-10f + sp;
-  const float t = mu * rcp_ftz(sigma);
-  const float q = 0.5f * t * t;
-  FastKey k;
-  k.key = -q - log_fast(sigma) - 0.9189385332046727f;
-  k.margin = fmaf(2e-5f, q, 2e-5f);
-  return k;
-}
-
 // per-tensor state in the workspace
 struct PruneState {
   // general path
@@ -89,14 +70,14 @@ struct PruneState {
   int64_t k_rem;             // how many still to take inside the current prefix class
   int64_t eq_total;          // elements equal to the final threshold
   // sampled path
-  uint32_t lo, hi;           // candidate bracket (ordered keys, inclusive)
-  uint32_t n_cand;           // candidates appended (may exceed the capacity: overflow)
+  float scale, offs_minus, offs_plus;    // grid: y = fma(key2 bound, scale, offs), bins [0, 2048)
   uint32_t general;          // 1: this tensor goes through the general path
-  unsigned long long count_gt;   // elements with key > hi
-  uint32_t T;                // exact threshold (ordered key of the k-th largest)
-  uint32_t idx_bound;        // among key == T take the elements with index <= idx_bound
-  uint32_t take_all_eq;      // every key == T is taken
-  uint32_t pad;
+  unsigned long long count_above;   // sweep 1: elements certified above the grid
+  float a_thr, b_thr;        // sweep 2: y_minus >= a_thr -> pruned; y_plus < b_thr -> kept; else deferred
+  uint32_t defer_all;        // small tensor: every element is deferred (exact select over the whole tensor)
+  uint32_t n_take;           // how many of the deferred elements are pruned
+  uint32_t expect_deferred;  // size of the deferred list, known from the histograms before sweep 2
+  uint32_t n_deferred;       // entries appended by sweep 2
 };
 
 struct PruneDesc {
@@ -104,15 +85,17 @@ struct PruneDesc {
   float* rho;
   uint8_t* mask;
   float* keys_out;
-  uint32_t* keys;            // workspace: ordered keys (general path) / (key, index) candidates (sampled path)
-  uint32_t* hist;            // workspace: 2048 bins
+  uint32_t* keys;            // workspace: ordered keys (general path) / deferred [index | mu | rho] x defer_cap, then
+                             // (key, index) pairs x defer_cap (sampled path)
+  uint32_t* hist;            // workspace: 2048 bins (lower interval ends / general path digits)
+  uint32_t* hist_plus;       // workspace: 2048 bins (upper interval ends)
   int64_t* chunk_cnt;        // workspace: per-chunk count of keys equal to the threshold (then offsets)
   PruneState* state;
   int64_t numel;
   int64_t k;
   int64_t chunk_begin;
   int64_t n_chunks;
-  uint32_t cand_cap;         // capacity of the candidate buffer in (key, index) pairs
+  uint32_t defer_cap;        // capacity of the deferred list in entries
   uint32_t force_general;
   int vec;                   // mu / rho (and mask) aligned for 128-bit access
   int pad;
@@ -124,6 +107,7 @@ struct PruneTable {
   int64_t total_chunks;
   uint32_t* any_general;     // workspace header: != 0 once some tensor needs the general path
 };
+
 
 __device__ __forceinline__ int find_tensor(const int64_t* chunk_begin, int n, int64_t chunk, int t = 0) {
 #pragma unroll 1
@@ -175,55 +159,30 @@ __device__ __forceinline__ void warp_find_bin(const uint32_t* hist, bool descend
   *before_out = before_g + excl2 + (first ? 0 : c0s);
 }
 
-// descending rank r (0 = largest) -> value, by <= 3 histogram passes over `n` keys in shared memory.  Digits are
-// taken relative to the minimum key [mn, mx] so that a narrow key range still spreads over the 2048 bins
-// (trained posteriors put every key into two or three top-bit bins: same-address shared atomics).
-__device__ uint32_t smem_select_desc(const uint32_t* keys, int n, int rank, uint32_t mn, uint32_t mx, uint32_t* hist,
-                                     uint32_t* bcast) {
-  const uint32_t range = mx - mn;
-  const int bits = range == 0u ? 0 : 32 - __clz(range);
-  const int s0 = max(bits - 11, 0), s1 = max(bits - 22, 0);
-  uint32_t prefix = 0, prefix_mask = 0;
-  int rem = rank;
-  for (int pass = 0; pass < 3; ++pass) {
-    const int shift = pass == 0 ? s0 : (pass == 1 ? s1 : 0);
-    const int top = pass == 0 ? bits : (pass == 1 ? s0 : s1);
-    if (top == shift) continue;
-    const uint32_t digit_mask = (1u << (top - shift)) - 1u;
-    for (int b = threadIdx.x; b < kBins; b += blockDim.x) hist[b] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint32_t k = keys[i] - mn;
-      if (((k ^ prefix) & prefix_mask) == 0u) atomicAdd(&hist[(k >> shift) & digit_mask], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      uint32_t bin;
-      uint64_t before;
-      warp_find_bin(hist, true, static_cast<uint64_t>(rem), &bin, &before);
-      if (threadIdx.x == 0) { bcast[0] = bin; bcast[1] = static_cast<uint32_t>(before); }
-    }
-    __syncthreads();
-    prefix |= bcast[0] << shift;
-    prefix_mask |= digit_mask << shift;
-    rem -= static_cast<int>(bcast[1]);
-    __syncthreads();
-  }
-  return prefix + mn;
-}
+// key2 = (key + log sqrt(2 pi)) * log2(e): the domain of the certified intervals and of the grid
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kHalfLog2Pi = 0.9189385332046727f;
+constexpr float kDelta2 = 4e-5f * 1.4426950408889634f;      // absolute part of the key margin, in key2 units
+__device__ __forceinline__ float key2_of(uint32_t ordered) { return (unorder_key(ordered) + kHalfLog2Pi) * kLog2e; }
 
-// 1. one block per tensor: bracket (lo, hi) of the k-th largest key from a strided sample
+// 1. one block per tensor: bracket of the k-th largest key from a strided sample -> the grid
 __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __grid_constant__ PruneTable tab) {
   extern __shared__ uint32_t s_keys[];          // kSample keys
-  __shared__ uint32_t s_hist[kBins];
-  __shared__ uint32_t s_bcast[2];
+  __shared__ uint32_t s_hist[kBins], s_hist2[kBins];
+  __shared__ uint32_t s_bcast[2], s_sel[6];
   const PruneDesc& d = tab.t[blockIdx.x];
   PruneState st;
   st.prefix = 0; st.need_ranks = 0; st.k_rem = d.k; st.eq_total = 0;
-  st.lo = 0u; st.hi = 0xffffffffu; st.n_cand = 0; st.count_gt = 0ull;
-  st.T = 0; st.idx_bound = 0xffffffffu; st.take_all_eq = 1; st.pad = 0;
+  st.scale = 0.f; st.offs_minus = 0.f; st.offs_plus = 0.f;
+  st.count_above = 0ull; st.a_thr = INFINITY; st.b_thr = -INFINITY;
+  st.defer_all = 0; st.n_take = 0; st.expect_deferred = 0; st.n_deferred = 0;
   const bool trivial = d.k <= 0 || d.k >= d.numel;
   st.general = (d.force_general || d.numel >= (int64_t(1) << 32)) ? 1u : 0u;
+  if (!trivial && !st.general && d.numel <= kSmallTensor) {
+    st.defer_all = 1;
+    st.n_take = static_cast<uint32_t>(d.k);
+    st.expect_deferred = static_cast<uint32_t>(d.numel);
+  }
   if (!trivial && !st.general && d.numel > kSmallTensor) {
     const int m = kSample;
     for (int j0 = 0; j0 < m; j0 += 8 * kResolveThreads) {          // 8 independent strided loads in flight
@@ -260,8 +219,68 @@ __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __g
     __syncthreads();
     mn = s_bcast[0]; mx = s_bcast[1];
     __syncthreads();
-    if (r_hi >= 0) st.hi = smem_select_desc(s_keys, m, r_hi, mn, mx, s_hist, s_bcast);
-    if (r_lo < m) st.lo = smem_select_desc(s_keys, m, r_lo, mn, mx, s_hist, s_bcast);
+    // bracket ends; a rank outside the sample leaves that side at the sample extreme (the thin tail beyond it simply
+    // lands in the outermost bin or outside the grid — both are handled exactly by the bracket step)
+    uint32_t hi = mx, lo = mn;
+    {
+      // both order statistics in two shared histogram passes (11 + 11 bits of the key range; below that the bracket
+      // ends are sub-bin edges, which only widens the bracket by < 2^-22 of the range)
+      const uint32_t range = mx - mn;
+      const int bits = range == 0u ? 0 : 32 - __clz(range);
+      const int s0 = max(bits - 11, 0), s1 = max(bits - 22, 0);
+      for (int b = threadIdx.x; b < kBins; b += blockDim.x) { s_hist[b] = 0; s_hist2[b] = 0; }
+      __syncthreads();
+      for (int j = threadIdx.x; j < m; j += blockDim.x) atomicAdd(&s_hist[(s_keys[j] - mn) >> s0], 1u);
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        uint32_t bin_a = 0, bin_b = 0;
+        uint64_t before_a = 0, before_b = 0;
+        if (r_hi >= 0) warp_find_bin(s_hist, true, static_cast<uint64_t>(r_hi), &bin_a, &before_a);
+        if (r_lo < m) warp_find_bin(s_hist, true, static_cast<uint64_t>(r_lo), &bin_b, &before_b);
+        if (threadIdx.x == 0) {
+          s_sel[0] = bin_a; s_sel[1] = static_cast<uint32_t>(before_a);
+          s_sel[2] = bin_b; s_sel[3] = static_cast<uint32_t>(before_b);
+        }
+      }
+      __syncthreads();
+      const uint32_t bin_a = s_sel[0], before_a = s_sel[1], bin_b = s_sel[2], before_b = s_sel[3];
+      uint32_t sub_a = 0, sub_b = 0;
+      if (s0 > 0) {
+        for (int b = threadIdx.x; b < kBins; b += blockDim.x) s_hist[b] = 0;
+        __syncthreads();
+        const uint32_t sub_mask = (1u << (s0 - s1)) - 1u;
+        for (int j = threadIdx.x; j < m; j += blockDim.x) {
+          const uint32_t v = s_keys[j] - mn, dgt = v >> s0, sub = (v >> s1) & sub_mask;
+          if (dgt == bin_a) atomicAdd(&s_hist[sub], 1u);
+          if (dgt == bin_b) atomicAdd(&s_hist2[sub], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+          uint32_t a = 0, b = 0;
+          uint64_t before = 0;
+          if (r_hi >= 0) warp_find_bin(s_hist, true, static_cast<uint64_t>(r_hi) - before_a, &a, &before);
+          if (r_lo < m) warp_find_bin(s_hist2, true, static_cast<uint64_t>(r_lo) - before_b, &b, &before);
+          if (threadIdx.x == 0) { s_sel[4] = a; s_sel[5] = b; }
+        }
+        __syncthreads();
+        sub_a = s_sel[4]; sub_b = s_sel[5];
+      }
+      if (r_hi >= 0) {
+        const uint64_t top = static_cast<uint64_t>(mn) + ((static_cast<uint64_t>(bin_a) << s0) | (static_cast<uint64_t>(sub_a) << s1)) +
+                             ((uint64_t(1) << s1) - 1);
+        hi = top < mx ? static_cast<uint32_t>(top) : mx;
+      }
+      if (r_lo < m) lo = mn + ((bin_b << s0) | (sub_b << s1));
+    }
+    const float g_lo = key2_of(lo), g_hi = key2_of(hi);
+    const float range = fmaxf(g_hi - g_lo, 2e-4f + 1e-5f * fabsf(g_lo));      // never degenerate
+    if (g_lo == g_lo && range < INFINITY) {                                   // no NaN / inf among the bracket keys
+      st.scale = static_cast<float>(kBins) / range;
+      st.offs_minus = -(g_lo + kDelta2) * st.scale;
+      st.offs_plus = -(g_lo - kDelta2) * st.scale;
+    } else {
+      st.general = 1u;
+    }
   }
   if (threadIdx.x == 0) {
     *d.state = st;
@@ -269,66 +288,64 @@ __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __g
   }
 }
 
-// Fast classification of one element against the bracket: 2 = above hi, 0 = below lo, 1 = needs the exact key.
-// With Q = (mu / sigma)^2 = 2q and a = -log(sigma):  key = -Q/2 + a - c.  The fast value is within
-// margin = 2e-5 * q + 2e-5 of the exact key (see prune_key_fast), so
-//   key - margin > hi  <=>  fma(Q, -(1 + 2e-5)/2, a) > hi + c + 2e-5 =: hi_t
-//   key + margin < lo  <=>  fma(Q, -(1 - 2e-5)/2, a) < lo + c - 2e-5 =: lo_t
-// Branch-free for rho <= ln(1/4) (series softplus); 4 MUFU + ~16 FP32 operations per element.
-__device__ __forceinline__ int classify_fast_small_rho(float mu, float rho, float lo_t, float hi_t) {
-  const float e = exp_fast(rho);                       // flushed to 0 below rho ~ -87: sigma = 1e-10, as in fp32 torch
-  const float z = e * rcp_ftz(2.0f + e);
-  const float z2 = z * z;
-  float p = fmaf(z2, 0.1111111111f, 0.1428571429f);
-  p = fmaf(z2, p, 0.2f);
-  p = fmaf(z2, p, 0.3333333333f);
-  p = fmaf(z2, p, 1.0f);
-  const float sigma = fmaf(2.0f * z, p, 1e-10f);       // >= 1e-10: normal range for rcp / lg2
-  const float t = mu * rcp_ftz(sigma);
-  const float Q = t * t;
-  const float a = lg2_ftz(sigma) * -0.6931471805599453f;
-  const bool above = fmaf(Q, -0.50001f, a) > hi_t;
-  const bool below = fmaf(Q, -0.49999f, a) < lo_t;
-  return above ? 2 : (below ? 0 : 1);
+// Certified interval of one element's key in grid coordinates.  With Q = (mu / sigma)^2 = 2q and L = log2(sigma):
+// key2 = -Q * log2e / 2 - L.  The fast value is within 2e-5 * q + 4e-5 (key units) of the exact fp32 key that torch's
+// op order produces: sigma carries <= ~1.5e-6 relative error (ex2.approx and its argument rounding, the degree-4
+// minimax polynomial of log1p(e)/e on [0, 1/4] — 2.8e-7 in fp32 Horner form —, lg2.approx for e > 1/4), rcp.approx 1 ulp, lg2.approx
+// <= 2^-22 relative (8e-6 at sigma = 1e-10); the exact key itself rounds within a few ulp.  So
+//   y_minus = ((-Q * 0.50001 * log2e - L) - delta - g_lo) * scale  <=  y(exact key)  <=
+//   y_plus  = ((-Q * 0.49999 * log2e - L) + delta - g_lo) * scale
+// Both sweeps call THIS function: only explicitly rounded operations and MUFU instructions, so the two sweeps compute
+// bit-identical intervals (the histograms of sweep 1 predict sweep 2 exactly).  Every step is monotone, NaN stays NaN
+// (such elements are always deferred).  3 MUFU + 15 FP32 operations per element when every rho <= ln(1/4).
+struct Grid { float sA, sB, nscale, offs_minus, offs_plus; };
+__device__ __forceinline__ Grid make_grid(const PruneState* st) {
+  Grid g;
+  const float scale = st->scale;
+  g.sA = __fmul_rn(-0.50001f * kLog2e, scale);
+  g.sB = __fmul_rn(-0.49999f * kLog2e, scale);
+  g.nscale = -scale;
+  g.offs_minus = st->offs_minus;
+  g.offs_plus = st->offs_plus;
+  return g;
 }
-__device__ __forceinline__ int classify_fast(float mu, float rho, float lo_t, float hi_t) {
-  if (rho <= -1.3862944f) return classify_fast_small_rho(mu, rho, lo_t, hi_t);
-  const FastKey f = prune_key_fast(mu, rho);
-  // same thresholds, general form: key - margin > hi  <=>  key + c - margin + 2e-5 > hi_t
-  if (f.key + 0.9189385332046727f - f.margin + 2e-5f > hi_t) return 2;
-  if (f.key + 0.9189385332046727f + f.margin - 2e-5f < lo_t) return 0;
-  return 1;
+template <bool kAnyRho>
+__device__ __forceinline__ void key_interval(float mu, float rho, const Grid& g, float& y_minus, float& y_plus) {
+  const float e = ex2_ftz(__fmul_rn(rho, kLog2e));       // flushed to 0 below rho ~ -87: sigma = 1e-10, as in fp32 torch
+  float p = __fmaf_rn(e, 0.1237151250243187f, -0.23501642048358917f);
+  p = __fmaf_rn(e, p, 0.3320590555667877f);
+  p = __fmaf_rn(e, p, -0.4999610483646393f);
+  p = __fmaf_rn(e, p, 0.9999998211860657f);
+  float sigma = __fmaf_rn(e, p, 1e-10f);                 // >= 1e-10: normal range for rcp / lg2
+  if (kAnyRho) {
+    // e > 1/4: ln2 * lg2(1 + e); rho > 15: softplus = rho + exp(-rho) to 1e-13 (torch returns rho itself above 20)
+    const float big = __fmaf_rn(lg2_ftz(__fadd_rn(1.0f, e)), 0.6931471805599453f, 1e-10f);
+    const float huge = __fadd_rn(rho, ex2_ftz(__fmul_rn(rho, -kLog2e)));
+    sigma = rho > 15.0f ? huge : (e > 0.25f ? big : sigma);
+  }
+  const float t = __fmul_rn(mu, rcp_ftz(sigma));
+  const float Q = __fmul_rn(t, t);
+  const float L = lg2_ftz(sigma);
+  y_minus = __fmaf_rn(Q, g.sA, __fmaf_rn(L, g.nscale, g.offs_minus));
+  y_plus = __fmaf_rn(Q, g.sB, __fmaf_rn(L, g.nscale, g.offs_plus));
 }
 
-// 2. sweep: count the elements above the bracket, compact the candidates
-__global__ void __launch_bounds__(kThreads) prune_partition_kernel(const __grid_constant__ PruneTable tab) {
+// 2. sweep 1 (read only): count the elements certified above the grid, histogram the interval ends of the others.
+// Warps are independent (a warp owns one 512-element unit per chunk): no block-level synchronisation in the loop.
+__global__ void __launch_bounds__(kThreads) prune_bin_kernel(const __grid_constant__ PruneTable tab) {
   __shared__ int64_t s_begin[kMaxTensors];
-  __shared__ unsigned int s_cnt[kThreads / 32];
-  __shared__ uint16_t s_work[kChunk];          // element offsets (within the chunk) that need the exact key
-  __shared__ uint32_t s_cand[2 * kChunk];      // (key, index) candidates of this chunk
-  __shared__ unsigned int s_nwork, s_n;
-  __shared__ uint32_t s_base;
+  __shared__ float2 s_queue[(4 * kVecPerThread + 1) * kThreads];      // per lane: 16 slots + 1 for the trailing store
   if (threadIdx.x < tab.n) s_begin[threadIdx.x] = tab.t[threadIdx.x].chunk_begin;
-  if (threadIdx.x == 0) { s_n = 0; s_nwork = 0; }
   __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int cur = -1;
   bool active = false;
-  uint32_t lo = 0, hi = 0;
-  float lo_f = 0.f, hi_f = 0.f;
-  int hshift = 0;
-  unsigned int gt = 0;
-  auto flush = [&]() {
-    // block-wide (uniform) — adds this block's count of "above" elements of tensor `cur`
-    unsigned int v = warp_sum(gt);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long tot = 0;
-      for (int w = 0; w < kThreads / 32; ++w) tot += s_cnt[w];
-      if (tot) atomicAdd(&tab.t[cur].state->count_gt, tot);
-    }
-    gt = 0;
+  Grid g = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float above_f = 0.f;      // per-thread count between two flushes: far below 2^24, exact in fp32
+  auto flush = [&]() {      // warp-wide: adds this warp's count of "above" elements of tensor `cur`
+    const unsigned int v = warp_sum(static_cast<unsigned int>(above_f));
+    if (lane == 0 && v != 0u) atomicAdd(&tab.t[cur].state->count_above, static_cast<unsigned long long>(v));
+    above_f = 0.f;
   };
   for (int64_t chunk = blockIdx.x; chunk < tab.total_chunks; chunk += gridDim.x) {
     const int t = find_tensor(s_begin, tab.n, chunk, cur < 0 ? 0 : cur);
@@ -336,28 +353,31 @@ __global__ void __launch_bounds__(kThreads) prune_partition_kernel(const __grid_
       if (cur >= 0 && active) flush();
       cur = t;
       const PruneDesc& d0 = tab.t[t];
-      const PruneState st = *d0.state;
-      active = !st.general && d0.k > 0 && d0.k < d0.numel;
-      lo = st.lo; hi = st.hi;
-      // thresholds of classify_fast (open brackets: +-inf) and the digit shift of the candidates' first-level histogram
-      lo_f = lo == 0u ? -INFINITY : unorder_key(lo) + 0.9189385332046727f - 2e-5f;
-      hi_f = hi == 0xffffffffu ? INFINITY : unorder_key(hi) + 0.9189385332046727f + 2e-5f;
-      const uint32_t range = hi - lo;
-      const int bits = range == 0u ? 0 : 32 - __clz(range);
-      hshift = bits > 11 ? bits - 11 : 0;
+      const PruneState* st = d0.state;
+      active = !st->general && !st->defer_all && d0.k > 0 && d0.k < d0.numel;
+      g = make_grid(st);
     }
     if (!active) continue;
     const PruneDesc& d = tab.t[t];
-    const int64_t base = (chunk - d.chunk_begin) * kChunk;
-    // phase 1: fast keys; decided elements are counted, the undecided ones are remembered in a per-thread
-    // bit mask and listed with ONE warp scan + ONE shared atomic per warp
-    uint32_t undecided = 0;          // bit e: this thread's e-th element of the chunk needs the exact key
-    const bool vec_chunk = d.vec && base + kChunk <= d.numel;
-    if (vec_chunk) {
+    const int64_t ubase = (chunk - d.chunk_begin) * kChunk + warp * kUnit;
+    if (ubase >= d.numel) continue;        // warp-uniform
+    // ~3 % of the elements overlap the grid, but in almost every warp-wide slot SOME lane does: a branch per element
+    // would be entered all the time.  Instead every element stores its interval UNCONDITIONALLY into the lane's own
+    // shared-memory queue and only the queue position advances when it overlaps (a following store overwrites a
+    // skipped one); the histogram updates run afterwards over the few queued intervals.
+    int pos = 0;
+    float2* const q_lane = s_queue + threadIdx.x;          // slot s of this lane: q_lane[s * kThreads]
+    auto account = [&](float y_minus, float y_plus) {
+      q_lane[pos * kThreads] = make_float2(y_minus, y_plus);
+      const bool ab = y_minus >= static_cast<float>(kBins);
+      above_f += ab ? 1.0f : 0.0f;
+      pos += (!ab && !(y_plus < 0.0f)) ? 1 : 0;            // overlaps the grid (or NaN)
+    };
+    if (d.vec && ubase + kUnit <= d.numel) {
       float4 m[kVecPerThread], r[kVecPerThread];
 #pragma unroll
       for (int j = 0; j < kVecPerThread; ++j) {
-        const int64_t i = base + (static_cast<int64_t>(j) * kThreads + threadIdx.x) * 4;
+        const int64_t i = ubase + (j * 32 + lane) * 4;
         m[j] = ldg_stream4(d.mu + i);
         r[j] = ldg_stream4(d.rho + i);
       }
@@ -365,106 +385,228 @@ __global__ void __launch_bounds__(kThreads) prune_partition_kernel(const __grid_
       for (int j = 0; j < kVecPerThread; ++j) {
         const float mm[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
         const float rr[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
+        float ym[4], yp[4];
         if (fmaxf(fmaxf(rr[0], rr[1]), fmaxf(rr[2], rr[3])) <= -1.3862944f) {      // one branch per 4 elements
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int c = classify_fast_small_rho(mm[q], rr[q], lo_f, hi_f);
-            gt += (c == 2);
-            undecided |= (c == 1 ? 1u : 0u) << (j * 4 + q);
-          }
+          for (int q = 0; q < 4; ++q) key_interval<false>(mm[q], rr[q], g, ym[q], yp[q]);
         } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int c = classify_fast(mm[q], rr[q], lo_f, hi_f);
-            gt += (c == 2);
-            undecided |= (c == 1 ? 1u : 0u) << (j * 4 + q);
-          }
+          for (int q = 0; q < 4; ++q) key_interval<true>(mm[q], rr[q], g, ym[q], yp[q]);
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) account(ym[q], yp[q]);
       }
     } else {
-#pragma unroll 4
+#pragma unroll 1
       for (int j = 0; j < 4 * kVecPerThread; ++j) {
-        const uint32_t off = static_cast<uint32_t>(j * kThreads + threadIdx.x);
-        int c = 0;
-        if (base + off < d.numel) c = classify_fast(d.mu[base + off], d.rho[base + off], lo_f, hi_f);
-        gt += (c == 2);
-        undecided |= (c == 1 ? 1u : 0u) << j;
+        const int64_t i = ubase + j * 32 + lane;
+        float ym = -INFINITY, yp = -INFINITY;          // past the end: below the grid, no effect
+        if (i < d.numel) key_interval<true>(d.mu[i], d.rho[i], g, ym, yp);
+        account(ym, yp);
       }
     }
-    {
-      const int lane = threadIdx.x & 31;
-      const unsigned int mine = __popc(undecided);
-      unsigned int incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
-      unsigned int wbase = 0;
-      if (total != 0u) {           // warp-uniform
-        if (lane == 31) wbase = atomicAdd(&s_nwork, total);
-        wbase = __shfl_sync(0xffffffffu, wbase, 31);
-        unsigned int slot = wbase + incl - mine;
-        while (undecided != 0u) {
-          const int e = __ffs(undecided) - 1;
-          undecided &= undecided - 1u;
-          const uint32_t off = vec_chunk ? static_cast<uint32_t>(((e >> 2) * kThreads + threadIdx.x) * 4 + (e & 3))
-                                         : static_cast<uint32_t>(e * kThreads + threadIdx.x);
-          s_work[slot++] = static_cast<uint16_t>(off);
-        }
-      }
+    for (int s = 0; s < pos; ++s) {                    // rarely more than two rounds
+      const float2 y = q_lane[s * kThreads];
+      const int bm = __float2int_rd(fminf(fmaxf(y.x, 0.0f), static_cast<float>(kBins - 1)));     // NaN -> 0
+      const int bp = __float2int_rd(fmaxf(fminf(y.y, static_cast<float>(kBins - 1)), 0.0f));     // NaN -> 2047
+      atomicAdd(d.hist + bm, 1u);
+      atomicAdd(d.hist_plus + bp, 1u);
     }
-    __syncthreads();
-    // phase 2: exact keys of the listed elements, evaluated densely
-    const unsigned int n_work = s_nwork;
-    for (unsigned int w0 = 0; w0 < n_work; w0 += kThreads) {       // uniform trip count
-      const unsigned int w = w0 + threadIdx.x;
-      int c = 0;
-      uint32_t ok = 0, idx = 0;
-      if (w < n_work) {
-        const int64_t i = base + s_work[w];
-        idx = static_cast<uint32_t>(i);
-        ok = order_key(prune_key(d.mu[i], d.rho[i]));
-        c = ok > hi ? 2 : (ok >= lo ? 1 : 0);
-        if (c == 1) {      // first-level histogram of the candidates (digits relative to lo), read by the resolve kernel
-          const uint32_t bin = (ok - lo) >> hshift;
-          atomicAdd(d.hist + (bin < static_cast<uint32_t>(kBins) ? bin : static_cast<uint32_t>(kBins - 1)), 1u);
-        }
-      }
-      gt += (c == 2);
-      const unsigned int bal = __ballot_sync(0xffffffffu, c == 1);
-      if (bal != 0u) {
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(bal) - 1;
-        unsigned int sb = 0;
-        if (lane == leader) sb = atomicAdd(&s_n, static_cast<unsigned int>(__popc(bal)));
-        sb = __shfl_sync(0xffffffffu, sb, leader);
-        if (c == 1) {
-          const unsigned int slot = sb + __popc(bal & ((1u << lane) - 1u));
-          s_cand[2 * slot] = ok;
-          s_cand[2 * slot + 1] = idx;
-        }
-      }
-    }
-    __syncthreads();
-    // phase 3: one global reservation per block and chunk, coalesced copy-out
-    const unsigned int n_here = s_n;
-    if (n_here != 0u) {           // uniform
-      if (threadIdx.x == 0) s_base = atomicAdd(&d.state->n_cand, n_here);
-      __syncthreads();
-      const uint32_t gbase = s_base;
-      for (unsigned int c = threadIdx.x; c < n_here; c += kThreads) {
-        const uint64_t slot = static_cast<uint64_t>(gbase) + c;
-        if (slot < d.cand_cap)
-          *reinterpret_cast<uint2*>(d.keys + 2 * slot) = make_uint2(s_cand[2 * c], s_cand[2 * c + 1]);
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { s_n = 0; s_nwork = 0; }
-    __syncthreads();
   }
   if (cur >= 0 && active) flush();
+}
+
+// 3. one block per tensor: the bins that provably enclose the k-th key.  With need = k - |above grid|:
+//   j_hi = bin of descending rank need - 1 among the UPPER interval ends: fewer than `need` elements can have a key
+//          in a bin above j_hi, so the k-th key is in a bin <= j_hi;
+//   j_lo = bin of descending rank need - 1 among the LOWER interval ends: at least `need` elements have a key in a bin
+//          >= j_lo, so the k-th key is in a bin >= j_lo.
+// Elements whose lower end is above j_hi are in the top k; elements whose upper end is below j_lo are not; the others
+// (counted exactly from the histograms) are resolved by exact keys in the finish kernel.
+__global__ void __launch_bounds__(kThreads) prune_bracket_kernel(const __grid_constant__ PruneTable tab) {
+  __shared__ uint32_t s_minus[kBins], s_plus[kBins];
+  __shared__ uint32_t s_out[4];
+  __shared__ unsigned long long s_cnt[3];
+  const PruneDesc& d = tab.t[blockIdx.x];
+  for (int b = threadIdx.x; b < kBins; b += blockDim.x) {
+    s_minus[b] = d.hist[b];
+    s_plus[b] = d.hist_plus[b];
+    d.hist[b] = 0;                                   // clean for the general path / the next call
+    d.hist_plus[b] = 0;
+  }
+  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0ull;
+  __syncthreads();
+  PruneState st = *d.state;
+  if (st.general || st.defer_all || d.k <= 0 || d.k >= d.numel) return;
+  // total of the binned elements
+  unsigned long long part = 0;
+  for (int b = threadIdx.x; b < kBins; b += blockDim.x) part += s_plus[b];
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0 && part) atomicAdd(&s_cnt[0], part);
+  __syncthreads();
+  const uint64_t k = static_cast<uint64_t>(d.k), n_binned = s_cnt[0];
+  const bool ok = st.count_above < k && k <= st.count_above + n_binned;
+  if (ok) {
+    const uint64_t need = k - st.count_above;
+    if (threadIdx.x < 32) {
+      uint32_t j_hi, j_lo;
+      uint64_t before;
+      warp_find_bin(s_plus, true, need - 1, &j_hi, &before);
+      warp_find_bin(s_minus, true, need - 1, &j_lo, &before);
+      if (threadIdx.x == 0) { s_out[0] = j_hi; s_out[1] = j_lo; }
+    }
+    __syncthreads();
+    const int j_hi = static_cast<int>(s_out[0]), j_lo = static_cast<int>(s_out[1]);
+    // |lower end > j_hi| and |upper end >= j_lo|
+    unsigned long long a = 0, c = 0;
+    for (int b = threadIdx.x; b < kBins; b += blockDim.x) {
+      if (b > j_hi) a += s_minus[b];
+      if (b >= j_lo) c += s_plus[b];
+    }
+    a = warp_sum(a);
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) {
+      if (a) atomicAdd(&s_cnt[1], a);
+      if (c) atomicAdd(&s_cnt[2], c);
+    }
+    __syncthreads();
+    const uint64_t above_all = st.count_above + s_cnt[1];      // pruned by sweep 2 without an exact key
+    const uint64_t deferred = s_cnt[2] - s_cnt[1];
+    if (j_lo <= j_hi && above_all < k && deferred <= d.defer_cap && k - above_all <= deferred) {
+      st.a_thr = static_cast<float>(j_hi + 1);
+      st.b_thr = static_cast<float>(j_lo);
+      st.n_take = static_cast<uint32_t>(k - above_all);
+      st.expect_deferred = static_cast<uint32_t>(deferred);
+    } else {
+      st.general = 1u;
+    }
+  } else {
+    st.general = 1u;
+  }
+  if (threadIdx.x == 0) {
+    *d.state = st;
+    if (st.general) atomicOr(tab.any_general, 1u);
+  }
+}
+
+// 4. sweep 2: prune what is certified above the bracket, defer what overlaps it
+__global__ void __launch_bounds__(kThreads, 4) prune_apply_sampled_kernel(const __grid_constant__ PruneTable tab) {
+  __shared__ int64_t s_begin[kMaxTensors];
+  if (threadIdx.x < tab.n) s_begin[threadIdx.x] = tab.t[threadIdx.x].chunk_begin;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int cur = -1;
+  int mode = 0;            // 0 skip tensor, 1 none, 2 all, 3 select
+  Grid g = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float a_thr = 0.f, b_thr = 0.f;
+  for (int64_t chunk = blockIdx.x; chunk < tab.total_chunks; chunk += gridDim.x) {
+    const int t = find_tensor(s_begin, tab.n, chunk, cur < 0 ? 0 : cur);
+    if (t != cur) {
+      cur = t;
+      const PruneDesc& d0 = tab.t[t];
+      const PruneState* st = d0.state;
+      mode = st->general ? 0 : (d0.k <= 0 ? 1 : (d0.k >= d0.numel ? 2 : 3));
+      g = make_grid(st);
+      a_thr = st->a_thr; b_thr = st->b_thr;          // defer_all: +inf / -inf, every element is deferred
+    }
+    if (mode == 0) continue;
+    const PruneDesc& d = tab.t[t];
+    const int64_t ubase = (chunk - d.chunk_begin) * kChunk + warp * kUnit;
+    if (ubase >= d.numel) continue;        // warp-uniform
+    // deferred elements are rare: one warp-aggregated reservation per occurrence
+    auto defer = [&](bool mine, int64_t i, float mu, float rho) {
+      const unsigned int bal = __ballot_sync(0xffffffffu, mine);
+      if (bal == 0u) return;
+      const int leader = __ffs(bal) - 1;
+      unsigned int base = 0;
+      if (lane == leader) base = atomicAdd(&d.state->n_deferred, static_cast<unsigned int>(__popc(bal)));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (mine) {
+        const unsigned int slot = base + __popc(bal & ((1u << lane) - 1u));
+        if (slot < d.defer_cap) {
+          d.keys[slot] = static_cast<uint32_t>(i);            // numel < 2^32 on this path
+          d.keys[d.defer_cap + slot] = __float_as_uint(mu);
+          d.keys[2u * d.defer_cap + slot] = __float_as_uint(rho);
+        }
+      }
+    };
+    if (d.vec && ubase + kUnit <= d.numel) {
+      if (mode != 3) {
+#pragma unroll
+        for (int j = 0; j < kVecPerThread; ++j) {
+          const int64_t i = ubase + (j * 32 + lane) * 4;
+          if (mode == 2) {
+            *reinterpret_cast<float4*>(d.mu + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(d.rho + i) = make_float4(-30.f, -30.f, -30.f, -30.f);
+          }
+          if (d.mask != nullptr) {
+            const unsigned char v = mode == 2 ? 1 : 0;
+            *reinterpret_cast<uchar4*>(d.mask + i) = make_uchar4(v, v, v, v);
+          }
+        }
+        continue;
+      }
+      float4 m[kVecPerThread], r[kVecPerThread];
+#pragma unroll
+      for (int j = 0; j < kVecPerThread; ++j) {
+        const int64_t i = ubase + (j * 32 + lane) * 4;
+        m[j] = ldg_stream4(d.mu + i);
+        r[j] = ldg_stream4(d.rho + i);
+      }
+#pragma unroll
+      for (int j = 0; j < kVecPerThread; ++j) {
+        const int64_t i = ubase + (j * 32 + lane) * 4;
+        const float mm[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
+        const float rr[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
+        float ym[4], yp[4];
+        if (fmaxf(fmaxf(rr[0], rr[1]), fmaxf(rr[2], rr[3])) <= -1.3862944f) {      // one branch per 4 elements
+#pragma unroll
+          for (int q = 0; q < 4; ++q) key_interval<false>(mm[q], rr[q], g, ym[q], yp[q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) key_interval<true>(mm[q], rr[q], g, ym[q], yp[q]);
+        }
+        bool tk[4], df[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          tk[q] = ym[q] >= a_thr;
+          df[q] = !tk[q] && !(yp[q] < b_thr);
+        }
+        if (__any_sync(0xffffffffu, df[0] || df[1] || df[2] || df[3])) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) defer(df[q], i + q, mm[q], rr[q]);
+        }
+        if (tk[0] || tk[1] || tk[2] || tk[3]) {      // the old values are in registers: whole-vector stores
+          *reinterpret_cast<float4*>(d.mu + i) =
+              make_float4(tk[0] ? 0.f : mm[0], tk[1] ? 0.f : mm[1], tk[2] ? 0.f : mm[2], tk[3] ? 0.f : mm[3]);
+          *reinterpret_cast<float4*>(d.rho + i) = make_float4(tk[0] ? -30.f : rr[0], tk[1] ? -30.f : rr[1],
+                                                              tk[2] ? -30.f : rr[2], tk[3] ? -30.f : rr[3]);
+        }
+        if (d.mask != nullptr)
+          *reinterpret_cast<uchar4*>(d.mask + i) = make_uchar4(tk[0], tk[1], tk[2], tk[3]);
+      }
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < 4 * kVecPerThread; ++j) {       // warp-uniform trip count (defer() votes)
+        const int64_t i = ubase + j * 32 + lane;
+        const bool in = i < d.numel;
+        bool take = mode == 2, df = false;
+        float mu = 0.f, rho = 0.f;
+        if (in && mode == 3) {
+          mu = d.mu[i]; rho = d.rho[i];
+          float ym, yp;
+          key_interval<true>(mu, rho, g, ym, yp);
+          take = ym >= a_thr;
+          df = !take && !(yp < b_thr);
+        }
+        defer(df, i, mu, rho);
+        if (in) {
+          if (take) { d.mu[i] = 0.0f; d.rho[i] = -30.0f; }
+          if (d.mask != nullptr) d.mask[i] = take ? 1 : 0;
+        }
+      }
+    }
+  }
 }
 
 // rank-th (0-based) value of the `n` candidates' field (`field` 0 = key descending, 1 = index ascending), restricted
@@ -579,176 +721,47 @@ __device__ uint32_t cand_select(const uint32_t* cand, uint32_t n, int field, uin
   return prefix + mn;
 }
 
-// 3. one block per tensor: exact threshold among the candidates.  The partition sweep left a 2048-bin histogram of the
-// candidates; the bin holding the wanted rank is found from it, its members (a few hundred) are filtered into shared
-// memory in ONE pass over the candidate list, and the exact select runs there.  A bin with more members than the
-// shared list holds (massive ties) takes the multi-pass select over the whole list instead.
+// 5. one block per tensor: exact keys of the deferred elements, exact select of the n_take largest (ties -> lowest
+// index), scattered writes.  The usual list (~1000 entries) is handled in shared memory; longer ones (ties, small
+// tensors that defer everything) go through (key, index) pairs in the workspace.
 constexpr uint32_t kResolveList = 4096;      // (key, index) pairs in shared memory
 
-__global__ void __launch_bounds__(kResolveThreads) prune_resolve_kernel(const __grid_constant__ PruneTable tab) {
+__global__ void __launch_bounds__(kResolveThreads) prune_finish_kernel(const __grid_constant__ PruneTable tab) {
   __shared__ uint32_t s_hist[kBins];
   __shared__ uint32_t s_bcast[4];
-  __shared__ uint32_t s_list[2 * kResolveList];
-  __shared__ unsigned int s_count;
+  __shared__ __align__(8) uint32_t s_list[2 * kResolveList];
   const PruneDesc& d = tab.t[blockIdx.x];
-  PruneState st = *d.state;
+  const PruneState st = *d.state;
   if (st.general || d.k <= 0 || d.k >= d.numel) return;
-  const uint64_t k = static_cast<uint64_t>(d.k);
-  const bool ok = st.n_cand <= d.cand_cap && st.count_gt < k && k <= st.count_gt + st.n_cand;
-  for (int b = threadIdx.x; b < kBins; b += blockDim.x) {
-    s_hist[b] = d.hist[b];
-    d.hist[b] = 0;                                   // clean for the general path / the next call
+  uint32_t n = st.n_deferred < d.defer_cap ? st.n_deferred : d.defer_cap;     // == expect_deferred by construction
+  const uint32_t* e_idx = d.keys;
+  const uint32_t* e_mu = d.keys + d.defer_cap;
+  const uint32_t* e_rho = d.keys + 2u * static_cast<size_t>(d.defer_cap);
+  uint32_t* pairs = n <= kResolveList ? s_list : d.keys + 3u * static_cast<size_t>(d.defer_cap);
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    pairs[2 * static_cast<size_t>(i)] = order_key(prune_key(__uint_as_float(e_mu[i]), __uint_as_float(e_rho[i])));
+    pairs[2 * static_cast<size_t>(i) + 1] = e_idx[i];
   }
-  if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
-  if (ok) {
-    const uint64_t rank = k - st.count_gt - 1;                  // 0-based, descending, among the candidates
-    const uint32_t range = st.hi - st.lo;
-    const int bits = range == 0u ? 0 : 32 - __clz(range);
-    const int hshift = bits > 11 ? bits - 11 : 0;
-    if (threadIdx.x < 32) {
-      uint32_t bin;
-      uint64_t before;
-      warp_find_bin(s_hist, true, rank, &bin, &before);
-      if (threadIdx.x == 0) { s_bcast[0] = bin; s_bcast[1] = static_cast<uint32_t>(before); s_bcast[2] = s_hist[bin]; }
-    }
-    __syncthreads();
-    const uint32_t bin = s_bcast[0], before_bins = s_bcast[1], in_bin = s_bcast[2];
-    __syncthreads();
-    uint64_t above = 0;
-    uint32_t eq = 0, T = 0;
-    const bool small = in_bin <= kResolveList;
-    if (small) {
-      // one pass: members of the bin -> shared list
-      for (uint32_t i0 = 0; i0 < st.n_cand; i0 += 8u * blockDim.x) {
-        uint2 e[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t i = i0 + u * blockDim.x + threadIdx.x;
-          e[u] = i < st.n_cand ? reinterpret_cast<const uint2*>(d.keys)[i] : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t i = i0 + u * blockDim.x + threadIdx.x;
-          if (i >= st.n_cand) continue;
-          uint32_t b = (e[u].x - st.lo) >> hshift;
-          b = b < static_cast<uint32_t>(kBins) ? b : static_cast<uint32_t>(kBins - 1);
-          if (b == bin) {
-            const unsigned int slot = atomicAdd(&s_count, 1u);
-            if (slot < kResolveList) { s_list[2 * slot] = e[u].x; s_list[2 * slot + 1] = e[u].y; }
-          }
-        }
-      }
-      __syncthreads();
-      const uint32_t n_list = s_count < kResolveList ? s_count : kResolveList;
-      T = cand_select(s_list, n_list, 0, 0u, rank - before_bins, s_hist, s_bcast, &above, &eq);
-      above += before_bins;
-      const uint64_t take_eq = rank - above + 1;
-      st.T = T;
-      st.take_all_eq = take_eq >= eq ? 1u : 0u;
-      st.idx_bound = 0xffffffffu;
-      if (!st.take_all_eq) {
-        uint64_t b2 = 0;
-        uint32_t e2 = 0;
-        st.idx_bound = cand_select(s_list, n_list, 1, T, take_eq - 1, s_hist, s_bcast, &b2, &e2);
-      }
-    } else {
-      T = cand_select(d.keys, st.n_cand, 0, 0u, rank, s_hist, s_bcast, &above, &eq);
-      const uint64_t take_eq = rank - above + 1;                // how many of the key == T entries are taken
-      st.T = T;
-      st.take_all_eq = take_eq >= eq ? 1u : 0u;
-      st.idx_bound = 0xffffffffu;
-      if (!st.take_all_eq) {
-        uint64_t b2 = 0;
-        uint32_t e2 = 0;
-        st.idx_bound = cand_select(d.keys, st.n_cand, 1, T, take_eq - 1, s_hist, s_bcast, &b2, &e2);
-      }
-    }
-  } else {
-    st.general = 1u;
+  uint32_t take = st.n_take < n ? st.n_take : n;
+  if (take == 0u) return;
+  uint64_t above = 0;
+  uint32_t eq = 0;
+  const uint32_t T = cand_select(pairs, n, 0, 0u, static_cast<uint64_t>(take) - 1, s_hist, s_bcast, &above, &eq);
+  const uint64_t take_eq = take - above;                    // how many of the key == T entries are taken
+  const bool all_eq = take_eq >= eq;
+  uint32_t idx_bound = 0xffffffffu;
+  if (!all_eq) {
+    uint64_t b2 = 0;
+    uint32_t e2 = 0;
+    idx_bound = cand_select(pairs, n, 1, T, take_eq - 1, s_hist, s_bcast, &b2, &e2);
   }
-  if (threadIdx.x == 0) {
-    *d.state = st;
-    if (st.general) atomicOr(tab.any_general, 1u);
-  }
-}
-
-// 4. second sweep: apply the mask
-__global__ void __launch_bounds__(kThreads) prune_apply_sampled_kernel(const __grid_constant__ PruneTable tab) {
-  __shared__ int64_t s_begin[kMaxTensors];
-  if (threadIdx.x < tab.n) s_begin[threadIdx.x] = tab.t[threadIdx.x].chunk_begin;
-  __syncthreads();
-  int cur = -1;
-  int mode = 0;            // 0 skip tensor, 1 none, 2 all, 3 select
-  uint32_t T = 0, idx_bound = 0, all_eq = 0;
-  float T_f = 0.f;
-  for (int64_t chunk = blockIdx.x; chunk < tab.total_chunks; chunk += gridDim.x) {
-    const int t = find_tensor(s_begin, tab.n, chunk, cur < 0 ? 0 : cur);
-    if (t != cur) {
-      cur = t;
-      const PruneDesc& d0 = tab.t[t];
-      const PruneState st = *d0.state;
-      mode = st.general ? 0 : (d0.k <= 0 ? 1 : (d0.k >= d0.numel ? 2 : 3));
-      T = st.T; idx_bound = st.idx_bound; all_eq = st.take_all_eq;
-      T_f = unorder_key(T);
-    }
-    if (mode == 0) continue;
-    const PruneDesc& d = tab.t[t];
-    const int64_t base = (chunk - d.chunk_begin) * kChunk;
-    auto decide = [&](float mu, float rho, uint32_t idx) -> bool {
-      if (mode != 3) return mode == 2;
-      const FastKey f = prune_key_fast(mu, rho);
-      if (f.key - f.margin > T_f) return true;
-      if (f.key + f.margin < T_f) return false;
-      const uint32_t ok = order_key(prune_key(mu, rho));
-      return ok > T || (ok == T && (all_eq || idx <= idx_bound));
-    };
-    if (d.vec && base + kChunk <= d.numel) {
-      float4 m[kVecPerThread], r[kVecPerThread];
-      if (mode == 3) {
-#pragma unroll
-        for (int j = 0; j < kVecPerThread; ++j) {
-          const int64_t i = base + (static_cast<int64_t>(j) * kThreads + threadIdx.x) * 4;
-          m[j] = ldg_stream4(d.mu + i);
-          r[j] = ldg_stream4(d.rho + i);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kVecPerThread; ++j) {
-        const int64_t i = base + (static_cast<int64_t>(j) * kThreads + threadIdx.x) * 4;
-        const uint32_t i32 = static_cast<uint32_t>(i);
-        bool tk[4];
-        if (mode == 3) {
-          tk[0] = decide(m[j].x, r[j].x, i32);
-          tk[1] = decide(m[j].y, r[j].y, i32 + 1);
-          tk[2] = decide(m[j].z, r[j].z, i32 + 2);
-          tk[3] = decide(m[j].w, r[j].w, i32 + 3);
-        } else {
-          tk[0] = tk[1] = tk[2] = tk[3] = (mode == 2);
-        }
-        const bool any = tk[0] || tk[1] || tk[2] || tk[3];
-        const bool all = tk[0] && tk[1] && tk[2] && tk[3];
-        if (all) {
-          *reinterpret_cast<float4*>(d.mu + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(d.rho + i) = make_float4(-30.f, -30.f, -30.f, -30.f);
-        } else if (any) {      // mode 3 only: the old values are in registers, store whole vectors
-          *reinterpret_cast<float4*>(d.mu + i) =
-              make_float4(tk[0] ? 0.f : m[j].x, tk[1] ? 0.f : m[j].y, tk[2] ? 0.f : m[j].z, tk[3] ? 0.f : m[j].w);
-          *reinterpret_cast<float4*>(d.rho + i) = make_float4(tk[0] ? -30.f : r[j].x, tk[1] ? -30.f : r[j].y,
-                                                              tk[2] ? -30.f : r[j].z, tk[3] ? -30.f : r[j].w);
-        }
-        if (d.mask != nullptr)
-          *reinterpret_cast<uchar4*>(d.mask + i) = make_uchar4(tk[0], tk[1], tk[2], tk[3]);
-      }
-    } else {
-      for (int j = 0; j < 4 * kVecPerThread; ++j) {
-        const int64_t i = base + static_cast<int64_t>(j) * kThreads + threadIdx.x;
-        if (i < d.numel) {
-          const bool take = mode == 3 ? decide(d.mu[i], d.rho[i], static_cast<uint32_t>(i)) : (mode == 2);
-          if (take) { d.mu[i] = 0.0f; d.rho[i] = -30.0f; }
-          if (d.mask != nullptr) d.mask[i] = take ? 1 : 0;
-        }
-      }
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t key = pairs[2 * static_cast<size_t>(i)], idx = pairs[2 * static_cast<size_t>(i) + 1];
+    if (key > T || (key == T && (all_eq || idx <= idx_bound))) {
+      d.mu[idx] = 0.0f;
+      d.rho[idx] = -30.0f;
+      if (d.mask != nullptr) d.mask[idx] = 1;
     }
   }
 }
@@ -965,18 +978,31 @@ __global__ void __launch_bounds__(kThreads) prune_apply_kernel(const __grid_cons
   }
 }
 
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// Workspace: [group flags][state + two histograms per tensor] — cleared by ONE memset — then per tensor the keys
+// region and the chunk counts.  The keys region holds the ordered keys of the general path (4 B/element) or, on the
+// sampled path, the deferred list ([index | mu | rho] x defer_cap) followed by (key, index) pairs x defer_cap.
+constexpr size_t kStateBytes = 256;                            // PruneState, padded
+constexpr size_t kSmallBytes = kStateBytes + 2 * kBins * 4;    // state + histograms of one tensor
+static_assert(sizeof(PruneState) <= kStateBytes, "PruneState outgrew its slot");
 
-size_t keys_bytes(int64_t numel) {       // ordered keys (general) or (key, index) candidates (sampled)
-  const int64_t small = numel < kSmallTensor ? numel : kSmallTensor;
-  const int64_t a = numel * 4, b = small * 8;
-  return static_cast<size_t>(a > b ? a : b);
+uint32_t defer_cap_for(int64_t numel) {
+  if (numel <= kSmallTensor) return static_cast<uint32_t>(numel);
+  int64_t cap = numel / 16;                                    // far above the ~3 % that overlap the first bracket
+  if (cap < 4096) cap = 4096;
+  if (cap > (int64_t(1) << 28)) cap = int64_t(1) << 28;
+  return static_cast<uint32_t>(cap);
 }
-
+size_t keys_bytes(int64_t numel) {
+  const size_t general = static_cast<size_t>(numel) * 4, sampled = static_cast<size_t>(defer_cap_for(numel)) * 20;
+  return align_up(general > sampled ? general : sampled, 256);
+}
+size_t header_bytes(int n_tensors) {       // one "some tensor needs the general path" flag per group of kMaxTensors
+  const int groups = (n_tensors + kMaxTensors - 1) / kMaxTensors;
+  return align_up(static_cast<size_t>(groups > 0 ? groups : 1) * 4, 256);
+}
 size_t prune_ws_one(int64_t numel) {
   const int64_t chunks = (numel + kChunk - 1) / kChunk;
-  return align_up(keys_bytes(numel), 256) + align_up(kBins * 4, 256) +
-         align_up(static_cast<size_t>(chunks) * 8, 256) + align_up(sizeof(PruneState), 256);
+  return keys_bytes(numel) + align_up(static_cast<size_t>(chunks) * 8, 256);
 }
 
 }  // namespace
@@ -987,8 +1013,8 @@ using namespace bnn;
 extern "C" {
 
 size_t bnn_prune_workspace_size(const bnn_prune_tensor* tensors, int32_t n_tensors) {
-  size_t total = 256;
-  if (tensors == nullptr) return total;
+  if (tensors == nullptr || n_tensors <= 0) return 256;
+  size_t total = header_bytes(n_tensors) + static_cast<size_t>(n_tensors) * kSmallBytes;
   for (int i = 0; i < n_tensors; ++i) total += prune_ws_one(tensors[i].numel > 0 ? tensors[i].numel : 0);
   return total;
 }
@@ -1012,8 +1038,10 @@ int bnn_prune(const bnn_prune_tensor* tensors, int32_t n_tensors, void* workspac
   int rc = check_device();
   if (rc != BNN_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  uint32_t* any_general = reinterpret_cast<uint32_t*>(workspace);
-  char* ws = static_cast<char*>(workspace) + 256;
+  uint32_t* group_flags = reinterpret_cast<uint32_t*>(workspace);
+  char* small = static_cast<char*>(workspace) + header_bytes(n_tensors);
+  char* ws = small + static_cast<size_t>(n_tensors) * kSmallBytes;
+  BNN_CUDA_OK(cudaMemsetAsync(workspace, 0, static_cast<size_t>(ws - static_cast<char*>(workspace)), st));
   const int max_grid = sm_count() * 8;
   static bool smem_set = false;
   const size_t sample_smem = static_cast<size_t>(kSample) * sizeof(uint32_t);
@@ -1028,46 +1056,50 @@ int bnn_prune(const bnn_prune_tensor* tensors, int32_t n_tensors, void* workspac
     PruneTable tab;
     tab.n = 0;
     tab.pad = 0;
-    tab.any_general = any_general;
+    tab.any_general = group_flags + first / kMaxTensors;
     int64_t chunks = 0;
     for (int i = 0; i < n; ++i) {
       const bnn_prune_tensor& t = tensors[first + i];
       if (t.numel == 0) continue;
       PruneDesc& d = tab.t[tab.n++];
       const int64_t nch = (t.numel + kChunk - 1) / kChunk;
+      char* mine = small + static_cast<size_t>(first + i) * kSmallBytes;
       d.mu = t.mu; d.rho = t.rho; d.mask = t.mask_out; d.keys_out = t.keys_out;
       d.numel = t.numel; d.k = t.k; d.chunk_begin = chunks; d.n_chunks = nch;
-      d.keys = reinterpret_cast<uint32_t*>(ws);
-      d.cand_cap = static_cast<uint32_t>(keys_bytes(t.numel) / 8);
-      ws += align_up(keys_bytes(t.numel), 256);
-      d.hist = reinterpret_cast<uint32_t*>(ws); ws += align_up(kBins * 4, 256);
+      d.state = reinterpret_cast<PruneState*>(mine);
+      d.hist = reinterpret_cast<uint32_t*>(mine + kStateBytes);
+      d.hist_plus = d.hist + kBins;
+      d.keys = reinterpret_cast<uint32_t*>(ws); ws += keys_bytes(t.numel);
+      d.defer_cap = defer_cap_for(t.numel);
       d.chunk_cnt = reinterpret_cast<int64_t*>(ws); ws += align_up(static_cast<size_t>(nch) * 8, 256);
-      d.state = reinterpret_cast<PruneState*>(ws); ws += align_up(sizeof(PruneState), 256);
       d.force_general = ((t.flags & BNN_PRUNE_GENERAL) != 0u || t.keys_out != nullptr) ? 1u : 0u;
       d.vec = aligned16(t.mu) && aligned16(t.rho) && (t.mask_out == nullptr || (reinterpret_cast<uintptr_t>(t.mask_out) & 3u) == 0);
       d.pad = 0;
-      BNN_CUDA_OK(cudaMemsetAsync(d.hist, 0, kBins * 4, st));
       chunks += nch;
     }
     if (tab.n == 0) continue;
     tab.total_chunks = chunks;
-    BNN_CUDA_OK(cudaMemsetAsync(any_general, 0, sizeof(uint32_t), st));
     const int grid = static_cast<int>(chunks < max_grid ? chunks : max_grid);
     // sampled path
     prune_sample_kernel<<<tab.n, kResolveThreads, sample_smem, st>>>(tab);
-    prune_partition_kernel<<<grid, kThreads, 0, st>>>(tab);
-    prune_resolve_kernel<<<tab.n, kResolveThreads, 0, st>>>(tab);
+    prune_bin_kernel<<<grid, kThreads, 0, st>>>(tab);
+    prune_bracket_kernel<<<tab.n, kThreads, 0, st>>>(tab);
     prune_apply_sampled_kernel<<<grid, kThreads, 0, st>>>(tab);
-    // general path (kernels return immediately unless a tensor asked for it)
-    prune_hist_kernel<0><<<grid, kThreads, 0, st>>>(tab);
+    prune_finish_kernel<<<tab.n, kResolveThreads, 0, st>>>(tab);
+    // general path (kernels return immediately unless a tensor asked for it; when no tensor is known to need it they
+    // are launched with one block per SM — all of them loop over the chunks — so that the idle launches stay cheap)
+    bool forced = false;
+    for (int i = 0; i < tab.n; ++i) forced = forced || tab.t[i].force_general != 0u || tab.t[i].numel >= (int64_t(1) << 32);
+    const int ggrid = forced ? grid : (grid < sm_count() ? grid : sm_count());
+    prune_hist_kernel<0><<<ggrid, kThreads, 0, st>>>(tab);
     prune_select_kernel<0><<<tab.n, kThreads, 0, st>>>(tab);
-    prune_hist_kernel<1><<<grid, kThreads, 0, st>>>(tab);
+    prune_hist_kernel<1><<<ggrid, kThreads, 0, st>>>(tab);
     prune_select_kernel<1><<<tab.n, kThreads, 0, st>>>(tab);
-    prune_hist_kernel<2><<<grid, kThreads, 0, st>>>(tab);
+    prune_hist_kernel<2><<<ggrid, kThreads, 0, st>>>(tab);
     prune_select_kernel<2><<<tab.n, kThreads, 0, st>>>(tab);
-    prune_count_eq_kernel<<<grid, kThreads, 0, st>>>(tab);
+    prune_count_eq_kernel<<<ggrid, kThreads, 0, st>>>(tab);
     prune_scan_kernel<<<tab.n, kThreads, 0, st>>>(tab);
-    prune_apply_kernel<<<grid, kThreads, 0, st>>>(tab);
+    prune_apply_kernel<<<ggrid, kThreads, 0, st>>>(tab);
     BNN_CUDA_OK(cudaGetLastError());
   }
   return BNN_OK;

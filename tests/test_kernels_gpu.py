@@ -217,6 +217,44 @@ def test_prune_sampled_path_equals_general_path(C, numel, p):
     assert torch.equal(outs[0][0][~ref].cpu(), mu[~ref.cpu()])
 
 
+@pytest.mark.parametrize("kind", ["wide_rho", "pruned_mix", "strided_structure", "outliers", "nonfinite_free_extremes"])
+def test_prune_sampled_path_hard_distributions(C, kind):
+    """Inputs that stress the certified-interval arithmetic of the sampled path (every softplus regime, rho above
+    torch's threshold of 20, keys of very different magnitude, already pruned entries) or defeat its strided sample
+    (structure with the sample's period: the bracket misses and the tensor must fall back to the general path).
+    Masks must equal the stable descending order of torch's own keys on the device for every k."""
+    n = 1 << 20
+    g = torch.Generator().manual_seed(21)
+    mu, rho = init_params((n,), g, fan_in=400)
+    if kind == "wide_rho":
+        rho = torch.rand(n, generator=g) * 70 - 40                       # -40 .. 30
+        mu = torch.randn(n, generator=g) * torch.pow(10.0, torch.rand(n, generator=g) * 4 - 3)
+    elif kind == "pruned_mix":
+        dead = torch.rand(n, generator=g) < 0.6
+        mu[dead], rho[dead] = 0.0, -30.0
+    elif kind == "strided_structure":
+        mu[::32] *= 1e-3                                                  # 2^20 / 32768 samples: stride 32
+    elif kind == "outliers":
+        mu[::1000] = 1e6
+        rho[::1000] = -80.0
+        mu[5::777] = 0.0
+    elif kind == "nonfinite_free_extremes":
+        rho[::3] = 25.0
+        rho[1::3] = -100.0
+        mu[1::3] *= 1e-8
+    keys = torch_keys_same_device(mu.cuda(), rho.cuda())
+    assert bool(torch.isfinite(keys).all())
+    for k in (1, n // 100, n // 3, int(0.7 * n), n - n // 50, n - 1):
+        dmu, drho = mu.cuda(), rho.cuda()
+        mask = torch.empty(n, dtype=torch.uint8, device="cuda")
+        C.prune([(dmu, drho, k, mask, None)])
+        ref = orc.prune_mask_from_keys(keys, k)
+        assert int(mask.sum()) == k, (kind, k)
+        assert torch.equal(mask.bool(), ref), (kind, k)
+        assert bool((dmu[ref] == 0).all()) and bool((drho[ref] == -30).all())
+        assert torch.equal(dmu[~ref].cpu(), mu[~ref.cpu()]) and torch.equal(drho[~ref].cpu(), rho[~ref.cpu()])
+
+
 @pytest.mark.parametrize("classes", [1, 2, 3])
 def test_prune_large_tie_classes(C, classes):
     """Huge tie classes on a tensor large enough for the sampled path: the bracket collapses onto one key
