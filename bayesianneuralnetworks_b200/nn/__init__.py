@@ -8,10 +8,11 @@ from .flipout import (FlipoutNormalLinear, FlipOutNormalConvNd, FlipOutNormalCon
                       FlipOutNormalConv3d)
 from .mvn import WeightMultivariateNormal, MultivariateNormalLinear
 from .loss import KLDivergence, Entropy
+from .elbo import MCSamples, mc_mean_loss
 
 __all__ = [
     'BayesianModule', 'BayesianNetworkModule', 'WeightNormal', 'BayesianLinear', 'NormalLinear',
     'BayesianConvNd', 'NormalConvNd', 'NormalConv1d', 'NormalConv2d', 'NormalConv3d', 'FlipoutNormalLinear',
     'FlipOutNormalConvNd', 'FlipOutNormalConv1d', 'FlipOutNormalConv2d', 'FlipOutNormalConv3d', 'WeightMultivariateNormal',
-    'MultivariateNormalLinear', 'KLDivergence', 'Entropy',
+    'MultivariateNormalLinear', 'KLDivergence', 'Entropy', 'MCSamples', 'mc_mean_loss',
 ]

@@ -12,6 +12,7 @@ from torch.nn import Module
 
 from .. import runtime
 from ..utils.traversal import _item_or_list, traverse
+from .elbo import MCSamples
 
 # leaf modules that act row by row along dim 0 (safe to see S*B rows instead of S passes of B rows)
 _ROWWISE = [
@@ -130,7 +131,9 @@ class BayesianNetworkModule(Module):
             with torch.no_grad():
                 for bn in bns:
                     bn.num_batches_tracked += samples - 1
-        return list(out.view((local, rows) + tuple(out.shape[1:])).unbind(0))
+        result = MCSamples(out.view((local, rows) + tuple(out.shape[1:])).unbind(0))
+        result.batched = out           # nn.mc_mean_loss evaluates a row-mean criterion on it in one call
+        return result
 
     def forward(self, x, samples=None, *args, **kwargs):
         if samples is None:

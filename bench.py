@@ -165,9 +165,10 @@ class Trainer:
     once into a CUDA graph and replayed: the Philox streams advance through a device-side step counter
     (bnn.graph_safe_rng), so every replay draws fresh eps."""
 
-    def __init__(self, workload, device, world, samples, graph):
+    def __init__(self, workload, device, world, samples, graph, loss_tail="batched"):
         import bayesianneuralnetworks_b200 as bnn
         self.bnn = bnn
+        self.loss_tail = loss_tail
         torch.manual_seed(0)
         bnn.graph_safe_rng(graph)
         self.model = build_model(workload, samples).to(device)
@@ -191,7 +192,10 @@ class Trainer:
             self.opt.zero_grad(set_to_none=True)
         preds = self.model(x)
         divergence = self.kld(self.model)
-        likelihood = torch.stack([F.cross_entropy(p, y) for p in preds]).mean()
+        if self.loss_tail == "loop":        # the reference loop body verbatim (train.py:59-61)
+            likelihood = torch.stack([F.cross_entropy(p, y) for p in preds]).mean()
+        else:                               # the same mean as ONE cross-entropy over the S*B rows
+            likelihood = self.bnn.nn.mc_mean_loss(F.cross_entropy, preds, y)
         loss = likelihood + divergence
         loss.backward()
         return loss
@@ -282,7 +286,7 @@ def run_b200(args):
         if S % world != 0:
             raise SystemExit(f"{S} MC samples do not split over {world} ranks")
         bnn.set_sample_partition(rank, world)
-    trainer = Trainer(args.workload, device, world, S, graph=not args.no_graph)
+    trainer = Trainer(args.workload, device, world, S, graph=not args.no_graph, loss_tail=args.loss_tail)
     gen = torch.Generator().manual_seed(1 if sample_parallel else 1 + rank)
     n_host = 8
     host = [tuple(t.pin_memory() for t in synthetic_batch(args.workload, B, gen)) for _ in range(n_host)]
@@ -386,7 +390,10 @@ def run_b200(args):
                        "parallelism": (f"sp{world} (MC samples sharded, {S // world} per GPU)" if sample_parallel
                                        else f"dp{world}") if world > 1 else "single", "n_batches": N_BATCHES,
                        "optimizer": "Adam (torch fused)", "launch": graph_note, "l2": "flushed between steps (256 MiB write, untimed); each step "
-                       "timed with its own CUDA event pair", "step": "zero_grad+forward(S)+KL+CE+backward+Adam"},
+                       "timed with its own CUDA event pair", "step": "zero_grad+forward(S)+KL+CE+backward+Adam",
+                       "loss_tail": ("nn.mc_mean_loss: mean of the S per-sample cross-entropies evaluated as one call over "
+                                     "the S*B rows (identical value and gradients, tests/test_modules_gpu.py)"
+                                     if args.loss_tail == "batched" else "reference loop: S cross-entropy calls")},
             "e2e": {"value": units / e2e_s, "unit": "samples*MC/s",
                     "h2d_bytes_per_step": x0.numel() * x0.element_size() + y0.numel() * y0.element_size(),
                     "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * e2e_s / args.steps, "last_loss": last_loss},
@@ -421,35 +428,56 @@ def measured_traffic(workload, name):
         return None
 
 
+# per workload: the Bayesian layers as (rows per (batch row, MC sample), N, K, input elements per (row, sample))
+# — the conv layers' K is Cin*kh*kw of the implicit GEMM, their algorithmic input is the un-expanded NCHW tensor
+HOT_LAYERS = {
+    "c2": [(9, 64, 576, 64 * 6 * 6), (1, 10, 576, 576)],
+    "c3": [(16, 128, 1152, 128 * 4 * 4), (1, 10, 128, 128)],
+    "c4": [(1, 4096, 4096, 4096)] * 4,
+}
+
+
 def roofline(workload, B, S, per_kernel, pk):
-    """Dominant hot-path kernel = the libbnn_b200 CONTRACTION entry point with the largest time share of the step
-    (the path's bound is the tensor pipe; the bandwidth-bound helpers are listed in hot_path.kernels_ms_per_step)."""
+    """Dominant hot-path kernel = the libbnn_b200 CONTRACTION entry point with the largest time share of the step.
+    Its roof follows from its arithmetic intensity: algorithmic flops / algorithmic bytes (operands read once, results
+    written once, fp32) against the ridge point peak_tensor / peak_hbm — the narrow layers of C2/C3 (N = 64 / 128 / 10)
+    sit on the bandwidth side, the 4096-wide layers of C4 on the tensor side.  Both fractions are reported."""
     if not per_kernel:
         return None
     gemms = {k: v for k, v in per_kernel.items() if k.startswith("bnn_sampled_gemm")}
     name = max(gemms or per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
-    contractions = {"bnn_sampled_gemm_fwd": 1, "bnn_sampled_gemm_dgrad": 1, "bnn_sampled_gemm_wgrad": 1}
     k = per_kernel[name]
-    if name in contractions:
-        # flops of ALL launches of this entry point per step / their summed duration
-        if workload == "c2":
-            per_row = 2 * 9 * 64 * 576 + 2 * 10 * 576
-        elif workload == "c3":
-            per_row = 2 * 16 * 128 * 1152 + 2 * 10 * 128
-        else:
-            per_row = (3 if name == "bnn_sampled_gemm_dgrad" else 4) * 2 * 4096 * 4096
-        flops = B * S * per_row
-        achieved = flops / (k["ms_per_step"] * 1e-3) / 1e12
-        peak = pk["bf16_sustained"] / 2.0        # TF32 dense = half the bf16 rate on this tensor pipe
-        return {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": measured_traffic(workload, name),
-                "launches_per_step": k["launches_per_step"],
-                "avg_launch_us": 1e3 * k["ms_per_step"] / k["launches_per_step"],
-                "peak_note": "TF32 dense peak taken as half of the measured sustained bf16 cuBLAS rate "
-                             f"({pk['source']}); fp32 mode issues 3 TF32 MMAs per product"}
-    return {"kernel": name, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None,
-            "traffic": None, "launches_per_step": k["launches_per_step"],
+    base = {"kernel": name, "launches_per_step": k["launches_per_step"],
             "avg_launch_us": 1e3 * k["ms_per_step"] / k["launches_per_step"]}
+    if name not in gemms:
+        return dict(base, bound="hbm", achieved=None, peak=pk["hbm"], unit="GB/s", frac=None, traffic=None)
+    layers = HOT_LAYERS[workload]
+    if name == "bnn_sampled_gemm_dgrad" and workload == "c4":
+        layers = layers[1:]                      # the first layer needs no input gradient
+    rows = B * S
+    flops = sum(2 * r * n * kk for r, n, kk, _ in layers) * rows
+    if name == "bnn_sampled_gemm_fwd":           # x, (mu, sigma) -> y (+ bias)
+        nbytes = sum(rows * (x_in + r * n) + 2 * n * kk for r, n, kk, x_in in layers) * 4
+    elif name == "bnn_sampled_gemm_dgrad":       # dy, (mu, sigma) -> dx
+        nbytes = sum(rows * (r * n + x_in) + 2 * n * kk for r, n, kk, x_in in layers) * 4
+    else:                                        # dy, x, rho -> dmu, drho
+        nbytes = sum(rows * (r * n + x_in) + 3 * n * kk for r, n, kk, x_in in layers) * 4
+    seconds = k["ms_per_step"] * 1e-3
+    tensor_peak = pk["bf16_sustained"] / 2.0      # TF32 dense = half the bf16 rate on this tensor pipe
+    tflops, gbs = flops / seconds / 1e12, nbytes / seconds / 1e9
+    intensity, ridge = flops / nbytes, tensor_peak * 1e12 / (pk["hbm"] * 1e9)
+    out = dict(base, arithmetic_intensity=intensity, ridge_point=ridge,
+               tensor={"achieved": tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tflops / tensor_peak},
+               hbm={"achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]},
+               traffic=measured_traffic(workload, name), algorithmic_bytes_per_step=nbytes,
+               algorithmic_flops_per_step=flops,
+               peak_note="TF32 dense peak taken as half of the measured sustained bf16 cuBLAS rate "
+                         f"({pk['source']}); fp32 mode issues 3 TF32 MMAs per product; timed eagerly with CUDA events "
+                         "around the C-ABI call (includes its launch latency)")
+    side = "tensor" if intensity >= ridge else "hbm"
+    out.update(bound=side, achieved=out[side]["achieved"], peak=out[side]["peak"], unit=out[side]["unit"],
+               frac=out[side]["frac"])
+    return out
 
 
 def bench_kl_prune(device, pk, pairs=1 << 28, world=1):
@@ -630,6 +658,8 @@ def main():
                     help="hot-path contraction mode: tf32 (2e-3 parity class) or fp32 = 3xTF32 split (1e-5 class)")
     ap.add_argument("--parallel", default="data", choices=["data", "sample"],
                     help="N > 1: shard the batch (weak scaling, default) or the MC samples of one batch (strong scaling)")
+    ap.add_argument("--loss-tail", default="batched", choices=["batched", "loop"],
+                    help="likelihood term: nn.mc_mean_loss (one CE over the S*B rows) or the reference's per-sample loop")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the kl_prune and cpu_baseline legs (profiling runs)")
     args = ap.parse_args()

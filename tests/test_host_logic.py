@@ -211,3 +211,33 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
                                     ctypes.byref(rng), None, 0, null) == 6                          # BNN_ERR_UNSUPPORTED
     geom = _C.bnn_conv2d_geom(1, 4, 8, 8, 2, 4, 3, 3, 6, 6, 1, 1, 0, 0, 1, 1)                       # c0 + Cg > C
     assert lib.bnn_im2col(one, one, ctypes.byref(geom), null) == 1 and "geometry" in msg()
+
+
+def test_mc_mean_loss_host_logic():
+    """nn.mc_mean_loss == the reference loop body torch.stack([criterion(p, y) for p in preds]).mean()
+    (examples/MNIST/train.py:59-61): one call over the batched rows when the list is an MCSamples of row blocks and
+    the criterion is a row mean, the loop otherwise."""
+    import torch.nn.functional as F
+    from bayesianneuralnetworks_b200.nn import MCSamples, mc_mean_loss
+    torch.manual_seed(0)
+    S, B, C = 5, 7, 4
+    base = torch.randn(S * B, C, requires_grad=True)
+    y = torch.randint(0, C, (B,))
+    preds = MCSamples(base.view(S, B, C).unbind(0))
+    preds.batched = base
+    assert isinstance(preds, list) and len(preds) == S
+    w = torch.tensor([0.5, 1.0, 2.0, 1.5])
+    for crit in (F.cross_entropy, torch.nn.CrossEntropyLoss(), torch.nn.CrossEntropyLoss(weight=w, label_smoothing=0.1),
+                 torch.nn.CrossEntropyLoss(reduction='sum'), lambda p, t: F.cross_entropy(p, t) * 2):
+        ref = torch.stack([crit(p, y) for p in preds]).mean()
+        got = mc_mean_loss(crit, preds, y)
+        assert torch.allclose(got, ref, rtol=1e-6, atol=1e-7)
+        g_ref, = torch.autograd.grad(ref, base, retain_graph=True)
+        g_got, = torch.autograd.grad(got, base)
+        assert torch.allclose(g_got, g_ref, rtol=1e-5, atol=1e-8)
+    # regression criterion with a [B, C] target, a plain list (no batched tensor), and the bare tensor of S == 1
+    t2 = torch.randn(B, C)
+    assert torch.allclose(mc_mean_loss(F.mse_loss, preds, t2), torch.stack([F.mse_loss(p, t2) for p in preds]).mean())
+    plain = [p.detach() for p in preds]
+    assert torch.allclose(mc_mean_loss(F.cross_entropy, plain, y), torch.stack([F.cross_entropy(p, y) for p in plain]).mean())
+    assert torch.equal(mc_mean_loss(F.cross_entropy, plain[0], y), F.cross_entropy(plain[0], y))

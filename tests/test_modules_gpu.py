@@ -518,6 +518,34 @@ def _example_bcnn(samples):
     return Net(seq, samples)
 
 
+def test_mc_mean_loss_equals_the_reference_loop_body():
+    """the batched likelihood term (one criterion call over the S*B rows of the batched Monte-Carlo
+    forward) gives the loss and every gradient of torch.stack([CE(p, y) for p in preds]).mean() (train.py:59-61)."""
+    bnn.set_precision("fp32")
+    torch.manual_seed(0)
+    model = _example_bcnn(6).cuda()
+    bnn.nn.register_rowwise_module(_ExampleFlatten)
+    x = torch.rand(32, 1, 28, 28, device="cuda")
+    y = torch.arange(32, device="cuda") % 10
+    grads = []
+    for form in ("loop", "batched"):
+        for m in model.modules():                              # identical eps streams for both forms: rewind the draws
+            if isinstance(m, bnn.nn.WeightNormal):
+                m._draw = 0
+        model.zero_grad()
+        preds = model(x)
+        assert isinstance(preds, list) and len(preds) == 6 and preds.batched.shape[0] == 6 * 32
+        if form == "loop":
+            loss = torch.stack([F.cross_entropy(p, y) for p in preds]).mean()
+        else:
+            loss = bnn.nn.mc_mean_loss(F.cross_entropy, preds, y)
+        loss.backward()
+        grads.append((float(loss), [p.grad.clone() for p in model.parameters()]))
+    assert grads[0][0] == pytest.approx(grads[1][0], rel=1e-6)
+    for a, b in zip(grads[0][1], grads[1][1]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-7)
+
+
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
 def test_example_training_loop_learns_and_prunes(prec):
     """The body of examples/MNIST/train.py:53-65 and examples/MNIST/prune.py:47-50 on synthetic, separable data:
