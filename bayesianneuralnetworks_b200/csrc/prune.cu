@@ -161,9 +161,57 @@ __device__ __forceinline__ void warp_find_bin(const uint32_t* hist, bool descend
 
 // key2 = (key + log sqrt(2 pi)) * log2(e): the domain of the certified intervals and of the grid
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kHalfLog2Pi = 0.9189385332046727f;
 constexpr float kDelta2 = 4e-5f * 1.4426950408889634f;      // absolute part of the key margin, in key2 units
-__device__ __forceinline__ float key2_of(uint32_t ordered) { return (unorder_key(ordered) + kHalfLog2Pi) * kLog2e; }
+
+// Certified interval of one element's key in grid coordinates.  With Q = (mu / sigma)^2 = 2q and L = log2(sigma):
+// key2 = -Q * log2e / 2 - L.  The fast value is within 2e-5 * q + 4e-5 (key units) of the exact fp32 key that torch's
+// op order produces: sigma carries <= ~1.5e-6 relative error (ex2.approx and its argument rounding, the degree-4
+// minimax polynomial of log1p(e)/e on [0, 1/4] — 2.8e-7 in fp32 Horner form —, lg2.approx for e > 1/4), rcp.approx 1 ulp, lg2.approx
+// <= 2^-22 relative (8e-6 at sigma = 1e-10); the exact key itself rounds within a few ulp.  So
+//   y_minus = ((-Q * 0.50001 * log2e - L) - delta - g_lo) * scale  <=  y(exact key)  <=
+//   y_plus  = ((-Q * 0.49999 * log2e - L) + delta - g_lo) * scale
+// Both sweeps call THIS function: only explicitly rounded operations and MUFU instructions, so the two sweeps compute
+// bit-identical intervals (the histograms of sweep 1 predict sweep 2 exactly).  Every step is monotone, NaN stays NaN
+// (such elements are always deferred).  3 MUFU + 15 FP32 operations per element when every rho <= ln(1/4).
+struct Grid { float sA, sB, nscale, offs_minus, offs_plus; };
+__device__ __forceinline__ Grid make_grid(const PruneState* st) {
+  Grid g;
+  const float scale = st->scale;
+  g.sA = __fmul_rn(-0.50001f * kLog2e, scale);
+  g.sB = __fmul_rn(-0.49999f * kLog2e, scale);
+  g.nscale = -scale;
+  g.offs_minus = st->offs_minus;
+  g.offs_plus = st->offs_plus;
+  return g;
+}
+template <bool kAnyRho>
+__device__ __forceinline__ void key_interval(float mu, float rho, const Grid& g, float& y_minus, float& y_plus) {
+  const float e = ex2_ftz(__fmul_rn(rho, kLog2e));       // flushed to 0 below rho ~ -87: sigma = 1e-10, as in fp32 torch
+  float p = __fmaf_rn(e, 0.1237151250243187f, -0.23501642048358917f);
+  p = __fmaf_rn(e, p, 0.3320590555667877f);
+  p = __fmaf_rn(e, p, -0.4999610483646393f);
+  p = __fmaf_rn(e, p, 0.9999998211860657f);
+  float sigma = __fmaf_rn(e, p, 1e-10f);                 // >= 1e-10: normal range for rcp / lg2
+  if (kAnyRho) {
+    // e > 1/4: ln2 * lg2(1 + e); rho > 15: softplus = rho + exp(-rho) to 1e-13 (torch returns rho itself above 20)
+    const float big = __fmaf_rn(lg2_ftz(__fadd_rn(1.0f, e)), 0.6931471805599453f, 1e-10f);
+    const float huge = __fadd_rn(rho, ex2_ftz(__fmul_rn(rho, -kLog2e)));
+    sigma = rho > 15.0f ? huge : (e > 0.25f ? big : sigma);
+  }
+  const float t = __fmul_rn(mu, rcp_ftz(sigma));
+  const float Q = __fmul_rn(t, t);
+  const float L = lg2_ftz(sigma);
+  y_minus = __fmaf_rn(Q, g.sA, __fmaf_rn(L, g.nscale, g.offs_minus));
+  y_plus = __fmaf_rn(Q, g.sB, __fmaf_rn(L, g.nscale, g.offs_plus));
+}
+
+// The sample only PROPOSES the grid (sweep 1 and the bracket step prove or reject it), so its keys are the fast ones.
+__device__ __forceinline__ float key2_fast(float mu, float rho) {
+  const Grid g = {-0.5f * kLog2e, -0.5f * kLog2e, -1.0f, 0.0f, 0.0f};
+  float lo, hi;
+  key_interval<true>(mu, rho, g, lo, hi);
+  return lo;
+}
 
 // 1. one block per tensor: bracket of the k-th largest key from a strided sample -> the grid
 __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __grid_constant__ PruneTable tab) {
@@ -195,7 +243,7 @@ __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __g
         rv[u] = __ldg(d.rho + i);
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) s_keys[j0 + u * kResolveThreads + threadIdx.x] = order_key(prune_key(mv[u], rv[u]));
+      for (int u = 0; u < 8; ++u) s_keys[j0 + u * kResolveThreads + threadIdx.x] = order_key(key2_fast(mv[u], rv[u]));
     }
     __syncthreads();
     const double p = static_cast<double>(d.k) / static_cast<double>(d.numel);
@@ -272,7 +320,7 @@ __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __g
       }
       if (r_lo < m) lo = mn + ((bin_b << s0) | (sub_b << s1));
     }
-    const float g_lo = key2_of(lo), g_hi = key2_of(hi);
+    const float g_lo = unorder_key(lo), g_hi = unorder_key(hi);      // the sampled keys are key2 values already
     const float range = fmaxf(g_hi - g_lo, 2e-4f + 1e-5f * fabsf(g_lo));      // never degenerate
     if (g_lo == g_lo && range < INFINITY) {                                   // no NaN / inf among the bracket keys
       st.scale = static_cast<float>(kBins) / range;
@@ -286,48 +334,6 @@ __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __g
     *d.state = st;
     if (st.general) atomicOr(tab.any_general, 1u);
   }
-}
-
-// Certified interval of one element's key in grid coordinates.  With Q = (mu / sigma)^2 = 2q and L = log2(sigma):
-// key2 = -Q * log2e / 2 - L.  The fast value is within 2e-5 * q + 4e-5 (key units) of the exact fp32 key that torch's
-// op order produces: sigma carries <= ~1.5e-6 relative error (ex2.approx and its argument rounding, the degree-4
-// minimax polynomial of log1p(e)/e on [0, 1/4] — 2.8e-7 in fp32 Horner form —, lg2.approx for e > 1/4), rcp.approx 1 ulp, lg2.approx
-// <= 2^-22 relative (8e-6 at sigma = 1e-10); the exact key itself rounds within a few ulp.  So
-//   y_minus = ((-Q * 0.50001 * log2e - L) - delta - g_lo) * scale  <=  y(exact key)  <=
-//   y_plus  = ((-Q * 0.49999 * log2e - L) + delta - g_lo) * scale
-// Both sweeps call THIS function: only explicitly rounded operations and MUFU instructions, so the two sweeps compute
-// bit-identical intervals (the histograms of sweep 1 predict sweep 2 exactly).  Every step is monotone, NaN stays NaN
-// (such elements are always deferred).  3 MUFU + 15 FP32 operations per element when every rho <= ln(1/4).
-struct Grid { float sA, sB, nscale, offs_minus, offs_plus; };
-__device__ __forceinline__ Grid make_grid(const PruneState* st) {
-  Grid g;
-  const float scale = st->scale;
-  g.sA = __fmul_rn(-0.50001f * kLog2e, scale);
-  g.sB = __fmul_rn(-0.49999f * kLog2e, scale);
-  g.nscale = -scale;
-  g.offs_minus = st->offs_minus;
-  g.offs_plus = st->offs_plus;
-  return g;
-}
-template <bool kAnyRho>
-__device__ __forceinline__ void key_interval(float mu, float rho, const Grid& g, float& y_minus, float& y_plus) {
-  const float e = ex2_ftz(__fmul_rn(rho, kLog2e));       // flushed to 0 below rho ~ -87: sigma = 1e-10, as in fp32 torch
-  float p = __fmaf_rn(e, 0.1237151250243187f, -0.23501642048358917f);
-  p = __fmaf_rn(e, p, 0.3320590555667877f);
-  p = __fmaf_rn(e, p, -0.4999610483646393f);
-  p = __fmaf_rn(e, p, 0.9999998211860657f);
-  float sigma = __fmaf_rn(e, p, 1e-10f);                 // >= 1e-10: normal range for rcp / lg2
-  if (kAnyRho) {
-    // e > 1/4: ln2 * lg2(1 + e); rho > 15: softplus = rho + exp(-rho) to 1e-13 (torch returns rho itself above 20)
-    const float big = __fmaf_rn(lg2_ftz(__fadd_rn(1.0f, e)), 0.6931471805599453f, 1e-10f);
-    const float huge = __fadd_rn(rho, ex2_ftz(__fmul_rn(rho, -kLog2e)));
-    sigma = rho > 15.0f ? huge : (e > 0.25f ? big : sigma);
-  }
-  const float t = __fmul_rn(mu, rcp_ftz(sigma));
-  const float Q = __fmul_rn(t, t);
-  const float L = lg2_ftz(sigma);
-  y_minus = __fmaf_rn(Q, g.sA, __fmaf_rn(L, g.nscale, g.offs_minus));
-  y_plus = __fmaf_rn(Q, g.sB, __fmaf_rn(L, g.nscale, g.offs_plus));
 }
 
 // 2. sweep 1 (read only): count the elements certified above the grid, histogram the interval ends of the others.
