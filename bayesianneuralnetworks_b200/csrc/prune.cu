@@ -35,6 +35,7 @@ constexpr int kVecPerThread = 4;
 constexpr int kChunk = kThreads * 4 * kVecPerThread;           // 4096 elements
 constexpr int kMaxTensors = 24;
 constexpr int kBins = 2048;
+constexpr int kHistStride = kBins + 64;                        // a histogram slot: 2049 used entries, 256-byte multiple
 constexpr int kSample = 32768;                                 // sampled keys per tensor (128 KiB of smem)
 constexpr int kSmallTensor = 65536;                            // at or below: every element is deferred to the exact select
 constexpr int kResolveThreads = 1024;
@@ -43,6 +44,7 @@ constexpr int kUnit = 512;                                     // elements one w
 // ordered key: unsigned order == float order (larger float -> larger uint)
 __device__ __forceinline__ uint32_t order_key(float f) {
   const uint32_t u = __float_as_uint(f);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;      // NaN of either sign ranks first, as in torch.topk
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __device__ __forceinline__ float unorder_key(uint32_t o) {
@@ -412,83 +414,97 @@ __global__ void __launch_bounds__(kThreads) prune_bin_kernel(const __grid_consta
       }
     }
     for (int s = 0; s < pos; ++s) {                    // rarely more than two rounds
+      // lower end: index 0 = below the grid (or NaN), index b + 1 = bin b; upper end: index b = bin b, index 2048 =
+      // above the grid (or NaN).  No clamping INTO the grid: an interval that sticks out may hold a key outside it.
       const float2 y = q_lane[s * kThreads];
-      const int bm = __float2int_rd(fminf(fmaxf(y.x, 0.0f), static_cast<float>(kBins - 1)));     // NaN -> 0
-      const int bp = __float2int_rd(fmaxf(fminf(y.y, static_cast<float>(kBins - 1)), 0.0f));     // NaN -> 2047
-      atomicAdd(d.hist + bm, 1u);
-      atomicAdd(d.hist_plus + bp, 1u);
+      const int im = !(y.x >= 0.0f) ? 0 : __float2int_rd(y.x) + 1;                            // y.x < 2048 in the queue
+      const int ip = !(y.y < static_cast<float>(kBins)) ? kBins : __float2int_rd(y.y);        // y.y >= 0 in the queue
+      atomicAdd(d.hist + im, 1u);
+      atomicAdd(d.hist_plus + ip, 1u);
     }
   }
   if (cur >= 0 && active) flush();
 }
 
-// 3. one block per tensor: the bins that provably enclose the k-th key.  With need = k - |above grid|:
-//   j_hi = bin of descending rank need - 1 among the UPPER interval ends: fewer than `need` elements can have a key
-//          in a bin above j_hi, so the k-th key is in a bin <= j_hi;
-//   j_lo = bin of descending rank need - 1 among the LOWER interval ends: at least `need` elements have a key in a bin
-//          >= j_lo, so the k-th key is in a bin >= j_lo.
-// Elements whose lower end is above j_hi are in the top k; elements whose upper end is below j_lo are not; the others
-// (counted exactly from the histograms) are resolved by exact keys in the finish kernel.
+// 3. one block per tensor: the bins that provably enclose the k-th key.  Bins are numbered -1 (below the grid),
+// 0 .. 2047, 2048 (above the grid); every element has a lower-end bin bm <= bin(exact key) <= bp, its upper-end bin
+// (elements counted as "above" in sweep 1: bm = bp = 2048; the uncounted rest below the grid: bm = bp = -1; NaN
+// intervals: bm = -1, bp = 2048).  With need = k - |above|:
+//   j_hi = smallest j with |{binned: bp > j}| < need: fewer than k elements can have a key in a bin above j_hi, so the
+//          k-th key is in a bin <= j_hi (j_hi = 2048 when even the grid's top cannot be excluded);
+//   j_lo = largest j with |{binned: bm >= j}| >= need: at least k elements have a key in a bin >= j_lo, so the k-th key
+//          is in a bin >= j_lo (j_lo = -1 when the grid's bottom cannot be excluded).
+// Elements with bm > j_hi are in the top k, elements with bp < j_lo are not; the others (counted exactly from the
+// histograms) are resolved by exact keys in the finish kernel.
 __global__ void __launch_bounds__(kThreads) prune_bracket_kernel(const __grid_constant__ PruneTable tab) {
-  __shared__ uint32_t s_minus[kBins], s_plus[kBins];
-  __shared__ uint32_t s_out[4];
-  __shared__ unsigned long long s_cnt[3];
+  __shared__ uint32_t s_minus[kHistStride], s_plus[kHistStride];     // index conventions of the bin kernel
+  __shared__ uint32_t s_out[2];
+  __shared__ unsigned long long s_cnt[4];
   const PruneDesc& d = tab.t[blockIdx.x];
-  for (int b = threadIdx.x; b < kBins; b += blockDim.x) {
+  for (int b = threadIdx.x; b < kHistStride; b += blockDim.x) {
     s_minus[b] = d.hist[b];
     s_plus[b] = d.hist_plus[b];
     d.hist[b] = 0;                                   // clean for the general path / the next call
     d.hist_plus[b] = 0;
   }
-  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0ull;
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
   __syncthreads();
   PruneState st = *d.state;
   if (st.general || st.defer_all || d.k <= 0 || d.k >= d.numel) return;
-  // total of the binned elements
-  unsigned long long part = 0;
-  for (int b = threadIdx.x; b < kBins; b += blockDim.x) part += s_plus[b];
+  // totals: all binned elements, and those whose lower end is inside the grid (bm >= 0)
+  unsigned long long part = 0, part_in = 0;
+  for (int b = threadIdx.x; b <= kBins; b += blockDim.x) {
+    part += s_plus[b];
+    if (b >= 1) part_in += s_minus[b];
+  }
   part = warp_sum(part);
-  if ((threadIdx.x & 31) == 0 && part) atomicAdd(&s_cnt[0], part);
+  part_in = warp_sum(part_in);
+  if ((threadIdx.x & 31) == 0) {
+    if (part) atomicAdd(&s_cnt[0], part);
+    if (part_in) atomicAdd(&s_cnt[1], part_in);
+  }
   __syncthreads();
-  const uint64_t k = static_cast<uint64_t>(d.k), n_binned = s_cnt[0];
-  const bool ok = st.count_above < k && k <= st.count_above + n_binned;
+  const uint64_t k = static_cast<uint64_t>(d.k), n_binned = s_cnt[0], n_lower_in = s_cnt[1];
+  const uint64_t n_above = st.count_above, n_below = static_cast<uint64_t>(d.numel) - n_above - n_binned;
+  bool ok = n_above < k && k <= n_above + n_binned;
   if (ok) {
-    const uint64_t need = k - st.count_above;
+    const uint64_t need = k - n_above;
+    const uint64_t top_out = s_plus[kBins];                        // upper end above the grid
     if (threadIdx.x < 32) {
-      uint32_t j_hi, j_lo;
+      uint32_t j_hi = kBins, j_lo = 0;
       uint64_t before;
-      warp_find_bin(s_plus, true, need - 1, &j_hi, &before);
-      warp_find_bin(s_minus, true, need - 1, &j_lo, &before);
+      if (top_out < need) warp_find_bin(s_plus, true, need - 1 - top_out, &j_hi, &before);       // bins 0 .. 2047
+      if (n_lower_in >= need) warp_find_bin(s_minus + 1, true, need - 1, &j_lo, &before);        // bins 0 .. 2047
       if (threadIdx.x == 0) { s_out[0] = j_hi; s_out[1] = j_lo; }
     }
     __syncthreads();
-    const int j_hi = static_cast<int>(s_out[0]), j_lo = static_cast<int>(s_out[1]);
-    // |lower end > j_hi| and |upper end >= j_lo|
+    const int j_hi = static_cast<int>(s_out[0]);                          // 2048: the grid's top is not excluded
+    const int j_lo = n_lower_in >= need ? static_cast<int>(s_out[1]) : -1;
+    // |binned: bm > j_hi| (lower-end index >= j_hi + 2) and |binned: bp >= j_lo|
     unsigned long long a = 0, c = 0;
-    for (int b = threadIdx.x; b < kBins; b += blockDim.x) {
-      if (b > j_hi) a += s_minus[b];
+    for (int b = threadIdx.x; b <= kBins; b += blockDim.x) {
+      if (b >= j_hi + 2) a += s_minus[b];
       if (b >= j_lo) c += s_plus[b];
     }
     a = warp_sum(a);
     c = warp_sum(c);
     if ((threadIdx.x & 31) == 0) {
-      if (a) atomicAdd(&s_cnt[1], a);
-      if (c) atomicAdd(&s_cnt[2], c);
+      if (a) atomicAdd(&s_cnt[2], a);
+      if (c) atomicAdd(&s_cnt[3], c);
     }
     __syncthreads();
-    const uint64_t above_all = st.count_above + s_cnt[1];      // pruned by sweep 2 without an exact key
-    const uint64_t deferred = s_cnt[2] - s_cnt[1];
-    if (j_lo <= j_hi && above_all < k && deferred <= d.defer_cap && k - above_all <= deferred) {
-      st.a_thr = static_cast<float>(j_hi + 1);
-      st.b_thr = static_cast<float>(j_lo);
-      st.n_take = static_cast<uint32_t>(k - above_all);
+    const bool top_open = j_hi >= kBins, bottom_open = j_lo < 0;
+    const uint64_t certain = top_open ? 0 : n_above + s_cnt[2];            // pruned by sweep 2 without an exact key
+    const uint64_t deferred = s_cnt[3] - s_cnt[2] + (top_open ? n_above : 0) + (bottom_open ? n_below : 0);
+    ok = j_lo <= j_hi && certain < k && deferred <= d.defer_cap && k - certain <= deferred;
+    if (ok) {
+      st.a_thr = top_open ? INFINITY : static_cast<float>(j_hi + 1);
+      st.b_thr = bottom_open ? -INFINITY : static_cast<float>(j_lo);
+      st.n_take = static_cast<uint32_t>(k - certain);
       st.expect_deferred = static_cast<uint32_t>(deferred);
-    } else {
-      st.general = 1u;
     }
-  } else {
-    st.general = 1u;
   }
+  if (!ok) st.general = 1u;
   if (threadIdx.x == 0) {
     *d.state = st;
     if (st.general) atomicOr(tab.any_general, 1u);
@@ -988,7 +1004,7 @@ __global__ void __launch_bounds__(kThreads) prune_apply_kernel(const __grid_cons
 // region and the chunk counts.  The keys region holds the ordered keys of the general path (4 B/element) or, on the
 // sampled path, the deferred list ([index | mu | rho] x defer_cap) followed by (key, index) pairs x defer_cap.
 constexpr size_t kStateBytes = 256;                            // PruneState, padded
-constexpr size_t kSmallBytes = kStateBytes + 2 * kBins * 4;    // state + histograms of one tensor
+constexpr size_t kSmallBytes = kStateBytes + 2 * kHistStride * 4;    // state + histograms of one tensor
 static_assert(sizeof(PruneState) <= kStateBytes, "PruneState outgrew its slot");
 
 uint32_t defer_cap_for(int64_t numel) {
@@ -1074,7 +1090,7 @@ int bnn_prune(const bnn_prune_tensor* tensors, int32_t n_tensors, void* workspac
       d.numel = t.numel; d.k = t.k; d.chunk_begin = chunks; d.n_chunks = nch;
       d.state = reinterpret_cast<PruneState*>(mine);
       d.hist = reinterpret_cast<uint32_t*>(mine + kStateBytes);
-      d.hist_plus = d.hist + kBins;
+      d.hist_plus = d.hist + kHistStride;
       d.keys = reinterpret_cast<uint32_t*>(ws); ws += keys_bytes(t.numel);
       d.defer_cap = defer_cap_for(t.numel);
       d.chunk_cnt = reinterpret_cast<int64_t*>(ws); ws += align_up(static_cast<size_t>(nch) * 8, 256);

@@ -286,6 +286,7 @@ def run_b200(args):
         if S % world != 0:
             raise SystemExit(f"{S} MC samples do not split over {world} ranks")
         bnn.set_sample_partition(rank, world)
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     trainer = Trainer(args.workload, device, world, S, graph=not args.no_graph, loss_tail=args.loss_tail)
     gen = torch.Generator().manual_seed(1 if sample_parallel else 1 + rank)
     n_host = 8
@@ -389,7 +390,7 @@ def run_b200(args):
                        "global_batch": B if sample_parallel else B * world,
                        "parallelism": (f"sp{world} (MC samples sharded, {S // world} per GPU)" if sample_parallel
                                        else f"dp{world}") if world > 1 else "single", "n_batches": N_BATCHES,
-                       "optimizer": "Adam (torch fused)", "launch": graph_note, "l2": "flushed between steps (256 MiB write, untimed); each step "
+                       "optimizer": "Adam (torch fused)", "cudnn_benchmark": not args.no_cudnn_benchmark, "launch": graph_note, "l2": "flushed between steps (256 MiB write, untimed); each step "
                        "timed with its own CUDA event pair", "step": "zero_grad+forward(S)+KL+CE+backward+Adam",
                        "loss_tail": ("nn.mc_mean_loss: mean of the S per-sample cross-entropies evaluated as one call over "
                                      "the S*B rows (identical value and gradients, tests/test_modules_gpu.py)"
@@ -666,6 +667,9 @@ def main():
                     help="N > 1: shard the batch (weak scaling, default) or the MC samples of one batch (strong scaling)")
     ap.add_argument("--loss-tail", default="batched", choices=["batched", "loop"],
                     help="likelihood term: nn.mc_mean_loss (one CE over the S*B rows) or the reference's per-sample loop")
+    ap.add_argument("--no-cudnn-benchmark", action="store_true",
+                    help="leave torch.backends.cudnn.benchmark off for the deterministic torch trunk (the examples' setting; "
+                         "the default run lets cuDNN pick its kernels by measurement, 0.73 -> 0.69 ms per C2 step)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the kl_prune and cpu_baseline legs (profiling runs)")
     args = ap.parse_args()

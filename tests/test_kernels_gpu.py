@@ -217,7 +217,8 @@ def test_prune_sampled_path_equals_general_path(C, numel, p):
     assert torch.equal(outs[0][0][~ref].cpu(), mu[~ref.cpu()])
 
 
-@pytest.mark.parametrize("kind", ["wide_rho", "pruned_mix", "strided_structure", "outliers", "nonfinite_free_extremes"])
+@pytest.mark.parametrize("kind", ["wide_rho", "pruned_mix", "strided_structure", "outliers", "nonfinite_free_extremes",
+                                  "nan_entries"])
 def test_prune_sampled_path_hard_distributions(C, kind):
     """Inputs that stress the certified-interval arithmetic of the sampled path (every softplus regime, rho above
     torch's threshold of 20, keys of very different magnitude, already pruned entries) or defeat its strided sample
@@ -242,9 +243,11 @@ def test_prune_sampled_path_hard_distributions(C, kind):
         rho[::3] = 25.0
         rho[1::3] = -100.0
         mu[1::3] *= 1e-8
+    elif kind == "nan_entries":                                          # NaN keys rank first, as in torch.topk / sort
+        mu[torch.randperm(n, generator=g)[:37]] = float("nan")
     keys = torch_keys_same_device(mu.cuda(), rho.cuda())
-    assert bool(torch.isfinite(keys).all())
-    for k in (1, n // 100, n // 3, int(0.7 * n), n - n // 50, n - 1):
+    assert kind == "nan_entries" or bool(torch.isfinite(keys).all())
+    for k in (1, 20, n // 100, n // 3, int(0.7 * n), n - n // 50, n - 1):
         dmu, drho = mu.cuda(), rho.cuda()
         mask = torch.empty(n, dtype=torch.uint8, device="cuda")
         C.prune([(dmu, drho, k, mask, None)])
@@ -252,7 +255,11 @@ def test_prune_sampled_path_hard_distributions(C, kind):
         assert int(mask.sum()) == k, (kind, k)
         assert torch.equal(mask.bool(), ref), (kind, k)
         assert bool((dmu[ref] == 0).all()) and bool((drho[ref] == -30).all())
-        assert torch.equal(dmu[~ref].cpu(), mu[~ref.cpu()]) and torch.equal(drho[~ref].cpu(), rho[~ref.cpu()])
+        keep = ~ref.cpu()
+        assert torch.equal(dmu.cpu()[keep], mu[keep], ) or kind == "nan_entries"
+        assert torch.equal(drho.cpu()[keep], rho[keep])
+        if kind == "nan_entries":                                         # NaN != NaN: compare the bit patterns
+            assert torch.equal(dmu.cpu()[keep].view(torch.int32), mu[keep].view(torch.int32))
 
 
 @pytest.mark.parametrize("classes", [1, 2, 3])
