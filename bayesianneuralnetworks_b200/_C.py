@@ -87,6 +87,8 @@ _SIGNATURES = {
     "bnn_prune_workspace_size": (ctypes.c_size_t, [ctypes.POINTER(bnn_prune_tensor), ctypes.c_int32]),
     "bnn_prune": (ctypes.c_int, [ctypes.POINTER(bnn_prune_tensor), ctypes.c_int32, ctypes.c_void_p,
                                  ctypes.c_size_t, ctypes.c_void_p]),
+    "bnn_selftest_prune_interval": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_int32,
+                                                   ctypes.c_void_p]),
     "bnn_selftest_umma": (ctypes.c_int, [_c_f32p, ctypes.c_void_p]),
     "bnn_selftest_umma_mn": (ctypes.c_int, [_c_f32p, ctypes.c_void_p]),
 }
@@ -368,6 +370,17 @@ def prune(entries, flags=0):
     with torch.cuda.device(device):
         _call("bnn_prune", table, n, ctypes.c_void_p(base), nbytes, _stream())
     _count(14 * ((n + 23) // 24))
+
+
+def selftest_prune_interval(mu, rho, variant=1):
+    """(lo, hi): the certified key2 interval bnn_prune uses for every element (see include/bnn_b200.h)."""
+    require_cuda(mu, rho)
+    _f32c(mu, "mu"), _f32c(rho, "rho")
+    lo, hi = torch.empty_like(mu), torch.empty_like(mu)
+    with torch.cuda.device(mu.device):
+        _call("bnn_selftest_prune_interval", _ptr(mu), _ptr(rho), mu.numel(), _ptr(lo), _ptr(hi), int(variant), _stream())
+    _count()
+    return lo, hi
 
 
 def selftest_umma(device="cuda", mn_major=False):

@@ -338,6 +338,19 @@ __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __g
   }
 }
 
+// self test: the interval on the identity grid (scale 1, origin 0), i.e. in key2 units
+template <bool kAnyRho>
+__global__ void prune_interval_selftest_kernel(const float* mu, const float* rho, int64_t n, float* lo_out, float* hi_out) {
+  const Grid g = {-0.50001f * kLog2e, -0.49999f * kLog2e, -1.0f, -kDelta2, kDelta2};
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float a, b;
+    key_interval<kAnyRho>(mu[i], rho[i], g, a, b);
+    lo_out[i] = a;
+    hi_out[i] = b;
+  }
+}
+
 // 2. sweep 1 (read only): count the elements certified above the grid, histogram the interval ends of the others.
 // Warps are independent (a warp owns one 512-element unit per chunk): no block-level synchronisation in the loop.
 __global__ void __launch_bounds__(kThreads) prune_bin_kernel(const __grid_constant__ PruneTable tab) {
@@ -1039,6 +1052,22 @@ size_t bnn_prune_workspace_size(const bnn_prune_tensor* tensors, int32_t n_tenso
   size_t total = header_bytes(n_tensors) + static_cast<size_t>(n_tensors) * kSmallBytes;
   for (int i = 0; i < n_tensors; ++i) total += prune_ws_one(tensors[i].numel > 0 ? tensors[i].numel : 0);
   return total;
+}
+
+int bnn_selftest_prune_interval(const float* mu, const float* rho, int64_t numel, float* lo_out, float* hi_out,
+                                int32_t variant, void* stream) {
+  BNN_REQUIRE(numel >= 0 && (variant == 0 || variant == 1), BNN_ERR_BAD_ARGUMENT,
+              "bnn_selftest_prune_interval: numel >= 0 and variant in {0, 1}");
+  if (numel == 0) return BNN_OK;
+  BNN_REQUIRE(mu && rho && lo_out && hi_out, BNN_ERR_BAD_ARGUMENT, "bnn_selftest_prune_interval: NULL pointer");
+  int rc = check_device();
+  if (rc != BNN_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = static_cast<int>((numel + 255) / 256 < sm_count() * 8 ? (numel + 255) / 256 : sm_count() * 8);
+  if (variant == 0) prune_interval_selftest_kernel<false><<<grid, 256, 0, st>>>(mu, rho, numel, lo_out, hi_out);
+  else prune_interval_selftest_kernel<true><<<grid, 256, 0, st>>>(mu, rho, numel, lo_out, hi_out);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
 }
 
 int bnn_prune(const bnn_prune_tensor* tensors, int32_t n_tensors, void* workspace,

@@ -207,6 +207,13 @@ size_t bnn_prune_workspace_size(const bnn_prune_tensor* tensors, int32_t n_tenso
 int bnn_prune(const bnn_prune_tensor* tensors /* HOST array */, int32_t n_tensors,
               void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- self test of the prune path's certified key intervals: for every element writes the interval [lo, hi] that the
+ * two sweeps of bnn_prune use to classify it, in "key2" units: key2 = (log N(0; mu, sigma) + log sqrt(2 pi)) * log2(e).
+ * The exact fp32 key that torch computes (prune.py:11) must lie inside.  variant 0: the fast path taken when every
+ * rho of a 4-element group is <= ln(1/4) (only valid for such rho); variant 1: the path for any rho. */
+int bnn_selftest_prune_interval(const float* mu, const float* rho, int64_t numel, float* lo_out, float* hi_out,
+                                int32_t variant, void* stream);
+
 /* ---- self test of the tcgen05 path (one 128xNx32 TF32 tile against a serial fp32 loop run by
  * the same kernel's thread 0); returns BNN_OK and writes max |err| to *max_err_dev. */
 int bnn_selftest_umma(float* max_err_dev, void* stream);

@@ -217,6 +217,44 @@ def test_prune_sampled_path_equals_general_path(C, numel, p):
     assert torch.equal(outs[0][0][~ref].cpu(), mu[~ref.cpu()])
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_prune_certified_intervals_contain_the_exact_key(C, variant):
+    """The rigor of the sampled prune path rests on one claim: the fast-math interval [lo, hi] of an element contains
+    the exact fp32 key that torch's op order produces (prune.py:11 -> Normal.log_prob(0)).  Checked directly on 2^22
+    random elements per regime: every softplus regime of rho (variant 0 is the branch taken for rho <= ln(1/4) only),
+    |mu| over 12 decades, pruned entries, and values placed next to the regime switches."""
+    g = torch.Generator().manual_seed(77)
+    n = 1 << 22
+    regimes = []
+    if variant == 0:
+        regimes.append(torch.rand(n, generator=g) * 98.6 - 100.0)            # -100 .. ln(1/4)
+        regimes.append(torch.randn(n, generator=g) * 0.15 - 2.0)             # the reference initialisation
+        regimes.append(torch.full((n,), -1.3862944))
+    else:
+        regimes.append(torch.rand(n, generator=g) * 140.0 - 100.0)           # -100 .. 40
+        regimes.append(torch.rand(n, generator=g) * 4.0 - 2.5)               # around e = 1/4
+        regimes.append(torch.rand(n, generator=g) * 12.0 + 12.0)             # around rho = 15 and torch's threshold 20
+        regimes.append(torch.randn(n, generator=g) * 0.15 - 2.0)
+    worst = 0.0
+    for rho in regimes:
+        mu = torch.randn(n, generator=g) * torch.pow(10.0, torch.rand(n, generator=g) * 12 - 9)
+        mu[::7] = 0.0
+        dmu, drho = mu.cuda(), rho.cuda()
+        lo, hi = C.selftest_prune_interval(dmu, drho, variant)
+        key = torch_keys_same_device(dmu, drho)                              # fp32, torch's op order, same device
+        key2 = (key.double() + 0.9189385332046727) * 1.4426950408889634
+        finite = torch.isfinite(key2)
+        assert bool(finite.float().mean() > 0.9)
+        lo, hi = lo.double(), hi.double()
+        assert bool((lo[finite] <= key2[finite]).all()), "exact key below its certified interval"
+        assert bool((key2[finite] <= hi[finite]).all()), "exact key above its certified interval"
+        assert bool((lo[finite] <= hi[finite]).all())
+        # the margins are not loose either: width within 2 * (1.5e-5 * q + 5e-5) * log2(e) of the key magnitude scale
+        q2 = (key2[finite] - lo[finite]).clamp_min(0) + (hi[finite] - key2[finite]).clamp_min(0)
+        worst = max(worst, float((q2 / (1e-4 + 3e-5 * key2[finite].abs() + 3e-5 * (torch.log2(1e-10 + F.softplus(drho[finite].double())).abs()))).max()))
+    assert worst < 4.0, worst
+
+
 @pytest.mark.parametrize("kind", ["wide_rho", "pruned_mix", "strided_structure", "outliers", "nonfinite_free_extremes",
                                   "nan_entries"])
 def test_prune_sampled_path_hard_distributions(C, kind):
