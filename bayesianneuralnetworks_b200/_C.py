@@ -369,7 +369,7 @@ def prune(entries, flags=0):
     base = (ws.data_ptr() + 255) & ~255
     with torch.cuda.device(device):
         _call("bnn_prune", table, n, ctypes.c_void_p(base), nbytes, _stream())
-    _count(14 * ((n + 23) // 24))
+    _count(15 * ((n + 23) // 24))
 
 
 def selftest_prune_interval(mu, rho, variant=1):

@@ -7,8 +7,8 @@
 //  * sampled path (default; two reads of (mu, rho), one write, no key workspace traffic).  Every element gets a cheap
 //    CERTIFIED INTERVAL for its key (fast math + a rigorous error margin), expressed in grid coordinates y: a 2048-bin
 //    grid laid over a bracket of the k-th key.
-//      1. sample    exact keys of <= 32768 strided elements -> two order statistics that bracket the k-th key with
-//                   ~6 sigma of the sampling distribution -> the grid
+//      1. sample    fast keys of 32768 strided elements (gathered by a machine-wide kernel) -> two order statistics
+//                   that bracket the k-th key with ~6 sigma of the sampling distribution -> the grid
 //      2. bin       sweep 1 (read only): elements whose interval lies above / below the grid are counted, the others
 //                   (~3 %) enter two histograms: bin of the interval's lower end, bin of its upper end
 //      3. bracket   from the two histograms: bins j_lo <= j_hi that PROVABLY enclose the k-th key, the exact number of
@@ -215,7 +215,27 @@ __device__ __forceinline__ float key2_fast(float mu, float rho) {
   return lo;
 }
 
-// 1. one block per tensor: bracket of the k-th largest key from a strided sample -> the grid
+// 1a. the sample: kSample strided elements per tensor, spread over the whole machine (one SM cannot keep enough of
+// these scattered sector reads in flight), ordered fast keys into the tensor's (still unused) keys region
+static_assert((kSample & (kSample - 1)) == 0, "kSample must be a power of two");
+__global__ void __launch_bounds__(kResolveThreads) prune_sample_keys_kernel(const __grid_constant__ PruneTable tab) {
+  const PruneDesc& d = tab.t[blockIdx.y];
+  if (d.k <= 0 || d.k >= d.numel || d.force_general || d.numel >= (int64_t(1) << 32) || d.numel <= kSmallTensor) return;
+  constexpr int kPer = 4;
+  float mv[kPer], rv[kPer];
+  const int j0 = blockIdx.x * (kPer * kResolveThreads) + threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < kPer; ++u) {
+    const uint64_t j = static_cast<uint64_t>(j0 + u * kResolveThreads);
+    const int64_t i = static_cast<int64_t>((j * static_cast<uint64_t>(d.numel)) / kSample);      // a shift; numel < 2^32
+    mv[u] = __ldg(d.mu + i);
+    rv[u] = __ldg(d.rho + i);
+  }
+#pragma unroll
+  for (int u = 0; u < kPer; ++u) d.keys[j0 + u * kResolveThreads] = order_key(key2_fast(mv[u], rv[u]));
+}
+
+// 1b. one block per tensor: bracket of the k-th largest key from the sample -> the grid
 __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __grid_constant__ PruneTable tab) {
   extern __shared__ uint32_t s_keys[];          // kSample keys
   __shared__ uint32_t s_hist[kBins], s_hist2[kBins];
@@ -235,18 +255,8 @@ __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __g
   }
   if (!trivial && !st.general && d.numel > kSmallTensor) {
     const int m = kSample;
-    for (int j0 = 0; j0 < m; j0 += 8 * kResolveThreads) {          // 8 independent strided loads in flight
-      float mv[8], rv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int j = j0 + u * kResolveThreads + threadIdx.x;
-        const int64_t i = static_cast<int64_t>((static_cast<uint64_t>(j) * static_cast<uint64_t>(d.numel)) / m);   // numel < 2^32
-        mv[u] = __ldg(d.mu + i);
-        rv[u] = __ldg(d.rho + i);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) s_keys[j0 + u * kResolveThreads + threadIdx.x] = order_key(key2_fast(mv[u], rv[u]));
-    }
+    for (int j = threadIdx.x * 4; j < m; j += 4 * kResolveThreads)       // keys written by prune_sample_keys_kernel
+      *reinterpret_cast<uint4*>(s_keys + j) = *reinterpret_cast<const uint4*>(d.keys + j);
     __syncthreads();
     const double p = static_cast<double>(d.k) / static_cast<double>(d.numel);
     const int r = static_cast<int>(p * m);                              // descending rank of the k-th key
@@ -1132,6 +1142,7 @@ int bnn_prune(const bnn_prune_tensor* tensors, int32_t n_tensors, void* workspac
     tab.total_chunks = chunks;
     const int grid = static_cast<int>(chunks < max_grid ? chunks : max_grid);
     // sampled path
+    prune_sample_keys_kernel<<<dim3(kSample / (4 * kResolveThreads), tab.n), kResolveThreads, 0, st>>>(tab);
     prune_sample_kernel<<<tab.n, kResolveThreads, sample_smem, st>>>(tab);
     prune_bin_kernel<<<grid, kThreads, 0, st>>>(tab);
     prune_bracket_kernel<<<tab.n, kThreads, 0, st>>>(tab);
