@@ -113,6 +113,9 @@ def _conv_out(size, k, s, p, d):
     return (size + 2 * p - d * (k - 1) - 1) // s + 1
 
 
+_KEEP_COL_BYTES = 2 << 30      # im2col matrices up to this size are kept from forward to backward
+
+
 class SampledConv2d(torch.autograd.Function):
     """y[s] = conv2d(x[s], W_s, b_s) for S samples (conv.py:65-73,112-119): im2col lowering of the
     activations per group, then the sampled GEMM writing straight into the NCHW output.
@@ -161,6 +164,10 @@ class SampledConv2d(torch.autograd.Function):
                                 spec_b.rng(g * Ng) if has_bias else None, precision)
         ctx.save_for_backward(x, mu_w_c, rho_w_c, sigma_w, rho_b)
         ctx.meta = (S, shared, spec_w, spec_b, precision, geo)
+        # the weight gradient contracts dY with the same im2col matrix: keep it for the backward pass instead of
+        # lowering x a second time (one launch and one write of the matrix less), unless it is very large
+        keep = groups == 1 and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and col.numel() * 4 <= _KEEP_COL_BYTES
+        ctx.col = col if keep else None
         return y
 
     @staticmethod
@@ -190,7 +197,10 @@ class SampledConv2d(torch.autograd.Function):
         dx = torch.empty_like(x) if need_x else None
         grads = torch.zeros((2,) + tuple(mu_w.shape), device=x.device, dtype=torch.float32) if need_w else None
         bg = torch.zeros((2, Cout), device=x.device, dtype=torch.float32) if need_b else None
-        col = torch.empty((rows * P, Kg), device=x.device, dtype=torch.float32) if need_w else None
+        kept = ctx.col if need_w else None
+        ctx.col = None
+        col = kept if kept is not None else (
+            torch.empty((rows * P, Kg), device=x.device, dtype=torch.float32) if need_w else None)
         dcol = torch.empty((rows * P, Kg), device=x.device, dtype=torch.float32) if need_x else None
         for g in range(groups):
             lo, hi = g * Ng * Kg, (g + 1) * Ng * Kg
@@ -206,7 +216,8 @@ class SampledConv2d(torch.autograd.Function):
                                       precision)
                 _C.col2im(dcol, dx, geom, False)
             if need_w:
-                _C.im2col(x, col, geom)
+                if kept is None:
+                    _C.im2col(x, col, geom)
                 _C.sampled_gemm_wgrad(dy_view, dy_ss, col, Kg, a_stride, rho_w.view(-1)[lo:hi], eps_w,
                                       grads[0].view(-1)[lo:hi], grads[1].view(-1)[lo:hi], M, Ng, Kg, S,
                                       spec_w.sample_begin, spec_w.rng(lo), precision)

@@ -189,9 +189,11 @@ int bnn_kl(const bnn_kl_tensor* tensors /* HOST array */, int32_t n_tensors,
  * unspecified; identical masks whenever the k-th key is unique).
  * All tensors of one call are processed by the same launches.  `mask_out` (optional, uint8
  * [numel]) receives the selection.  `keys_out` (optional) receives the keys.
- * Two exact implementations are chosen per tensor on the device: a sampled two-sweep path (bracket
- * the k-th key from a sample, compact the few candidates, resolve exactly, apply) and the general
- * three-pass radix select over a key workspace, which also catches every case the first declines. */
+ * Two exact implementations are chosen per tensor on the device: a sampled two-sweep path (a grid
+ * around the k-th key from a sample; sweep 1 histograms a certified interval of every key and proves
+ * which bins hold the k-th key; sweep 2 prunes what is certainly above, defers the ~1000 elements that
+ * overlap and resolves those by their exact keys) and the general three-pass radix select over a key
+ * workspace, which also catches every case the first declines.  NaN keys rank first, as in torch.topk. */
 #define BNN_PRUNE_GENERAL 1u   /* flags: force the general radix-select path (tests; implied by keys_out) */
 typedef struct bnn_prune_tensor {
   float* mu;
