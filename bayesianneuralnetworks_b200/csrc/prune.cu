@@ -87,10 +87,10 @@ struct PruneDesc {
   float* rho;
   uint8_t* mask;
   float* keys_out;
-  uint32_t* keys;            // workspace: ordered keys (general path) / deferred [index | mu | rho] x defer_cap, then
-                             // (key, index) pairs x defer_cap (sampled path)
-  uint32_t* hist;            // workspace: 2048 bins (lower interval ends / general path digits)
-  uint32_t* hist_plus;       // workspace: 2048 bins (upper interval ends)
+  uint32_t* keys;            // workspace: ordered keys (general path) / on the sampled path first the kSample sampled keys,
+                             // later the deferred [index | mu | rho] x defer_cap, then (key, index) pairs x defer_cap
+  uint32_t* hist;            // workspace: kHistStride entries (lower interval ends: 2049 used / general path digits: 2048)
+  uint32_t* hist_plus;       // workspace: kHistStride entries (upper interval ends: 2049 used)
   int64_t* chunk_cnt;        // workspace: per-chunk count of keys equal to the threshold (then offsets)
   PruneState* state;
   int64_t numel;

@@ -213,6 +213,36 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     assert lib.bnn_im2col(one, one, ctypes.byref(geom), null) == 1 and "geometry" in msg()
 
 
+def test_prune_workspace_plan_and_selftest_argument_checks():
+    """bnn_prune_workspace_size is a pure host function: it must cover the general path's key workspace (4 B per
+    element), the deferred list of small tensors (every element: 20 B each) and grow with every tensor added; the
+    interval self test validates its arguments before touching the device."""
+    lib = _C.lib()
+    null = ctypes.c_void_p(None)
+
+    def size(numels):
+        t = (_C.bnn_prune_tensor * len(numels))()
+        for i, n in enumerate(numels):
+            t[i].mu, t[i].rho, t[i].numel, t[i].k = 16, 16, n, n // 2
+        return lib.bnn_prune_workspace_size(t, len(numels))
+
+    assert lib.bnn_prune_workspace_size(None, 0) == 256
+    prev = 0
+    for numels in ([10], [10, 4099], [10, 4099, 65536], [10, 4099, 65536, 65537], [10, 4099, 65536, 65537, 1 << 24]):
+        s = size(numels)
+        assert s % 256 == 0 and s > prev
+        general = sum(4 * n for n in numels)
+        small = sum(20 * n for n in numels if n <= 65536)
+        assert s >= max(general, small) + len(numels) * (256 + 2 * 2049 * 4)
+        prev = s
+    assert size([1 << 24]) < 4.2 * (1 << 24) + (1 << 20)          # no more than the key workspace plus small change
+    assert size([40] * 30) > size([40] * 24)                       # more than one group of descriptors
+    assert lib.bnn_selftest_prune_interval(null, null, -1, null, null, 0, null) == 1
+    assert lib.bnn_selftest_prune_interval(null, null, 4, null, null, 2, null) == 1
+    assert lib.bnn_selftest_prune_interval(null, null, 4, null, null, 1, null) == 1 and "NULL" in lib.bnn_last_error_string().decode()
+    assert lib.bnn_selftest_prune_interval(null, null, 0, null, null, 1, null) == 0
+
+
 def test_mc_mean_loss_host_logic():
     """nn.mc_mean_loss == the reference loop body torch.stack([criterion(p, y) for p in preds]).mean()
     (examples/MNIST/train.py:59-61): one call over the batched rows when the list is an MCSamples of row blocks and
