@@ -560,6 +560,23 @@ def bench_kl_prune(device, pk, pairs=1 << 28, world=1):
         torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b) * 1e-3)
     res["prune_p0.75"] = entry(8 + 8 * p, over_ranks(best))
+    # the example's sweep (examples/MNIST/prune.py:49-50): successive levels on the SAME tensors — what was pruned at
+    # one level (mu = 0, rho = -30: the largest key there is) is re-selected first at the next
+    for (m, r), (sm, sr) in zip(zip(mus, rhos), saved):
+        m.copy_(sm), r.copy_(sr)
+    torch.cuda.synchronize()
+    sweep = []
+    for level in torch.linspace(.75, 1, 6).tolist():
+        kk = int(level * 4096 * 4096)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _C.prune([(m, r, kk, None, None) for m, r in zip(mus, rhos)])
+        b.record()
+        torch.cuda.synchronize()
+        t = over_ranks(a.elapsed_time(b) * 1e-3)
+        sweep.append(dict(entry(8 if kk == 4096 * 4096 else 8 + 8 * level, t), p=round(level, 2)))      # p = 1 writes only
+    pruned = sum(int((r == -30).sum()) for r in rhos)
+    res["prune_sweep"] = {"levels": sweep, "all_pruned_after_p1": pruned == n_t * 4096 * 4096}
     return res
 
 
