@@ -63,6 +63,7 @@ class BayesianNetworkModule(Module):
     def _mc_plan(self):
         """(foldable, [BatchNorm modules that update running statistics]) from the module tree."""
         from .layers import _FusedBayesianLayer
+        from .mvn import WeightMultivariateNormal
         from .variational import WeightNormal
         key = (self.training, len(_ROWWISE))
         cached = self.__dict__.get('_mc_plan_cache')
@@ -71,10 +72,11 @@ class BayesianNetworkModule(Module):
         ok, bns, n_bayes = True, [], 0
         rowwise = tuple(_ROWWISE)
         for m in self.modules():
-            if m is self or isinstance(m, (WeightNormal, torch.nn.Sequential, torch.nn.ModuleList, torch.nn.ModuleDict)):
+            if m is self or isinstance(m, (WeightNormal, WeightMultivariateNormal, torch.nn.Sequential,
+                                           torch.nn.ModuleList, torch.nn.ModuleDict)):
                 continue
-            if isinstance(m, _FusedBayesianLayer) and m._fused:
-                n_bayes += 1
+            if (isinstance(m, _FusedBayesianLayer) and m._fused) or getattr(m, '_mc_composite', False):
+                n_bayes += 1        # fused sample-and-contract layers and the torch composites (Flipout, full covariance)
             elif isinstance(m, _BATCHNORM):
                 if m.training and m.track_running_stats:
                     ok = ok and m.momentum is not None

@@ -12,6 +12,7 @@ import torch
 import torch.nn.functional as F
 from torch.distributions.normal import Normal
 
+from .. import runtime
 from ..utils.traversal import _pair, _single, _triple
 from .layers import NormalConvNd, NormalLinear
 
@@ -21,7 +22,8 @@ def _signs(*shape, device):
 
 
 class FlipoutNormalLinear(NormalLinear):
-    _fused = False        # evaluated by torch ops: not part of the batched Monte-Carlo launch
+    _fused = False        # evaluated by torch ops, not by the fused sample-and-contract kernels
+    _mc_composite = True  # ... but it takes part in the batched Monte-Carlo forward (S sign draws in one call)
 
     def __init__(self, in_features, out_features, prior=Normal(0, .1)):
         super(FlipoutNormalLinear, self).__init__(in_features, out_features, False, prior)
@@ -35,6 +37,15 @@ class FlipoutNormalLinear(NormalLinear):
         return (self.R, self.S)
 
     def forward(self, x, sample=True):
+        S, x, ctx = runtime.mc_expand_rows(x)
+        if ctx is not None and S > 1 and sample:
+            # S Monte-Carlo passes at once: one sign pair per sample, shared by that sample's B rows (dense.py:71-75)
+            R = _signs(S, 1, self.weight.size(0), device=self.weight.device)
+            Sg = _signs(S, 1, self.weight.size(1), device=self.weight.device)
+            self.R, self.S = R[-1, 0], Sg[-1, 0]
+            x3 = x.reshape(S, -1, x.shape[-1])
+            perturbation = ((x3 * Sg).matmul(self.weight.stddev.t()) * R).reshape(x.shape[:-1] + (self.weight.size(0),))
+            return F.linear(x, self.weight.mean) + perturbation
         if sample:
             self.sample()
         perturbation = (x * self.S).matmul(self.weight.stddev.t()) * self.R
@@ -43,6 +54,8 @@ class FlipoutNormalLinear(NormalLinear):
 
 class FlipOutNormalConvNd(NormalConvNd):
     _op = None            # set by the dimensional subclasses
+    _fused = False
+    _mc_composite = True  # the signs are per example (conv.py:154-161): S*B rows simply draw S*B sign sets
 
     def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation, transposed, groups, prior):
         super(FlipOutNormalConvNd, self).__init__(in_channels, out_channels, _single(kernel_size), stride, padding,
@@ -57,6 +70,7 @@ class FlipOutNormalConvNd(NormalConvNd):
         return (self.R, self.S)
 
     def _flipout(self, x, nd, sample):
+        _, x, _ = runtime.mc_expand_rows(x)
         if sample:
             self.sample(x.size(0), (1,) * nd)
         op = type(self)._op

@@ -13,6 +13,7 @@ from torch.distributions import MultivariateNormal
 from torch.nn import Module, init
 from torch.nn.parameter import Parameter
 
+from .. import runtime
 from .layers import BayesianLinear
 
 
@@ -56,8 +57,16 @@ class WeightMultivariateNormal(Module):
         noise = torch.rand_like(self.mean).unsqueeze(-1)
         self.sampled = self.mean + torch.matmul(self.stddev, noise).squeeze(-1)
 
+    def sample_many(self, count):
+        """[count, *shape]: `count` independent draws of sample() in one call; `.sampled` keeps the last one."""
+        noise = torch.rand((count,) + tuple(self.mean.shape), device=self.device, dtype=self.mean.dtype).unsqueeze(-1)
+        draws = self.mean + torch.matmul(self.stddev, noise).squeeze(-1)
+        self.sampled = draws[-1]
+        return draws
+
 
 class MultivariateNormalLinear(BayesianLinear):
+    _mc_composite = True      # takes part in the batched Monte-Carlo forward (S weight draws, one batched matmul)
 
     def __init__(self, in_features, out_features, bias=True, weight_prior=None, bias_prior=None):
         if not weight_prior:
@@ -92,6 +101,16 @@ class MultivariateNormalLinear(BayesianLinear):
         self.sampled = (self.weight.sampled, self.bias.sampled if self.bias is not None else None)
 
     def forward(self, x, sample=True):
+        S, x, ctx = runtime.mc_expand_rows(x)
+        if ctx is not None and S > 1 and sample:
+            w = self.weight.sample_many(S)                                   # [S, out, in]
+            b = self.bias.sample_many(S) if self.bias is not None else None  # [S, out]
+            self.sampled = (self.weight.sampled, self.bias.sampled if self.bias is not None else None)
+            x3 = x.reshape(S, -1, x.shape[-1])
+            y = torch.matmul(x3, w.transpose(1, 2))
+            if b is not None:
+                y = y + b.unsqueeze(1)
+            return y.reshape(x.shape[:-1] + (w.shape[1],))
         if sample:
             self.sample()
         return torch.nn.functional.linear(x, *self.sampled)

@@ -121,6 +121,22 @@ def current_mc():
     return getattr(_tls, "mc", None)
 
 
+def mc_expand_rows(x):
+    """For the torch-composite Bayesian layers (Flipout, full covariance) inside a batched Monte-Carlo pass:
+    (S, x with S*B sample-major rows, context).  The first Bayesian layer of the network receives the B un-expanded
+    rows and repeats them; later layers already see S*B rows.  Outside a batched pass: (1, x, None)."""
+    ctx = current_mc()
+    if ctx is None:
+        return 1, x, None
+    if not ctx.expanded:
+        if x.shape[0] != ctx.rows:
+            raise RuntimeError("batched Monte-Carlo forward: the first Bayesian layer must see the network "
+                               f"input rows ({ctx.rows}), got {x.shape[0]}")
+        x = x.unsqueeze(0).expand((ctx.samples,) + tuple(x.shape)).reshape((ctx.samples * x.shape[0],) + tuple(x.shape[1:]))
+        ctx.expanded = True
+    return ctx.samples, x, ctx
+
+
 @contextlib.contextmanager
 def mc_batch(ctx):
     prev = getattr(_tls, "mc", None)

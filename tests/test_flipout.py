@@ -66,8 +66,8 @@ def test_flipout_contract():
         assert out.shape == (2, 4) + (6,) * nd and conv.bias is None
         assert conv.sampled[0].shape == (2, 4) + (1,) * nd and conv.sampled[1].shape == (2, 3) + (1,) * nd
     net = Net(torch.nn.Sequential(FlipOutNormalConv2d(1, 2, 3), torch.nn.Flatten(), FlipoutNormalLinear(8, 3)), samples=4)
-    assert net._mc_plan()[0] is False                       # torch composites: the reference loop, not the batched launch
-    outs = net(torch.rand(2, 1, 4, 4))
+    assert net._mc_plan()[0] is True                        # torch composites join the batched pass (on CUDA inputs)
+    outs = net(torch.rand(2, 1, 4, 4))                      # a CPU input takes the reference loop
     assert isinstance(outs, list) and len(outs) == 4 and outs[0].shape == (2, 3)
 
 
@@ -79,6 +79,59 @@ def test_flipout_on_gpu_with_fused_kl():
     kl.backward()
     assert torch.allclose(lin.weight.mean.grad.cpu(), T(z["lin_g_mean"]), rtol=2e-3, atol=2e-3)
     assert torch.allclose(lin.weight.scale.grad.cpu(), T(z["lin_g_scale"]), rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.gpu
+def test_composite_layers_join_the_batched_monte_carlo_forward():
+    """Flipout and full-covariance layers are torch composites, but they take part in the batched Monte-Carlo forward
+    (trunk once, S*B rows through every later layer, S noise draws per layer in one call).  Checked against the
+    reference loop: identical in the noise-free limit, same first and second moments with noise."""
+    import bayesianneuralnetworks_b200 as bnn
+    from bayesianneuralnetworks_b200.nn import MultivariateNormalLinear
+    torch.manual_seed(3)
+    S, B = 6, 4
+    net = Net(torch.nn.Sequential(torch.nn.Conv2d(1, 2, 3, padding=1), torch.nn.ELU(),
+                                  FlipOutNormalConv2d(2, 2, 3, padding=1), torch.nn.ELU(), torch.nn.Flatten(),
+                                  FlipoutNormalLinear(32, 5), torch.nn.ELU(), MultivariateNormalLinear(5, 3)),
+              samples=S).cuda()
+    assert net._mc_plan()[0] is True
+    x = torch.rand(B, 1, 4, 4, device="cuda")
+    saved = {n: p.detach().clone() for n, p in net.named_parameters()}
+    try:
+        with torch.no_grad():                               # noise-free limit: sigma ~ 1e-10
+            for n, p in net.named_parameters():
+                if n.endswith(".scale"):
+                    p.fill_(-100.0)
+        bnn.set_mc_batching("always")
+        batched = net(x)
+        bnn.set_mc_batching("never")
+        loop = net(x)
+        assert isinstance(batched, list) and len(batched) == S and batched[0].shape == (B, 3)
+        assert batched.batched.shape == (S * B, 3)
+        for a, b in zip(batched, loop):
+            assert torch.allclose(a, b, rtol=5e-3, atol=2e-3)         # cuDNN / cuBLAS may use TF32 and pick other kernels
+        with torch.no_grad():
+            for n, p in net.named_parameters():
+                p.copy_(saved[n])
+        # with noise: moments over many Monte-Carlo samples agree between the two evaluation orders
+        n_mc = 1500
+        bnn.set_mc_batching("always")
+        big = torch.stack(net(x, samples=n_mc))
+        bnn.set_mc_batching("never")
+        ref = torch.stack([torch.stack(net(x, samples=50)) for _ in range(n_mc // 50)]).flatten(0, 1)
+        assert big.shape == ref.shape == (n_mc, B, 3)
+        assert float(big.std(0).mean()) > 1e-3              # the samples do differ
+        se = ref.std(0) / n_mc ** 0.5
+        assert bool(((big.mean(0) - ref.mean(0)).abs() < 6 * se + 1e-4).all())
+        assert torch.allclose(big.std(0), ref.std(0), rtol=0.15, atol=1e-4)
+        # gradients flow to every variational parameter through the batched pass
+        bnn.set_mc_batching("always")
+        net.zero_grad()
+        torch.stack(net(x)).square().mean().backward()
+        for n, p in net.named_parameters():
+            assert p.grad is not None and bool(torch.isfinite(p.grad).all()), n
+    finally:
+        bnn.set_mc_batching("auto")
 
 
 # ------------------------------------------------------------------------------------------------ full covariance (f-4)
