@@ -518,6 +518,55 @@ def _example_bcnn(samples):
     return Net(seq, samples)
 
 
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", 4e-3)])
+def test_c1_mlp_elbo_step_matches_the_oracle(prec, tol):
+    """BASELINE.json configs[0]: Bayesian MLP 784-400-400-10, batch 128, one MC sample,
+    ELBO = NLL + KL, the whole step (forward, KL, cross-entropy, backward) against the CPU oracle's restatement of
+    examples/MNIST/train.py:55-65 with the same injected eps; 1e-5 class in fp32 mode, 2e-3 class in TF32 mode."""
+    from oracle import variational_oracle as orc
+    bnn.set_precision(prec)
+    torch.manual_seed(11)
+    B, S = 128, 1
+
+    class MLP(BayesianNetworkModule):
+        def __init__(self):
+            super().__init__(784, 10, S)
+            self.layers = torch.nn.Sequential(torch.nn.Flatten(), NormalLinear(784, 400), torch.nn.ELU(),
+                                              NormalLinear(400, 400), torch.nn.ELU(), NormalLinear(400, 10),
+                                              torch.nn.Softmax(dim=-1))
+
+        def _forward(self, x):
+            return self.layers(x)
+
+    net = MLP()
+    lins = [net.layers[1], net.layers[3], net.layers[5]]
+    x, y = torch.rand(B, 1, 28, 28), torch.randint(0, 10, (B,))
+    tensors = [w for l in lins for w in (l.weight, l.bias)]
+    eps = {w: torch.randn((S,) + tuple(w.shape)) for w in tensors}
+    P = {w: (w.mean.detach().clone().requires_grad_(True), w.scale.detach().clone().requires_grad_(True)) for w in tensors}
+    stages = [('torch', torch.nn.Flatten())]
+    for i, l in enumerate(lins):
+        stages.append(('linear', *P[l.weight], *P[l.bias], 0.0, 0.1))
+        stages.append(('torch', torch.nn.ELU() if i < 2 else torch.nn.Softmax(dim=-1)))
+    order = iter([eps[w][s] for s in range(S) for w in tensors])
+    ref_loss, ref_pred = orc.ElboStepOracle(stages, S, 469).loss(x, y, eps_fn=lambda t: next(order))
+    ref_loss.backward()
+    net.cuda()
+    with bnn.injected_eps(eps):
+        pred = net(x.cuda())
+    assert torch.is_tensor(pred) and pred.shape == (B, 10)              # S == 1: the bare tensor (utils.py:10-11)
+    loss = F.cross_entropy(pred, y.cuda()) + KLDivergence(number_of_batches=469)(net)
+    loss.backward()
+
+    def rel(a, b):
+        return float((a.detach().cpu().double() - b.detach().double()).abs().max() / b.detach().abs().max().clamp_min(1e-30))
+    assert abs(float(loss) - float(ref_loss)) <= tol * abs(float(ref_loss))
+    ref_pred = ref_pred[0] if isinstance(ref_pred, (list, tuple)) else ref_pred
+    assert rel(pred, ref_pred) < tol
+    for w in tensors:
+        assert rel(w.mean.grad, P[w][0].grad) < 2 * tol and rel(w.scale.grad, P[w][1].grad) < 2 * tol
+
+
 def test_mc_mean_loss_equals_the_reference_loop_body():
     """the batched likelihood term (one criterion call over the S*B rows of the batched Monte-Carlo
     forward) gives the loss and every gradient of torch.stack([CE(p, y) for p in preds]).mean() (train.py:59-61)."""
