@@ -481,15 +481,16 @@ def roofline(workload, B, S, per_kernel, pk):
     return out
 
 
-def bench_kl_prune(device, pk, pairs=1 << 28, world=1):
-    """KL forward, KL forward+grad and prune over `pairs` (mu, rho) pairs PER GPU in 16 tensors of 4096x4096 (the C5
-    layout, BASELINE.json configs[4]: 64 tensors sharded round-robin over the GPUs — at N=8 this is C5 at full size,
-    at N=1 a quarter of it so the default run stays short); working set 2 GiB per GPU >> L2.  Algorithmic bytes
-    (SURVEY §8d): KL fwd 8 B/pair, fwd+grad 16 B/pair, prune 8 + 8p B/pair.  With several GPUs the KL legs include the
-    one scalar all-reduce of the sharded sum, prune needs no exchange; times are the max over ranks and
-    GB/s the aggregate."""
+def bench_kl_prune(device, pk, world=1, tensors=64):
+    """C5 (BASELINE.json configs[4]): KL forward, KL forward+grad and the pruning sweep over 2^30
+    (mu, rho) pairs — 64 tensors of 4096x4096, 8 GiB — sharded round-robin by tensor over the GPUs (64 / N tensors per
+    GPU; one GPU sweeps all of them); the working set per GPU is 8 GiB / N >> L2.  Algorithmic bytes: KL
+    fwd 8 B/pair, fwd+grad 16 B/pair, prune 8 + 8p B/pair.  With several GPUs the KL legs include the one scalar
+    all-reduce of the sharded sum, prune needs no exchange; times are the max over ranks and GB/s the
+    aggregate."""
     from bayesianneuralnetworks_b200 import _C
-    n_t = pairs // (4096 * 4096)
+    n_t = max(1, tensors // world)
+    pairs = n_t * 4096 * 4096
     gen = torch.Generator(device=device).manual_seed(5)
     mus = [(torch.rand(4096, 4096, device=device, generator=gen) * 2 - 1) / 64 for _ in range(n_t)]
     rhos = [torch.randn(4096, 4096, device=device, generator=gen) * 0.15 - 2.0 for _ in range(n_t)]
@@ -534,7 +535,9 @@ def bench_kl_prune(device, pk, pairs=1 << 28, world=1):
         gbps = bytes_per_pair * pairs * world / t / 1e9
         return {"GBps": gbps, "frac_of_measured_hbm": gbps / (pk["hbm"] * world), "ms": t * 1e3}
 
-    res = {"pairs_per_gpu": pairs, "tensors_per_gpu": n_t, "n_gpus": world, "l2": "working set 2 GiB per GPU, larger than L2",
+    res = {"workload": "C5: 64 tensors of 4096x4096 (2^30 pairs, 8 GiB of mu/rho), sharded by tensor over the GPUs",
+           "pairs_per_gpu": pairs, "tensors_per_gpu": n_t, "n_gpus": world,
+           "l2": f"working set {pairs * 8 / 2 ** 30:.0f} GiB per GPU, larger than L2",
            "timing": "CUDA events; KL legs: average of 8 back-to-back calls (best of 5); prune: one call per measurement "
                      "(it modifies its input, restored untimed), best of 3"}
     res["kl_fwd"] = entry(8, time_it(lambda: kl_leg(fwd)))
