@@ -372,11 +372,11 @@ __global__ void __launch_bounds__(kThreads) prune_bin_kernel(const __grid_consta
   int cur = -1;
   bool active = false;
   Grid g = {0.f, 0.f, 0.f, 0.f, 0.f};
-  float above_f = 0.f;      // per-thread count between two flushes: far below 2^24, exact in fp32
+  unsigned int above = 0;
   auto flush = [&]() {      // warp-wide: adds this warp's count of "above" elements of tensor `cur`
-    const unsigned int v = warp_sum(static_cast<unsigned int>(above_f));
+    const unsigned int v = warp_sum(above);
     if (lane == 0 && v != 0u) atomicAdd(&tab.t[cur].state->count_above, static_cast<unsigned long long>(v));
-    above_f = 0.f;
+    above = 0;
   };
   for (int64_t chunk = blockIdx.x; chunk < tab.total_chunks; chunk += gridDim.x) {
     const int t = find_tensor(s_begin, tab.n, chunk, cur < 0 ? 0 : cur);
@@ -396,13 +396,23 @@ __global__ void __launch_bounds__(kThreads) prune_bin_kernel(const __grid_consta
     // would be entered all the time.  Instead every element stores its interval UNCONDITIONALLY into the lane's own
     // shared-memory queue and only the queue position advances when it overlaps (a following store overwrites a
     // skipped one); the histogram updates run afterwards over the few queued intervals.
-    int pos = 0;
     float2* const q_lane = s_queue + threadIdx.x;          // slot s of this lane: q_lane[s * kThreads]
+    const uint32_t q_base = static_cast<uint32_t>(__cvta_generic_to_shared(q_lane));
+    uint32_t q_addr = q_base;                              // shared-memory address of the lane's next slot
+    // five instructions per element (two compares, the store, two predicated adds) — written as PTX because the
+    // compiler turns the conditional increments into add + select pairs:
+    //   below2048 = !(y_minus >= 2048) [or NaN];  overlap = below2048 && !(y_plus < 0) [or NaN]
     auto account = [&](float y_minus, float y_plus) {
-      q_lane[pos * kThreads] = make_float2(y_minus, y_plus);
-      const bool ab = y_minus >= static_cast<float>(kBins);
-      above_f += ab ? 1.0f : 0.0f;
-      pos += (!ab && !(y_plus < 0.0f)) ? 1 : 0;            // overlaps the grid (or NaN)
+      asm volatile(
+          "{\n\t.reg .pred p1, p2;\n\t"
+          "st.shared.v2.f32 [%0], {%2, %3};\n\t"
+          "setp.ltu.f32 p1, %2, 2048.0;\n\t"
+          "setp.geu.and.f32 p2, %3, 0.0, p1;\n\t"
+          "@!p1 add.u32 %1, %1, 1;\n\t"
+          "@p2 add.u32 %0, %0, %4;\n\t}"
+          : "+r"(q_addr), "+r"(above)
+          : "f"(y_minus), "f"(y_plus), "n"(kThreads * 8)
+          : "memory");
     };
     if (d.vec && ubase + kUnit <= d.numel) {
       float4 m[kVecPerThread], r[kVecPerThread];
@@ -436,6 +446,7 @@ __global__ void __launch_bounds__(kThreads) prune_bin_kernel(const __grid_consta
         account(ym, yp);
       }
     }
+    const int pos = static_cast<int>((q_addr - q_base) / (kThreads * 8));
     for (int s = 0; s < pos; ++s) {                    // rarely more than two rounds
       // lower end: index 0 = below the grid (or NaN), index b + 1 = bin b; upper end: index b = bin b, index 2048 =
       // above the grid (or NaN).  No clamping INTO the grid: an interval that sticks out may hold a key outside it.
