@@ -54,6 +54,13 @@ class bnn_prune_tensor(ctypes.Structure):
                 ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
+class bnn_adam_tensor(ctypes.Structure):
+    _fields_ = [("mu", ctypes.c_void_p), ("rho", ctypes.c_void_p), ("g_mu", ctypes.c_void_p), ("g_rho", ctypes.c_void_p),
+                ("m_mu", ctypes.c_void_p), ("v_mu", ctypes.c_void_p), ("m_rho", ctypes.c_void_p), ("v_rho", ctypes.c_void_p),
+                ("numel", ctypes.c_int64), ("prior_loc", ctypes.c_float), ("prior_scale", ctypes.c_float),
+                ("kl_coeff", ctypes.c_float), ("reserved", ctypes.c_float)]
+
+
 _SIGNATURES = {
     "bnn_abi_version": (ctypes.c_int, []),
     "bnn_last_error_string": (ctypes.c_char_p, []),
@@ -87,6 +94,8 @@ _SIGNATURES = {
     "bnn_prune_workspace_size": (ctypes.c_size_t, [ctypes.POINTER(bnn_prune_tensor), ctypes.c_int32]),
     "bnn_prune": (ctypes.c_int, [ctypes.POINTER(bnn_prune_tensor), ctypes.c_int32, ctypes.c_void_p,
                                  ctypes.c_size_t, ctypes.c_void_p]),
+    "bnn_adam_kl_step": (ctypes.c_int, [ctypes.POINTER(bnn_adam_tensor), ctypes.c_int32, ctypes.c_float, ctypes.c_float,
+                                        ctypes.c_float, ctypes.c_float, _c_f32p, ctypes.c_int64, ctypes.c_void_p]),
     "bnn_selftest_prune_interval": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_int32,
                                                    ctypes.c_void_p]),
     "bnn_selftest_umma": (ctypes.c_int, [_c_f32p, ctypes.c_void_p]),
@@ -370,6 +379,32 @@ def prune(entries, flags=0):
     with torch.cuda.device(device):
         _call("bnn_prune", table, n, ctypes.c_void_p(base), nbytes, _stream())
     _count(15 * ((n + 23) // 24))
+
+
+def adam_kl_step(entries, lr, beta1, beta2, eps, step_dev=None, step=0):
+    """entries: list of (mu, rho, g_mu|None, g_rho|None, m_mu, v_mu, m_rho, v_rho, prior_loc, prior_scale, kl_coeff);
+    parameters and moments are updated in place (include/bnn_b200.h: bnn_adam_kl_step)."""
+    n = len(entries)
+    if n == 0:
+        return
+    table = (bnn_adam_tensor * n)()
+    device = entries[0][0].device
+    for i, (mu, rho, g_mu, g_rho, m_mu, v_mu, m_rho, v_rho, loc, scale, coeff) in enumerate(entries):
+        require_cuda(mu, rho, g_mu, g_rho, m_mu, v_mu, m_rho, v_rho)
+        for name, t in (("mu", mu), ("rho", rho), ("g_mu", g_mu), ("g_rho", g_rho), ("m_mu", m_mu), ("v_mu", v_mu),
+                        ("m_rho", m_rho), ("v_rho", v_rho)):
+            _f32c(t, name)
+        e = table[i]
+        e.mu, e.rho = mu.data_ptr(), rho.data_ptr()
+        e.g_mu = None if g_mu is None else g_mu.data_ptr()
+        e.g_rho = None if g_rho is None else g_rho.data_ptr()
+        e.m_mu, e.v_mu, e.m_rho, e.v_rho = m_mu.data_ptr(), v_mu.data_ptr(), m_rho.data_ptr(), v_rho.data_ptr()
+        e.numel, e.prior_loc, e.prior_scale, e.kl_coeff, e.reserved = mu.numel(), loc, scale, coeff, 0.0
+    if step_dev is not None:
+        require_cuda(step_dev)
+    with torch.cuda.device(device):
+        _call("bnn_adam_kl_step", table, n, lr, beta1, beta2, eps, _ptr(step_dev), int(step), _stream())
+    _count((n + 15) // 16)
 
 
 def selftest_prune_interval(mu, rho, variant=1):

@@ -165,7 +165,7 @@ class Trainer:
     once into a CUDA graph and replayed: the Philox streams advance through a device-side step counter
     (bnn.graph_safe_rng), so every replay draws fresh eps."""
 
-    def __init__(self, workload, device, world, samples, graph, loss_tail="batched"):
+    def __init__(self, workload, device, world, samples, graph, loss_tail="batched", optimizer="elbo-adam"):
         import bayesianneuralnetworks_b200 as bnn
         self.bnn = bnn
         self.loss_tail = loss_tail
@@ -173,8 +173,11 @@ class Trainer:
         bnn.graph_safe_rng(graph)
         self.model = build_model(workload, samples).to(device)
         self.kld = bnn.nn.KLDivergence(number_of_batches=N_BATCHES)
-        # torch's single-pass fused Adam (same update rule as the reference's torch.optim.Adam, train.py:43)
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-3, capturable=graph, fused=True)
+        self.optimizer = optimizer
+        if optimizer == "elbo-adam":      # KL gradient + Adam in one pass, likelihood-only backward
+            self.opt = bnn.optim.ELBOAdam(self.model, number_of_batches=N_BATCHES, lr=1e-3, capturable=graph)
+        else:                             # torch's single-pass fused Adam (the reference's torch.optim.Adam, train.py:43)
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-3, capturable=graph, fused=True)
         self.world = world
         self.params = [p for p in self.model.parameters()]
         self.graph = None
@@ -191,11 +194,18 @@ class Trainer:
         else:
             self.opt.zero_grad(set_to_none=True)
         preds = self.model(x)
-        divergence = self.kld(self.model)
+        if self.optimizer == "elbo-adam":
+            with torch.no_grad():
+                divergence = self.kld(self.model)
+        else:
+            divergence = self.kld(self.model)
         if self.loss_tail == "loop":        # the reference loop body verbatim (train.py:59-61)
             likelihood = torch.stack([F.cross_entropy(p, y) for p in preds]).mean()
         else:                               # the same mean as ONE cross-entropy over the S*B rows
             likelihood = self.bnn.nn.mc_mean_loss(F.cross_entropy, preds, y)
+        if self.optimizer == "elbo-adam":   # the optimizer adds the closed-form KL gradient; the value is still reported
+            likelihood.backward()
+            return likelihood.detach() + divergence
         loss = likelihood + divergence
         loss.backward()
         return loss
@@ -287,7 +297,8 @@ def run_b200(args):
             raise SystemExit(f"{S} MC samples do not split over {world} ranks")
         bnn.set_sample_partition(rank, world)
     torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
-    trainer = Trainer(args.workload, device, world, S, graph=not args.no_graph, loss_tail=args.loss_tail)
+    trainer = Trainer(args.workload, device, world, S, graph=not args.no_graph, loss_tail=args.loss_tail,
+                      optimizer=args.optimizer)
     gen = torch.Generator().manual_seed(1 if sample_parallel else 1 + rank)
     n_host = 8
     host = [tuple(t.pin_memory() for t in synthetic_batch(args.workload, B, gen)) for _ in range(n_host)]
@@ -390,8 +401,8 @@ def run_b200(args):
                        "global_batch": B if sample_parallel else B * world,
                        "parallelism": (f"sp{world} (MC samples sharded, {S // world} per GPU)" if sample_parallel
                                        else f"dp{world}") if world > 1 else "single", "n_batches": N_BATCHES,
-                       "optimizer": "Adam (torch fused)", "cudnn_benchmark": not args.no_cudnn_benchmark, "launch": graph_note, "l2": "flushed between steps (256 MiB write, untimed); each step "
-                       "timed with its own CUDA event pair", "step": "zero_grad+forward(S)+KL+CE+backward+Adam",
+                       "optimizer": "Adam (torch fused)" if args.optimizer == "adam" else "bnn.optim.ELBOAdam (KL gradient + Adam in one pass; torch fused Adam for the deterministic layers)", "cudnn_benchmark": not args.no_cudnn_benchmark, "launch": graph_note, "l2": "flushed between steps (256 MiB write, untimed); each step "
+                       "timed with its own CUDA event pair", "step": "zero_grad+forward(S)+KL+CE+backward+Adam" + (" (KL gradient applied inside the optimizer pass)" if args.optimizer == "elbo-adam" else ""),
                        "loss_tail": ("nn.mc_mean_loss: mean of the S per-sample cross-entropies evaluated as one call over "
                                      "the S*B rows (identical value and gradients, tests/test_modules_gpu.py)"
                                      if args.loss_tail == "batched" else "reference loop: S cross-entropy calls")},
@@ -690,6 +701,9 @@ def main():
     ap.add_argument("--no-cudnn-benchmark", action="store_true",
                     help="leave torch.backends.cudnn.benchmark off for the deterministic torch trunk (the examples' setting; "
                          "the default run lets cuDNN pick its kernels by measurement, 0.73 -> 0.69 ms per C2 step)")
+    ap.add_argument("--optimizer", default="elbo-adam", choices=["adam", "elbo-adam"],
+                    help="elbo-adam: bnn.optim.ELBOAdam (KL gradient + Adam in one pass, likelihood-only backward; same "
+                         "trajectory); adam: torch's fused Adam on likelihood + KL, the reference loop verbatim")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the kl_prune and cpu_baseline legs (profiling runs)")
     args = ap.parse_args()

@@ -181,6 +181,31 @@ int bnn_kl(const bnn_kl_tensor* tensors /* HOST array */, int32_t n_tensors,
                               1 / (numel_t * n_tensors * n_batches) (loss.py:28,38) */,
            const float* grad_scale_dev, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- optimizer step with the KL gradient folded in ----
+ * For every (mu, rho) pair: g = likelihood gradient (g_mu / g_rho, NULL = zero) + kl_coeff * dKL/d(mu, rho) with the
+ * closed forms given for bnn_kl above, then torch.optim.Adam's update (no weight decay, no amsgrad; the optimizer of
+ * examples/MNIST/train.py:43) of the parameters and their moment buffers, all in one pass.  `step_dev` (device scalar,
+ * float) holds the number of THIS step (1, 2, ...), so that a captured CUDA graph replays with a fresh bias correction;
+ * when NULL, `step_host` is used.  kl_coeff = 1 / (numel_t * n_tensors * n_batches) reproduces the gradient of
+ * KLDivergence.forward (pytorch_bayesian/nn/loss.py:28,38); kl_coeff = 0 is plain Adam. */
+typedef struct bnn_adam_tensor {
+  float* mu;
+  float* rho;
+  const float* g_mu;   /* optional */
+  const float* g_rho;  /* optional */
+  float* m_mu;
+  float* v_mu;
+  float* m_rho;
+  float* v_rho;
+  int64_t numel;
+  float prior_loc;
+  float prior_scale;
+  float kl_coeff;
+  float reserved;
+} bnn_adam_tensor;
+int bnn_adam_kl_step(const bnn_adam_tensor* tensors /* HOST array */, int32_t n_tensors, float lr, float beta1, float beta2,
+                     float eps, const float* step_dev, int64_t step_host, void* stream);
+
 /* ---- pruning ----
  * key_i = log N(0; mu_i, sigma_i) evaluated with the exact op order of torch's Normal.log_prob
  * (torch/distributions/normal.py:87-102) on softplus(rho)+1e-10; the k largest keys get

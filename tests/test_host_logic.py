@@ -48,6 +48,7 @@ def test_binding_struct_sizes_match_the_header():
     assert ctypes.sizeof(_C.bnn_conv2d_geom) == 64
     assert ctypes.sizeof(_C.bnn_kl_tensor) == 56
     assert ctypes.sizeof(_C.bnn_prune_tensor) == 56
+    assert ctypes.sizeof(_C.bnn_adam_tensor) == 88
 
 
 def test_hot_path_rejects_cpu_tensors():
@@ -237,6 +238,12 @@ def test_prune_workspace_plan_and_selftest_argument_checks():
         prev = s
     assert size([1 << 24]) < 4.2 * (1 << 24) + (1 << 20)          # no more than the key workspace plus small change
     assert size([40] * 30) > size([40] * 24)                       # more than one group of descriptors
+    at = (_C.bnn_adam_tensor * 1)()
+    at[0].mu, at[0].rho, at[0].numel, at[0].kl_coeff, at[0].prior_scale = 16, 16, 4, 1.0, 0.1
+    assert lib.bnn_adam_kl_step(at, 1, 1e-3, 0.9, 0.999, 1e-8, null, 1, null) == 1 and "moment" in lib.bnn_last_error_string().decode()
+    assert lib.bnn_adam_kl_step(at, 1, 1e-3, 1.0, 0.999, 1e-8, null, 1, null) == 1                 # beta1 = 1
+    assert lib.bnn_adam_kl_step(at, 1, 1e-3, 0.9, 0.999, 1e-8, null, 0, null) == 1 and "step" in lib.bnn_last_error_string().decode()
+    assert lib.bnn_adam_kl_step(None, 0, 1e-3, 0.9, 0.999, 1e-8, null, 1, null) == 0
     assert lib.bnn_selftest_prune_interval(null, null, -1, null, null, 0, null) == 1
     assert lib.bnn_selftest_prune_interval(null, null, 4, null, null, 2, null) == 1
     assert lib.bnn_selftest_prune_interval(null, null, 4, null, null, 1, null) == 1 and "NULL" in lib.bnn_last_error_string().decode()
@@ -315,3 +322,39 @@ def test_reference_example_models_construct_unchanged_on_the_drop_in():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_elbo_adam_plans_the_same_tensors_and_coefficients_as_kl_divergence():
+    """bnn.optim.ELBOAdam folds the gradient of KLDivergence(n_batches)(model) into its step: it must see the tensors the
+    reference's traverse sees (weights and biases as separate entries, loss.py:30-38), give each the coefficient
+    1 / (numel * n_tensors * n_batches), and leave every other parameter to torch's Adam."""
+    from torch.nn import Conv2d, ELU, Flatten, Sequential
+
+    class Hidden(torch.nn.Module):                 # a Bayesian layer inside a plain module: invisible to traverse
+        def __init__(self):
+            super().__init__()
+            self.inner = NormalLinear(10, 10)
+
+        def forward(self, x):
+            return self.inner(x)
+
+    class Net(BayesianNetworkModule):
+        def __init__(self):
+            super().__init__(1, 10, 2)
+            self.layers = Sequential(Conv2d(1, 4, 3), ELU(), NormalConv2d(4, 4, 3), Flatten(),
+                                     NormalLinear(16, 10, bias=False), Hidden())
+
+        def _forward(self, x):
+            return self.layers(x)
+
+    net = Net()
+    opt = bnn.optim.ELBOAdam(net, number_of_batches=5, lr=1e-2)
+    seen = [e["w"] for e in opt._var]
+    assert seen == [net.layers[2].weight, net.layers[2].bias, net.layers[4].weight]
+    for e in opt._var:
+        assert e["coeff"] == pytest.approx(1.0 / (e["w"].mean.numel() * 3 * 5)) and (e["loc"], e["scale"]) == (0.0, pytest.approx(0.1))
+    others = {id(p) for g in opt.param_groups for p in g["params"]}
+    assert others == {id(p) for p in list(net.layers[0].parameters()) + list(net.layers[5].parameters())}
+    net.layers[0].weight.grad = torch.ones_like(net.layers[0].weight)
+    opt.zero_grad()
+    assert net.layers[0].weight.grad is None

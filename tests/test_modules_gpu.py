@@ -567,6 +567,44 @@ def test_c1_mlp_elbo_step_matches_the_oracle(prec, tol):
         assert rel(w.mean.grad, P[w][0].grad) < 2 * tol and rel(w.scale.grad, P[w][1].grad) < 2 * tol
 
 
+def test_elbo_adam_equals_adam_on_likelihood_plus_kl():
+    """SURVEY §8f-3, optimizer half: ELBOAdam (likelihood back-propagated, KL gradient + Adam in one pass of
+    bnn_adam_kl_step) walks the same trajectory as the reference's torch.optim.Adam on likelihood + KLDivergence
+    (examples/MNIST/train.py:43,57-65), for the variational tensors and the deterministic trunk alike."""
+    import copy
+    bnn.set_precision("fp32")
+    torch.manual_seed(5)
+    ref_model = _example_bcnn(3).cuda()
+    bnn.nn.register_rowwise_module(_ExampleFlatten)
+    new_model = copy.deepcopy(ref_model)
+    x = torch.rand(16, 1, 28, 28, device="cuda")
+    y = torch.arange(16, device="cuda") % 10
+    kld = KLDivergence(number_of_batches=7)
+    ref_opt = torch.optim.Adam(ref_model.parameters(), lr=2e-3)
+    new_opt = bnn.optim.ELBOAdam(new_model, number_of_batches=7, lr=2e-3)
+
+    def rewind(model, step):            # the same eps streams for both models: identical tensor ids, identical draws
+        ids = iter(range(10_000, 20_000))
+        for m in model.modules():
+            if isinstance(m, bnn.nn.WeightNormal):
+                m._tensor_id, m._draw = next(ids), 3 * step
+
+    for step in range(6):
+        rewind(ref_model, step), rewind(new_model, step)
+        ref_opt.zero_grad()
+        loss = bnn.nn.mc_mean_loss(F.cross_entropy, ref_model(x), y) + kld(ref_model)
+        loss.backward()
+        ref_opt.step()
+        new_opt.zero_grad()
+        bnn.nn.mc_mean_loss(F.cross_entropy, new_model(x), y).backward()
+        new_opt.step()
+    for (n, a), (_, b) in zip(ref_model.named_parameters(), new_model.named_parameters()):
+        if n == "layers.0.bias":        # a conv bias in front of BatchNorm: its gradient is rounding noise (~1e-9), which
+            continue                    # Adam normalises into lr-sized steps of random sign — not comparable
+        assert torch.allclose(a, b, rtol=2e-4, atol=2e-6), (n, float((a - b).abs().max()))
+    assert float(kld(new_model)) == pytest.approx(float(kld(ref_model)), rel=1e-5)
+
+
 def test_mc_mean_loss_equals_the_reference_loop_body():
     """the batched likelihood term (one criterion call over the S*B rows of the batched Monte-Carlo
     forward) gives the loss and every gradient of torch.stack([CE(p, y) for p in preds]).mean() (train.py:59-61)."""
