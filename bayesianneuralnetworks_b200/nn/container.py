@@ -29,7 +29,8 @@ _BATCHNORM = (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)
 def register_rowwise_module(cls):
     """Declare a user module class as acting independently on every row of dim 0 (e.g. a custom
     Flatten), so that networks containing it qualify for the batched Monte-Carlo forward."""
-    _ROWWISE.append(cls)
+    if cls not in _ROWWISE:
+        _ROWWISE.append(cls)
     return cls
 
 
