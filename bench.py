@@ -236,12 +236,16 @@ class Trainer:
         if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         self.sx, self.sy = x.clone(), y.clone()
-        total = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(total, device=x.device, dtype=torch.float32)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        if self.world > 1:
+            # the gradients are views of ONE flat buffer: a single all-reduce, static addresses for both graphs
+            total = sum(p.numel() for p in self.params)
+            self.flat = torch.zeros(total, device=x.device, dtype=torch.float32)
+            off = 0
+            for p in self.params:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        # one GPU: zero_grad(set_to_none=True) inside the captured step — autograd then hands the freshly computed
+        # gradient tensors (static addresses in the graph's pool) to .grad without an accumulation pass
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
