@@ -165,13 +165,18 @@ class Trainer:
     once into a CUDA graph and replayed: the Philox streams advance through a device-side step counter
     (bnn.graph_safe_rng), so every replay draws fresh eps."""
 
-    def __init__(self, workload, device, world, samples, graph, loss_tail="batched", optimizer="elbo-adam"):
+    def __init__(self, workload, device, world, samples, graph, loss_tail="batched", optimizer="elbo-adam",
+                 channels_last=False):
         import bayesianneuralnetworks_b200 as bnn
         self.bnn = bnn
         self.loss_tail = loss_tail
         torch.manual_seed(0)
         bnn.graph_safe_rng(graph)
         self.model = build_model(workload, samples).to(device)
+        if channels_last:                 # torch-side knob for the deterministic trunk: cuDNN's NHWC kernels without
+            for m in self.model.modules():     # layout conversions around each call; (mu, rho) stay row-major OIHW
+                if isinstance(m, (torch.nn.Conv2d, torch.nn.BatchNorm2d)):
+                    m.to(memory_format=torch.channels_last)
         self.kld = bnn.nn.KLDivergence(number_of_batches=N_BATCHES)
         self.optimizer = optimizer
         if optimizer == "elbo-adam":      # SURVEY §8f-3: KL gradient + Adam in one pass, likelihood-only backward
@@ -302,7 +307,7 @@ def run_b200(args):
         bnn.set_sample_partition(rank, world)
     torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     trainer = Trainer(args.workload, device, world, S, graph=not args.no_graph, loss_tail=args.loss_tail,
-                      optimizer=args.optimizer)
+                      optimizer=args.optimizer, channels_last=args.channels_last)
     gen = torch.Generator().manual_seed(1 if sample_parallel else 1 + rank)
     n_host = 8
     host = [tuple(t.pin_memory() for t in synthetic_batch(args.workload, B, gen)) for _ in range(n_host)]
@@ -325,7 +330,9 @@ def run_b200(args):
         for i in range(n_steps):
             flush.zero_()
             starts[i].record()
-            if feed_from_host:
+            if feed_from_host and trainer.graph is not None:
+                x, y = host[i % n_host]       # pinned host -> the graph's static input buffers, one async copy each
+            elif feed_from_host:
                 hx, hy = host[i % n_host]
                 x, y = hx.to(device, non_blocking=True), hy.to(device, non_blocking=True)
             else:
@@ -405,7 +412,7 @@ def run_b200(args):
                        "global_batch": B if sample_parallel else B * world,
                        "parallelism": (f"sp{world} (MC samples sharded, {S // world} per GPU)" if sample_parallel
                                        else f"dp{world}") if world > 1 else "single", "n_batches": N_BATCHES,
-                       "optimizer": "Adam (torch fused)" if args.optimizer == "adam" else "bnn.optim.ELBOAdam (KL gradient + Adam in one pass; torch fused Adam for the deterministic layers)", "cudnn_benchmark": not args.no_cudnn_benchmark, "launch": graph_note, "l2": "flushed between steps (256 MiB write, untimed); each step "
+                       "optimizer": "Adam (torch fused)" if args.optimizer == "adam" else "bnn.optim.ELBOAdam (KL gradient + Adam in one pass; torch fused Adam for the deterministic layers)", "cudnn_benchmark": not args.no_cudnn_benchmark, "trunk_memory_format": "channels_last" if args.channels_last else "contiguous (NCHW)", "launch": graph_note, "l2": "flushed between steps (256 MiB write, untimed); each step "
                        "timed with its own CUDA event pair", "step": "zero_grad+forward(S)+KL+CE+backward+Adam" + (" (KL gradient applied inside the optimizer pass)" if args.optimizer == "elbo-adam" else ""),
                        "loss_tail": ("nn.mc_mean_loss: mean of the S per-sample cross-entropies evaluated as one call over "
                                      "the S*B rows (identical value and gradients, tests/test_modules_gpu.py)"
@@ -708,6 +715,9 @@ def main():
     ap.add_argument("--optimizer", default="elbo-adam", choices=["adam", "elbo-adam"],
                     help="elbo-adam: bnn.optim.ELBOAdam (KL gradient + Adam in one pass, likelihood-only backward; same "
                          "trajectory); adam: torch's fused Adam on likelihood + KL, the reference loop verbatim")
+    ap.add_argument("--channels-last", action="store_true",
+                    help="keep the deterministic torch trunk (Conv2d / BatchNorm2d / ELU) in torch.channels_last memory "
+                         "format; the Bayesian layers take any input layout")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the kl_prune and cpu_baseline legs (profiling runs)")
     args = ap.parse_args()
