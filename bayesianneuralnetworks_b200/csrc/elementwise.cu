@@ -205,6 +205,132 @@ col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dx, bnn_conv2d
   }
 }
 
+// Staged variants (the shapes of the examples: small feature maps, many channels).  One block per (image, channel
+// slice): the block's input — im2col: the slice's cs x H x W activations; col2im: the slice's columns of the image's
+// OH*OW matrix rows — is read once, coalesced, into shared memory; every output element is then produced from shared
+// memory with 32-bit index arithmetic and written coalesced (128-bit stores for the matrix rows).  The generic kernels
+// above (64-bit div/mod per element, gathers from global memory) remain the fallback for images that do not fit.
+constexpr int kStageThreads = 512;
+constexpr size_t kStageSmemTarget = 48 * 1024;      // preferred slice size: several blocks per SM
+constexpr size_t kStageSmemHard = 160 * 1024;
+
+// Channels per slice `cs` and the number of slices for B images of Cg channels, `bytes_per_channel` of shared memory each.
+inline bool plan_slices(int B, int Cg, size_t bytes_per_channel, int* cs_out, int* slices_out) {
+  if (bytes_per_channel == 0 || bytes_per_channel > kStageSmemHard) return false;
+  int64_t max_cs = static_cast<int64_t>(kStageSmemTarget / bytes_per_channel);
+  if (max_cs < 4) max_cs = static_cast<int64_t>(kStageSmemHard / bytes_per_channel);
+  if (max_cs > Cg) max_cs = Cg;
+  int64_t slices = (2 * static_cast<int64_t>(sm_count()) + B - 1) / B;          // fill the machine about twice
+  const int64_t need = (Cg + max_cs - 1) / max_cs;
+  if (slices < need) slices = need;
+  if (slices > Cg) slices = Cg;
+  int64_t cs = (Cg + slices - 1) / slices;
+  const int64_t cs4 = (cs + 3) & ~int64_t(3);                                   // multiples of 4 keep the rows 16-byte aligned
+  if (static_cast<size_t>(cs4) * bytes_per_channel <= kStageSmemHard) cs = cs4;
+  if (static_cast<size_t>(cs) * bytes_per_channel > kStageSmemHard) return false;
+  *cs_out = static_cast<int>(cs);
+  *slices_out = static_cast<int>((Cg + cs - 1) / cs);
+  return true;
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kStageThreads)
+im2col_staged_kernel(const float* __restrict__ x, float* __restrict__ col, bnn_conv2d_geom g, int cs, int vec_in) {
+  extern __shared__ __align__(16) float s_stage[];
+  const int b = blockIdx.x, c_lo = blockIdx.y * cs;
+  const int cn = min(cs, g.Cg - c_lo);
+  const int HW = g.H * g.W, KK = g.KH * g.KW, Kg = g.Cg * KK, P = g.OH * g.OW;
+  const float* src = x + (static_cast<int64_t>(b) * g.C + g.c0 + c_lo) * HW;      // cn channels, contiguous in NCHW
+  const int n_in = cn * HW;
+  if (vec_in) {
+    for (int i = threadIdx.x * 4; i < n_in; i += 4 * kStageThreads)
+      *reinterpret_cast<float4*>(s_stage + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+  } else {
+    for (int i = threadIdx.x; i < n_in; i += kStageThreads) s_stage[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int seg = cn * KK;                                   // the columns of every matrix row this block writes
+  float* dst = col + static_cast<int64_t>(b) * P * Kg + c_lo * KK;
+  auto gather = [&](int ih0, int iw0, int j) {
+    const int c = j / KK, r = j - c * KK;
+    const int kh = r / g.KW, kw = r - kh * g.KW;
+    const int ih = ih0 + kh * g.dh, iw = iw0 + kw * g.dw;
+    return (static_cast<unsigned>(ih) < static_cast<unsigned>(g.H) && static_cast<unsigned>(iw) < static_cast<unsigned>(g.W))
+               ? s_stage[(c * g.H + ih) * g.W + iw] : 0.f;
+  };
+  if (kVec) {
+    const int seg4 = seg >> 2;
+    for (int t = threadIdx.x; t < P * seg4; t += kStageThreads) {
+      const int m = t / seg4, j = (t - m * seg4) * 4;
+      const int oh = m / g.OW, ow = m - oh * g.OW;
+      const int ih0 = oh * g.sh - g.ph, iw0 = ow * g.sw - g.pw;
+      float4 v;
+      v.x = gather(ih0, iw0, j); v.y = gather(ih0, iw0, j + 1); v.z = gather(ih0, iw0, j + 2); v.w = gather(ih0, iw0, j + 3);
+      *reinterpret_cast<float4*>(dst + static_cast<int64_t>(m) * Kg + j) = v;
+    }
+  } else {
+    for (int t = threadIdx.x; t < P * seg; t += kStageThreads) {
+      const int m = t / seg, j = t - m * seg;
+      const int oh = m / g.OW, ow = m - oh * g.OW;
+      dst[static_cast<int64_t>(m) * Kg + j] = gather(oh * g.sh - g.ph, ow * g.sw - g.pw, j);
+    }
+  }
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kStageThreads)
+col2im_staged_kernel(const float* __restrict__ dcol, float* __restrict__ dx, bnn_conv2d_geom g, int cs, int accumulate) {
+  extern __shared__ __align__(16) float s_stage[];
+  const int b = blockIdx.x, c_lo = blockIdx.y * cs;
+  const int cn = min(cs, g.Cg - c_lo);
+  const int HW = g.H * g.W, KK = g.KH * g.KW, Kg = g.Cg * KK, P = g.OH * g.OW;
+  const int seg = cn * KK, pitch = cs * KK;
+  const float* src = dcol + static_cast<int64_t>(b) * P * Kg + c_lo * KK;
+  if (kVec) {
+    const int seg4 = seg >> 2;
+    for (int t = threadIdx.x; t < P * seg4; t += kStageThreads) {
+      const int m = t / seg4, j = (t - m * seg4) * 4;
+      *reinterpret_cast<float4*>(s_stage + m * pitch + j) =
+          __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(m) * Kg + j));
+    }
+  } else {
+    for (int t = threadIdx.x; t < P * seg; t += kStageThreads) {
+      const int m = t / seg, j = t - m * seg;
+      s_stage[m * pitch + j] = __ldg(src + static_cast<int64_t>(m) * Kg + j);
+    }
+  }
+  __syncthreads();
+  float* dst = dx + (static_cast<int64_t>(b) * g.C + g.c0 + c_lo) * HW;            // cn channels, contiguous in NCHW
+  for (int t = threadIdx.x; t < cn * HW; t += kStageThreads) {
+    const int c = t / HW, r = t - c * HW;
+    const int h = r / g.W, w = r - h * g.W;
+    float acc = 0.f;                                    // same (kh, kw) order as the generic kernel
+    for (int kh = 0; kh < g.KH; ++kh) {
+      const int hn = h + g.ph - kh * g.dh;
+      if (hn < 0 || hn % g.sh != 0) continue;
+      const int oh = hn / g.sh;
+      if (oh >= g.OH) continue;
+      for (int kw = 0; kw < g.KW; ++kw) {
+        const int wn = w + g.pw - kw * g.dw;
+        if (wn < 0 || wn % g.sw != 0) continue;
+        const int ow = wn / g.sw;
+        if (ow >= g.OW) continue;
+        acc += s_stage[(oh * g.OW + ow) * pitch + (c * g.KH + kh) * g.KW + kw];
+      }
+    }
+    dst[t] = accumulate ? dst[t] + acc : acc;
+  }
+}
+
+template <typename Kernel>
+int allow_stage_smem(Kernel kernel, bool* done) {
+  if (!*done) {
+    BNN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kStageSmemHard)));
+    *done = true;
+  }
+  return BNN_OK;
+}
+
 int check_geom(const bnn_conv2d_geom* g) {
   BNN_REQUIRE(g != nullptr, BNN_ERR_BAD_ARGUMENT, "conv geometry is NULL");
   BNN_REQUIRE(g->B > 0 && g->C > 0 && g->H > 0 && g->W > 0 && g->Cg > 0 && g->c0 >= 0 &&
@@ -289,8 +415,32 @@ int bnn_im2col(const float* x, float* col, const bnn_conv2d_geom* g, void* strea
   BNN_REQUIRE(x && col, BNN_ERR_BAD_ARGUMENT, "bnn_im2col: NULL pointer");
   rc = check_device();
   if (rc != BNN_OK) return rc;
-  const int64_t total = static_cast<int64_t>(g->B) * g->OH * g->OW * g->Cg * g->KH * g->KW;
-  im2col_kernel<<<grid_for(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, col, *g);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t HW = static_cast<int64_t>(g->H) * g->W, KK = static_cast<int64_t>(g->KH) * g->KW;
+  const int64_t Kg = g->Cg * KK, P = static_cast<int64_t>(g->OH) * g->OW;
+  int cs = 0, slices = 0;
+  if (P * Kg < (int64_t(1) << 30) && plan_slices(g->B, g->Cg, static_cast<size_t>(HW) * 4, &cs, &slices) &&
+      slices <= 65535) {
+    const bool vec = Kg % 4 == 0 && (static_cast<int64_t>(cs) * KK) % 4 == 0 && aligned16(col);
+    const int vec_in = (static_cast<int64_t>(cs) * HW) % 4 == 0 && (static_cast<int64_t>(g->C) * HW) % 4 == 0 &&
+                       (static_cast<int64_t>(g->c0) * HW) % 4 == 0 && (static_cast<int64_t>(g->Cg - (slices - 1) * cs) * HW) % 4 == 0 &&
+                       aligned16(x);
+    const size_t smem = static_cast<size_t>(cs) * HW * 4;
+    const dim3 grid(g->B, slices);
+    static bool attr_vec = false, attr_scalar = false;
+    if (vec) {
+      rc = allow_stage_smem(im2col_staged_kernel<true>, &attr_vec);
+      if (rc != BNN_OK) return rc;
+      im2col_staged_kernel<true><<<grid, kStageThreads, smem, st>>>(x, col, *g, cs, vec_in);
+    } else {
+      rc = allow_stage_smem(im2col_staged_kernel<false>, &attr_scalar);
+      if (rc != BNN_OK) return rc;
+      im2col_staged_kernel<false><<<grid, kStageThreads, smem, st>>>(x, col, *g, cs, vec_in);
+    }
+  } else {
+    const int64_t total = static_cast<int64_t>(g->B) * P * Kg;
+    im2col_kernel<<<grid_for(total, kThreads), kThreads, 0, st>>>(x, col, *g);
+  }
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
 }
@@ -301,8 +451,29 @@ int bnn_col2im(const float* dcol, float* dx, const bnn_conv2d_geom* g, int32_t a
   BNN_REQUIRE(dcol && dx, BNN_ERR_BAD_ARGUMENT, "bnn_col2im: NULL pointer");
   rc = check_device();
   if (rc != BNN_OK) return rc;
-  const int64_t total = static_cast<int64_t>(g->B) * g->Cg * g->H * g->W;
-  col2im_kernel<<<grid_for(total, kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(dcol, dx, *g, accumulate);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t HW = static_cast<int64_t>(g->H) * g->W, KK = static_cast<int64_t>(g->KH) * g->KW;
+  const int64_t Kg = g->Cg * KK, P = static_cast<int64_t>(g->OH) * g->OW;
+  int cs = 0, slices = 0;
+  if (static_cast<int64_t>(g->Cg) * HW < (int64_t(1) << 30) &&
+      plan_slices(g->B, g->Cg, static_cast<size_t>(P * KK) * 4, &cs, &slices) && slices <= 65535) {
+    const bool vec = Kg % 4 == 0 && (static_cast<int64_t>(cs) * KK) % 4 == 0 && aligned16(dcol);
+    const size_t smem = static_cast<size_t>(cs) * P * KK * 4;
+    const dim3 grid(g->B, slices);
+    static bool attr_vec = false, attr_scalar = false;
+    if (vec) {
+      rc = allow_stage_smem(col2im_staged_kernel<true>, &attr_vec);
+      if (rc != BNN_OK) return rc;
+      col2im_staged_kernel<true><<<grid, kStageThreads, smem, st>>>(dcol, dx, *g, cs, accumulate);
+    } else {
+      rc = allow_stage_smem(col2im_staged_kernel<false>, &attr_scalar);
+      if (rc != BNN_OK) return rc;
+      col2im_staged_kernel<false><<<grid, kStageThreads, smem, st>>>(dcol, dx, *g, cs, accumulate);
+    }
+  } else {
+    const int64_t total = static_cast<int64_t>(g->B) * g->Cg * HW;
+    col2im_kernel<<<grid_for(total, kThreads), kThreads, 0, st>>>(dcol, dx, *g, accumulate);
+  }
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
 }

@@ -584,21 +584,59 @@ bool pair_enabled() {
   return v == 1;
 }
 
+// Debugging / test aid, read on every call: BNN_CONTRACT_VARIANT = pair | mb4 | mb2 | mb1 forces one kernel variant
+// (pair needs more than four 128-row blocks), so that small test shapes reach every variant.
+int forced_variant() {
+  const char* e = getenv("BNN_CONTRACT_VARIANT");
+  if (e == nullptr || e[0] == 0) return -1;
+  if (e[0] == 'p') return 0;
+  if (e[0] == 'm' && e[1] == 'b') return e[2] == '4' ? 4 : (e[2] == '2' ? 2 : (e[2] == '1' ? 1 : -1));
+  return -1;
+}
+
 template <bool kDgrad>
 int dispatch_tma_contract(const TmaContractParams& p, int n_cols, cudaStream_t st) {
   const int m_blocks = (p.M + 127) / 128;
   const int gx = (n_cols + 127) / 128, gz = p.sum_samples ? 1 : p.S;
   const int sms = sm_count();
-  auto ctas = [&](int mb) { return static_cast<int64_t>(gx) * ((m_blocks + mb - 1) / mb) * gz; };
-  // Rows per CTA: as many 128-row blocks as possible share one generated weight tile (4, doubled by the CTA pair) —
-  // but never at the price of leaving SMs idle: small problems take fewer blocks per CTA so that the k-loop of each
-  // CTA is short and every SM has one.
-  if (m_blocks > 4 && pair_enabled() && ctas(8) * 2 >= sms) {     // two CTAs (one cluster) per 1024 rows
+  const int n_red = kDgrad ? p.N : p.K;
+  // Rows per CTA by a cost model of the measured kernels, in cycles per 32-wide k-block: a CTA generates
+  // its weight tile at ~1.86 weights/clk whatever the number of 128-row blocks that reuse it (128 x 32 tile: ~2200
+  // cycles; half of it per CTA of a pair), its MMAs + operand delivery cost ~425 cycles per block (~468 per block pair
+  // with cta_group::2), so a k-block takes the larger of the two; a launch takes waves x (fixed cost + k-blocks x that).
+  // Small problems thereby keep few rows per CTA (every SM gets a short k-loop) and large ones share each generated
+  // tile between 1024 rows — without insisting on a CTA for every SM: 144 busy SMs with 4x the reuse beat 148.
+  const double iters = static_cast<double>((n_red + kBK - 1) / kBK) * (p.sum_samples ? p.S : 1);
+  const double w_rows = n_cols < 128 ? n_cols : 128;
+  auto cost_single = [&](int mb) {
+    const int64_t ctas = static_cast<int64_t>(gx) * ((m_blocks + mb - 1) / mb) * gz;
+    const double waves = static_cast<double>((ctas + sms - 1) / sms);
+    const double gen = w_rows * kBK / 1.86, mma = 425.0 * (mb < m_blocks ? mb : m_blocks);
+    return waves * (4000.0 + 600.0 * mb + iters * ((gen > mma ? gen : mma) + 100.0));
+  };
+  auto cost_pair = [&]() {
+    const int64_t pairs = static_cast<int64_t>(gx) * ((m_blocks + 7) / 8) * gz;
+    const int slots = sms / 2;
+    const double waves = static_cast<double>((pairs + slots - 1) / slots);
+    const double gen = (w_rows > 64 ? 64 : w_rows) * kBK / 1.86, mma = 468.0 * 4;
+    return waves * (5000.0 + 600.0 * 4 + iters * ((gen > mma ? gen : mma) + 100.0));
+  };
+  int best = 1;
+  double best_cost = cost_single(1);
+  for (int mb = 2; mb <= 4; mb *= 2) {
+    if (m_blocks < mb) break;
+    const double c = cost_single(mb);
+    if (c < best_cost) { best_cost = c; best = mb; }
+  }
+  if (m_blocks > 4 && pair_enabled() && cost_pair() < 0.9 * best_cost) best = 0;       // a clear win only: the model is coarse
+  const int forced = forced_variant();
+  if (forced > 0 || (forced == 0 && m_blocks > 4)) best = forced;
+  if (best == 0) {                                                // two CTAs (one cluster) per 1024 rows
     const int pairs = (m_blocks + 7) / 8;
     return launch_pair_contract<4, kDgrad>(p, dim3(2 * pairs, gx, gz), st);
   }
-  if (m_blocks >= 4 && ctas(4) >= sms) return launch_tma_contract<4, kDgrad>(p, dim3(gx, (m_blocks + 3) / 4, gz), st);
-  if (m_blocks >= 2 && ctas(2) >= sms) return launch_tma_contract<2, kDgrad>(p, dim3(gx, (m_blocks + 1) / 2, gz), st);
+  if (best == 4) return launch_tma_contract<4, kDgrad>(p, dim3(gx, (m_blocks + 3) / 4, gz), st);
+  if (best == 2) return launch_tma_contract<2, kDgrad>(p, dim3(gx, (m_blocks + 1) / 2, gz), st);
   return launch_tma_contract<1, kDgrad>(p, dim3(gx, m_blocks, gz), st);
 }
 

@@ -2,6 +2,8 @@
 stream and implements the closed-form backward of SURVEY §3.2 with the fused kernels (eps is
 regenerated from the Philox counters, never stored).  No CPU path: non-CUDA tensors raise.
 """
+import math
+
 import torch
 
 from . import _C
@@ -31,6 +33,19 @@ def _check_f32_cuda(name, t):
     _C.require_cuda(t)
     if t.dtype != torch.float32:
         raise TypeError(f"{name}: the variational hot path computes in float32, got {t.dtype}")
+
+
+def _zero_grads(w_shape, n_bias, device):
+    """Zeroed accumulators [2, *w_shape] (d mean, d scale of the weight) and [2, n_bias] (of the bias) carved out of ONE
+    buffer: the gradient kernels accumulate into them, so a layer's backward needs a single fill."""
+    nw = 2 * math.prod(w_shape) if w_shape is not None else 0
+    nb = 2 * n_bias if n_bias is not None else 0
+    if nw + nb == 0:
+        return None, None
+    flat = torch.zeros(nw + nb, device=device, dtype=torch.float32)
+    grads = flat[:nw].view((2,) + tuple(w_shape)) if nw else None
+    bg = flat[nw:].view(2, n_bias) if nb else None
+    return grads, bg
 
 
 def _eps_slice(spec, S, numel, lo=None, hi=None):
@@ -95,13 +110,14 @@ class SampledLinear(torch.autograd.Function):
             dx = torch.empty_like(x)
             _C.sampled_gemm_dgrad(dy_view, M * ldy, mu_w, sigma_w, eps_w, dx, K, a_stride, M, N, K, S,
                                   spec_w.sample_begin, spec_w.rng(), precision)
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            grads = torch.zeros((2, N, K), device=x.device, dtype=torch.float32)
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        need_b = rho_b is not None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
+        grads, bg = _zero_grads((N, K) if need_w else None, N if need_b else None, x.device)
+        if need_w:
             dmu_w, drho_w = grads[0], grads[1]
             _C.sampled_gemm_wgrad(dy_view, M * ldy, x, K, a_stride, rho_w, eps_w, dmu_w, drho_w, M, N, K, S,
                                   spec_w.sample_begin, spec_w.rng(), precision)
-        if rho_b is not None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
-            bg = torch.zeros((2, N), device=x.device, dtype=torch.float32)
+        if need_b:
             dmu_b, drho_b = bg[0], bg[1]
             _C.bias_grad(dy_view, M * ldy, rho_b.contiguous(), _eps_slice(spec_b, S, N), dmu_b, drho_b, M, N, S,
                          spec_b.sample_begin, spec_b.rng())
@@ -195,8 +211,7 @@ class SampledConv2d(torch.autograd.Function):
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         need_b = rho_b is not None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
         dx = torch.empty_like(x) if need_x else None
-        grads = torch.zeros((2,) + tuple(mu_w.shape), device=x.device, dtype=torch.float32) if need_w else None
-        bg = torch.zeros((2, Cout), device=x.device, dtype=torch.float32) if need_b else None
+        grads, bg = _zero_grads(tuple(mu_w.shape) if need_w else None, Cout if need_b else None, x.device)
         kept = ctx.col if need_w else None
         ctx.col = None
         col = kept if kept is not None else (

@@ -472,6 +472,31 @@ def test_sampled_gemm_backward_injected(C, M, N, K, S, shared, prec):
     assert rel_err(drhob, d_rhob) < 1e-5
 
 
+@pytest.mark.parametrize("variant", ["pair", "mb4", "mb2", "mb1"])
+@pytest.mark.parametrize("M,N,K,S,shared", [(700, 136, 96, 3, True), (1024, 256, 128, 2, False), (1100, 64, 288, 2, True)])
+def test_every_tma_contraction_variant_on_small_shapes(C, monkeypatch, variant, M, N, K, S, shared):
+    """The launcher picks rows-per-CTA / CTA pairs from a cost model, so small shapes normally run one variant only;
+    BNN_CONTRACT_VARIANT forces each of them (TF32 mode) through forward and input gradient, shared activations
+    (the input gradient sums the samples inside the kernel) and per-sample ones."""
+    monkeypatch.setenv("BNN_CONTRACT_VARIANT", variant)
+    g = torch.Generator().manual_seed(12)
+    a, mu_w, rho_w, mu_b, rho_b, eps_w, eps_b = gemm_inputs(M, N, K, S, shared, g)
+    y = run_fwd(C, a, mu_w, rho_w, mu_b, rho_b, eps_w, eps_b, S, 0)
+    dy = torch.randn(S, M, N, generator=g)
+    d_a = torch.zeros(a.shape, dtype=torch.float64)
+    for s in range(S):
+        w = mu_w.double() + orc.stddev(rho_w.double()) * eps_w[s].double()
+        ref = orc.linear_forward(a[0 if shared else s].double(), mu_w.double(), rho_w.double(), eps_w[s].double(),
+                                 mu_b.double(), rho_b.double(), eps_b[s].double())
+        assert rel_err(y[s], ref) < TOL[0], f"forward, sample {s}"
+        d_a[0 if shared else s] += dy[s].double() @ w
+    ddy = dy.cuda()
+    da = torch.full(tuple(a.shape), float("nan"), device="cuda")
+    C.sampled_gemm_dgrad(C.make_view(ddy.data_ptr(), N, 1), M * N, mu_w.cuda(), C.stddev(rho_w.cuda()), eps_w.cuda(), da,
+                         K, 0 if shared else M * K, M, N, K, S, 0, C.make_rng(0, 0, 0), 0)
+    assert rel_err(da, d_a) < TOL[0]
+
+
 def test_wgrad_philox_equals_injected(C):
     g = torch.Generator().manual_seed(9)
     M, N, K, S = 96, 72, 136, 5
@@ -498,6 +523,9 @@ CONV_CASES = [
     (3, 64, 6, 6, 64, 3, 2, 1, 1, 1),       # C2 Bayesian conv
     (2, 8, 9, 7, 6, 3, 2, 0, 2, 2),         # stride, dilation, groups, non-square
     (1, 1, 10, 10, 1, 1, 1, 1, 1, 1),       # 1x1 kernel with padding (conftest.py:270)
+    (4, 128, 4, 4, 128, 3, 1, 1, 1, 1),     # C3 Bayesian conv (staged lowering, several channel slices per image)
+    (1, 16, 40, 40, 16, 3, 1, 1, 1, 1),     # col2im slab of one channel > 48 KiB: two-channel slices, scalar rows
+    (1, 2, 224, 224, 2, 3, 2, 1, 1, 1),     # one channel exceeds the staging limit: generic kernels
 ]
 
 
