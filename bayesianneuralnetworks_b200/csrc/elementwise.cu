@@ -233,6 +233,12 @@ inline bool plan_slices(int B, int Cg, size_t bytes_per_channel, int* cs_out, in
   return true;
 }
 
+// Shared-memory layout of both staged kernels: [slab floats, rounded up to 4][lookup table ints].
+// The lookup tables replace every per-element division by the kernel geometry (the kernels are instruction bound):
+//   im2col: one entry per matrix column j of the slice = slab offset of (c, kh*dh, kw*dw) | kh*dh << 16 | kw*dw << 24
+//   col2im: th[h * KH + kh] = oh or -1, tw[w * KW + kw] = ow or -1 (the output position that tap (kh, kw) maps h / w to)
+__host__ __device__ inline int stage_round4(int n) { return (n + 3) & ~3; }
+
 template <bool kVec>
 __global__ void __launch_bounds__(kStageThreads)
 im2col_staged_kernel(const float* __restrict__ x, float* __restrict__ col, bnn_conv2d_geom g, int cs, int vec_in) {
@@ -242,37 +248,49 @@ im2col_staged_kernel(const float* __restrict__ x, float* __restrict__ col, bnn_c
   const int HW = g.H * g.W, KK = g.KH * g.KW, Kg = g.Cg * KK, P = g.OH * g.OW;
   const float* src = x + (static_cast<int64_t>(b) * g.C + g.c0 + c_lo) * HW;      // cn channels, contiguous in NCHW
   const int n_in = cn * HW;
+  const int seg = cn * KK;                                   // the columns of every matrix row this block writes
+  uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_stage + stage_round4(cs * HW));
   if (vec_in) {
     for (int i = threadIdx.x * 4; i < n_in; i += 4 * kStageThreads)
       *reinterpret_cast<float4*>(s_stage + i) = __ldg(reinterpret_cast<const float4*>(src + i));
   } else {
     for (int i = threadIdx.x; i < n_in; i += kStageThreads) s_stage[i] = __ldg(src + i);
   }
-  __syncthreads();
-  const int seg = cn * KK;                                   // the columns of every matrix row this block writes
-  float* dst = col + static_cast<int64_t>(b) * P * Kg + c_lo * KK;
-  auto gather = [&](int ih0, int iw0, int j) {
+  for (int j = threadIdx.x; j < stage_round4(seg); j += kStageThreads) {
     const int c = j / KK, r = j - c * KK;
     const int kh = r / g.KW, kw = r - kh * g.KW;
-    const int ih = ih0 + kh * g.dh, iw = iw0 + kw * g.dw;
+    const int khd = kh * g.dh, kwd = kw * g.dw;
+    s_tab[j] = static_cast<uint32_t>((c * g.H + khd) * g.W + kwd) | (static_cast<uint32_t>(khd) << 16) |
+               (static_cast<uint32_t>(kwd) << 24);
+  }
+  __syncthreads();
+  float* dst = col + static_cast<int64_t>(b) * P * Kg + c_lo * KK;
+  auto gather = [&](int ih0, int iw0, int base, uint32_t e) {
+    const int ih = ih0 + static_cast<int>((e >> 16) & 0xffu), iw = iw0 + static_cast<int>(e >> 24);
     return (static_cast<unsigned>(ih) < static_cast<unsigned>(g.H) && static_cast<unsigned>(iw) < static_cast<unsigned>(g.W))
-               ? s_stage[(c * g.H + ih) * g.W + iw] : 0.f;
+               ? s_stage[base + static_cast<int>(e & 0xffffu)] : 0.f;
   };
   if (kVec) {
     const int seg4 = seg >> 2;
-    for (int t = threadIdx.x; t < P * seg4; t += kStageThreads) {
-      const int m = t / seg4, j = (t - m * seg4) * 4;
+    int m = threadIdx.x / seg4, j4 = threadIdx.x - m * seg4;          // one division, then incremental
+    const int dm = kStageThreads / seg4, dj = kStageThreads - dm * seg4;
+    for (; m < P;) {
       const int oh = m / g.OW, ow = m - oh * g.OW;
-      const int ih0 = oh * g.sh - g.ph, iw0 = ow * g.sw - g.pw;
+      const int ih0 = oh * g.sh - g.ph, iw0 = ow * g.sw - g.pw, base = ih0 * g.W + iw0;
+      const uint4 e = *reinterpret_cast<const uint4*>(s_tab + 4 * j4);
       float4 v;
-      v.x = gather(ih0, iw0, j); v.y = gather(ih0, iw0, j + 1); v.z = gather(ih0, iw0, j + 2); v.w = gather(ih0, iw0, j + 3);
-      *reinterpret_cast<float4*>(dst + static_cast<int64_t>(m) * Kg + j) = v;
+      v.x = gather(ih0, iw0, base, e.x); v.y = gather(ih0, iw0, base, e.y);
+      v.z = gather(ih0, iw0, base, e.z); v.w = gather(ih0, iw0, base, e.w);
+      *reinterpret_cast<float4*>(dst + static_cast<int64_t>(m) * Kg + 4 * j4) = v;
+      m += dm; j4 += dj;
+      if (j4 >= seg4) { j4 -= seg4; ++m; }
     }
   } else {
     for (int t = threadIdx.x; t < P * seg; t += kStageThreads) {
       const int m = t / seg, j = t - m * seg;
       const int oh = m / g.OW, ow = m - oh * g.OW;
-      dst[static_cast<int64_t>(m) * Kg + j] = gather(oh * g.sh - g.ph, ow * g.sw - g.pw, j);
+      const int ih0 = oh * g.sh - g.ph, iw0 = ow * g.sw - g.pw;
+      dst[static_cast<int64_t>(m) * Kg + j] = gather(ih0, iw0, ih0 * g.W + iw0, s_tab[j]);
     }
   }
 }
@@ -286,12 +304,17 @@ col2im_staged_kernel(const float* __restrict__ dcol, float* __restrict__ dx, bnn
   const int HW = g.H * g.W, KK = g.KH * g.KW, Kg = g.Cg * KK, P = g.OH * g.OW;
   const int seg = cn * KK, pitch = cs * KK;
   const float* src = dcol + static_cast<int64_t>(b) * P * Kg + c_lo * KK;
+  int* s_th = reinterpret_cast<int*>(s_stage + stage_round4(P * pitch));
+  int* s_tw = s_th + g.H * g.KH;
   if (kVec) {
     const int seg4 = seg >> 2;
-    for (int t = threadIdx.x; t < P * seg4; t += kStageThreads) {
-      const int m = t / seg4, j = (t - m * seg4) * 4;
-      *reinterpret_cast<float4*>(s_stage + m * pitch + j) =
-          __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(m) * Kg + j));
+    int m = threadIdx.x / seg4, j4 = threadIdx.x - m * seg4;
+    const int dm = kStageThreads / seg4, dj = kStageThreads - dm * seg4;
+    for (; m < P;) {
+      *reinterpret_cast<float4*>(s_stage + m * pitch + 4 * j4) =
+          __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(m) * Kg + 4 * j4));
+      m += dm; j4 += dj;
+      if (j4 >= seg4) { j4 -= seg4; ++m; }
     }
   } else {
     for (int t = threadIdx.x; t < P * seg; t += kStageThreads) {
@@ -299,23 +322,31 @@ col2im_staged_kernel(const float* __restrict__ dcol, float* __restrict__ dx, bnn
       s_stage[m * pitch + j] = __ldg(src + static_cast<int64_t>(m) * Kg + j);
     }
   }
+  for (int i = threadIdx.x; i < g.H * g.KH + g.W * g.KW; i += kStageThreads) {
+    const bool is_h = i < g.H * g.KH;
+    const int e = is_h ? i : i - g.H * g.KH;
+    const int taps = is_h ? g.KH : g.KW, pad = is_h ? g.ph : g.pw, dil = is_h ? g.dh : g.dw;
+    const int str = is_h ? g.sh : g.sw, lim = is_h ? g.OH : g.OW;
+    const int pos = e / taps, tap = e - pos * taps;
+    const int num = pos + pad - tap * dil;
+    int o = -1;
+    if (num >= 0 && num % str == 0 && num / str < lim) o = num / str;
+    s_th[i] = o;                                        // s_tw follows s_th directly
+  }
   __syncthreads();
   float* dst = dx + (static_cast<int64_t>(b) * g.C + g.c0 + c_lo) * HW;            // cn channels, contiguous in NCHW
   for (int t = threadIdx.x; t < cn * HW; t += kStageThreads) {
     const int c = t / HW, r = t - c * HW;
     const int h = r / g.W, w = r - h * g.W;
+    const float* s_c = s_stage + c * KK;
     float acc = 0.f;                                    // same (kh, kw) order as the generic kernel
     for (int kh = 0; kh < g.KH; ++kh) {
-      const int hn = h + g.ph - kh * g.dh;
-      if (hn < 0 || hn % g.sh != 0) continue;
-      const int oh = hn / g.sh;
-      if (oh >= g.OH) continue;
+      const int oh = s_th[h * g.KH + kh];
+      if (oh < 0) continue;
       for (int kw = 0; kw < g.KW; ++kw) {
-        const int wn = w + g.pw - kw * g.dw;
-        if (wn < 0 || wn % g.sw != 0) continue;
-        const int ow = wn / g.sw;
-        if (ow >= g.OW) continue;
-        acc += s_stage[(oh * g.OW + ow) * pitch + (c * g.KH + kh) * g.KW + kw];
+        const int ow = s_tw[w * g.KW + kw];
+        if (ow < 0) continue;
+        acc += s_c[(oh * g.OW + ow) * pitch + kh * g.KW + kw];
       }
     }
     dst[t] = accumulate ? dst[t] + acc : acc;
@@ -325,7 +356,7 @@ col2im_staged_kernel(const float* __restrict__ dcol, float* __restrict__ dx, bnn
 template <typename Kernel>
 int allow_stage_smem(Kernel kernel, bool* done) {
   if (!*done) {
-    BNN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kStageSmemHard)));
+    BNN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kStageSmemHard + 1024)));      // + rounding of the two regions
     *done = true;
   }
   return BNN_OK;
@@ -419,13 +450,15 @@ int bnn_im2col(const float* x, float* col, const bnn_conv2d_geom* g, void* strea
   const int64_t HW = static_cast<int64_t>(g->H) * g->W, KK = static_cast<int64_t>(g->KH) * g->KW;
   const int64_t Kg = g->Cg * KK, P = static_cast<int64_t>(g->OH) * g->OW;
   int cs = 0, slices = 0;
-  if (P * Kg < (int64_t(1) << 30) && plan_slices(g->B, g->Cg, static_cast<size_t>(HW) * 4, &cs, &slices) &&
-      slices <= 65535) {
+  // table entry: slab offset < 2^16, dilated tap offsets < 2^8
+  if (P * Kg < (int64_t(1) << 30) && static_cast<int64_t>(g->KH - 1) * g->dh < 256 && static_cast<int64_t>(g->KW - 1) * g->dw < 256 &&
+      plan_slices(g->B, g->Cg, static_cast<size_t>(HW + KK) * 4, &cs, &slices) && slices <= 65535 &&
+      static_cast<int64_t>(cs) * HW + static_cast<int64_t>(g->KH) * g->dh * g->W < 65536) {
     const bool vec = Kg % 4 == 0 && (static_cast<int64_t>(cs) * KK) % 4 == 0 && aligned16(col);
     const int vec_in = (static_cast<int64_t>(cs) * HW) % 4 == 0 && (static_cast<int64_t>(g->C) * HW) % 4 == 0 &&
                        (static_cast<int64_t>(g->c0) * HW) % 4 == 0 && (static_cast<int64_t>(g->Cg - (slices - 1) * cs) * HW) % 4 == 0 &&
                        aligned16(x);
-    const size_t smem = static_cast<size_t>(cs) * HW * 4;
+    const size_t smem = (static_cast<size_t>(stage_round4(static_cast<int>(cs * HW))) + stage_round4(static_cast<int>(cs * KK))) * 4;
     const dim3 grid(g->B, slices);
     static bool attr_vec = false, attr_scalar = false;
     if (vec) {
@@ -456,9 +489,11 @@ int bnn_col2im(const float* dcol, float* dx, const bnn_conv2d_geom* g, int32_t a
   const int64_t Kg = g->Cg * KK, P = static_cast<int64_t>(g->OH) * g->OW;
   int cs = 0, slices = 0;
   if (static_cast<int64_t>(g->Cg) * HW < (int64_t(1) << 30) &&
-      plan_slices(g->B, g->Cg, static_cast<size_t>(P * KK) * 4, &cs, &slices) && slices <= 65535) {
+      static_cast<int64_t>(g->H) * g->KH + static_cast<int64_t>(g->W) * g->KW <= 2048 &&
+      plan_slices(g->B, g->Cg, static_cast<size_t>(P * KK) * 4, &cs, &slices) && slices <= 65535 &&
+      static_cast<size_t>(cs) * P * KK * 4 + 8192 + 16 <= kStageSmemHard) {
     const bool vec = Kg % 4 == 0 && (static_cast<int64_t>(cs) * KK) % 4 == 0 && aligned16(dcol);
-    const size_t smem = static_cast<size_t>(cs) * P * KK * 4;
+    const size_t smem = (static_cast<size_t>(stage_round4(static_cast<int>(cs * P * KK))) + g->H * g->KH + g->W * g->KW) * 4;
     const dim3 grid(g->B, slices);
     static bool attr_vec = false, attr_scalar = false;
     if (vec) {
