@@ -96,6 +96,13 @@ _SIGNATURES = {
                                  ctypes.c_size_t, ctypes.c_void_p]),
     "bnn_adam_kl_step": (ctypes.c_int, [ctypes.POINTER(bnn_adam_tensor), ctypes.c_int32, ctypes.c_float, ctypes.c_float,
                                         ctypes.c_float, ctypes.c_float, _c_f32p, ctypes.c_int64, ctypes.c_void_p]),
+    "bnn_mc_cross_entropy_workspace_size": (ctypes.c_size_t, []),
+    "bnn_mc_cross_entropy_fwd": (ctypes.c_int, [_c_f32p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                                ctypes.c_int32, ctypes.c_int64, _c_f32p, _c_f32p, _c_f32p, ctypes.c_void_p,
+                                                ctypes.c_size_t, ctypes.c_void_p]),
+    "bnn_mc_cross_entropy_bwd": (ctypes.c_int, [_c_f32p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                                ctypes.c_int32, ctypes.c_int64, _c_f32p, _c_f32p, _c_f32p, _c_f32p,
+                                                ctypes.c_int64, ctypes.c_void_p]),
     "bnn_selftest_prune_interval": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_int32,
                                                    ctypes.c_void_p]),
     "bnn_selftest_umma": (ctypes.c_int, [_c_f32p, ctypes.c_void_p]),
@@ -405,6 +412,52 @@ def adam_kl_step(entries, lr, beta1, beta2, eps, step_dev=None, step=0):
     with torch.cuda.device(device):
         _call("bnn_adam_kl_step", table, n, lr, beta1, beta2, eps, _ptr(step_dev), int(step), _stream())
     _count((n + 15) // 16)
+
+
+_ce_ws = {}
+
+
+def _check_ce(x, target):
+    require_cuda(x, target)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1 or x.stride(0) < x.shape[1]:
+        raise TypeError("x must be a float32 [rows, classes] matrix with unit column stride")
+    if target.dtype != torch.int64 or target.dim() != 1 or not target.is_contiguous():
+        raise TypeError("target must be a contiguous int64 vector of class indices")
+    if target.numel() == 0 or x.shape[0] % target.numel() != 0:
+        raise ValueError(f"{x.shape[0]} rows are not a whole number of blocks of {target.numel()} labels")
+
+
+def mc_cross_entropy_fwd(x, target, ignore_index=-100):
+    """(loss, lse, count) of bnn_mc_cross_entropy_fwd: x [S*B, C] float32 (row pitch x.stride(0)), target [B] int64."""
+    _check_ce(x, target)
+    rows, classes = x.shape
+    lse = torch.empty(rows, dtype=torch.float32, device=x.device)
+    out = torch.empty(2, dtype=torch.float32, device=x.device)          # loss, count
+    nbytes = lib().bnn_mc_cross_entropy_workspace_size()
+    ws = _ce_ws.get(x.device)
+    if ws is None or ws.numel() < nbytes + 256:
+        ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=x.device)      # zero once; calls leave it ready
+        _ce_ws[x.device] = ws
+    base = (ws.data_ptr() + 255) & ~255
+    with torch.cuda.device(x.device):
+        _call("bnn_mc_cross_entropy_fwd", _ptr(x), x.stride(0), _ptr(target), rows, target.numel(), classes,
+              int(ignore_index), _ptr(lse), _ptr(out[0]), _ptr(out[1]), ctypes.c_void_p(base), nbytes, _stream())
+    _count()
+    return out[0], lse, out[1]
+
+
+def mc_cross_entropy_bwd(x, target, lse, count, grad_loss, ignore_index=-100):
+    """dx [S*B, C] of bnn_mc_cross_entropy_bwd (grad_loss: 0-dim float32 device tensor)."""
+    _check_ce(x, target)
+    require_cuda(lse, count, grad_loss)
+    _f32c(lse, "lse"), _f32c(count, "count"), _f32c(grad_loss, "grad_loss")
+    rows, classes = x.shape
+    dx = torch.empty((rows, classes), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _call("bnn_mc_cross_entropy_bwd", _ptr(x), x.stride(0), _ptr(target), rows, target.numel(), classes,
+              int(ignore_index), _ptr(lse), _ptr(count), _ptr(grad_loss), _ptr(dx), classes, _stream())
+    _count()
+    return dx
 
 
 def selftest_prune_interval(mu, rho, variant=1):

@@ -309,3 +309,29 @@ class KLSum(torch.autograd.Function):
             entries.append((mu, rho, gm, gr, priors[t][0], priors[t][1], coeffs[t]))
         _C.kl(entries, want_sums=False, want_total=False, grad_scale=scale)
         return (None, None) + tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------------
+class MCCrossEntropy(torch.autograd.Function):
+    """Mean cross-entropy of the [S*B, C] score matrix `x` against the B labels shared by the S Monte-Carlo samples
+    (examples/MNIST/train.py:59-61 with CrossEntropyLoss): one forward and one backward kernel
+    (bnn_mc_cross_entropy_fwd / _bwd) instead of torch's log_softmax + nll_loss chains over a replicated target."""
+
+    @staticmethod
+    def forward(ctx, x, target, ignore_index):
+        if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
+            x = x.contiguous()
+        target = target.contiguous()
+        loss, lse, count = _C.mc_cross_entropy_fwd(x, target, ignore_index)
+        ctx.save_for_backward(x, target, lse, count)
+        ctx.ignore_index = ignore_index
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, target, lse, count = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None
+        g = g.detach().to(torch.float32).reshape(()).contiguous()
+        return _C.mc_cross_entropy_bwd(x, target, lse, count, g, ctx.ignore_index), None, None

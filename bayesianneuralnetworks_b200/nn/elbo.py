@@ -4,7 +4,8 @@ The reference's loop body averages a row-mean criterion over the list of S predi
 `torch.stack([criterion(pred, y) for pred in preds]).mean()` (examples/MNIST/train.py:59-61): 3 S launches forward and
 as many backward for S tiny tensors.  When the predictions are the row blocks of ONE [S*B, ...] tensor — which is what
 the batched Monte-Carlo forward of `BayesianNetworkModule` produces — the mean of the S block means is the mean over
-all S*B rows, i.e. one criterion call.  `mc_mean_loss` does that and falls back to the reference loop otherwise.
+all S*B rows, i.e. one criterion call.  `mc_mean_loss` does that and falls back to the reference loop otherwise.  Plain
+cross-entropy on CUDA (the examples' criterion) goes to the fused kernels bnn_mc_cross_entropy_fwd / _bwd.
 """
 import torch
 import torch.nn.functional as F
@@ -30,6 +31,17 @@ def _row_mean(criterion):
     return any(criterion is f for f in _MEAN_FUNCTIONS)
 
 
+def _plain_cross_entropy(criterion):
+    """ignore_index when `criterion` is cross-entropy with mean reduction, class-index targets and no class weights or
+    label smoothing (the criterion of the reference examples, train.py:40); None otherwise."""
+    if criterion is F.cross_entropy:
+        return -100
+    if (type(criterion) is torch.nn.CrossEntropyLoss and criterion.weight is None and criterion.reduction == 'mean'
+            and criterion.label_smoothing == 0.0):
+        return criterion.ignore_index
+    return None
+
+
 def mc_mean_loss(criterion, preds, target):
     """mean_s criterion(preds[s], target) for the list of Monte-Carlo predictions `preds` (a bare tensor when S == 1,
     as the reference returns it)."""
@@ -39,5 +51,10 @@ def mc_mean_loss(criterion, preds, target):
     n = len(preds)
     if (base is not None and n > 1 and _row_mean(criterion) and torch.is_tensor(target) and target.dim() >= 1
             and base.shape[0] == n * target.shape[0]):
+        ignore_index = _plain_cross_entropy(criterion)
+        if (ignore_index is not None and base.is_cuda and base.dtype == torch.float32 and base.dim() == 2
+                and target.dim() == 1 and target.dtype == torch.int64 and target.device == base.device):
+            from ..functional import MCCrossEntropy       # one fused kernel each way, labels not replicated
+            return MCCrossEntropy.apply(base, target, ignore_index)
         return criterion(base, target.repeat((n,) + (1,) * (target.dim() - 1)))
     return torch.stack([criterion(p, target) for p in preds]).mean()

@@ -206,6 +206,27 @@ typedef struct bnn_adam_tensor {
 int bnn_adam_kl_step(const bnn_adam_tensor* tensors /* HOST array */, int32_t n_tensors, float lr, float beta1, float beta2,
                      float eps, const float* step_dev, int64_t step_host, void* stream);
 
+/* ---- likelihood tail: mean cross-entropy over the S Monte-Carlo predictions ----
+ * Replaces the loop body `torch.stack([criterion(pred, y) for pred in preds]).mean()` with criterion =
+ * CrossEntropyLoss() — examples/MNIST/train.py:59-61 — when the S predictions are the row blocks of one
+ * [rows = S*labels][classes] matrix x (row pitch ldx floats): row r is scored against target[r % labels], so the B
+ * labels are shared by the samples and never replicated.
+ *   loss  = sum_r (logsumexp(x[r,:]) - x[r, target]) / count over the rows whose target != ignore_index
+ *           (torch.nn.functional.cross_entropy, reduction 'mean'; a target outside [0, classes) that is not
+ *           ignore_index makes the loss NaN instead of torch's device assert)
+ *   lse   [rows]: logsumexp of every row, kept for the backward pass;  count: number of rows that counted (float).
+ *   dx    = grad_loss / count * (softmax(x[r,:]) - onehot(target)), 0 for ignored rows; written, not accumulated.
+ * Forward reads x once (one warp per row, online max/sum), backward reads x once and writes dx once.
+ * `workspace`: bnn_mc_cross_entropy_workspace_size() bytes, 16-byte aligned, ZERO when first used; a call leaves it
+ * ready for the next call on the same stream.  loss / count / grad_loss are device scalars. */
+size_t bnn_mc_cross_entropy_workspace_size(void);
+int bnn_mc_cross_entropy_fwd(const float* x, int64_t ldx, const int64_t* target, int64_t rows, int64_t labels,
+                             int32_t classes, int64_t ignore_index, float* lse, float* loss, float* count,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int bnn_mc_cross_entropy_bwd(const float* x, int64_t ldx, const int64_t* target, int64_t rows, int64_t labels,
+                             int32_t classes, int64_t ignore_index, const float* lse, const float* count,
+                             const float* grad_loss, float* dx, int64_t lddx, void* stream);
+
 /* ---- pruning ----
  * key_i = log N(0; mu_i, sigma_i) evaluated with the exact op order of torch's Normal.log_prob
  * (torch/distributions/normal.py:87-102) on softplus(rho)+1e-10; the k largest keys get

@@ -516,6 +516,56 @@ def test_wgrad_philox_equals_injected(C):
     assert rel_err(outs[1][1], outs[0][1].cpu()) < 1e-6
 
 
+# ------------------------------------------------------------------------------------------------ likelihood tail
+@pytest.mark.parametrize("S,B,classes,pitch", [(8, 256, 10, 10), (3, 32, 4096, 4096), (5, 7, 13, 13), (2, 9, 12, 16),
+                                               (1, 1, 1, 1), (4, 300, 100, 100)])
+def test_mc_cross_entropy_matches_torch(C, S, B, classes, pitch):
+    """bnn_mc_cross_entropy_fwd / _bwd == F.cross_entropy over the S*B rows with the labels replicated S times
+    (the reference loop of train.py:59-61 is the mean of the S block means = the mean over all rows), fp32, 1e-6."""
+    g = torch.Generator().manual_seed(13)
+    store = torch.rand(S * B, pitch, generator=g).cuda()               # probabilities-like scores, as the models emit
+    x = store[:, :classes]
+    y = torch.randint(0, classes, (B,), generator=g).cuda()
+    if B > 4:
+        y[1] = -100                                                     # ignored rows (torch's default ignore_index)
+    xr = x.detach().clone().contiguous().requires_grad_(True)
+    ref = F.cross_entropy(xr, y.repeat(S))
+    (ref * 3.0).backward()
+    loss, lse, count = C.mc_cross_entropy_fwd(x, y)
+    assert abs(float(loss) - float(ref)) <= 1e-6 * abs(float(ref)) + 1e-7
+    assert float(count) == S * int((y != -100).sum())
+    assert torch.allclose(lse, torch.logsumexp(x, dim=1), rtol=1e-6, atol=1e-6)
+    dx = C.mc_cross_entropy_bwd(x, y, lse, count, torch.tensor(3.0, device="cuda"))
+    assert torch.allclose(dx, xr.grad, rtol=1e-5, atol=1e-9)
+    # widely spread logits (the online max / sum rescaling), same tolerances relative to the loss
+    z = (torch.randn(S * B, classes, generator=g) * 30).cuda()
+    zr = z.clone().requires_grad_(True)
+    ref2 = F.cross_entropy(zr, y.repeat(S))
+    ref2.backward()
+    loss2, lse2, count2 = C.mc_cross_entropy_fwd(z, y)
+    if bool((y != -100).any()):
+        assert abs(float(loss2) - float(ref2)) <= 2e-6 * abs(float(ref2)) + 1e-6
+        dz = C.mc_cross_entropy_bwd(z, y, lse2, count2, torch.tensor(1.0, device="cuda"))
+        assert torch.allclose(dz, zr.grad, rtol=1e-4, atol=1e-8)
+
+
+def test_mc_cross_entropy_edge_cases(C):
+    x = torch.rand(6, 5, device="cuda")
+    ignored = torch.full((3,), -100, dtype=torch.int64, device="cuda")
+    loss, _, count = C.mc_cross_entropy_fwd(x, ignored)
+    assert float(count) == 0 and bool(torch.isnan(loss))                # torch returns NaN as well
+    bad = torch.tensor([0, 7, 1], device="cuda")                        # class 7 of 5: NaN instead of a device assert
+    assert bool(torch.isnan(C.mc_cross_entropy_fwd(x, bad)[0]))
+    with pytest.raises(ValueError):
+        C.mc_cross_entropy_fwd(x, torch.zeros(4, dtype=torch.int64, device="cuda"))      # 6 rows, 4 labels
+    with pytest.raises(TypeError):
+        C.mc_cross_entropy_fwd(x, torch.zeros(3, dtype=torch.int32, device="cuda"))
+    # back-to-back calls reuse the self-resetting workspace
+    y = torch.tensor([1, 4, 0], device="cuda")
+    a = [float(C.mc_cross_entropy_fwd(x, y)[0]) for _ in range(3)]
+    assert a[0] == a[1] == a[2] and abs(a[0] - float(F.cross_entropy(x, y.repeat(2)))) < 1e-6
+
+
 # ------------------------------------------------------------------------------------------------ conv lowering
 CONV_CASES = [
     # B, C, H, W, Cout, k, stride, pad, dil, groups
