@@ -247,7 +247,9 @@ class Trainer:
             self.flat = torch.zeros(total, device=x.device, dtype=torch.float32)
             off = 0
             for p in self.params:
-                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                # same strides as the parameter (channels_last trunk weights are dense permutations of their storage):
+                # torch's fused Adam wants gradients in the parameter's layout
+                p.grad = torch.as_strided(self.flat, p.size(), p.stride(), off)
                 off += p.numel()
         # one GPU: zero_grad(set_to_none=True) inside the captured step — autograd then hands the freshly computed
         # gradient tensors (static addresses in the graph's pool) to .grad without an accumulation pass

@@ -52,6 +52,12 @@ def _worker(rank, world, port, results):
         assert torch.allclose(lin.weight.grad, torch.full((3, 5), 3.0))       # (2*1 + 2*2) / 2
         assert torch.allclose(lin.bias.grad, torch.full((3,), 2.0))
         assert torch.allclose(extra.grad, torch.full((4,), 1.0))              # (2 + 0) / 2
+        # --- parameters kept in channels_last (bench.py's torch trunk): gradients are reduced in logical order
+        conv = torch.nn.Conv2d(2, 3, 3).to(memory_format=torch.channels_last)
+        conv(torch.full((1, 2, 4, 4), float(rank + 1))).sum().backward()
+        parallel.allreduce_gradients(list(conv.parameters()))
+        assert torch.allclose(conv.weight.grad, torch.full((3, 2, 3, 3), 6.0))   # 4 positions * (1 + 2) / 2
+        assert torch.allclose(conv.bias.grad, torch.full((3,), 4.0))
         results[rank] = "ok"
     finally:
         dist.destroy_process_group()
