@@ -2,7 +2,8 @@
 //   bnn_stddev       sigma = 1e-10 + softplus(rho)                (reference core.py:25-27)
 //   bnn_materialize  W_s = mu + sigma * eps(s)                    (reference core.py:44-45)
 //   bnn_bias_grad    reparameterised bias gradient                (autograd of dense.py:46-60)
-//   bnn_im2col / bnn_col2im  conv2d lowering for the sampled GEMM (conv.py:112-119)
+//   bnn_im2col / bnn_col2im  conv2d lowering for the sampled GEMM (conv.py:112-119): staged through shared memory per
+//                    (image, channel slice) with table-driven indexing; generic gather kernels as the fallback
 #include "common.cuh"
 
 namespace bnn {

@@ -15,6 +15,11 @@ pinned host memory with the loss read back every step; `roofline`: the dominant 
 live with CUDA events; `cpu_baseline`: the oracle's restatement of the reference step on the host
 cores (bounded sample); `kl_prune`: the bandwidth-bound KL / prune sweeps (C5 shape, bounded size).
 `--impl reference` times the reference's CPU path (oracle port) on the same config.
+
+Torch-side settings of the deterministic trunk (Conv2d / BatchNorm2d / ELU / Linear of the example models, outside the
+hot path but inside the measured step): cuDNN autotuning (`--no-cudnn-benchmark`), torch.channels_last for the trunk
+modules (`--nchw-trunk`), allow_tf32 in TF32 mode.  The likelihood term goes through nn.mc_mean_loss
+(`--loss-tail loop` = the reference loop verbatim), the optimizer is bnn.optim.ELBOAdam (`--optimizer adam`).
 """
 import argparse
 import json

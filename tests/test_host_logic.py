@@ -212,6 +212,15 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
                                     ctypes.byref(rng), None, 0, null) == 6                          # BNN_ERR_UNSUPPORTED
     geom = _C.bnn_conv2d_geom(1, 4, 8, 8, 2, 4, 3, 3, 6, 6, 1, 1, 0, 0, 1, 1)                       # c0 + Cg > C
     assert lib.bnn_im2col(one, one, ctypes.byref(geom), null) == 1 and "geometry" in msg()
+    # likelihood tail: rows must be whole sample blocks, pitches must hold a row, the workspace is checked last
+    ce_ws = lib.bnn_mc_cross_entropy_workspace_size()
+    assert ce_ws >= 16 + 2 * 8 * 148
+    assert lib.bnn_mc_cross_entropy_fwd(one, 4, one, 10, 3, 4, -100, one, one, one, one, ce_ws, null) == 1 and "sample blocks" in msg()
+    assert lib.bnn_mc_cross_entropy_fwd(one, 3, one, 9, 3, 4, -100, one, one, one, one, ce_ws, null) == 1 and "pitch" in msg()
+    assert lib.bnn_mc_cross_entropy_fwd(null, 4, one, 9, 3, 4, -100, one, one, one, one, ce_ws, null) == 1 and "NULL" in msg()
+    assert lib.bnn_mc_cross_entropy_fwd(one, 4, one, 0, 3, 4, -100, one, one, one, one, ce_ws, null) == 1 and "empty" in msg()
+    assert lib.bnn_mc_cross_entropy_bwd(one, 4, one, 9, 3, 4, -100, one, one, one, null, 4, null) == 1 and "NULL" in msg()
+    assert lib.bnn_mc_cross_entropy_bwd(one, 4, one, 9, 3, 4, -100, one, one, one, one, 2, null) == 1 and "pitch" in msg()
 
 
 def test_prune_workspace_plan_and_selftest_argument_checks():
@@ -278,6 +287,33 @@ def test_mc_mean_loss_host_logic():
     plain = [p.detach() for p in preds]
     assert torch.allclose(mc_mean_loss(F.cross_entropy, plain, y), torch.stack([F.cross_entropy(p, y) for p in plain]).mean())
     assert torch.equal(mc_mean_loss(F.cross_entropy, plain[0], y), F.cross_entropy(plain[0], y))
+
+
+def test_fused_cross_entropy_eligibility_and_gradient_buffers():
+    """Which criteria nn.mc_mean_loss may send to bnn_mc_cross_entropy (plain mean cross-entropy over class indices,
+    the examples' criterion, train.py:40) and the single zeroed buffer a layer's backward accumulates into."""
+    import torch.nn.functional as F
+    from bayesianneuralnetworks_b200.functional import _zero_grads
+    from bayesianneuralnetworks_b200.nn.elbo import _plain_cross_entropy
+    assert _plain_cross_entropy(F.cross_entropy) == -100
+    assert _plain_cross_entropy(torch.nn.CrossEntropyLoss()) == -100
+    assert _plain_cross_entropy(torch.nn.CrossEntropyLoss(ignore_index=3)) == 3
+    for other in (torch.nn.CrossEntropyLoss(weight=torch.ones(4)), torch.nn.CrossEntropyLoss(label_smoothing=0.1),
+                  torch.nn.CrossEntropyLoss(reduction='sum'), torch.nn.NLLLoss(), F.nll_loss,
+                  lambda p, t: F.cross_entropy(p, t)):
+        assert _plain_cross_entropy(other) is None
+
+    class Sub(torch.nn.CrossEntropyLoss):          # a subclass may override forward: not assumed to be plain
+        pass
+    assert _plain_cross_entropy(Sub()) is None
+    grads, bias = _zero_grads((6, 4, 3, 3), 6, 'cpu')
+    assert grads.shape == (2, 6, 4, 3, 3) and bias.shape == (2, 6) and not grads.any() and not bias.any()
+    assert grads.is_contiguous() and bias.is_contiguous()
+    assert bias.data_ptr() == grads.data_ptr() + 4 * grads.numel()         # one allocation, one fill
+    assert _zero_grads(None, None, 'cpu') == (None, None)
+    assert _zero_grads(None, 5, 'cpu')[0] is None and _zero_grads((2, 3), None, 'cpu')[1] is None
+    with pytest.raises(RuntimeError, match="CUDA"):
+        _C.mc_cross_entropy_fwd(torch.zeros(4, 3), torch.zeros(2, dtype=torch.int64))
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="the reference checkout is only mounted in the build container")
