@@ -986,18 +986,36 @@ int tma_wgrad(bnn_view dy, int64_t dy_sample_stride, const float* a, int64_t lda
   p.shared_a = shared ? 1 : 0;
   const int tiles = ((N + 127) / 128) * ((K + 127) / 128);
   const int m_total = (M + kWgRows - 1) / kWgRows;         // 64-row stages
-  int want = (2 * sm_count() + tiles - 1) / tiles;        // CTAs per output tile that fill the machine twice
-  if (want < 1) want = 1;
-  int n_chunks = 1;
-  if (want > S) {                                         // few samples / tiles: also split the M reduction
-    n_chunks = (want + S - 1) / S;
-    const int max_chunks = (m_total + 3) / 4;             // keep >= 4 stages (256 rows) per unit (epilogue cost per unit)
-    if (n_chunks > max_chunks) n_chunks = max_chunks;
-    if (n_chunks < 1) n_chunks = 1;
+  // Work units = (sample, M-chunk); a CTA = (tile, group) walks `per` consecutive units, the epilogue of one unit
+  // (TMEM drain + eps regeneration for 128 x 128 weights, ~6 stage times) overlapping the MMAs of the next.  The plan
+  // minimises  waves x (per x (stages per unit + 0.5) + 6)  over the number of M-chunks and units per CTA: small layers
+  // get ONE wave of CTAs with long units instead of several waves of short ones (every extra unit costs an epilogue),
+  // and no CTA is launched without work.  Units keep >= 4 stages (256 rows).
+  const int sms = sm_count();
+  const int max_chunks = (m_total + 3) / 4 < 64 ? (m_total + 3) / 4 : 64;
+  double best_cost = 0.0;
+  int best_cb = m_total, best_n = 1, best_per = S;
+  bool have = false;
+  for (int n = 1; n <= (max_chunks < 1 ? 1 : max_chunks); ++n) {
+    const int cb = (m_total + n - 1) / n, n_eff = (m_total + cb - 1) / cb;
+    if (n_eff != n) continue;
+    const int64_t units = static_cast<int64_t>(S) * n;
+    for (int c = 0; c < 32; ++c) {
+      const int64_t per = c < 16 ? c + 1 : (units + (c - 16)) / (c - 15);        // 1..16, then units / (1..16) rounded up
+      if (per < 1 || per > units) continue;
+      const int64_t groups = (units + per - 1) / per;
+      if (groups > 65535) continue;
+      const int64_t ctas = static_cast<int64_t>(tiles) * groups;
+      const double waves = static_cast<double>((ctas + sms - 1) / sms);
+      const double cost = waves * (static_cast<double>(per) * (cb + 0.5) + 6.0);
+      if (!have || cost < best_cost * 0.999 || (cost <= best_cost * 1.001 && ctas < static_cast<int64_t>(tiles) * ((static_cast<int64_t>(S) * best_n + best_per - 1) / best_per))) {
+        have = true; best_cost = cost; best_cb = cb; best_n = n; best_per = static_cast<int>(per);
+      }
+    }
   }
-  p.chunk_blocks = (m_total + n_chunks - 1) / n_chunks;
-  p.n_chunks = (m_total + p.chunk_blocks - 1) / p.chunk_blocks;
-  int groups = want < S * p.n_chunks ? want : S * p.n_chunks;
+  p.chunk_blocks = best_cb;
+  p.n_chunks = best_n;
+  const int groups = static_cast<int>((static_cast<int64_t>(S) * best_n + best_per - 1) / best_per);
   static bool attr_set = false;
   if (!attr_set) {
     BNN_CUDA_OK(cudaFuncSetAttribute(wgrad_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
