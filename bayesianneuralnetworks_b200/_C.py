@@ -61,6 +61,13 @@ class bnn_adam_tensor(ctypes.Structure):
                 ("kl_coeff", ctypes.c_float), ("reserved", ctypes.c_float)]
 
 
+MAX_PEERS = 8
+
+
+class bnn_peer_grads(ctypes.Structure):
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("base", ctypes.c_void_p * MAX_PEERS)]
+
+
 _SIGNATURES = {
     "bnn_abi_version": (ctypes.c_int, []),
     "bnn_last_error_string": (ctypes.c_char_p, []),
@@ -96,6 +103,11 @@ _SIGNATURES = {
                                  ctypes.c_size_t, ctypes.c_void_p]),
     "bnn_adam_kl_step": (ctypes.c_int, [ctypes.POINTER(bnn_adam_tensor), ctypes.c_int32, ctypes.c_float, ctypes.c_float,
                                         ctypes.c_float, ctypes.c_float, _c_f32p, ctypes.c_int64, ctypes.c_void_p]),
+    "bnn_adam_kl_step_peers": (ctypes.c_int, [ctypes.POINTER(bnn_adam_tensor), ctypes.c_int32, ctypes.c_float, ctypes.c_float,
+                                              ctypes.c_float, ctypes.c_float, _c_f32p, ctypes.c_int64,
+                                              ctypes.POINTER(bnn_peer_grads), ctypes.c_void_p]),
+    "bnn_peer_barrier": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                        ctypes.c_void_p]),
     "bnn_mc_cross_entropy_workspace_size": (ctypes.c_size_t, []),
     "bnn_mc_cross_entropy_fwd": (ctypes.c_int, [_c_f32p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                                 ctypes.c_int32, ctypes.c_int64, _c_f32p, _c_f32p, _c_f32p, ctypes.c_void_p,
@@ -105,6 +117,7 @@ _SIGNATURES = {
                                                 ctypes.c_int64, ctypes.c_void_p]),
     "bnn_selftest_prune_interval": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_int32,
                                                    ctypes.c_void_p]),
+    "bnn_debug_force_contract_variant": (ctypes.c_int, [ctypes.c_int32]),
     "bnn_selftest_umma": (ctypes.c_int, [_c_f32p, ctypes.c_void_p]),
     "bnn_selftest_umma_mn": (ctypes.c_int, [_c_f32p, ctypes.c_void_p]),
 }
@@ -388,9 +401,11 @@ def prune(entries, flags=0):
     _count(15 * ((n + 23) // 24))
 
 
-def adam_kl_step(entries, lr, beta1, beta2, eps, step_dev=None, step=0):
-    """entries: list of (mu, rho, g_mu|None, g_rho|None, m_mu, v_mu, m_rho, v_rho, prior_loc, prior_scale, kl_coeff);
-    parameters and moments are updated in place (include/bnn_b200.h: bnn_adam_kl_step)."""
+def adam_kl_step(entries, lr, beta1, beta2, eps, step_dev=None, step=0, peers=None):
+    """entries: list of (mu, rho|None, g_mu|None, g_rho|None, m_mu, v_mu, m_rho|None, v_rho|None, prior_loc, prior_scale,
+    kl_coeff); parameters and moments are updated in place (include/bnn_b200.h: bnn_adam_kl_step).  rho None = a plain
+    parameter (Adam only).  peers = (rank, [base pointer of every rank's flat gradient buffer]) averages the gradients
+    over the ranks inside the kernel (bnn_adam_kl_step_peers)."""
     n = len(entries)
     if n == 0:
         return
@@ -400,18 +415,54 @@ def adam_kl_step(entries, lr, beta1, beta2, eps, step_dev=None, step=0):
         require_cuda(mu, rho, g_mu, g_rho, m_mu, v_mu, m_rho, v_rho)
         for name, t in (("mu", mu), ("rho", rho), ("g_mu", g_mu), ("g_rho", g_rho), ("m_mu", m_mu), ("v_mu", v_mu),
                         ("m_rho", m_rho), ("v_rho", v_rho)):
-            _f32c(t, name)
+            if t is not None and t.dtype != torch.float32:
+                raise TypeError(f"{name} must be float32, got {t.dtype}")
+            # dense storage in any dimension order (channels_last conv weights): the update is elementwise, all arrays of
+            # one tensor only have to share the order
+            if t is not None and not ((t.is_contiguous() and mu.is_contiguous())
+                                      or (t.stride() == mu.stride() and _dense(t))):
+                raise ValueError(f"{name} must be dense with the strides of the parameter")
         e = table[i]
-        e.mu, e.rho = mu.data_ptr(), rho.data_ptr()
+        e.mu, e.rho = mu.data_ptr(), None if rho is None else rho.data_ptr()
         e.g_mu = None if g_mu is None else g_mu.data_ptr()
         e.g_rho = None if g_rho is None else g_rho.data_ptr()
-        e.m_mu, e.v_mu, e.m_rho, e.v_rho = m_mu.data_ptr(), v_mu.data_ptr(), m_rho.data_ptr(), v_rho.data_ptr()
+        e.m_mu, e.v_mu = m_mu.data_ptr(), v_mu.data_ptr()
+        e.m_rho, e.v_rho = (None, None) if rho is None else (m_rho.data_ptr(), v_rho.data_ptr())
         e.numel, e.prior_loc, e.prior_scale, e.kl_coeff, e.reserved = mu.numel(), loc, scale, coeff, 0.0
     if step_dev is not None:
         require_cuda(step_dev)
     with torch.cuda.device(device):
-        _call("bnn_adam_kl_step", table, n, lr, beta1, beta2, eps, _ptr(step_dev), int(step), _stream())
+        if peers is None:
+            _call("bnn_adam_kl_step", table, n, lr, beta1, beta2, eps, _ptr(step_dev), int(step), _stream())
+        else:
+            rank, bases = peers
+            pg = bnn_peer_grads()
+            pg.world, pg.rank = len(bases), rank
+            for r, b in enumerate(bases):
+                pg.base[r] = b
+            _call("bnn_adam_kl_step_peers", table, n, lr, beta1, beta2, eps, _ptr(step_dev), int(step), ctypes.byref(pg),
+                  _stream())
     _count((n + 15) // 16)
+
+
+def _dense(t):
+    """True when `t` covers its elements without gaps or overlap (a permutation of a contiguous tensor)."""
+    sizes_strides = sorted((st, sz) for sz, st in zip(t.shape, t.stride()) if sz > 1)
+    expect = 1
+    for st, sz in sizes_strides:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
+def peer_barrier(flag_ptrs, rank, epoch, device):
+    """bnn_peer_barrier: flag_ptrs = [every rank's flag block as mapped here], epoch = local uint32/int32 [1] tensor."""
+    world = len(flag_ptrs)
+    arr = (ctypes.c_void_p * world)(*flag_ptrs)
+    with torch.cuda.device(device):
+        _call("bnn_peer_barrier", arr, world, rank, _ptr(epoch), _stream())
+    _count()
 
 
 _ce_ws = {}
@@ -469,6 +520,12 @@ def selftest_prune_interval(mu, rho, variant=1):
         _call("bnn_selftest_prune_interval", _ptr(mu), _ptr(rho), mu.numel(), _ptr(lo), _ptr(hi), int(variant), _stream())
     _count()
     return lo, hi
+
+
+def force_contract_variant(variant):
+    """Test aid: 'pair' | 'mb4' | 'mb2' | 'mb1' | None (cost model) for the TMA-fed forward / data-gradient kernels."""
+    code = {None: -1, "pair": 0, "mb1": 1, "mb2": 2, "mb4": 4}[variant]
+    _check(lib().bnn_debug_force_contract_variant(code), "bnn_debug_force_contract_variant")
 
 
 def selftest_umma(device="cuda", mn_major=False):

@@ -7,6 +7,14 @@
 // (c) applies torch.optim.Adam's update (examples/MNIST/train.py:43,65: Adam over all parameters, no weight decay, no
 // amsgrad) to mu, rho and their moment buffers.  The separate path reads and writes the gradients three more times (KL
 // gradient kernel, autograd accumulation, optimizer).  Bandwidth bound: 8 loads + 6 stores of 4 bytes per (mu, rho) pair.
+// A tensor with rho == NULL is a plain (deterministic) parameter: Adam on `mu` alone, so one launch updates a whole model.
+//
+// bnn_adam_kl_step_peers folds the data-/sample-parallel gradient exchange (ONE all-reduce of the flat
+// gradient buffer) into the same pass: every rank keeps its gradients in a buffer that all ranks of the node have mapped
+// (NVLink peer memory), and each rank's optimizer kernel reads the R copies of a gradient element straight from the R
+// buffers, averages them and applies the update — a one-shot all-reduce whose only output is the updated parameters.
+// bnn_peer_barrier is the flag barrier around it (all gradients written before anyone reads; all reads done before
+// anyone overwrites), so the whole training step is one capturable graph without a NCCL call.
 #include "common.cuh"
 
 namespace bnn {
@@ -27,6 +35,9 @@ struct AdamDesc {
 struct AdamTable {
   AdamDesc t[kMaxTensors];
   int n;
+  int world;                 // > 1: gradients are averaged over `world` peer buffers (bnn_adam_kl_step_peers)
+  const float* peer[BNN_MAX_PEERS];   // rank r's flat gradient buffer, mapped here; peer[rank] is the local one
+  int rank;
   int pad;
   int64_t total_chunks;
   float lr, beta1, beta2, eps;
@@ -59,6 +70,36 @@ __device__ __forceinline__ void elbo_adam_pair(float& mu, float& rho, float g_mu
   adam_element(rho, g_rho, m_rho, v_rho, h);
 }
 
+// loads that bypass the (non-coherent) L1: peer buffers are rewritten by their owners between launches
+__device__ __forceinline__ float4 ld_peer4(const float* p) { return __ldcv(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float ld_peer1(const float* p) { return __ldcv(p); }
+
+// mean over the ranks of the gradient element(s) at `g` (a pointer into the LOCAL buffer): same offset in every peer
+// buffer, summed in rank order so that every rank obtains bit-identical parameters
+template <bool kPeers>
+__device__ __forceinline__ float4 grad4(const AdamTable& tab, const float* g) {
+  if (g == nullptr) return make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!kPeers) return ldg_stream4(g);
+  const int64_t off = g - tab.peer[tab.rank];
+  float4 acc = ld_peer4(tab.peer[0] + off);
+  for (int r = 1; r < tab.world; ++r) {
+    const float4 v = ld_peer4(tab.peer[r] + off);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const float inv = 1.0f / static_cast<float>(tab.world);
+  return make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+}
+template <bool kPeers>
+__device__ __forceinline__ float grad1(const AdamTable& tab, const float* g) {
+  if (g == nullptr) return 0.f;
+  if (!kPeers) return *g;
+  const int64_t off = g - tab.peer[tab.rank];
+  float acc = ld_peer1(tab.peer[0] + off);
+  for (int r = 1; r < tab.world; ++r) acc += ld_peer1(tab.peer[r] + off);
+  return acc / static_cast<float>(tab.world);
+}
+
+template <bool kPeers>
 __global__ void __launch_bounds__(kThreads) adam_kl_kernel(const __grid_constant__ AdamTable tab) {
   __shared__ int64_t s_begin[kMaxTensors];
   if (threadIdx.x < tab.n) s_begin[threadIdx.x] = tab.t[threadIdx.x].block_begin;
@@ -74,10 +115,32 @@ __global__ void __launch_bounds__(kThreads) adam_kl_kernel(const __grid_constant
     const AdamDesc& d = tab.t[t];
     const int64_t i0 = (chunk - d.block_begin) * kChunk + threadIdx.x * kPerThread;
     if (i0 >= d.numel) continue;
+    if (d.rho == nullptr) {                       // plain parameter: Adam on mu alone
+      if (d.vec && i0 + kPerThread <= d.numel) {
+        float4 mu = *reinterpret_cast<const float4*>(d.mu + i0);
+        const float4 gm = grad4<kPeers>(tab, d.g_mu ? d.g_mu + i0 : nullptr);
+        float4 mm = *reinterpret_cast<const float4*>(d.m_mu + i0), vm = *reinterpret_cast<const float4*>(d.v_mu + i0);
+        adam_element(mu.x, gm.x, mm.x, vm.x, h);
+        adam_element(mu.y, gm.y, mm.y, vm.y, h);
+        adam_element(mu.z, gm.z, mm.z, vm.z, h);
+        adam_element(mu.w, gm.w, mm.w, vm.w, h);
+        *reinterpret_cast<float4*>(d.mu + i0) = mu;
+        *reinterpret_cast<float4*>(d.m_mu + i0) = mm; *reinterpret_cast<float4*>(d.v_mu + i0) = vm;
+      } else {
+        for (int e = 0; e < kPerThread; ++e) {
+          const int64_t i = i0 + e;
+          if (i >= d.numel) break;
+          float mu = d.mu[i], mm = d.m_mu[i], vm = d.v_mu[i];
+          adam_element(mu, grad1<kPeers>(tab, d.g_mu ? d.g_mu + i : nullptr), mm, vm, h);
+          d.mu[i] = mu; d.m_mu[i] = mm; d.v_mu[i] = vm;
+        }
+      }
+      continue;
+    }
     if (d.vec && i0 + kPerThread <= d.numel) {
       float4 mu = *reinterpret_cast<const float4*>(d.mu + i0), rho = *reinterpret_cast<const float4*>(d.rho + i0);
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 gm = d.g_mu ? ldg_stream4(d.g_mu + i0) : z, gr = d.g_rho ? ldg_stream4(d.g_rho + i0) : z;
+      const float4 gm = grad4<kPeers>(tab, d.g_mu ? d.g_mu + i0 : nullptr);
+      const float4 gr = grad4<kPeers>(tab, d.g_rho ? d.g_rho + i0 : nullptr);
       float4 mm = *reinterpret_cast<const float4*>(d.m_mu + i0), vm = *reinterpret_cast<const float4*>(d.v_mu + i0);
       float4 mr = *reinterpret_cast<const float4*>(d.m_rho + i0), vr = *reinterpret_cast<const float4*>(d.v_rho + i0);
       elbo_adam_pair(mu.x, rho.x, gm.x, gr.x, mm.x, vm.x, mr.x, vr.x, d.loc, d.inv_scale2, d.coeff, h);
@@ -92,35 +155,46 @@ __global__ void __launch_bounds__(kThreads) adam_kl_kernel(const __grid_constant
         const int64_t i = i0 + e;
         if (i >= d.numel) break;
         float mu = d.mu[i], rho = d.rho[i], mm = d.m_mu[i], vm = d.v_mu[i], mr = d.m_rho[i], vr = d.v_rho[i];
-        elbo_adam_pair(mu, rho, d.g_mu ? d.g_mu[i] : 0.f, d.g_rho ? d.g_rho[i] : 0.f, mm, vm, mr, vr, d.loc, d.inv_scale2,
-                       d.coeff, h);
+        elbo_adam_pair(mu, rho, grad1<kPeers>(tab, d.g_mu ? d.g_mu + i : nullptr),
+                       grad1<kPeers>(tab, d.g_rho ? d.g_rho + i : nullptr), mm, vm, mr, vr, d.loc, d.inv_scale2, d.coeff, h);
         d.mu[i] = mu; d.rho[i] = rho; d.m_mu[i] = mm; d.v_mu[i] = vm; d.m_rho[i] = mr; d.v_rho[i] = vr;
       }
     }
   }
 }
 
-}  // namespace
-}  // namespace bnn
-
-using namespace bnn;
-
-extern "C" int bnn_adam_kl_step(const bnn_adam_tensor* tensors, int32_t n_tensors, float lr, float beta1, float beta2,
-                                float eps, const float* step_dev, int64_t step_host, void* stream) {
-  BNN_REQUIRE(n_tensors >= 0, BNN_ERR_BAD_ARGUMENT, "bnn_adam_kl_step: n_tensors < 0");
+int adam_launch(const bnn_adam_tensor* tensors, int32_t n_tensors, float lr, float beta1, float beta2, float eps,
+                const float* step_dev, int64_t step_host, const bnn_peer_grads* peers, void* stream, const char* who) {
+  BNN_REQUIRE(n_tensors >= 0, BNN_ERR_BAD_ARGUMENT, "%s: n_tensors < 0", who);
   if (n_tensors == 0) return BNN_OK;
-  BNN_REQUIRE(tensors != nullptr, BNN_ERR_BAD_ARGUMENT, "bnn_adam_kl_step: tensor table is NULL");
+  BNN_REQUIRE(tensors != nullptr, BNN_ERR_BAD_ARGUMENT, "%s: tensor table is NULL", who);
   BNN_REQUIRE(lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, BNN_ERR_BAD_ARGUMENT,
-              "bnn_adam_kl_step: need lr >= 0, 0 <= beta < 1, eps >= 0");
+              "%s: need lr >= 0, 0 <= beta < 1, eps >= 0", who);
   BNN_REQUIRE(step_dev != nullptr || step_host >= 1, BNN_ERR_BAD_ARGUMENT,
-              "bnn_adam_kl_step: the step number starts at 1 (pass step_dev or step_host >= 1)");
+              "%s: the step number starts at 1 (pass step_dev or step_host >= 1)", who);
+  const bool use_peers = peers != nullptr && peers->world > 1;
+  if (peers != nullptr) {
+    BNN_REQUIRE(peers->world >= 1 && peers->world <= BNN_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
+                BNN_ERR_BAD_ARGUMENT, "%s: need 1 <= world <= %d and 0 <= rank < world", who, BNN_MAX_PEERS);
+    for (int r = 0; r < peers->world; ++r)
+      BNN_REQUIRE(peers->base[r] != nullptr && aligned16(peers->base[r]), BNN_ERR_BAD_ARGUMENT,
+                  "%s: peer gradient buffer %d is NULL or not 16-byte aligned", who, r);
+  }
   for (int i = 0; i < n_tensors; ++i) {
     const bnn_adam_tensor& t = tensors[i];
-    BNN_REQUIRE(t.numel >= 0, BNN_ERR_BAD_ARGUMENT, "bnn_adam_kl_step: tensor %d has numel < 0", i);
-    BNN_REQUIRE(t.numel == 0 || (t.mu && t.rho && t.m_mu && t.v_mu && t.m_rho && t.v_rho), BNN_ERR_BAD_ARGUMENT,
-                "bnn_adam_kl_step: tensor %d has a NULL parameter or moment pointer", i);
-    BNN_REQUIRE(t.kl_coeff == 0.f || t.prior_scale > 0.f, BNN_ERR_BAD_ARGUMENT,
-                "bnn_adam_kl_step: tensor %d needs prior scale > 0", i);
+    BNN_REQUIRE(t.numel >= 0, BNN_ERR_BAD_ARGUMENT, "%s: tensor %d has numel < 0", who, i);
+    BNN_REQUIRE(t.numel == 0 || (t.mu && t.m_mu && t.v_mu), BNN_ERR_BAD_ARGUMENT,
+                "%s: tensor %d has a NULL parameter or moment pointer", who, i);
+    BNN_REQUIRE(t.numel == 0 || t.rho == nullptr || (t.m_rho && t.v_rho), BNN_ERR_BAD_ARGUMENT,
+                "%s: tensor %d has rho but no moment buffers for it", who, i);
+    BNN_REQUIRE(t.rho != nullptr || (t.kl_coeff == 0.f && t.g_rho == nullptr), BNN_ERR_BAD_ARGUMENT,
+                "%s: tensor %d is a plain parameter (rho NULL): kl_coeff must be 0 and g_rho NULL", who, i);
+    BNN_REQUIRE(t.kl_coeff == 0.f || t.prior_scale > 0.f, BNN_ERR_BAD_ARGUMENT, "%s: tensor %d needs prior scale > 0", who, i);
+    if (use_peers) {
+      BNN_REQUIRE((t.g_mu == nullptr || t.g_mu >= peers->base[peers->rank]) &&
+                      (t.g_rho == nullptr || t.g_rho >= peers->base[peers->rank]),
+                  BNN_ERR_BAD_ARGUMENT, "%s: tensor %d: gradients must live inside this rank's peer-visible buffer", who, i);
+    }
   }
   int rc = check_device();
   if (rc != BNN_OK) return rc;
@@ -130,6 +204,9 @@ extern "C" int bnn_adam_kl_step(const bnn_adam_tensor* tensors, int32_t n_tensor
     const int n = n_tensors - first < kMaxTensors ? n_tensors - first : kMaxTensors;
     AdamTable tab;
     tab.n = 0; tab.pad = 0;
+    tab.world = use_peers ? peers->world : 1;
+    tab.rank = use_peers ? peers->rank : 0;
+    for (int r = 0; r < BNN_MAX_PEERS; ++r) tab.peer[r] = (use_peers && r < peers->world) ? peers->base[r] : nullptr;
     tab.lr = lr; tab.beta1 = beta1; tab.beta2 = beta2; tab.eps = eps;
     tab.step_dev = step_dev; tab.step_host = static_cast<float>(step_host);
     int64_t chunks = 0;
@@ -142,15 +219,86 @@ extern "C" int bnn_adam_kl_step(const bnn_adam_tensor* tensors, int32_t n_tensor
       d.numel = t.numel; d.block_begin = chunks;
       d.loc = t.prior_loc; d.coeff = t.kl_coeff;
       d.inv_scale2 = t.kl_coeff != 0.f ? 1.0f / (t.prior_scale * t.prior_scale) : 0.f;
-      d.vec = aligned16(t.mu) && aligned16(t.rho) && aligned16(t.m_mu) && aligned16(t.v_mu) && aligned16(t.m_rho) &&
-              aligned16(t.v_rho) && (t.g_mu == nullptr || aligned16(t.g_mu)) && (t.g_rho == nullptr || aligned16(t.g_rho));
+      d.vec = aligned16(t.mu) && aligned16(t.m_mu) && aligned16(t.v_mu) &&
+              (t.rho == nullptr || (aligned16(t.rho) && aligned16(t.m_rho) && aligned16(t.v_rho))) &&
+              (t.g_mu == nullptr || aligned16(t.g_mu)) && (t.g_rho == nullptr || aligned16(t.g_rho));
       chunks += (t.numel + kChunk - 1) / kChunk;
     }
     if (tab.n == 0) continue;
     tab.total_chunks = chunks;
     const int grid = static_cast<int>(chunks < max_grid ? chunks : max_grid);
-    adam_kl_kernel<<<grid, kThreads, 0, st>>>(tab);
+    if (use_peers) adam_kl_kernel<true><<<grid, kThreads, 0, st>>>(tab);
+    else adam_kl_kernel<false><<<grid, kThreads, 0, st>>>(tab);
     BNN_CUDA_OK(cudaGetLastError());
   }
+  return BNN_OK;
+}
+
+// ---- flag barrier between the ranks of one node (one rank per GPU; every rank launches it at the same point of its
+// stream).  flags[r] = rank r's flag block (BNN_MAX_PEERS uint32 words, zero before first use) as mapped here.  Thread p
+// publishes this rank's arrival number in peer p's block (release, system scope: the gradient stores of the earlier
+// kernels of this stream are visible to whoever acquires the flag), then waits until peer p's arrival shows up in the
+// local block.  The arrival number lives in device memory and advances by one per launch, so a captured graph replays it.
+struct BarrierParams {
+  uint32_t* flags[BNN_MAX_PEERS];
+  uint32_t* epoch;
+  int world, rank;
+};
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ BarrierParams p) {
+  const int t = threadIdx.x;
+  const uint32_t e = *p.epoch + 1u;
+  __syncwarp();
+  if (t < p.world && t != p.rank) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[t] + p.rank), "r"(e) : "memory");
+    const uint32_t* mine = p.flags[p.rank] + t;
+    uint64_t t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (static_cast<int32_t>(v - e) >= 0) break;
+      uint64_t t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 10000000000ull) __trap();      // 10 s: a rank that never arrives must fail the launch, not hang the box
+    }
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (t == 0) *p.epoch = e;
+}
+
+}  // namespace
+}  // namespace bnn
+
+using namespace bnn;
+
+extern "C" int bnn_adam_kl_step(const bnn_adam_tensor* tensors, int32_t n_tensors, float lr, float beta1, float beta2,
+                                float eps, const float* step_dev, int64_t step_host, void* stream) {
+  return adam_launch(tensors, n_tensors, lr, beta1, beta2, eps, step_dev, step_host, nullptr, stream, "bnn_adam_kl_step");
+}
+
+extern "C" int bnn_adam_kl_step_peers(const bnn_adam_tensor* tensors, int32_t n_tensors, float lr, float beta1, float beta2,
+                                      float eps, const float* step_dev, int64_t step_host, const bnn_peer_grads* peers,
+                                      void* stream) {
+  BNN_REQUIRE(peers != nullptr, BNN_ERR_BAD_ARGUMENT, "bnn_adam_kl_step_peers: peers is NULL");
+  return adam_launch(tensors, n_tensors, lr, beta1, beta2, eps, step_dev, step_host, peers, stream,
+                     "bnn_adam_kl_step_peers");
+}
+
+extern "C" int bnn_peer_barrier(uint32_t* const* flags, int32_t world, int32_t rank, uint32_t* epoch_dev, void* stream) {
+  BNN_REQUIRE(flags != nullptr && epoch_dev != nullptr, BNN_ERR_BAD_ARGUMENT, "bnn_peer_barrier: NULL pointer");
+  BNN_REQUIRE(world >= 1 && world <= BNN_MAX_PEERS && rank >= 0 && rank < world, BNN_ERR_BAD_ARGUMENT,
+              "bnn_peer_barrier: need 1 <= world <= %d and 0 <= rank < world", BNN_MAX_PEERS);
+  int rc = check_device();
+  if (rc != BNN_OK) return rc;
+  BarrierParams p;
+  for (int r = 0; r < BNN_MAX_PEERS; ++r) {
+    p.flags[r] = r < world ? flags[r] : nullptr;
+    BNN_REQUIRE(r >= world || flags[r] != nullptr, BNN_ERR_BAD_ARGUMENT, "bnn_peer_barrier: flag block %d is NULL", r);
+  }
+  p.epoch = epoch_dev; p.world = world; p.rank = rank;
+  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
 }

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <atomic>
 #include "../../include/bnn_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -34,6 +35,22 @@ int sm_count();                             // multiprocessor count of the curre
   } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Opt-in to more than 48 KiB of dynamic shared memory.  The attribute is PER DEVICE, so the "already done" state is a
+// bit per device ordinal (relaxed atomics: cudaFuncSetAttribute is idempotent, two racing threads both set it).
+struct SmemOptIn {
+  std::atomic<uint64_t> done{0};
+};
+template <typename Kernel>
+inline int allow_dynamic_smem(Kernel kernel, size_t bytes, SmemOptIn* state) {
+  int dev = 0;
+  BNN_CUDA_OK(cudaGetDevice(&dev));
+  const uint64_t bit = uint64_t(1) << (dev & 63);
+  if (state->done.load(std::memory_order_relaxed) & bit) return BNN_OK;
+  BNN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  state->done.fetch_or(bit, std::memory_order_relaxed);
+  return BNN_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // single-MUFU approximations (flush-to-zero forms: no denormal range fix-ups around the MUFU op; every use below

@@ -97,6 +97,7 @@ int tma_wgrad(bnn_view dy, int64_t dy_sample_stride, const float* a, int64_t lda
               const float* rho_w, const float* eps_w, float* dmu_w, float* drho_w, int M, int N, int K, int S,
               uint32_t sample_begin, const bnn_rng* rng_w, cudaStream_t st);
 int tma_selftest(float* max_err_dev, cudaStream_t st);
+int tma_force_variant(int variant);   // test aid: 0 = CTA pair, 1 / 2 / 4 = row blocks per CTA, -1 = cost model (default)
 int tma_wait_counters(unsigned long long* out8, int reset);   // profiling builds (-DBNN_PROFILE_WAITS) only
 
 }  // namespace contract

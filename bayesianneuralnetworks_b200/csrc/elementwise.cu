@@ -355,12 +355,8 @@ col2im_staged_kernel(const float* __restrict__ dcol, float* __restrict__ dx, bnn
 }
 
 template <typename Kernel>
-int allow_stage_smem(Kernel kernel, bool* done) {
-  if (!*done) {
-    BNN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kStageSmemHard + 1024)));      // + rounding of the two regions
-    *done = true;
-  }
-  return BNN_OK;
+int allow_stage_smem(Kernel kernel, SmemOptIn* done) {
+  return allow_dynamic_smem(kernel, kStageSmemHard + 1024, done);      // + rounding of the two regions
 }
 
 int check_geom(const bnn_conv2d_geom* g) {
@@ -461,7 +457,7 @@ int bnn_im2col(const float* x, float* col, const bnn_conv2d_geom* g, void* strea
                        aligned16(x);
     const size_t smem = (static_cast<size_t>(stage_round4(static_cast<int>(cs * HW))) + stage_round4(static_cast<int>(cs * KK))) * 4;
     const dim3 grid(g->B, slices);
-    static bool attr_vec = false, attr_scalar = false;
+    static SmemOptIn attr_vec, attr_scalar;
     if (vec) {
       rc = allow_stage_smem(im2col_staged_kernel<true>, &attr_vec);
       if (rc != BNN_OK) return rc;
@@ -496,7 +492,7 @@ int bnn_col2im(const float* dcol, float* dx, const bnn_conv2d_geom* g, int32_t a
     const bool vec = Kg % 4 == 0 && (static_cast<int64_t>(cs) * KK) % 4 == 0 && aligned16(dcol);
     const size_t smem = (static_cast<size_t>(stage_round4(static_cast<int>(cs * P * KK))) + g->H * g->KH + g->W * g->KW) * 4;
     const dim3 grid(g->B, slices);
-    static bool attr_vec = false, attr_scalar = false;
+    static SmemOptIn attr_vec, attr_scalar;
     if (vec) {
       rc = allow_stage_smem(col2im_staged_kernel<true>, &attr_vec);
       if (rc != BNN_OK) return rc;

@@ -1115,13 +1115,10 @@ int bnn_prune(const bnn_prune_tensor* tensors, int32_t n_tensors, void* workspac
   char* ws = small + static_cast<size_t>(n_tensors) * kSmallBytes;
   BNN_CUDA_OK(cudaMemsetAsync(workspace, 0, static_cast<size_t>(ws - static_cast<char*>(workspace)), st));
   const int max_grid = sm_count() * 8;
-  static bool smem_set = false;
+  static SmemOptIn sample_opt_in;
   const size_t sample_smem = static_cast<size_t>(kSample) * sizeof(uint32_t);
-  if (!smem_set) {
-    BNN_CUDA_OK(cudaFuncSetAttribute(prune_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(sample_smem)));
-    smem_set = true;
-  }
+  rc = allow_dynamic_smem(prune_sample_kernel, sample_smem, &sample_opt_in);
+  if (rc != BNN_OK) return rc;
 
   for (int first = 0; first < n_tensors; first += kMaxTensors) {
     const int n = (n_tensors - first < kMaxTensors) ? n_tensors - first : kMaxTensors;

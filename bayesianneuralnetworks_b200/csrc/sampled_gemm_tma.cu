@@ -352,12 +352,9 @@ constexpr size_t kContractSmem = kSmemAux + 1024 + static_cast<size_t>(kASlots +
 
 template <int MB, bool kDgrad>
 int launch_tma_contract(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    BNN_CUDA_OK(cudaFuncSetAttribute(contract_tma_kernel<MB, kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(kContractSmem)));
-    attr_set = true;
-  }
+  static SmemOptIn opt_in;
+  const int rc = allow_dynamic_smem(contract_tma_kernel<MB, kDgrad>, kContractSmem, &opt_in);
+  if (rc != BNN_OK) return rc;
   contract_tma_kernel<MB, kDgrad><<<grid, kThreadsTma, kContractSmem, st>>>(p);
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
@@ -564,12 +561,9 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
 
 template <int MB, bool kDgrad>
 int launch_pair_contract(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    BNN_CUDA_OK(cudaFuncSetAttribute(contract_pair_kernel<MB, kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(kPairSmem)));
-    attr_set = true;
-  }
+  static SmemOptIn opt_in;
+  const int rc = allow_dynamic_smem(contract_pair_kernel<MB, kDgrad>, kPairSmem, &opt_in);
+  if (rc != BNN_OK) return rc;
   contract_pair_kernel<MB, kDgrad><<<grid, kThreadsTma, kPairSmem, st>>>(p);
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
@@ -584,14 +578,19 @@ bool pair_enabled() {
   return v == 1;
 }
 
-// Debugging / test aid, read on every call: BNN_CONTRACT_VARIANT = pair | mb4 | mb2 | mb1 forces one kernel variant
-// (pair needs more than four 128-row blocks), so that small test shapes reach every variant.
+// Test aid: force one kernel variant (0 = pair, 1 / 2 / 4 = rows blocks per CTA, -1 = cost model) so that small test
+// shapes reach every variant.  Set through bnn_debug_force_contract_variant (tests) — the environment variable
+// BNN_CONTRACT_VARIANT = pair | mb4 | mb2 | mb1 only provides the initial value, read once.
+std::atomic<int> g_forced_variant{-2};
 int forced_variant() {
+  int v = g_forced_variant.load(std::memory_order_relaxed);
+  if (v != -2) return v;
+  v = -1;
   const char* e = getenv("BNN_CONTRACT_VARIANT");
-  if (e == nullptr || e[0] == 0) return -1;
-  if (e[0] == 'p') return 0;
-  if (e[0] == 'm' && e[1] == 'b') return e[2] == '4' ? 4 : (e[2] == '2' ? 2 : (e[2] == '1' ? 1 : -1));
-  return -1;
+  if (e != nullptr && e[0] == 'p') v = 0;
+  else if (e != nullptr && e[0] == 'm' && e[1] == 'b') v = e[2] == '4' ? 4 : (e[2] == '2' ? 2 : (e[2] == '1' ? 1 : -1));
+  g_forced_variant.store(v, std::memory_order_relaxed);
+  return v;
 }
 
 template <bool kDgrad>
@@ -943,7 +942,9 @@ int tma_fwd(const float* a, int64_t lda, int64_t a_sample_stride, const float* m
   p.rng_w = *rng_w; p.rng_b = rng_b ? *rng_b : *rng_w;
   p.shared_l = shared ? 1 : 0;
   p.sum_samples = 0;
+#ifdef BNN_PROFILE_WAITS
   { const char* e = getenv("BNN_EXP_FLAGS"); p.exp_flags = e ? atoi(e) : 0; }
+#endif
   p.vec_out = (y.P == 1) && (y.batch_stride % 4 == 0) && (y_sample_stride % 4 == 0) && aligned16(y.base);
   return dispatch_tma_contract<false>(p, N, st);
 }
@@ -1016,14 +1017,11 @@ int tma_wgrad(bnn_view dy, int64_t dy_sample_stride, const float* a, int64_t lda
   p.chunk_blocks = best_cb;
   p.n_chunks = best_n;
   const int groups = static_cast<int>((static_cast<int64_t>(S) * best_n + best_per - 1) / best_per);
-  static bool attr_set = false;
-  if (!attr_set) {
-    BNN_CUDA_OK(cudaFuncSetAttribute(wgrad_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(kWgradSmem)));
-    BNN_CUDA_OK(cudaFuncSetAttribute(wgrad_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(kWgradSmem)));
-    attr_set = true;
-  }
+  static SmemOptIn opt_in_single, opt_in_pair;
+  rc = allow_dynamic_smem(wgrad_tma_kernel<false>, kWgradSmem, &opt_in_single);
+  if (rc != BNN_OK) return rc;
+  rc = allow_dynamic_smem(wgrad_tma_kernel<true>, kWgradSmem, &opt_in_pair);
+  if (rc != BNN_OK) return rc;
   const int n_tiles = (N + 127) / 128, k_tiles = (K + 127) / 128;
   if (n_tiles >= 2 && pair_enabled() && static_cast<int64_t>(tiles) * groups >= 2 * sm_count()) {
     // CTA pairs over adjacent n-tiles (large problems: the kernel is paced by operand delivery, a pair halves the A^T traffic)
@@ -1059,9 +1057,13 @@ int tma_wait_counters(unsigned long long* out8, int reset) {
 #endif
 }
 
+int tma_force_variant(int variant) {
+  g_forced_variant.store(variant < -1 || variant > 4 || variant == 3 ? -1 : variant, std::memory_order_relaxed);
+  return BNN_OK;
+}
+
 int tma_selftest(float* max_err_dev, cudaStream_t st) {
-  const char* v = getenv("BNN_SELFTEST_VARIANT");      // debugging aid: operand-layout variants of the self test
-  selftest_mn_kernel<<<1, 128, 0, st>>>(max_err_dev, v ? atoi(v) : 3);
+  selftest_mn_kernel<<<1, 128, 0, st>>>(max_err_dev, 3);
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
 }

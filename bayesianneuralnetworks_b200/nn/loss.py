@@ -10,7 +10,7 @@ import warnings
 import torch
 from torch.nn import Module
 
-from torch.distributions import MultivariateNormal
+from torch.distributions import MultivariateNormal, Normal
 from torch.distributions.kl import kl_divergence
 
 from ..functional import KLSum
@@ -19,12 +19,17 @@ from .mvn import WeightMultivariateNormal
 from .variational import WeightNormal
 
 
-def _scalar_prior(prior, what):
+def _is_scalar_normal(prior):
     loc, scale = getattr(prior, 'loc', None), getattr(prior, 'scale', None)
-    if loc is None or scale is None or torch.as_tensor(loc).numel() != 1 or torch.as_tensor(scale).numel() != 1:
+    return (isinstance(prior, Normal) and loc is not None and scale is not None
+            and torch.as_tensor(loc).numel() == 1 and torch.as_tensor(scale).numel() == 1)
+
+
+def _scalar_prior(prior, what):
+    if not _is_scalar_normal(prior):
         raise NotImplementedError(
-            f"KLDivergence: the fused kernel needs a scalar Normal(loc, scale) prior for {what}; got {prior!r}")
-    return float(loc), float(scale)
+            f"the fused kernel needs a scalar Normal(loc, scale) prior for {what}; got {prior!r}")
+    return float(prior.loc), float(prior.scale)
 
 
 class KLDivergence(Module):
@@ -38,25 +43,66 @@ class KLDivergence(Module):
         torch.distributions and come back as their mean KL."""
         prior = module.weight_prior if type == 'w' else module.bias_prior
         if isinstance(param, WeightMultivariateNormal):
-            prior = MultivariateNormal(prior.mean.to(param.device), scale_tril=prior.scale_tril.to(param.device))
-            return kl_divergence(param.dist, prior).mean()
+            # the prior's tensors live on the CPU (SURVEY App. A-7): keep one device copy per (module, tensor) instead of
+            # an H2D copy per call, and skip argument validation (a device->host sync per object, SURVEY App. A-13) —
+            # both are what makes this term capturable in a CUDA graph; the arithmetic is torch's
+            cache = module.__dict__.setdefault('_bnn_prior_cache', {})
+            key = (type, param.device)
+            hit = cache.get(key)
+            if hit is None or hit[0] is not prior:
+                hit = (prior, MultivariateNormal(prior.mean.to(param.device), scale_tril=prior.scale_tril.to(param.device),
+                                                 validate_args=False))
+                cache[key] = hit
+            posterior = MultivariateNormal(param.mean, scale_tril=param.variance, validate_args=False)
+            return kl_divergence(posterior, hit[1]).mean()
         if not isinstance(param, WeightNormal):
             raise NotImplementedError(f"KLDivergence: unsupported variational tensor {param.__class__.__name__}")
+        if not _is_scalar_normal(prior):
+            # a tensor-valued (per-element) or non-Normal prior, which the reference accepts: torch.distributions, as
+            # loss.py:28 does (the prior's tensors follow the parameter's device; no validation sync)
+            if isinstance(prior, Normal):
+                prior = Normal(torch.as_tensor(prior.loc).to(param.device), torch.as_tensor(prior.scale).to(param.device),
+                               validate_args=False)
+            return kl_divergence(Normal(param.mean, param.stddev, validate_args=False), prior).mean()
         return (param, _scalar_prior(prior, f"{module.__class__.__name__}.{'weight' if type == 'w' else 'bias'}"))
 
-    def forward(self, model):
-        found = model.traverse(lambda m: apply_wb(m, self.compute_kl, pass_module=True, pass_type=True))
+    def _gather(self, model, which):
+        """(n, fused entries, torch-composite terms) of the traversal; `which` = 'fused' skips evaluating the composite
+        terms, 'composite' skips nothing but returns no fused entries' work."""
+        def visit(param, module, type):
+            fusable = isinstance(param, WeightNormal) and _is_scalar_normal(
+                module.weight_prior if type == 'w' else module.bias_prior)
+            if which == 'fused' and not fusable:
+                return 0.0                                  # counted in n, not evaluated
+            if which == 'composite' and fusable:
+                return 0.0
+            return self.compute_kl(param, module, type)
+        found = model.traverse(lambda m: apply_wb(m, visit, pass_module=True, pass_type=True))
         if found is None:
             raise ValueError('KLDivergence was not able to find BayasianModules')    # loss.py:34-36
-        n = len(found)                          # loss.py:38: mean over ALL listed tensors, / n_batches
-        fused = [f for f in found if isinstance(f, tuple)]
-        other = [f for f in found if not isinstance(f, tuple)]
-        total = None
-        if fused:
-            priors = [p for _, p in fused]
-            coeffs = [1.0 / (w.mean.numel() * n * self.n_batches) for w, _ in fused]
-            flat = [t for w, _ in fused for t in (w.mean, w.scale)]
-            total = KLSum.apply(priors, coeffs, *flat)
+        return len(found), [f for f in found if isinstance(f, tuple)], [f for f in found if torch.is_tensor(f)]
+
+    def _fused_total(self, n, fused):
+        priors = [p for _, p in fused]
+        coeffs = [1.0 / (w.mean.numel() * n * self.n_batches) for w, _ in fused]
+        flat = [t for w, _ in fused for t in (w.mean, w.scale)]
+        return KLSum.apply(priors, coeffs, *flat)
+
+    def fused_part(self, model):
+        """The share of forward() that the fused kernel evaluates (factorised Gaussians with scalar priors), or None."""
+        n, fused, _ = self._gather(model, 'fused')
+        return self._fused_total(n, fused) if fused else None
+
+    def composite_part(self, model):
+        """The share of forward() that goes through torch.distributions (full-covariance tensors, tensor-valued priors),
+        or None.  forward() == fused_part() + composite_part(); training.ElboTrainer differentiates only this share
+        through autograd — the fused share's gradient is a closed form added by optim.ELBOAdam."""
+        n, _, other = self._gather(model, 'composite')
+        return torch.stack(other).sum() / (n * self.n_batches) if other else None
+
+    def forward(self, model):
+        n, fused, other = self._gather(model, 'all')        # loss.py:38: mean over ALL listed tensors, / n_batches
+        total = self._fused_total(n, fused) if fused else None
         if other:
             rest = torch.stack(other).sum() / (n * self.n_batches)
             total = rest if total is None else total + rest

@@ -1,27 +1,35 @@
 #!/usr/bin/env python
 """bench.py — ELBO training throughput of the variational hot path on B200 (driver contract).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c2|c4]
 
-Metric (BASELINE.json): ELBO train samples*MC/sec = B*S*N / step time, where one step is the body
-of the reference's training loop, examples/MNIST/train.py:55-65: zero_grad -> model(x) (S Monte-Carlo
-predictions) -> KLDivergence(model) -> mean cross-entropy over the S predictions -> backward ->
-[gradient all-reduce] -> Adam step.  Default workload = BASELINE.json configs[1] ("c2"): the
-examples/MNIST/model.py topology (what the FashionMNIST topology is with NormalConv2d/NormalLinear,
-SURVEY §0-4), 28x28 inputs, batch 256 per GPU, S=8.  Synthetic data, reference initialisation.
+Metric (BASELINE.json): ELBO train samples*MC/sec = (rows x Monte-Carlo samples evaluated by all ranks) / step time, where
+one step is the body of the reference's training loop, examples/MNIST/train.py:55-65: zero_grad -> model(x) (S
+Monte-Carlo predictions) -> KLDivergence(model) -> mean cross-entropy over the S predictions -> backward -> [gradient
+exchange] -> Adam step.
 
-One JSON line on stdout (rank 0).  `value`: inputs resident in HBM; `e2e`: the same step fed from
-pinned host memory with the loss read back every step; `roofline`: the dominant hot-path kernel timed
-live with CUDA events; `cpu_baseline`: the oracle's restatement of the reference step on the host
-cores (bounded sample); `kl_prune`: the bandwidth-bound KL / prune sweeps (C5 shape, bounded size).
-`--impl reference` times the reference's CPU path (oracle port) on the same config.
+Default workload = C3, the configuration BASELINE.json quotes the 1/2/4/8-GPU metric on: examples/CIFAR10/model.py:20-39
+as is (NormalConv2d 128x128x3x3 on the hot path, full-covariance MultivariateNormalLinear head as a torch composite),
+32x32x3 inputs, batch 512 and S = 16 per GPU, TF32.  N > 1: the data x sample grid of SURVEY §8e (2 = 1x2, 4 = 2x2,
+8 = 2x4): rank (d, s) takes batch slice d and the global MC samples [16 s, 16 s + 16); per-GPU work is fixed (weak
+scaling), the gradients of all ranks are averaged inside the optimizer kernel over NVLink peer memory.
+Extra blocks of the same JSON line: `c2` (examples/MNIST topology, B = 256, S = 8), `c4` (4x NormalLinear(4096,4096),
+B = 1024, S = 32 on one GPU, sample-sharded S = 32 / N per GPU on N), `kl_prune` (C5: KL / prune sweeps over 2^30 pairs),
+`fp32` (the step in the 3xTF32 1e-5-class mode), `tf32_peak` (cuBLAS 8192^3 TF32, measured in this run: the roofline
+denominator), `reference_on_gpu` (N = 1: the unmodified reference classes on the same GPU through torch),
+`cpu_baseline`.
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM; `e2e`: the same step fed from pinned host memory with
+the loss read back every step; `roofline`: the dominant hot-path contraction timed live with CUDA events.
+`--impl reference` times the UNMODIFIED reference (baseline/_ref, installed by baseline/install_ref.py) on the host cores.
 
 Torch-side settings of the deterministic trunk (Conv2d / BatchNorm2d / ELU / Linear of the example models, outside the
 hot path but inside the measured step): cuDNN autotuning (`--no-cudnn-benchmark`), torch.channels_last for the trunk
-modules (`--nchw-trunk`), allow_tf32 in TF32 mode.  The likelihood term goes through nn.mc_mean_loss
-(`--loss-tail loop` = the reference loop verbatim), the optimizer is bnn.optim.ELBOAdam (`--optimizer adam`).
+modules (`--nchw-trunk` = the examples' layout; its step time is reported as `nchw_trunk_ms_per_step`), allow_tf32 in
+TF32 mode.
 """
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -34,16 +42,17 @@ import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = "WARN"        # NCCL's version banner goes to stdout; this program prints ONE JSON line there
+os.environ.setdefault("NCCL_DEBUG", "WARN")   # quiet by default; a caller's NCCL_DEBUG=INFO (rank lines) is left alone
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 N_BATCHES = 469          # ceil(60000 / 128), examples/MNIST/train.py:38 (any constant)
 WORKLOADS = {
-    "c2": dict(name="C2 examples/MNIST BCNN topology (NormalConv2d 64x64x3x3 s2 + NormalLinear 576x10), 28x28",
-               batch=256, samples=8),
-    "c3": dict(name="C3 examples/CIFAR10 BCNN topology (NormalConv2d 128x128x3x3 on 4x4 maps; the full-covariance "
-                    "MultivariateNormalLinear head, out of the hot path, replaced by NormalLinear(128,10)), 32x32x3",
-               batch=512, samples=16),
-    "c4": dict(name="C4 wide Bayesian MLP 4x NormalLinear(4096,4096)", batch=1024, samples=32),
+    "c2": dict(name="C2 examples/MNIST/model.py topology (NormalConv2d 64x64x3x3 s2 + NormalLinear 576x10), 28x28x1",
+               batch=256, samples=8, example="MNIST", cin=1),
+    "c3": dict(name="C3 examples/CIFAR10/model.py:20-39 as is (NormalConv2d 128x128x3x3 on 4x4 maps + "
+                    "MultivariateNormalLinear(128,10) head), 32x32x3",
+               batch=512, samples=16, example="CIFAR10", cin=3),
+    "c4": dict(name="C4 wide Bayesian MLP 4x NormalLinear(4096,4096)", batch=1024, samples=32, example=None, cin=4096),
 }
 
 
@@ -56,12 +65,50 @@ def peaks():
     return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
-# ------------------------------------------------------------------------------------------------ models
-def build_model(workload, samples):
-    import bayesianneuralnetworks_b200 as bnn
-    from torch.nn import BatchNorm2d, Conv2d, ELU, Flatten, Sequential, Softmax
+def measure_tf32_peak(device, seconds=2.0):
+    """cuBLAS TF32 GEMM 8192^3 (torch.matmul on fp32 operands with allow_tf32), measured the way MEASURED_PEAKS.json
+    measures bf16: best of 10 single calls (burst) and back-to-back calls for `seconds` (sustained, power capped)."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    n = 8192
+    a = torch.randn(n, n, device=device)
+    b = torch.randn(n, n, device=device)
+    c = torch.empty(n, n, device=device)
+    flops = 2.0 * n ** 3
+    for _ in range(3):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    reps = max(10, int(seconds * 1e3 / best))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b, out=c)
+    e1.record()
+    torch.cuda.synchronize()
+    sustained = e0.elapsed_time(e1) / reps
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    del a, b, c
+    return {"burst_tflops": flops / best / 1e9, "sustained_tflops": flops / sustained / 1e9,
+            "how": f"torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS TF32): best of 10 (burst), {reps} back to back (sustained)"}
 
-    class Net(bnn.nn.BayesianNetworkModule):
+
+# ------------------------------------------------------------------------------------------------ models
+def build_model(workload, samples, nn=None):
+    """The workload's network on `nn` (default: this package's nn; the reference arm passes pytorch_bayesian.nn)."""
+    from torch.nn import BatchNorm2d, Conv2d, ELU, Flatten, Linear, Sequential, Softmax
+    if nn is None:
+        import bayesianneuralnetworks_b200 as bnn
+        nn = bnn.nn
+
+    class Net(nn.BayesianNetworkModule):
         def __init__(self, layers, cin, cout):
             super().__init__(cin, cout, samples)
             self.layers = layers
@@ -73,20 +120,19 @@ def build_model(workload, samples):
         layers = Sequential(Conv2d(1, 32, 5, padding=2, stride=2), BatchNorm2d(32), ELU(),
                             Conv2d(32, 32, 3, padding=1, stride=1), ELU(),
                             Conv2d(32, 64, 3, padding=0, stride=2), ELU(),
-                            bnn.nn.NormalConv2d(64, 64, 3, padding=1, stride=2), ELU(), Flatten(),
-                            bnn.nn.NormalLinear(576, 10), Softmax(dim=-1))
+                            nn.NormalConv2d(64, 64, 3, padding=1, stride=2), ELU(), Flatten(),
+                            nn.NormalLinear(576, 10), Softmax(dim=-1))
         return Net(layers, 1, 10)
     if workload == "c3":        # examples/CIFAR10/model.py:20-39
-        from torch.nn import Linear
         layers = Sequential(Conv2d(3, 64, 5, padding=2, stride=2), BatchNorm2d(64), ELU(),
                             Conv2d(64, 128, 5, padding=2, stride=2), ELU(),
                             Conv2d(128, 128, 5, padding=2, stride=2), ELU(),
                             Conv2d(128, 128, 3, padding=1), ELU(), Conv2d(128, 128, 3, padding=1), ELU(),
-                            bnn.nn.NormalConv2d(128, 128, 3, padding=1), ELU(), Flatten(),
-                            Linear(2048, 128), ELU(), bnn.nn.NormalLinear(128, 10), Softmax(dim=-1))
+                            nn.NormalConv2d(128, 128, 3, padding=1), ELU(), Flatten(),
+                            Linear(2048, 128), ELU(), nn.MultivariateNormalLinear(128, 10), Softmax(dim=-1))
         return Net(layers, 3, 10)
-    layers = Sequential(bnn.nn.NormalLinear(4096, 4096), ELU(), bnn.nn.NormalLinear(4096, 4096), ELU(),
-                        bnn.nn.NormalLinear(4096, 4096), ELU(), bnn.nn.NormalLinear(4096, 4096), Softmax(dim=-1))
+    layers = Sequential(nn.NormalLinear(4096, 4096), ELU(), nn.NormalLinear(4096, 4096), ELU(),
+                        nn.NormalLinear(4096, 4096), ELU(), nn.NormalLinear(4096, 4096), Softmax(dim=-1))
     return Net(layers, 4096, 4096)
 
 
@@ -98,16 +144,21 @@ def synthetic_batch(workload, batch, gen):
     return torch.randn(batch, 4096, generator=gen), torch.randint(0, 4096, (batch,), generator=gen)
 
 
-def hot_flops_per_step(workload, batch, samples):
-    """Algorithmic flops of the hot-path contractions per step: fwd 2MNK, bwd 4MNK (2MNK for a
-    first layer without dX)."""
-    if workload == "c2":
-        conv = 2 * 9 * 64 * 576         # per sample*MC row, forward
-        lin = 2 * 10 * 576
-        return batch * samples * 3 * (conv + lin)
-    if workload == "c3":
-        return batch * samples * 3 * (2 * 16 * 128 * 1152 + 2 * 10 * 128)
-    return batch * samples * (4 * 6 - 2) * 4096 * 4096
+# per workload: the Bayesian layers ON THE HOT PATH as (rows per (batch row, MC sample), N, K, input elements per
+# (row, sample)) — the conv layers' K is Cin*kh*kw of the implicit GEMM, their algorithmic input is the un-expanded tensor
+HOT_LAYERS = {
+    "c2": [(9, 64, 576, 64 * 6 * 6), (1, 10, 576, 576)],
+    "c3": [(16, 128, 1152, 128 * 4 * 4)],
+    "c4": [(1, 4096, 4096, 4096)] * 4,
+}
+
+
+def hot_flops_per_step(workload, rows):
+    """Algorithmic flops of the hot-path contractions per step: fwd 2MNK, bwd 4MNK (2MNK for a first layer
+    without dX); `rows` = batch rows x MC samples."""
+    if workload == "c4":
+        return rows * (4 * 6 - 2) * 4096 * 4096
+    return rows * 3 * sum(2 * r * n * k for r, n, k, _ in HOT_LAYERS[workload])
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -139,16 +190,13 @@ class ClockSampler:
     def mark(self, t0, t1):
         self.windows.append((t0, t1))
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
+    def summary(self, windows=None):
+        windows = self.windows if windows is None else windows
         rows = [(t, r) for t, r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        inside = [r for t, r in rows if any(a - 0.05 <= t <= b + 0.05 for a, b in self.windows)]
+        inside = [r for t, r in rows if any(a - 0.05 <= t <= b + 0.05 for a, b in windows)]
         note = "inside the timed regions"
-        if not inside and rows and self.windows:
-            mid = sum(a + b for a, b in self.windows) / (2 * len(self.windows))
+        if not inside and rows and windows:
+            mid = sum(a + b for a, b in windows) / (2 * len(windows))
             inside = [r for _, r in sorted(rows, key=lambda tr: abs(tr[0] - mid))[:3]]
             note = "nearest to the timed regions (shorter than the sampling period)"
         sm = sorted(float(r[1]) for r in inside)
@@ -162,294 +210,184 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None, "window": note}
 
-
-# ------------------------------------------------------------------------------------------------ the step
-class Trainer:
-    """The reference training-loop body (train.py:55-65) on this repo's public API.  With `graph=True` the whole
-    step (RNG advance, zero_grad, S-sample forward, KL, CE, backward, gradient all-reduce, Adam) is captured
-    once into a CUDA graph and replayed: the Philox streams advance through a device-side step counter
-    (bnn.graph_safe_rng), so every replay draws fresh eps."""
-
-    def __init__(self, workload, device, world, samples, graph, loss_tail="batched", optimizer="elbo-adam",
-                 channels_last=False):
-        import bayesianneuralnetworks_b200 as bnn
-        self.bnn = bnn
-        self.loss_tail = loss_tail
-        torch.manual_seed(0)
-        bnn.graph_safe_rng(graph)
-        self.model = build_model(workload, samples).to(device)
-        if channels_last:                 # torch-side knob for the deterministic trunk: cuDNN's NHWC kernels without
-            for m in self.model.modules():     # layout conversions around each call; (mu, rho) stay row-major OIHW
-                if isinstance(m, (torch.nn.Conv2d, torch.nn.BatchNorm2d)):
-                    m.to(memory_format=torch.channels_last)
-        self.kld = bnn.nn.KLDivergence(number_of_batches=N_BATCHES)
-        self.optimizer = optimizer
-        if optimizer == "elbo-adam":      # SURVEY §8f-3: KL gradient + Adam in one pass, likelihood-only backward
-            self.opt = bnn.optim.ELBOAdam(self.model, number_of_batches=N_BATCHES, lr=1e-3, capturable=graph)
-        else:                             # torch's single-pass fused Adam (the reference's torch.optim.Adam, train.py:43)
-            self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-3, capturable=graph, fused=True)
-        self.world = world
-        self.params = [p for p in self.model.parameters()]
-        self.graph = None
-        self.graph_opt = None
-        self.flat = None
-        self.use_graph = graph
-        self.launches_per_step = None
-
-    def _forward_backward(self, x, y):
-        if self.use_graph:
-            self.bnn.advance_rng_step(x.device)
-        if self.flat is not None:
-            self.flat.zero_()                 # gradients are views of one flat buffer (static addresses)
-        else:
-            self.opt.zero_grad(set_to_none=True)
-        preds = self.model(x)
-        if self.optimizer == "elbo-adam":
-            with torch.no_grad():
-                divergence = self.kld(self.model)
-        else:
-            divergence = self.kld(self.model)
-        if self.loss_tail == "loop":        # the reference loop body verbatim (train.py:59-61)
-            likelihood = torch.stack([F.cross_entropy(p, y) for p in preds]).mean()
-        else:                               # SURVEY §8f-3: the same mean as ONE cross-entropy over the S*B rows
-            likelihood = self.bnn.nn.mc_mean_loss(F.cross_entropy, preds, y)
-        if self.optimizer == "elbo-adam":   # the optimizer adds the closed-form KL gradient; the value is still reported
-            likelihood.backward()
-            return likelihood.detach() + divergence
-        loss = likelihood + divergence
-        loss.backward()
-        return loss
-
-    def _allreduce(self):
-        """Data parallel: ONE all-reduce (avg) of the flat gradient buffer."""
-        import torch.distributed as dist
-        if self.flat is not None:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
-        else:
-            from bayesianneuralnetworks_b200 import parallel
-            parallel.allreduce_gradients(self.params)
-
-    def _body(self, x, y):
-        loss = self._forward_backward(x, y)
-        if self.world > 1:
-            self._allreduce()
-        self.opt.step()
-        return loss
-
-    def capture(self, x, y):
-        """Warm up eagerly on a side stream, then capture the step on static input buffers.  One GPU: one graph.
-        Several GPUs: forward+backward and the optimizer step are two graphs with the NCCL all-reduce of the flat
-        gradient buffer launched eagerly between them (collectives stay outside the captured region)."""
-        from bayesianneuralnetworks_b200 import _C
-        # warm-up runs on a side stream, capture on the capture stream: the gradient accumulators legitimately see two
-        # streams (neither is the legacy default stream), so silence torch's advisory about it
-        if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
-            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
-        self.sx, self.sy = x.clone(), y.clone()
-        if self.world > 1:
-            # the gradients are views of ONE flat buffer: a single all-reduce, static addresses for both graphs
-            total = sum(p.numel() for p in self.params)
-            self.flat = torch.zeros(total, device=x.device, dtype=torch.float32)
-            off = 0
-            for p in self.params:
-                # same strides as the parameter (channels_last trunk weights are dense permutations of their storage):
-                # torch's fused Adam wants gradients in the parameter's layout
-                p.grad = torch.as_strided(self.flat, p.size(), p.stride(), off)
-                off += p.numel()
-        # one GPU: zero_grad(set_to_none=True) inside the captured step — autograd then hands the freshly computed
-        # gradient tensors (static addresses in the graph's pool) to .grad without an accumulation pass
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                self._body(self.sx, self.sy)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        before = _C.launch_count
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.static_loss = self._forward_backward(self.sx, self.sy)
-            if self.world == 1:
-                self.opt.step()
-        if self.world > 1:
-            self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt):
-                self.opt.step()
-        self.launches_per_step = _C.launch_count - before
-
-    def step(self, x, y):
-        if self.graph is None:
-            return self._body(x, y)
-        self.sx.copy_(x, non_blocking=True)
-        self.sy.copy_(y, non_blocking=True)
-        self.graph.replay()
-        if self.world > 1:
-            self._allreduce()
-            self.graph_opt.replay()
-        return self.static_loss
+    def stop(self):
+        if self.proc is None:
+            return
+        time.sleep(0.12)
+        self.proc.terminate()
 
 
-def run_b200(args):
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
+# ------------------------------------------------------------------------------------------------ one workload
+class Env:
+    """Process-wide context of a b200 run."""
+
+    def __init__(self, args):
+        self.args = args
+        self.rank = int(os.environ.get("RANK", 0))
+        self.world = int(os.environ.get("WORLD_SIZE", 1))
+        self.local = int(os.environ.get("LOCAL_RANK", 0))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
-    from bayesianneuralnetworks_b200 import _C
-    import bayesianneuralnetworks_b200 as bnn
-    _C.lib()                          # fails loudly when the CUDA library is missing
-    wl = WORKLOADS[args.workload]
-    B, S = wl["batch"], wl["samples"]
-    bnn.set_precision(args.precision)
-    sample_parallel = args.parallel == "sample" and world > 1
-    if sample_parallel:          # SURVEY §8e: rank r evaluates the global MC samples [r*S/R, (r+1)*S/R) of the SAME batch
-        if S % world != 0:
-            raise SystemExit(f"{S} MC samples do not split over {world} ranks")
-        bnn.set_sample_partition(rank, world)
-    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
-    if args.precision == "tf32":      # SURVEY §8d (C3): TF32 hot path, "deterministic trunk through torch with allow_tf32"
-        torch.backends.cuda.matmul.allow_tf32 = True
-        torch.backends.cudnn.allow_tf32 = True
-    trainer = Trainer(args.workload, device, world, S, graph=not args.no_graph, loss_tail=args.loss_tail,
-                      optimizer=args.optimizer, channels_last=not args.nchw_trunk)
-    gen = torch.Generator().manual_seed(1 if sample_parallel else 1 + rank)
-    n_host = 8
-    host = [tuple(t.pin_memory() for t in synthetic_batch(args.workload, B, gen)) for _ in range(n_host)]
-    dev = [(x.to(device), y.to(device)) for x, y in host]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)      # > 126 MB L2
+        torch.cuda.set_device(self.local)
+        self.device = torch.device("cuda", self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.device)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.device)      # > 126 MB L2
+        self.clocks = ClockSampler(self.local)
+        self.pk = peaks()
 
-    def barrier():
-        if world > 1:
+    def barrier(self):
+        if self.world > 1:
             import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        import torch.distributed as dist
+        t = torch.tensor([v], device=self.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+
+def measure_step(env, workload, steps, warmup, precision, parallel_mode, with_e2e=True, with_roofline=True,
+                 channels_last=True, exchange="auto"):
+    """Builds the workload's ElboTrainer, times `steps` device-resident steps (and, with_e2e, as many host-fed ones) and
+    returns the measurements of this workload as a dict (rank 0: complete; other ranks: timing only)."""
+    import bayesianneuralnetworks_b200 as bnn
+    from bayesianneuralnetworks_b200 import _C, parallel
+    from bayesianneuralnetworks_b200.training import ElboTrainer
+    args, world, device = env.args, env.world, env.device
+    wl = WORKLOADS[workload]
+    B, S_local = wl["batch"], wl["samples"]
+    if world == 1:
+        data_groups, sample_groups, scaling = 1, 1, "weak"
+    elif parallel_mode == "grid":        # weak scaling: every rank keeps (B rows, S samples); SURVEY §8e
+        data_groups, sample_groups = parallel.default_grid(world) if args.sample_groups == 0 else (
+            world // args.sample_groups, args.sample_groups)
+        scaling = "weak"
+    elif parallel_mode == "sample":      # strong scaling: the S samples of ONE batch sharded over the ranks (C4)
+        if S_local % world != 0:
+            raise SystemExit(f"{S_local} MC samples do not split over {world} ranks")
+        data_groups, sample_groups, S_local, scaling = 1, world, S_local // world, "strong"
+    else:                                # plain data parallelism
+        data_groups, sample_groups, scaling = world, 1, "weak"
+    S_global = S_local * sample_groups
+    bnn.set_precision(precision)
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
+    tf32 = precision == "tf32"           # SURVEY §8d (C3): TF32 hot path, "deterministic trunk through torch with allow_tf32"
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.manual_seed(0)
+    model = build_model(workload, S_global).to(device)
+    if channels_last:                    # torch-side knob for the deterministic trunk: cuDNN's NHWC kernels without
+        for m in model.modules():        # layout conversions around each call; (mu, rho) stay row-major OIHW
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.BatchNorm2d)):
+                m.to(memory_format=torch.channels_last)
+    trainer = ElboTrainer(model, N_BATCHES, lr=1e-3, graph=not args.no_graph, optimizer=args.optimizer,
+                          loss_tail=args.loss_tail, exchange=exchange, sample_groups=sample_groups)
+    gen = torch.Generator().manual_seed(1 + trainer.data_index)      # a data group shares its batch slice
+    n_host = 8
+    host = [tuple(t.pin_memory() for t in synthetic_batch(workload, B, gen)) for _ in range(n_host)]
+    dev = [(x.to(device), y.to(device)) for x, y in host]
 
     def timed(n_steps, feed_from_host):
         """K steps, each bracketed by CUDA events on the current stream; L2 flushed (untimed) between steps."""
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps)]
         stops = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps)]
-        barrier()
-        t0 = time.perf_counter()
+        env.barrier()
+        t0, w0 = time.time(), time.perf_counter()
         last = None
         for i in range(n_steps):
-            flush.zero_()
+            env.flush.zero_()
             starts[i].record()
-            if feed_from_host and trainer.graph is not None:
-                x, y = host[i % n_host]       # pinned host -> the graph's static input buffers, one async copy each
-            elif feed_from_host:
-                hx, hy = host[i % n_host]
-                x, y = hx.to(device, non_blocking=True), hy.to(device, non_blocking=True)
-            else:
-                x, y = dev[i % n_host]
-            loss = trainer.step(x, y)
+            x, y = host[i % n_host] if feed_from_host else dev[i % n_host]
+            loss = trainer.step(x, y)     # host-fed: pinned host -> the graph's static inputs, one async copy each
             if feed_from_host:
-                last = loss.item()            # device -> host read of the step's result, every step
+                last = loss.item()        # device -> host read of the step's result, every step
             stops[i].record()
-        barrier()
-        wall = time.perf_counter() - t0
+        env.barrier()
+        wall = time.perf_counter() - w0
+        env.clocks.mark(t0, time.time())
         ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
-        return ms / 1e3, wall, last
+        return ms / 1e3, wall, last, (t0, time.time())
 
-    clocks = ClockSampler(local)
-    clocks.start()
     graph_note = "eager launches"
     if trainer.use_graph:
         try:
             trainer.capture(*dev[0])
             graph_note = ("whole step captured in one CUDA graph (device-side Philox step counter), replayed per step"
-                          if world == 1 else "forward+backward and optimizer captured as two CUDA graphs, the NCCL "
-                          "all-reduce of the flat gradient buffer launched eagerly between them")
+                          if trainer.graph_opt is None else "forward+backward and optimizer captured as two CUDA graphs")
         except Exception as exc:      # noqa: BLE001 — fall back to eager launches, say so in the result
+            if world > 1:
+                raise                 # ranks must not diverge (peer barriers pair up)
             sys.stderr.write(f"CUDA graph capture failed ({exc!r}); running eagerly\n")
             trainer.graph, trainer.graph_opt, trainer.use_graph = None, None, False
             bnn.graph_safe_rng(False)
-            graph_note = f"eager launches (graph capture failed: {type(exc).__name__})"
-    for i in range(max(args.warmup, 3)):
+            graph_note = f"eager launches (graph capture failed: {type(exc).__name__}: {str(exc)[:120]})"
+    for i in range(max(warmup, 3)):
         trainer.step(*dev[i % n_host])
     launches0 = _C.launch_count
-    t_a = time.time()
-    dev_s, dev_wall, _ = timed(args.steps, False)
-    clocks.mark(t_a, time.time())
+    dev_s, dev_wall, _, window = timed(steps, False)
     launches = _C.launch_count - launches0
     if trainer.graph is not None:
-        launches = trainer.launches_per_step * args.steps      # replays launch the captured kernels
-    timed(2, True)                                    # untimed: first-touch of the staging allocations of the host-fed path
-    t_a = time.time()
-    e2e_s, e2e_wall, last_loss = timed(args.steps, True)
-    clocks.mark(t_a, time.time())
-    clock_info = clocks.stop()
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        import torch.distributed as dist
-        t = torch.tensor([v], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
-
-    dev_s, e2e_s = max_over_ranks(dev_s), max_over_ranks(e2e_s)
-    units = B * S * (1 if sample_parallel else world) * args.steps
-    pk = peaks()
-
-    # ---- roofline of the dominant hot-path kernel, timed live with CUDA events on the launching stream
-    _C.set_kernel_timing(True)
-    n_prof = min(args.steps, 10)
-    for i in range(n_prof):
-        flush.zero_()
-        trainer._body(*dev[i % n_host])          # eager launches so that every library call can be bracketed
-    per_kernel = _C.kernel_timing_summary(n_prof)
-    _C.set_kernel_timing(False)
-    roof = roofline(args.workload, B, S, per_kernel, pk)
-
-    out = None
-    if rank == 0:
-        x0, y0 = host[0]
-        out = {
-            "metric": "ELBO train samples*MC/sec", "value": units / dev_s, "unit": "samples*MC/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
-            "scaling": "strong" if sample_parallel else "weak",
-            "vs_baseline": None,
-            "dtype": "tf32" if args.precision == "tf32" else "fp32 (3xTF32 split on tcgen05)",
-            "data": "synthetic",
-            "config": {"workload": wl["name"], "batch_per_gpu": B, "mc_samples": S,
-                       "global_batch": B if sample_parallel else B * world,
-                       "parallelism": (f"sp{world} (MC samples sharded, {S // world} per GPU)" if sample_parallel
-                                       else f"dp{world}") if world > 1 else "single", "n_batches": N_BATCHES,
-                       "optimizer": "Adam (torch fused)" if args.optimizer == "adam" else "bnn.optim.ELBOAdam (KL gradient + Adam in one pass; torch fused Adam for the deterministic layers)", "cudnn_benchmark": not args.no_cudnn_benchmark, "trunk_allow_tf32": args.precision == "tf32", "trunk_memory_format": "contiguous (NCHW)" if args.nchw_trunk else "channels_last (torch Conv2d / BatchNorm2d modules only)", "launch": graph_note, "l2": "flushed between steps (256 MiB write, untimed); each step "
-                       "timed with its own CUDA event pair", "step": "zero_grad+forward(S)+KL+CE+backward+Adam" + (" (KL gradient applied inside the optimizer pass)" if args.optimizer == "elbo-adam" else ""),
-                       "loss_tail": ("nn.mc_mean_loss: mean of the S per-sample cross-entropies evaluated as one call over "
-                                     "the S*B rows (identical value and gradients, tests/test_modules_gpu.py)"
-                                     if args.loss_tail == "batched" else "reference loop: S cross-entropy calls")},
-            "e2e": {"value": units / e2e_s, "unit": "samples*MC/s",
-                    "h2d_bytes_per_step": x0.numel() * x0.element_size() + y0.numel() * y0.element_size(),
-                    "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * e2e_s / args.steps, "last_loss": last_loss},
-            "gpu_launches": launches,
-            "wall_s": {"device_resident": dev_wall, "e2e": e2e_wall},
-            "clocks": clock_info,
-            "roofline": roof,
-            "hot_path": {"algorithmic_tflops_per_s": hot_flops_per_step(args.workload, B, S) * (1 if sample_parallel else world) /
-                         (dev_s / args.steps) / 1e12, "kernels_ms_per_step": per_kernel},
-            "peaks": pk,
-        }
-    if not args.no_extras:
-        kl_prune = bench_kl_prune(device, pk, world=world)          # every rank sweeps its shard of the tensors
-        if rank == 0:
-            out["kl_prune"] = kl_prune
-    if rank == 0 and world == 1 and not args.no_extras:
-        out["cpu_baseline"] = cpu_baseline(args.workload, bounded_seconds=20.0)
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank == 0:
-        print(json.dumps(out))
+        launches = trainer.launches_per_step * steps      # replays launch the captured kernels
+    res = {"ms_per_step": None}
+    e2e_s = e2e_wall = last_loss = None
+    if with_e2e:
+        timed(2, True)                                    # untimed: first touch of the staging path
+        e2e_s, e2e_wall, last_loss, _ = timed(steps, True)
+        e2e_s = env.max_over_ranks(e2e_s)
+    dev_s = env.max_over_ranks(dev_s)
+    units = B * data_groups * S_global * steps
+    per_kernel, roof = None, None
+    if with_roofline:
+        # the dominant hot-path kernel, timed live with CUDA events on the launching stream (eager launches so that
+        # every library call can be bracketed; all ranks run the same number of steps: the peer barriers pair up)
+        _C.set_kernel_timing(True)
+        n_prof = min(steps, 10)
+        for i in range(n_prof):
+            env.flush.zero_()
+            trainer._body(*dev[i % n_host])
+        per_kernel = _C.kernel_timing_summary(n_prof)
+        _C.set_kernel_timing(False)
+        roof = roofline(workload, B * S_local, per_kernel, env.pk, precision)
+    x0, y0 = host[0]
+    res = {
+        "workload": wl["name"], "value": units / dev_s, "unit": "samples*MC/s", "ms_per_step": 1e3 * dev_s / steps,
+        "steps": steps, "scaling": scaling,
+        "config": {"workload": wl["name"], "batch_per_gpu": B, "mc_samples_per_gpu": S_local,
+                   "global_batch": B * data_groups, "global_mc_samples": S_global,
+                   "parallelism": "single" if world == 1 else (
+                       f"grid {data_groups} data x {sample_groups} sample groups: rank (d, s) = batch slice d, global MC "
+                       f"samples [{S_local} s, {S_local} s + {S_local}); gradients averaged over all {world} ranks"),
+                   "gradient_exchange": trainer.exchange_note, "n_batches": N_BATCHES,
+                   "optimizer": "Adam (torch fused)" if args.optimizer == "adam" else
+                   "bnn.optim.ELBOAdam (KL gradient + Adam for every parameter in one kernel launch)",
+                   "cudnn_benchmark": not args.no_cudnn_benchmark, "trunk_allow_tf32": tf32,
+                   "trunk_memory_format": "channels_last (torch Conv2d / BatchNorm2d modules only)" if channels_last
+                   else "contiguous (NCHW, the examples' layout)",
+                   "launch": graph_note,
+                   "l2": "flushed between steps (256 MiB write, untimed); each step timed with its own CUDA event pair",
+                   "step": "zero_grad+forward(S)+KL+CE+backward+" + ("exchange+" if world > 1 else "") + "Adam"},
+        "dtype": "tf32" if tf32 else "fp32 (3xTF32 split on tcgen05)",
+        "gpu_launches": launches, "wall_s": dev_wall, "clocks": env.clocks.summary([window]),
+        "hot_path_algorithmic_tflops": hot_flops_per_step(workload, B * data_groups * S_global) / (dev_s / steps) / 1e12,
+    }
+    if with_e2e:
+        res["e2e"] = {"value": units / e2e_s, "unit": "samples*MC/s",
+                      "h2d_bytes_per_step": x0.numel() * x0.element_size() + y0.numel() * y0.element_size(),
+                      "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * e2e_s / steps, "last_loss": last_loss,
+                      "wall_s": e2e_wall}
+    if with_roofline:
+        res["roofline"] = roof
+        res["kernels_ms_per_step"] = per_kernel
+    trainer.release()
+    del trainer, model, dev, host
+    torch.cuda.empty_cache()
+    return res
 
 
 def measured_traffic(workload, name):
@@ -461,23 +399,14 @@ def measured_traffic(workload, name):
         return None
 
 
-# per workload: the Bayesian layers as (rows per (batch row, MC sample), N, K, input elements per (row, sample))
-# — the conv layers' K is Cin*kh*kw of the implicit GEMM, their algorithmic input is the un-expanded NCHW tensor
-HOT_LAYERS = {
-    "c2": [(9, 64, 576, 64 * 6 * 6), (1, 10, 576, 576)],
-    "c3": [(16, 128, 1152, 128 * 4 * 4), (1, 10, 128, 128)],
-    "c4": [(1, 4096, 4096, 4096)] * 4,
-}
-
-
-def roofline(workload, B, S, per_kernel, pk):
+def roofline(workload, rows, per_kernel, pk, precision):
     """Dominant hot-path kernel = the libbnn_b200 CONTRACTION entry point with the largest time share of the step.
     Its roof follows from its arithmetic intensity: algorithmic flops / algorithmic bytes (operands read once, results
-    written once, fp32) against the ridge point peak_tensor / peak_hbm — the narrow layers of C2/C3 (N = 64 / 128 / 10)
-    sit on the bandwidth side, the 4096-wide layers of C4 on the tensor side.  Both fractions are reported."""
+    written once, fp32) against the ridge point peak_tensor / peak_hbm.  Both fractions are reported.  The tensor peak
+    is the TF32 cuBLAS rate MEASURED in this run (sustained; burst beside it), not an assumed fraction of bf16."""
     if not per_kernel:
         return None
-    gemms = {k: v for k, v in per_kernel.items() if k.startswith("bnn_sampled_gemm")}
+    gemms = {k: v for k, v in per_kernel.items() if k.startswith("bnn_sampled_")}
     name = max(gemms or per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
     k = per_kernel[name]
     base = {"kernel": name, "launches_per_step": k["launches_per_step"],
@@ -485,34 +414,36 @@ def roofline(workload, B, S, per_kernel, pk):
     if name not in gemms:
         return dict(base, bound="hbm", achieved=None, peak=pk["hbm"], unit="GB/s", frac=None, traffic=None)
     layers = HOT_LAYERS[workload]
-    if name == "bnn_sampled_gemm_dgrad" and workload == "c4":
+    if name.endswith("dgrad") and workload == "c4":
         layers = layers[1:]                      # the first layer needs no input gradient
-    rows = B * S
     flops = sum(2 * r * n * kk for r, n, kk, _ in layers) * rows
-    if name == "bnn_sampled_gemm_fwd":           # x, (mu, sigma) -> y (+ bias)
+    if name.endswith("fwd"):                     # x, (mu, sigma) -> y (+ bias)
         nbytes = sum(rows * (x_in + r * n) + 2 * n * kk for r, n, kk, x_in in layers) * 4
-    elif name == "bnn_sampled_gemm_dgrad":       # dy, (mu, sigma) -> dx
+    elif name.endswith("dgrad"):                 # dy, (mu, sigma) -> dx
         nbytes = sum(rows * (r * n + x_in) + 2 * n * kk for r, n, kk, x_in in layers) * 4
     else:                                        # dy, x, rho -> dmu, drho
         nbytes = sum(rows * (r * n + x_in) + 3 * n * kk for r, n, kk, x_in in layers) * 4
     seconds = k["ms_per_step"] * 1e-3
-    tensor_peak = pk["bf16_sustained"] / 2.0      # TF32 dense = half the bf16 rate on this tensor pipe
+    tensor_peak = pk["tf32_sustained"]
     tflops, gbs = flops / seconds / 1e12, nbytes / seconds / 1e9
     intensity, ridge = flops / nbytes, tensor_peak * 1e12 / (pk["hbm"] * 1e9)
     out = dict(base, arithmetic_intensity=intensity, ridge_point=ridge,
-               tensor={"achieved": tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tflops / tensor_peak},
+               tensor={"achieved": tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tflops / tensor_peak,
+                       "frac_of_burst_peak": tflops / pk["tf32_burst"]},
                hbm={"achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]},
                traffic=measured_traffic(workload, name), algorithmic_bytes_per_step=nbytes,
                algorithmic_flops_per_step=flops,
-               peak_note="TF32 dense peak taken as half of the measured sustained bf16 cuBLAS rate "
-                         f"({pk['source']}); fp32 mode issues 3 TF32 MMAs per product; timed eagerly with CUDA events "
-                         "around the C-ABI call (includes its launch latency)")
+               peak_note=f"tensor peak = cuBLAS TF32 8192^3 measured in this run ({pk['tf32_sustained']:.0f} TFLOP/s "
+                         f"sustained, {pk['tf32_burst']:.0f} burst); HBM peak {pk['source']}; "
+                         + ("fp32 mode issues 3 TF32 MMAs per product; " if precision != "tf32" else "")
+                         + "timed eagerly with CUDA events around the C-ABI call (includes its launch latency)")
     side = "tensor" if intensity >= ridge else "hbm"
     out.update(bound=side, achieved=out[side]["achieved"], peak=out[side]["peak"], unit=out[side]["unit"],
                frac=out[side]["frac"])
     return out
 
 
+# ------------------------------------------------------------------------------------------------ C5
 def bench_kl_prune(device, pk, world=1, tensors=64):
     """C5 (BASELINE.json configs[4]): KL forward, KL forward+grad and the pruning sweep over 2^30
     (mu, rho) pairs — 64 tensors of 4096x4096, 8 GiB — sharded round-robin by tensor over the GPUs (64 / N tensors per
@@ -539,17 +470,19 @@ def bench_kl_prune(device, pk, world=1, tensors=64):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
+    total_buf = torch.zeros((), device=device, dtype=torch.float64)
+
     def kl_leg(entries):
         sums = _C.kl(entries)
         if world > 1:                       # tensor-sharded KL: one small all-reduce
             import torch.distributed as dist
-            total = sums.sum()
-            dist.all_reduce(total)
+            torch.sum(sums, dim=0, out=total_buf)
+            dist.all_reduce(total_buf)
 
     def time_it(fn, reps=5, inner=8):
         """Average duration of one call: `inner` back-to-back calls between one event pair (the host-side cost of
         preparing a launch overlaps the previous kernel, as it does in a training loop; every call streams the whole
-        2 GiB working set, so no call finds its data in L2), best of `reps`."""
+        working set, so no call finds its data in L2), best of `reps`."""
         fn()
         torch.cuda.synchronize()
         best = 1e30
@@ -579,27 +512,54 @@ def bench_kl_prune(device, pk, world=1, tensors=64):
     del gm, gr
     saved = [(m.clone(), r.clone()) for m, r in zip(mus, rhos)]
 
-    def prune_once():
-        _C.prune([(m, r, k, None, None) for m, r in zip(mus, rhos)])
-    prune_once()
-    torch.cuda.synchronize()
-    best = 1e30
-    for _ in range(3):
+    def restore():
         for (m, r), (sm, sr) in zip(zip(mus, rhos), saved):
             m.copy_(sm), r.copy_(sr)
         torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        prune_once()
-        b.record()
-        torch.cuda.synchronize()
-        best = min(best, a.elapsed_time(b) * 1e-3)
-    res["prune_p0.75"] = entry(8 + 8 * p, over_ranks(best))
+
+    def best_of(fn, reps=3, prepare=None):
+        best = 1e30
+        for _ in range(reps):
+            restore()
+            if prepare is not None:
+                prepare()
+                torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b) * 1e-3)
+        return over_ranks(best)
+
+    def prune_once():
+        _C.prune([(m, r, k, None, None) for m, r in zip(mus, rhos)])
+    prune_once()
+    res["prune_p0.75"] = entry(8 + 8 * p, best_of(prune_once))
+    res["prune_p0.75"]["what"] = "stand-alone PruneNormal sweep (prune.py:10-17): sample + interval histogram sweep + apply sweep"
+    if hasattr(_C, "kl_with_prune_plan"):
+        # north_star: "the pruning mask reuses that same pass" — the KL pass also histograms the certified key intervals
+        # (bnn_kl_prune_plan), the prune that follows is ONE read + write sweep (fused sweep 8 + 8p B/pair)
+        plan = {}
+
+        def kl_plan():
+            plan["p"] = _C.kl_with_prune_plan(fwd)
+
+        def prune_planned():
+            _C.prune_with_plan(plan["p"], [(m, r, k, None, None) for m, r in zip(mus, rhos)])
+        res["kl_fwd_with_prune_plan"] = entry(8, time_it(kl_plan, reps=3, inner=2))
+        res["prune_p0.75_after_kl"] = entry(8 + 8 * p, best_of(prune_planned, prepare=kl_plan))
+        res["prune_p0.75_after_kl"]["what"] = ("PruneNormal sweep that reuses the histograms of the preceding KL pass: "
+                                               "bracket + ONE apply sweep + exact finish")
+
+        def both_legs():
+            kl_plan()
+            prune_planned()
+        res["kl_plus_prune_p0.75"] = entry(8 + 8 * p, best_of(both_legs))
+        res["kl_plus_prune_p0.75"]["what"] = "KL forward (with plan) + prune, together, against the fused-sweep figure 8 + 8p B/pair"
     # the example's sweep (examples/MNIST/prune.py:49-50): successive levels on the SAME tensors — what was pruned at
     # one level (mu = 0, rho = -30: the largest key there is) is re-selected first at the next
-    for (m, r), (sm, sr) in zip(zip(mus, rhos), saved):
-        m.copy_(sm), r.copy_(sr)
-    torch.cuda.synchronize()
+    restore()
     sweep = []
     for level in torch.linspace(.75, 1, 6).tolist():
         kk = int(level * 4096 * 4096)
@@ -615,15 +575,63 @@ def bench_kl_prune(device, pk, world=1, tensors=64):
     return res
 
 
-# ------------------------------------------------------------------------------------------------ CPU arm
-def oracle_step_fn(workload, B, S):
-    """The reference step restated on CPU tensors by oracle/variational_oracle.py (ElboStepOracle)."""
-    from oracle import variational_oracle as orc
+# ------------------------------------------------------------------------------------------------ reference arm
+def load_reference():
+    """The unmodified reference package from baseline/_ref (None when it was not installed)."""
+    if not os.path.isdir(os.path.join(REF_DIR, "pytorch_bayesian")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import pytorch_bayesian          # noqa: F401
+    import pytorch_bayesian.nn as ref_nn
+    return ref_nn
+
+
+def reference_model(workload, samples, ref_nn):
+    """C2 / C3: the reference's own example model files, unmodified; C4: the same Sequential on the reference's classes."""
+    example = WORKLOADS[workload]["example"]
+    if example is None:
+        return build_model(workload, samples, nn=ref_nn)
+    spec = importlib.util.spec_from_file_location(f"_ref_example_{example}", os.path.join(REF_DIR, "examples", example, "model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.BCNN(WORKLOADS[workload]["cin"], 10, samples)
+
+
+def reference_step_fn(workload, B, S, device="cpu"):
+    """The loop body of examples/MNIST/train.py:55-65 on the reference's own classes (kind 'reference'), or — when
+    baseline/_ref is absent — on the oracle's restatement (kind 'port')."""
+    ref_nn = load_reference()
+    gen = torch.Generator().manual_seed(1)
+    x, y = synthetic_batch(workload, B, gen)
+    x, y = x.to(device), y.to(device)
     torch.manual_seed(0)
-    model = build_model(workload, S)      # used only as a container of identically initialised parameters
+    if ref_nn is not None:
+        model = reference_model(workload, S, ref_nn).to(device)
+        kld = ref_nn.KLDivergence(number_of_batches=N_BATCHES)
+        ce = torch.nn.CrossEntropyLoss()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+        def run():
+            opt.zero_grad()
+            preds = model(x)
+            if not isinstance(preds, list):
+                preds = [preds]
+            divergence = kld(model)
+            likelihood = torch.stack([ce(p, y) for p in preds]).mean()
+            loss = likelihood + divergence
+            loss.backward()
+            opt.step()
+            return loss
+        return run, "reference"
+    from oracle import variational_oracle as orc
+    import bayesianneuralnetworks_b200 as bnn
+    model = build_model("c2" if workload == "c2" else workload, S)
     stages, cur = [], []
     for m in model.layers:
         kind = type(m).__name__
+        if kind == "MultivariateNormalLinear":      # the port has no full-covariance stage: a NormalLinear head instead
+            m, kind = bnn.nn.NormalLinear(128, 10), "NormalLinear"
         if kind in ("NormalConv2d", "NormalLinear"):
             if cur:
                 stages.append(('torch', torch.nn.Sequential(*cur)))
@@ -640,54 +648,84 @@ def oracle_step_fn(workload, B, S):
         stages.append(('torch', torch.nn.Sequential(*cur)))
     step = orc.ElboStepOracle(stages, S, N_BATCHES)
     opt = torch.optim.Adam(step.parameters(), lr=1e-3)
-    gen = torch.Generator().manual_seed(1)
-    x, y = synthetic_batch(workload, B, gen)
 
     def run():
         opt.zero_grad()
         loss, _ = step.loss(x, y)
         loss.backward()
         opt.step()
-        return float(loss)
-    return run
+        return loss
+    return run, "port"
+
+
+def cpu_sample(workload):
+    wl = WORKLOADS[workload]
+    B, S = wl["batch"], wl["samples"]
+    if workload == "c4":            # a full C4 step is ~12 TFLOP on the CPU: time a 1-sample slice
+        return B, 1, "one MC sample of the step (B=1024, S=1 of 32), scaled by samples*MC"
+    return B, S, f"full step (B={B}, S={S})"
 
 
 def cpu_baseline(workload, bounded_seconds):
-    wl = WORKLOADS[workload]
-    B, S = wl["batch"], wl["samples"]
-    sample = "full step (B=%d, S=%d)" % (B, S)
-    if workload == "c4":            # a full C4 step is ~12 TFLOP on the CPU: time a 1-sample slice
-        S, sample = 1, "one MC sample of the step (B=1024, S=1 of 32), scaled by samples*MC"
+    B, S, sample = cpu_sample(workload)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    run = oracle_step_fn(workload, B, S)
+    run, kind = reference_step_fn(workload, B, S)
     run()
     t0, n = time.perf_counter(), 0
     while n < 3 or (time.perf_counter() - t0 < bounded_seconds and n < 200):
         run()
         n += 1
     dt = (time.perf_counter() - t0) / n
-    return {"value": B * S / dt, "unit": "samples*MC/s", "cores": cores, "kind": "port",
-            "sample": f"{sample}, {n} steps, torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads",
+    return {"value": B * S / dt, "unit": "samples*MC/s", "cores": cores, "kind": kind,
+            "sample": f"{sample}, {n} steps, torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads"
+                      + (", unmodified reference classes from baseline/_ref" if kind == "reference" else ", oracle port"),
             "ms_per_step": dt * 1e3}
 
 
+def reference_on_gpu(device, workload, steps):
+    """The UNMODIFIED reference classes on the same GPU through torch (cuBLAS / cuDNN + the unfused elementwise / RNG
+    launches of SURVEY §2a): the kernel sequence the fused path replaces.  Eager, allow_tf32 as in the b200 run."""
+    if load_reference() is None:
+        return {"unavailable": "baseline/_ref not installed"}
+    wl = WORKLOADS[workload]
+    B, S = wl["batch"], wl["samples"]
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    run, _ = reference_step_fn(workload, B, S, device=device)
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak = torch.cuda.max_memory_allocated(device) / 2 ** 30
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms, "value": B * S / (ms * 1e-3), "unit": "samples*MC/s", "steps": steps,
+            "what": f"{wl['name']}: reference classes (baseline/_ref) on cuda through torch {torch.__version__}, eager, "
+                    f"allow_tf32, B={B}, S={S}", "max_memory_allocated_gib": peak}
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (the oracle port: the reference is
-    Python on torch ops and cannot be vendored) on the host cores, same config / metric / unit."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (baseline/_ref when
+    installed, else the oracle port), same config / metric / unit."""
     if int(os.environ.get("RANK", 0)) != 0:
         return
     wl = WORKLOADS[args.workload]
-    B, S = wl["batch"], wl["samples"]
-    sample = f"full step (B={B}, S={S})"
-    if args.workload == "c4":
-        S, sample = 1, "one MC sample of the step (S=1 of 32)"
+    B, S, sample = cpu_sample(args.workload)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    run = oracle_step_fn(args.workload, B, S)
-    steps, warmup = min(args.steps, 20), min(max(args.warmup, 1), 3)
+    run, kind = reference_step_fn(args.workload, B, S)
+    warmup = min(max(args.warmup, 1), 3)
+    t0 = time.perf_counter()
     for _ in range(warmup):
         run()
+    per_step = (time.perf_counter() - t0) / warmup
+    steps = max(3, min(args.steps, 20, int(90.0 / max(per_step, 1e-3))))      # bounded: the whole run ends within minutes
     t0 = time.perf_counter()
     for _ in range(steps):
         run()
@@ -697,13 +735,75 @@ def run_reference(args):
         "impl": "reference", "metric": "ELBO train samples*MC/sec", "value": value, "unit": "samples*MC/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": wl["name"], "batch_per_gpu": B, "mc_samples": S, "n_batches": N_BATCHES,
+        "config": {"workload": wl["name"], "batch_per_gpu": B, "mc_samples_per_gpu": S, "n_batches": N_BATCHES,
                    "optimizer": "Adam", "step": "zero_grad+forward(S)+KL+CE+backward+Adam"},
-        "cpu_baseline": {"value": value, "unit": "samples*MC/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "samples*MC/s", "cores": cores, "kind": kind,
                          "sample": f"{sample}, {steps} steps, torch {torch.__version__} CPU fp32, "
-                                   f"{torch.get_num_threads()} threads"},
+                                   f"{torch.get_num_threads()} threads"
+                                   + (", unmodified reference classes from baseline/_ref (examples/*/model.py)"
+                                      if kind == "reference" else ", oracle port (baseline/_ref absent)")},
         "e2e": {"value": value, "unit": "samples*MC/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ------------------------------------------------------------------------------------------------ b200 arm
+def run_b200(args):
+    env = Env(args)
+    from bayesianneuralnetworks_b200 import _C
+    _C.lib()                          # fails loudly when the CUDA library is missing
+    rank, world, device = env.rank, env.world, env.device
+    env.clocks.start()
+    tf32_peak = measure_tf32_peak(device)
+    env.pk.update(tf32_burst=tf32_peak["burst_tflops"], tf32_sustained=tf32_peak["sustained_tflops"])
+    main_mode = {"c4": "sample"}.get(args.workload, "grid") if args.parallel == "auto" else args.parallel
+    main = measure_step(env, args.workload, args.steps, args.warmup, args.precision, main_mode,
+                        channels_last=not args.nchw_trunk, exchange=args.exchange)
+    out = {
+        "metric": "ELBO train samples*MC/sec", "value": main["value"], "unit": "samples*MC/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"],
+        "higher_is_better": True, "scaling": main["scaling"], "vs_baseline": None, "dtype": main["dtype"],
+        "data": "synthetic", "config": main["config"], "e2e": main["e2e"], "gpu_launches": main["gpu_launches"],
+        "wall_s": {"device_resident": main["wall_s"], "e2e": main["e2e"]["wall_s"]}, "clocks": main["clocks"],
+        "roofline": main["roofline"],
+        "hot_path": {"algorithmic_tflops_per_s": main["hot_path_algorithmic_tflops"],
+                     "kernels_ms_per_step": main["kernels_ms_per_step"]},
+        "peaks": env.pk, "tf32_peak": tf32_peak,
+    }
+    if not args.no_extras:
+        short = max(5, min(args.steps, 20))
+        for wl in ("c2", "c3", "c4"):
+            if wl == args.workload:
+                continue
+            block = measure_step(env, wl, short, 3, "tf32", "sample" if wl == "c4" else "grid")
+            out[wl] = {k: block[k] for k in ("workload", "value", "unit", "ms_per_step", "steps", "scaling", "config",
+                                             "dtype", "e2e", "gpu_launches", "clocks", "roofline",
+                                             "hot_path_algorithmic_tflops", "kernels_ms_per_step")}
+        other = "fp32" if args.precision == "tf32" else "tf32"
+        alt = measure_step(env, args.workload, short, 3, other, main_mode, with_e2e=False, with_roofline=False,
+                           channels_last=not args.nchw_trunk, exchange=args.exchange)
+        out[other] = {"ms_per_step": alt["ms_per_step"], "value": alt["value"], "dtype": alt["dtype"], "steps": short,
+                      "what": "the same workload and launch configuration in the other hot-path precision mode "
+                              "(fp32 = three-term TF32 split, 1e-5 parity class; the trunk then runs without allow_tf32)"}
+        if not args.nchw_trunk:
+            nchw = measure_step(env, args.workload, short, 3, args.precision, main_mode, with_e2e=False,
+                                with_roofline=False, channels_last=False, exchange=args.exchange)
+            out["nchw_trunk_ms_per_step"] = nchw["ms_per_step"]
+        out["kl_prune"] = bench_kl_prune(device, env.pk, world=world)          # every rank sweeps its shard of the tensors
+        if world == 1:
+            try:
+                out["reference_on_gpu"] = {"c2": reference_on_gpu(device, "c2", 5), "c3": reference_on_gpu(device, "c3", 3),
+                                           "c4": reference_on_gpu(device, "c4", 2)}
+            except Exception as exc:      # noqa: BLE001 — a comparator, never fatal
+                out["reference_on_gpu"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+            if rank == 0:
+                out["cpu_baseline"] = cpu_baseline(args.workload, bounded_seconds=20.0)
+    env.clocks.stop()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
 
 
 def main():
@@ -712,26 +812,29 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
                     help="hot-path contraction mode: tf32 (2e-3 parity class) or fp32 = 3xTF32 split (1e-5 class)")
-    ap.add_argument("--parallel", default="data", choices=["data", "sample"],
-                    help="N > 1: shard the batch (weak scaling, default) or the MC samples of one batch (strong scaling)")
+    ap.add_argument("--parallel", default="auto", choices=["auto", "grid", "data", "sample"],
+                    help="N > 1: grid = data x sample groups, per-GPU work fixed (weak scaling; default for c2 / c3); "
+                         "sample = the MC samples of one batch sharded over the ranks (strong scaling; default for c4); "
+                         "data = batch sharding only")
+    ap.add_argument("--sample-groups", type=int, default=0, help="sample groups of the grid (0 = 2 -> 2, 4 -> 2, 8 -> 4)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "bucketed", "flat"],
+                    help="gradient exchange at N > 1 (training.ElboTrainer): peer = averaged inside the optimizer kernel over "
+                         "NVLink peer memory, one CUDA graph; bucketed = NCCL buckets overlapped with backward; flat = one "
+                         "NCCL all-reduce between two graphs")
     ap.add_argument("--loss-tail", default="batched", choices=["batched", "loop"],
                     help="likelihood term: nn.mc_mean_loss (one CE over the S*B rows) or the reference's per-sample loop")
     ap.add_argument("--no-cudnn-benchmark", action="store_true",
-                    help="leave torch.backends.cudnn.benchmark off for the deterministic torch trunk (the examples' setting; "
-                         "the default run lets cuDNN pick its kernels by measurement, 0.73 -> 0.69 ms per C2 step)")
+                    help="leave torch.backends.cudnn.benchmark off for the deterministic torch trunk (the examples' setting)")
     ap.add_argument("--optimizer", default="elbo-adam", choices=["adam", "elbo-adam"],
                     help="elbo-adam: bnn.optim.ELBOAdam (KL gradient + Adam in one pass, likelihood-only backward; same "
                          "trajectory); adam: torch's fused Adam on likelihood + KL, the reference loop verbatim")
     ap.add_argument("--nchw-trunk", action="store_true",
-                    help="leave the deterministic torch trunk (Conv2d / BatchNorm2d / ELU) in torch's default NCHW memory "
-                         "format (the examples' setting).  Default: torch.channels_last for those modules — cuDNN's NHWC "
-                         "kernels without a layout conversion around each call (C2 0.64 -> 0.54 ms, C3 2.19 -> 1.91 ms); "
-                         "the Bayesian layers take either layout and keep (mu, rho) row-major OIHW")
+                    help="leave the deterministic torch trunk in torch's default NCHW memory format (the examples' setting)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--no-extras", action="store_true", help="skip the kl_prune and cpu_baseline legs (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="only the main workload (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

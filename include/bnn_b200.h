@@ -205,6 +205,34 @@ typedef struct bnn_adam_tensor {
 } bnn_adam_tensor;
 int bnn_adam_kl_step(const bnn_adam_tensor* tensors /* HOST array */, int32_t n_tensors, float lr, float beta1, float beta2,
                      float eps, const float* step_dev, int64_t step_host, void* stream);
+/* A tensor with rho == NULL (then g_rho, m_rho, v_rho are ignored and kl_coeff must be 0) is a plain parameter updated
+ * by Adam alone: the deterministic layers of a model (examples/MNIST/model.py:21-27) ride in the same launch. */
+
+/* ---- the same step with the multi-GPU gradient exchange folded in ("one allreduce (avg) of the flat
+ * [dmu, drho] gradient buffer") ----
+ * One process per GPU on one NVLink node.  Every rank keeps ALL its gradients in one flat buffer that every other rank
+ * has mapped into its address space (CUDA IPC / symmetric memory; `base[r]` = rank r's buffer as seen from THIS process,
+ * base[rank] = the local one).  g_mu / g_rho of the table point into the local buffer; the kernel reads the element at
+ * the same offset from all `world` buffers, averages in rank order (bit-identical result on every rank) and applies the
+ * update: a one-shot all-reduce without a reduced gradient ever being written.  Callers bracket it with
+ * bnn_peer_barrier: once after the backward pass (every rank's gradients are complete) and once after this call (every
+ * rank has finished reading, the buffers may be overwritten).  Replaces the loop body's loss.backward(); optimizer.step()
+ * (examples/MNIST/train.py:63-65) under data / sample parallelism. */
+#define BNN_MAX_PEERS 8
+typedef struct bnn_peer_grads {
+  int32_t world;
+  int32_t rank;
+  const float* base[BNN_MAX_PEERS];
+} bnn_peer_grads;
+int bnn_adam_kl_step_peers(const bnn_adam_tensor* tensors /* HOST array */, int32_t n_tensors, float lr, float beta1,
+                           float beta2, float eps, const float* step_dev, int64_t step_host,
+                           const bnn_peer_grads* peers, void* stream);
+/* Flag barrier between the ranks (one launch per rank, same point of every rank's stream; a rank that never arrives
+ * traps the waiting kernels after 10 s instead of hanging).  flags[r] (HOST array of `world` pointers): rank r's flag
+ * block — BNN_MAX_PEERS uint32 words in peer-visible memory, zero before first use — as mapped into this process.
+ * epoch_dev: local device counter (zero before first use), advanced by every launch, so a captured graph replays it. */
+int bnn_peer_barrier(uint32_t* const* flags /* HOST array */, int32_t world, int32_t rank, uint32_t* epoch_dev,
+                     void* stream);
 
 /* ---- likelihood tail: mean cross-entropy over the S Monte-Carlo predictions ----
  * Replaces the loop body `torch.stack([criterion(pred, y) for pred in preds]).mean()` with criterion =
@@ -267,6 +295,11 @@ int bnn_selftest_prune_interval(const float* mu, const float* rho, int64_t numel
 int bnn_selftest_umma(float* max_err_dev, void* stream);
 /* same for MN-major (transposed) operand tiles, the layout the data- and weight-gradient kernels use */
 int bnn_selftest_umma_mn(float* max_err_dev, void* stream);
+
+/* ---- test aid: force the TMA-fed forward / data-gradient contraction onto one kernel variant so that small test
+ * shapes reach all of them: 0 = CTA pair (needs more than four 128-row blocks), 1 / 2 / 4 = row blocks per CTA,
+ * -1 = the launcher's cost model (default).  Process-wide; not for production use. */
+int bnn_debug_force_contract_variant(int32_t variant);
 
 #ifdef __cplusplus
 }

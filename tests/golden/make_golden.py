@@ -209,27 +209,35 @@ def mvn_case():
              g_w_scale=np32(mvn.weight.scale.grad), g_lin_w_mean=np32(lin.weight.mean.grad))
 
 
+def _load_example_model(example, ckpt):
+    """examples/<example>/model.py BCNN with its shipped checkpoint (both example files define `model.BCNN`)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(f"_golden_{example}", os.path.join(REF, "examples", example, "model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    model = mod.BCNN(1, 10)
+    model.load_state_dict(torch.load(os.path.join(REF, "examples", example, ckpt), map_location="cpu"))
+    return model
+
+
 def checkpoint_fixtures():
-    sys.path.insert(0, os.path.join(REF, "examples", "MNIST"))
-    from model import BCNN  # examples/MNIST/model.py
+    """The Bayesian layers of the shipped checkpoints: KLDivergence(1) and PruneNormal mask fingerprints.
+    MNIST: NormalConv2d + NormalLinear (weights and biases); FashionMNIST: the Flipout layers (weights only)."""
     values = {}
-    for tag, path, cls_kwargs in (("mnist", "examples/MNIST/mnist_pretrained.pth", {}),):
-        model = BCNN(1, 10)
-        model.load_state_dict(torch.load(os.path.join(REF, path), map_location="cpu"))
+    for tag, example, ckpt in (("mnist", "MNIST", "mnist_pretrained.pth"), ("fmnist", "FashionMNIST", "fmnist_pretrained.pth")):
+        model = _load_example_model(example, ckpt)
         conv, lin = model.layers[7], model.layers[10]
-        np.savez(os.path.join(HERE, f"{tag}_ckpt_bayes_layers.npz"),
-                 conv_w_mean=np32(conv.weight.mean), conv_w_scale=np32(conv.weight.scale),
-                 conv_b_mean=np32(conv.bias.mean), conv_b_scale=np32(conv.bias.scale),
-                 lin_w_mean=np32(lin.weight.mean), lin_w_scale=np32(lin.weight.scale),
-                 lin_b_mean=np32(lin.bias.mean), lin_b_scale=np32(lin.bias.scale))
+        arrays = dict(conv_w_mean=np32(conv.weight.mean), conv_w_scale=np32(conv.weight.scale),
+                      lin_w_mean=np32(lin.weight.mean), lin_w_scale=np32(lin.weight.scale))
+        if conv.bias is not None:
+            arrays.update(conv_b_mean=np32(conv.bias.mean), conv_b_scale=np32(conv.bias.scale),
+                          lin_b_mean=np32(lin.bias.mean), lin_b_scale=np32(lin.bias.scale))
+        np.savez(os.path.join(HERE, f"{tag}_ckpt_bayes_layers.npz"), **arrays)
         values[tag] = {"kl_n_batches_1": float(KLDivergence(1)(model)), "prune": {}}
         for p in (0.75, 0.9):
-            m = BCNN(1, 10)
-            m.load_state_dict(torch.load(os.path.join(REF, path), map_location="cpu"))
-            before = [t.clone() for t in (m.layers[7].weight.mean, m.layers[7].bias.mean, m.layers[10].weight.mean,
-                                          m.layers[10].bias.mean)]
+            m = _load_example_model(example, ckpt)
             PruneNormal()(m, torch.tensor(p))           # p as a 0-dim tensor, like examples/MNIST/prune.py:49
-            after = [m.layers[7].weight, m.layers[7].bias, m.layers[10].weight, m.layers[10].bias]
+            after = [t for l in (m.layers[7], m.layers[10]) for t in (l.weight, l.bias) if t is not None]
             masks = [(a.scale == -30) for a in after]
             values[tag]["prune"][str(p)] = {
                 "counts": [int(mk.sum()) for mk in masks],

@@ -155,10 +155,14 @@ def test_mc_batching_plan():
     ok = Net(torch.nn.Sequential(torch.nn.Conv2d(1, 2, 3), torch.nn.BatchNorm2d(2), torch.nn.ELU(),
                                  NormalConv2d(2, 2, 3), torch.nn.Flatten(), NormalLinear(8, 3),
                                  torch.nn.Softmax(dim=-1)), samples=4)
-    foldable, bns = ok._mc_plan()
-    assert foldable and len(bns) == 1
+    plan = ok._mc_plan()
+    assert plan.ok and len(plan.bns) == 1 and not plan.probes
     ok.eval()
-    assert ok._mc_plan() == (True, [])
+    assert ok._mc_plan().ok and ok._mc_plan().bns == []
+    ok.layers[1].train()                          # a per-submodule toggle invalidates the cached plan
+    assert len(ok._mc_plan().bns) == 1
+    no_stats = Net(torch.nn.Sequential(torch.nn.BatchNorm1d(3, track_running_stats=False), NormalLinear(3, 3))).eval()
+    assert len(no_stats._mc_plan().bns) == 1      # batch statistics even in eval mode: guarded
     assert not Net(torch.nn.Sequential(torch.nn.Linear(3, 3)))._mc_plan()[0]             # nothing Bayesian
     assert not Net(torch.nn.Sequential(NormalLinear(3, 3), torch.nn.Softmax(dim=0)))._mc_plan()[0]
     assert not Net(torch.nn.Sequential(torch.nn.Dropout(0.5), NormalLinear(3, 3)))._mc_plan()[0]
@@ -166,9 +170,21 @@ def test_mc_batching_plan():
     class Custom(torch.nn.Module):
         def forward(self, x):
             return x.view(x.size(0), -1)
-    assert not Net(torch.nn.Sequential(Custom(), NormalLinear(3, 3)))._mc_plan()[0]
+    probed = Net(torch.nn.Sequential(Custom(), NormalLinear(3, 3)))._mc_plan()
+    assert probed.ok and len(probed.probes) == 1          # unknown stateless leaf: eligible, probed at run time
     bnn.nn.register_rowwise_module(Custom)
-    assert Net(torch.nn.Sequential(Custom(), NormalLinear(3, 3)))._mc_plan()[0]
+    registered = Net(torch.nn.Sequential(Custom(), NormalLinear(3, 3)))._mc_plan()
+    assert registered.ok and not registered.probes
+    bnn.nn.container._ROWWISE.remove(Custom)
+
+    class Stateful(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(3))
+
+        def forward(self, x):
+            return x * self.w
+    assert not Net(torch.nn.Sequential(Stateful(), NormalLinear(3, 3)))._mc_plan()[0]     # unknown code with state
     assert not Net(torch.nn.Sequential(NormalConv3d(1, 1, 1)))._mc_plan()[0]              # no fused 3-d path
 
 
@@ -344,14 +360,11 @@ def test_reference_example_models_construct_unchanged_on_the_drop_in():
             if ckpt and os.path.exists(f"/root/reference/examples/{example}/{ckpt}"):
                 sd = torch.load(f"/root/reference/examples/{example}/{ckpt}", map_location="cpu")
                 model.load_state_dict(sd)                      # same keys, same shapes
-            # their own Flatten is user code: one registration makes the network eligible for the batched forward
-            assert model._mc_plan()[0] is False
-            bnn.nn.register_rowwise_module(mod.Flatten)
-            model.__dict__.pop("_mc_plan_cache", None)
+            # their own Flatten is user code without state: eligible for the batched forward, probed at run time.
             # MNIST (NormalConv2d + NormalLinear) runs on the fused kernels; the Flipout layers of FashionMNIST (f-1)
             # and the full-covariance head of CIFAR10 (f-4) are torch composites that join the batched pass
-            assert model._mc_plan()[0] is True
-            bnn.nn.container._ROWWISE.remove(mod.Flatten)
+            plan = model._mc_plan()
+            assert plan.ok and [type(m) for m in plan.probes] == [mod.Flatten]
     finally:
         for k, v in saved.items():
             if v is None:
@@ -389,7 +402,9 @@ def test_elbo_adam_plans_the_same_tensors_and_coefficients_as_kl_divergence():
     assert seen == [net.layers[2].weight, net.layers[2].bias, net.layers[4].weight]
     for e in opt._var:
         assert e["coeff"] == pytest.approx(1.0 / (e["w"].mean.numel() * 3 * 5)) and (e["loc"], e["scale"]) == (0.0, pytest.approx(0.1))
-    others = {id(p) for g in opt.param_groups for p in g["params"]}
+    assert opt.param_groups[0]["variational"] and not opt.param_groups[1]["variational"]       # a torch Optimizer
+    assert {id(p) for p in opt.param_groups[0]["params"]} == {id(p) for w in seen for p in (w.mean, w.scale)}
+    others = {id(p) for p in opt.param_groups[1]["params"]}
     assert others == {id(p) for p in list(net.layers[0].parameters()) + list(net.layers[5].parameters())}
     net.layers[0].weight.grad = torch.ones_like(net.layers[0].weight)
     opt.zero_grad()

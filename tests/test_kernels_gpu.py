@@ -474,11 +474,12 @@ def test_sampled_gemm_backward_injected(C, M, N, K, S, shared, prec):
 
 @pytest.mark.parametrize("variant", ["pair", "mb4", "mb2", "mb1"])
 @pytest.mark.parametrize("M,N,K,S,shared", [(700, 136, 96, 3, True), (1024, 256, 128, 2, False), (1100, 64, 288, 2, True)])
-def test_every_tma_contraction_variant_on_small_shapes(C, monkeypatch, variant, M, N, K, S, shared):
+def test_every_tma_contraction_variant_on_small_shapes(C, request, variant, M, N, K, S, shared):
     """The launcher picks rows-per-CTA / CTA pairs from a cost model, so small shapes normally run one variant only;
-    BNN_CONTRACT_VARIANT forces each of them (TF32 mode) through forward and input gradient, shared activations
-    (the input gradient sums the samples inside the kernel) and per-sample ones."""
-    monkeypatch.setenv("BNN_CONTRACT_VARIANT", variant)
+    bnn_debug_force_contract_variant forces each of them (TF32 mode) through forward and input gradient, shared
+    activations (the input gradient sums the samples inside the kernel) and per-sample ones."""
+    C.force_contract_variant(variant)
+    request.addfinalizer(lambda: C.force_contract_variant(None))
     g = torch.Generator().manual_seed(12)
     a, mu_w, rho_w, mu_b, rho_b, eps_w, eps_b = gemm_inputs(M, N, K, S, shared, g)
     y = run_fwd(C, a, mu_w, rho_w, mu_b, rho_b, eps_w, eps_b, S, 0)

@@ -636,15 +636,16 @@ def test_mc_mean_loss_equals_the_reference_loop_body():
 @pytest.mark.parametrize("prec", ["fp32", "tf32"])
 def test_example_training_loop_learns_and_prunes(prec):
     """The body of examples/MNIST/train.py:53-65 and examples/MNIST/prune.py:47-50 on synthetic, separable data:
-    the ELBO goes down, accuracy goes up, pruning keeps the fractions — with the user-defined Flatten first on the
-    reference loop, then (after register_rowwise_module) on the batched Monte-Carlo forward."""
+    the ELBO goes down, accuracy goes up, pruning keeps the fractions — first on the reference loop
+    (set_mc_batching('never')), then on the batched Monte-Carlo forward, which the user-defined Flatten joins after
+    being probed at run time."""
     from bayesianneuralnetworks_b200.nn import container
-    if _ExampleFlatten in container._ROWWISE:               # registered by an earlier parametrisation of this test
+    if _ExampleFlatten in container._ROWWISE:               # registered by another test
         container._ROWWISE.remove(_ExampleFlatten)
     bnn.set_precision(prec)
     torch.manual_seed(0)
     model = _example_bcnn(4).cuda()
-    assert model._mc_plan()[0] is False                    # unknown user module -> the reference loop
+    bnn.set_mc_batching('never')
     protos = torch.rand(10, 1, 28, 28, device="cuda")
     y = torch.arange(64, device="cuda") % 10
     x = (protos[y] + 0.1 * torch.randn(64, 1, 28, 28, device="cuda")).clamp(0, 1)
@@ -663,10 +664,11 @@ def test_example_training_loop_learns_and_prunes(prec):
     first = step()
     for _ in range(10):
         step()
-    bnn.nn.register_rowwise_module(_ExampleFlatten)        # now eligible for the batched forward
-    assert model._mc_plan()[0] is True
+    bnn.set_mc_batching('auto')
     for _ in range(60):
         last = step()
+    plan = model._mc_plan()
+    assert plan.ok and plan.verified and plan.probes and plan.probes[0].__dict__['_bnn_rowwise'] is True
     assert last[0] < first[0] - 0.1 and last[1] > 0.5, (first, last)
     sd = model.state_dict()
     assert "layers.7.weight.mean" in sd and "layers.10.bias.scale" in sd

@@ -96,6 +96,26 @@ def test_kl_and_prune_oracle_match_reference_checkpoint_values():
             assert torch.equal(orc.prune_mask_lowest_index(mu, rho, k), mask)   # k-th key unique here
 
 
+def test_kl_and_prune_oracle_match_the_fashion_mnist_checkpoint_values():
+    """examples/FashionMNIST/fmnist_pretrained.pth (Flipout layers: weights only) — KLDivergence(1) =
+    0.289310575, per-tensor element sums 7308.5585 / 2190.8956, mask fingerprints 5ca0722d87fe / 61597c4bdbf7 (p = .75)
+    and ccd4f08bf1d4 / 811c69ed4772 (p = .9)."""
+    z = np.load(os.path.join(GOLD, "fmnist_ckpt_bayes_layers.npz"))
+    gold = json.load(open(os.path.join(GOLD, "golden_values.json")))["fmnist"]
+    assert gold["prune"]["0.75"]["sha1_12"] == ["5ca0722d87fe", "61597c4bdbf7"]
+    assert gold["prune"]["0.9"]["sha1_12"] == ["ccd4f08bf1d4", "811c69ed4772"]
+    tensors = [(T(z[n + "_mean"]), T(z[n + "_scale"]), 0.0, 0.1) for n in ("conv_w", "lin_w")]
+    assert float(orc.kl_divergence(tensors, 1)) == pytest.approx(0.289310575, rel=1e-6)
+    assert gold["kl_n_batches_1"] == pytest.approx(0.289310575, rel=1e-6)
+    for got, want in zip(orc.kl_tensor_sums(tensors), (7308.5585, 2190.8956)):
+        assert got == pytest.approx(want, rel=5e-4)
+    for p, g in gold["prune"].items():
+        for (mu, rho, _, _), h, c in zip(tensors, g["sha1_12"], g["counts"]):
+            mask = orc.prune_mask(mu, rho, torch.tensor(float(p)))
+            assert int(mask.sum()) == c
+            assert hashlib.sha1(mask.numpy().tobytes()).hexdigest()[:12] == h
+
+
 def test_reference_known_answers():
     """reference tests/test_nn/test_core.py:31-39, test_dense.py:57-70, test_conv.py:102-120."""
     rho = torch.full((4, 3), -100.0)
