@@ -41,6 +41,11 @@ class bnn_conv2d_geom(ctypes.Structure):
                 ("B", "C", "H", "W", "c0", "Cg", "KH", "KW", "OH", "OW", "sh", "sw", "ph", "pw", "dh", "dw")]
 
 
+class bnn_conv2d_nhwc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("B", "H", "W", "C", "OH", "OW", "Cout", "KH", "KW", "sh", "sw", "ph", "pw", "dh", "dw", "reserved")]
+
+
 class bnn_kl_tensor(ctypes.Structure):
     _fields_ = [("mu", ctypes.c_void_p), ("rho", ctypes.c_void_p), ("grad_mu", ctypes.c_void_p),
                 ("grad_rho", ctypes.c_void_p), ("numel", ctypes.c_int64),
@@ -95,6 +100,22 @@ _SIGNATURES = {
     "bnn_im2col": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.POINTER(bnn_conv2d_geom), ctypes.c_void_p]),
     "bnn_col2im": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.POINTER(bnn_conv2d_geom), ctypes.c_int32,
                                   ctypes.c_void_p]),
+    "bnn_sampled_conv2d_fwd": (ctypes.c_int, [_c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p,
+                                              bnn_view, ctypes.c_int64, ctypes.POINTER(bnn_conv2d_nhwc), ctypes.c_int32,
+                                              ctypes.c_uint32, ctypes.POINTER(bnn_rng), ctypes.POINTER(bnn_rng),
+                                              ctypes.c_void_p]),
+    "bnn_sampled_conv2d_dgrad": (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, ctypes.c_int64,
+                                                ctypes.POINTER(bnn_conv2d_nhwc), ctypes.c_int32, ctypes.c_uint32,
+                                                ctypes.POINTER(bnn_rng), ctypes.c_void_p]),
+    "bnn_sampled_conv2d_wgrad": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, _c_f32p, _c_f32p,
+                                                ctypes.POINTER(bnn_conv2d_nhwc), ctypes.c_int32, ctypes.c_uint32,
+                                                ctypes.POINTER(bnn_rng), ctypes.c_void_p]),
+    "bnn_conv2d_weight_layout": (ctypes.c_int, [_c_f32p, _c_f32p, _c_f32p, _c_f32p, _c_f32p, ctypes.c_int32, ctypes.c_int32,
+                                                ctypes.c_int32, ctypes.c_void_p]),
+    "bnn_conv2d_weight_unlayout": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                  ctypes.c_int32, ctypes.c_void_p]),
+    "bnn_im2col_nhwc": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.POINTER(bnn_conv2d_nhwc), ctypes.c_int64, ctypes.c_void_p]),
+    "bnn_col2im_nhwc": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.POINTER(bnn_conv2d_nhwc), ctypes.c_int64, ctypes.c_void_p]),
     "bnn_kl_workspace_size": (ctypes.c_size_t, [ctypes.c_int32]),
     "bnn_kl": (ctypes.c_int, [ctypes.POINTER(bnn_kl_tensor), ctypes.c_int32, ctypes.c_void_p, _c_f32p, _c_f32p,
                               ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
@@ -320,6 +341,76 @@ def im2col(x, col, geom):
 def col2im(dcol, dx, geom, accumulate):
     with torch.cuda.device(dx.device):
         _call("bnn_col2im", _ptr(dcol), _ptr(dx), ctypes.byref(geom), 1 if accumulate else 0, _stream())
+    _count()
+
+
+# ---- implicit-GEMM convolution (NHWC activations, (o, kh, kw, c) weights) ------------------------------------------
+def conv_geom(B, H, W, C, OH, OW, Cout, KH, KW, stride, padding, dilation):
+    return bnn_conv2d_nhwc(B, H, W, C, OH, OW, Cout, KH, KW, stride[0], stride[1], padding[0], padding[1], dilation[0],
+                           dilation[1], 0)
+
+
+def conv_weight_layout(mu, rho):
+    """OIHW mean / scale [Cout, Cg, KH, KW] -> one buffer [3, Cout*KH*KW*Cg] holding mean, sigma = 1e-10 + softplus(scale)
+    and scale in (o, kh, kw, c) order."""
+    require_cuda(mu, rho)
+    mu, rho = _f32c(mu, "mu"), _f32c(rho, "rho")
+    Cout, Cg = mu.shape[0], mu.shape[1]
+    taps = mu.numel() // (Cout * Cg)
+    out = torch.empty((3, mu.numel()), device=mu.device, dtype=torch.float32)
+    with torch.cuda.device(mu.device):
+        _call("bnn_conv2d_weight_layout", _ptr(mu), _ptr(rho), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), Cout, Cg, taps,
+              _stream())
+    _count()
+    return out
+
+
+def conv_weight_unlayout(grads_p, shape):
+    """[n, numel] arrays in (o, kh, kw, c) order -> [n, Cout, Cg, KH, KW] (OIHW)."""
+    Cout, Cg = shape[0], shape[1]
+    taps = grads_p.shape[1] // (Cout * Cg)
+    out = torch.empty((grads_p.shape[0],) + tuple(shape), device=grads_p.device, dtype=torch.float32)
+    with torch.cuda.device(grads_p.device):
+        _call("bnn_conv2d_weight_unlayout", _ptr(grads_p), _ptr(out), grads_p.shape[0], Cout, Cg, taps, _stream())
+    _count()
+    return out
+
+
+def im2col_nhwc(x_nhwc_ptr_tensor, geom, n_imgs):
+    K = geom.KH * geom.KW * geom.C
+    col = torch.empty((n_imgs * geom.OH * geom.OW, K), device=x_nhwc_ptr_tensor.device, dtype=torch.float32)
+    with torch.cuda.device(col.device):
+        _call("bnn_im2col_nhwc", _ptr(x_nhwc_ptr_tensor), _ptr(col), ctypes.byref(geom), n_imgs, _stream())
+    _count()
+    return col
+
+
+def col2im_nhwc(dcol, dx, geom, n_imgs):
+    with torch.cuda.device(dx.device):
+        _call("bnn_col2im_nhwc", _ptr(dcol), _ptr(dx), ctypes.byref(geom), n_imgs, _stream())
+    _count()
+
+
+def sampled_conv2d_fwd(x, x_sample_stride, mu_w, sigma_w, mu_b, sigma_b, eps_w, eps_b, y_view, y_sample_stride, geom, S,
+                       sample_begin, rng_w, rng_b):
+    with torch.cuda.device(x.device):
+        _call("bnn_sampled_conv2d_fwd", _ptr(x), x_sample_stride, _ptr(mu_w), _ptr(sigma_w), _ptr(mu_b), _ptr(sigma_b),
+              _ptr(eps_w), _ptr(eps_b), y_view, y_sample_stride, ctypes.byref(geom), S, sample_begin, ctypes.byref(rng_w),
+              ctypes.byref(rng_b) if rng_b is not None else None, _stream())
+    _count()
+
+
+def sampled_conv2d_dgrad(dy, mu_w, sigma_w, eps_w, dx, x_sample_stride, geom, S, sample_begin, rng_w):
+    with torch.cuda.device(dx.device):
+        _call("bnn_sampled_conv2d_dgrad", _ptr(dy), _ptr(mu_w), _ptr(sigma_w), _ptr(eps_w), _ptr(dx), x_sample_stride,
+              ctypes.byref(geom), S, sample_begin, ctypes.byref(rng_w), _stream())
+    _count()
+
+
+def sampled_conv2d_wgrad(dy, x, x_sample_stride, rho_w, eps_w, dmu_w, drho_w, geom, S, sample_begin, rng_w):
+    with torch.cuda.device(x.device):
+        _call("bnn_sampled_conv2d_wgrad", _ptr(dy), _ptr(x), x_sample_stride, _ptr(rho_w), _ptr(eps_w), _ptr(dmu_w),
+              _ptr(drho_w), ctypes.byref(geom), S, sample_begin, ctypes.byref(rng_w), _stream())
     _count()
 
 

@@ -96,6 +96,17 @@ int tma_dgrad(bnn_view dy, int64_t dy_sample_stride, const float* mu_w, const fl
 int tma_wgrad(bnn_view dy, int64_t dy_sample_stride, const float* a, int64_t lda, int64_t a_sample_stride,
               const float* rho_w, const float* eps_w, float* dmu_w, float* drho_w, int M, int N, int K, int S,
               uint32_t sample_begin, const bnn_rng* rng_w, cudaStream_t st);
+// implicit-GEMM convolution (NHWC activations through an im2col tensor map, weights [Cout][KH][KW][C])
+int tma_conv_fwd(const float* x, int64_t x_sample_stride, const float* mu_w, const float* sigma_w, const float* mu_b,
+                 const float* sigma_b, const float* eps_w, const float* eps_b, bnn_view y, int64_t y_sample_stride,
+                 const bnn_conv2d_nhwc* g, int S, uint32_t sample_begin, const bnn_rng* rng_w, const bnn_rng* rng_b,
+                 cudaStream_t st);
+int tma_conv_dgrad(const float* dy, const float* mu_w, const float* sigma_w, const float* eps_w, float* dx,
+                   int64_t x_sample_stride, const bnn_conv2d_nhwc* g, int S, uint32_t sample_begin, const bnn_rng* rng_w,
+                   cudaStream_t st);
+int tma_conv_wgrad(const float* dy, const float* x, int64_t x_sample_stride, const float* rho_w, const float* eps_w,
+                   float* dmu_w, float* drho_w, const bnn_conv2d_nhwc* g, int S, uint32_t sample_begin,
+                   const bnn_rng* rng_w, cudaStream_t st);
 int tma_selftest(float* max_err_dev, cudaStream_t st);
 int tma_force_variant(int variant);   // test aid: 0 = CTA pair, 1 / 2 / 4 = row blocks per CTA, -1 = cost model (default)
 int tma_wait_counters(unsigned long long* out8, int reset);   // profiling builds (-DBNN_PROFILE_WAITS) only

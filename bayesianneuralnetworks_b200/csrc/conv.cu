@@ -1,0 +1,242 @@
+// conv.cu — entry points of the implicit-GEMM convolution path (NormalConv2d / NormalConv1d, reference conv.py:65-73,
+// 89-96,112-119 and their autograd) and the small layout kernels around it.
+//
+// Layouts.  Activations NHWC (torch.channels_last memory): [S*B][H][W][C].  Weights in (o, kh, kw, c) order, so that the
+// GEMM's k index (tap, channel) walks memory contiguously and a 32-wide k-block is one filter tap x 32 channels — exactly
+// the box an im2col tensor map delivers.  bnn_conv2d_weight_layout produces that order (and sigma) from the reference's
+// OIHW parameters once per step; the layer's eps stream is DEFINED over the (o, kh, kw, c) order (eps is i.i.d., so the
+// distribution of the sampled weights is the reference's; `.sampled` and eps injection permute on the way in and out).
+//
+// bnn_im2col_nhwc / bnn_col2im_nhwc are the explicit lowering in the same (kh, kw, c) column order, for the requests
+// the TMA path does not take: fp32 (3xTF32) mode and the input gradient of strided layers.
+#include "contract.cuh"
+
+namespace bnn {
+namespace {
+
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads) weight_layout_kernel(const float* __restrict__ mu, const float* __restrict__ rho,
+                                                                 float* __restrict__ mu_p, float* __restrict__ sigma_p,
+                                                                 float* __restrict__ rho_p, int Cg, int taps, int64_t total) {
+  for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < total;
+       j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(j % Cg);
+    const int64_t t = j / Cg;
+    const int tap = static_cast<int>(t % taps);
+    const int64_t o = t / taps;
+    const int64_t i = (o * Cg + c) * taps + tap;          // OIHW index
+    const float r = __ldg(rho + i);
+    mu_p[j] = __ldg(mu + i);
+    if (sigma_p != nullptr) sigma_p[j] = stddev_exact(r);
+    if (rho_p != nullptr) rho_p[j] = r;
+  }
+}
+
+// out (OIHW) <- in ((o, kh, kw, c) order), n_arrays arrays back to back (the gradients of mean and scale)
+__global__ void __launch_bounds__(kThreads) weight_unlayout_kernel(const float* __restrict__ in, float* __restrict__ out, int Cg,
+                                                                   int taps, int64_t per_array, int64_t total) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t a = i / per_array, e = i - a * per_array;
+    const int tap = static_cast<int>(e % taps);
+    const int64_t t = e / taps;
+    const int c = static_cast<int>(t % Cg);
+    const int64_t o = t / Cg;
+    out[i] = __ldg(in + a * per_array + (o * taps + tap) * Cg + c);
+  }
+}
+
+// col[m][(kh * KW + kw) * C + c] = x[n][oh*sh - ph + kh*dh][ow*sw - pw + kw*dw][c]  (0 outside), m = (n, oh, ow); one
+// float4 of channels per thread: both sides coalesced
+__global__ void __launch_bounds__(kThreads) im2col_nhwc_kernel(const float* __restrict__ x, float* __restrict__ col,
+                                                               const bnn_conv2d_nhwc g, int64_t n_imgs) {
+  const int c4s = g.C / 4, taps = g.KH * g.KW;
+  const int64_t total = n_imgs * g.OH * g.OW * taps * c4s;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % c4s);
+    int64_t t = i / c4s;
+    const int tap = static_cast<int>(t % taps);
+    t /= taps;
+    const int ow = static_cast<int>(t % g.OW);
+    t /= g.OW;
+    const int oh = static_cast<int>(t % g.OH);
+    const int64_t n = t / g.OH;
+    const int kh = tap / g.KW, kw = tap - kh * g.KW;
+    const int h = oh * g.sh - g.ph + kh * g.dh, w = ow * g.sw - g.pw + kw * g.dw;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (h >= 0 && h < g.H && w >= 0 && w < g.W)
+      v = __ldg(reinterpret_cast<const float4*>(x + ((n * g.H + h) * g.W + w) * g.C) + c4);
+    reinterpret_cast<float4*>(col)[i] = v;
+  }
+}
+
+// dx[n][h][w][c] = sum over the (oh, kh), (ow, kw) that hit (h, w) of dcol[(n, oh, ow)][(kh*KW + kw)*C + c]: gather form
+__global__ void __launch_bounds__(kThreads) col2im_nhwc_kernel(const float* __restrict__ dcol, float* __restrict__ dx,
+                                                               const bnn_conv2d_nhwc g, int64_t n_imgs) {
+  const int c4s = g.C / 4, taps = g.KH * g.KW;
+  const int64_t total = n_imgs * g.H * g.W * c4s;
+  const int64_t K4 = static_cast<int64_t>(taps) * c4s;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % c4s);
+    int64_t t = i / c4s;
+    const int w = static_cast<int>(t % g.W);
+    t /= g.W;
+    const int h = static_cast<int>(t % g.H);
+    const int64_t n = t / g.H;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kh = 0; kh < g.KH; ++kh) {
+      const int hh = h + g.ph - kh * g.dh;
+      if (hh < 0 || hh % g.sh != 0) continue;
+      const int oh = hh / g.sh;
+      if (oh >= g.OH) continue;
+      for (int kw = 0; kw < g.KW; ++kw) {
+        const int ww = w + g.pw - kw * g.dw;
+        if (ww < 0 || ww % g.sw != 0) continue;
+        const int ow = ww / g.sw;
+        if (ow >= g.OW) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dcol) + ((n * g.OH + oh) * g.OW + ow) * K4 +
+                               static_cast<int64_t>(kh * g.KW + kw) * c4s + c4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    reinterpret_cast<float4*>(dx)[i] = acc;
+  }
+}
+
+int grid_for(int64_t items) {
+  const int64_t blocks = (items + kThreads - 1) / kThreads;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  return static_cast<int>(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+int check_geom(const bnn_conv2d_nhwc* g, const char* who) {
+  BNN_REQUIRE(g != nullptr, BNN_ERR_BAD_ARGUMENT, "%s: geometry is NULL", who);
+  BNN_REQUIRE(g->B > 0 && g->H > 0 && g->W > 0 && g->C > 0 && g->Cout > 0 && g->KH > 0 && g->KW > 0 && g->OH > 0 &&
+                  g->OW > 0 && g->sh > 0 && g->sw > 0 && g->dh > 0 && g->dw > 0 && g->ph >= 0 && g->pw >= 0,
+              BNN_ERR_BAD_ARGUMENT, "%s: bad geometry", who);
+  BNN_REQUIRE(g->OH == (g->H + 2 * g->ph - g->dh * (g->KH - 1) - 1) / g->sh + 1 &&
+                  g->OW == (g->W + 2 * g->pw - g->dw * (g->KW - 1) - 1) / g->sw + 1,
+              BNN_ERR_BAD_ARGUMENT, "%s: OH / OW do not match the geometry", who);
+  return BNN_OK;
+}
+
+}  // namespace
+}  // namespace bnn
+
+using namespace bnn;
+
+extern "C" {
+
+int bnn_conv2d_weight_layout(const float* mu, const float* rho, float* mu_p, float* sigma_p, float* rho_p, int32_t Cout,
+                             int32_t Cg, int32_t taps, void* stream) {
+  BNN_REQUIRE(mu && rho && mu_p, BNN_ERR_BAD_ARGUMENT, "bnn_conv2d_weight_layout: NULL pointer");
+  BNN_REQUIRE(Cout > 0 && Cg > 0 && taps > 0, BNN_ERR_BAD_ARGUMENT, "bnn_conv2d_weight_layout: bad shape");
+  int rc = check_device();
+  if (rc != BNN_OK) return rc;
+  const int64_t total = static_cast<int64_t>(Cout) * Cg * taps;
+  weight_layout_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(mu, rho, mu_p, sigma_p, rho_p, Cg,
+                                                                                            taps, total);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+int bnn_conv2d_weight_unlayout(const float* in, float* out, int32_t n_arrays, int32_t Cout, int32_t Cg, int32_t taps,
+                               void* stream) {
+  BNN_REQUIRE(in && out, BNN_ERR_BAD_ARGUMENT, "bnn_conv2d_weight_unlayout: NULL pointer");
+  BNN_REQUIRE(n_arrays > 0 && Cout > 0 && Cg > 0 && taps > 0, BNN_ERR_BAD_ARGUMENT, "bnn_conv2d_weight_unlayout: bad shape");
+  int rc = check_device();
+  if (rc != BNN_OK) return rc;
+  const int64_t per = static_cast<int64_t>(Cout) * Cg * taps;
+  weight_unlayout_kernel<<<grid_for(per * n_arrays), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(in, out, Cg, taps, per,
+                                                                                                      per * n_arrays);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+int bnn_im2col_nhwc(const float* x, float* col, const bnn_conv2d_nhwc* g, int64_t n_imgs, void* stream) {
+  int rc = check_geom(g, "bnn_im2col_nhwc");
+  if (rc != BNN_OK) return rc;
+  BNN_REQUIRE(x && col && n_imgs > 0, BNN_ERR_BAD_ARGUMENT, "bnn_im2col_nhwc: NULL pointer or no images");
+  BNN_REQUIRE(g->C % 4 == 0 && aligned16(x) && aligned16(col), BNN_ERR_MISALIGNED,
+              "bnn_im2col_nhwc: needs C %% 4 == 0 and 16-byte aligned pointers");
+  rc = check_device();
+  if (rc != BNN_OK) return rc;
+  const int64_t total = n_imgs * g->OH * g->OW * g->KH * g->KW * (g->C / 4);
+  im2col_nhwc_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, col, *g, n_imgs);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+int bnn_col2im_nhwc(const float* dcol, float* dx, const bnn_conv2d_nhwc* g, int64_t n_imgs, void* stream) {
+  int rc = check_geom(g, "bnn_col2im_nhwc");
+  if (rc != BNN_OK) return rc;
+  BNN_REQUIRE(dcol && dx && n_imgs > 0, BNN_ERR_BAD_ARGUMENT, "bnn_col2im_nhwc: NULL pointer or no images");
+  BNN_REQUIRE(g->C % 4 == 0 && aligned16(dcol) && aligned16(dx), BNN_ERR_MISALIGNED,
+              "bnn_col2im_nhwc: needs C %% 4 == 0 and 16-byte aligned pointers");
+  rc = check_device();
+  if (rc != BNN_OK) return rc;
+  const int64_t total = n_imgs * g->H * g->W * (g->C / 4);
+  col2im_nhwc_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(dcol, dx, *g, n_imgs);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+int bnn_sampled_conv2d_fwd(const float* x, int64_t x_sample_stride, const float* mu_w, const float* sigma_w,
+                           const float* mu_b, const float* sigma_b, const float* eps_w, const float* eps_b, bnn_view y,
+                           int64_t y_sample_stride, const bnn_conv2d_nhwc* g, int32_t S, uint32_t sample_begin,
+                           const bnn_rng* rng_w, const bnn_rng* rng_b, void* stream) {
+  int rc = check_geom(g, "bnn_sampled_conv2d_fwd");
+  if (rc != BNN_OK) return rc;
+  BNN_REQUIRE(x && mu_w && sigma_w && y.base && rng_w && S > 0 && S <= 65535, BNN_ERR_BAD_ARGUMENT,
+              "bnn_sampled_conv2d_fwd: NULL pointer or bad sample count");
+  BNN_REQUIRE((mu_b == nullptr) == (sigma_b == nullptr) && (mu_b == nullptr || rng_b != nullptr), BNN_ERR_BAD_ARGUMENT,
+              "bnn_sampled_conv2d_fwd: bias needs mu_b, sigma_b and rng_b");
+  BNN_REQUIRE(y.P >= 1, BNN_ERR_BAD_ARGUMENT, "bnn_sampled_conv2d_fwd: bad output view");
+  rc = check_device();
+  if (rc != BNN_OK) return rc;
+  rc = contract::tma_conv_fwd(x, x_sample_stride, mu_w, sigma_w, mu_b, sigma_b, eps_w, eps_b, y, y_sample_stride, g, S,
+                              sample_begin, rng_w, rng_b, static_cast<cudaStream_t>(stream));
+  if (rc == contract::kNotEligible)
+    return fail(BNN_ERR_UNSUPPORTED, "bnn_sampled_conv2d_fwd: needs C %% 32 == 0, 16-byte aligned tensors and a filter "
+                                     "window within the im2col descriptor's limits (use bnn_im2col_nhwc + bnn_sampled_gemm_fwd)");
+  return rc;
+}
+
+int bnn_sampled_conv2d_dgrad(const float* dy, const float* mu_w, const float* sigma_w, const float* eps_w, float* dx,
+                             int64_t x_sample_stride, const bnn_conv2d_nhwc* g, int32_t S, uint32_t sample_begin,
+                             const bnn_rng* rng_w, void* stream) {
+  int rc = check_geom(g, "bnn_sampled_conv2d_dgrad");
+  if (rc != BNN_OK) return rc;
+  BNN_REQUIRE(dy && mu_w && sigma_w && dx && rng_w && S > 0 && S <= 65535, BNN_ERR_BAD_ARGUMENT,
+              "bnn_sampled_conv2d_dgrad: NULL pointer or bad sample count");
+  rc = check_device();
+  if (rc != BNN_OK) return rc;
+  rc = contract::tma_conv_dgrad(dy, mu_w, sigma_w, eps_w, dx, x_sample_stride, g, S, sample_begin, rng_w,
+                                static_cast<cudaStream_t>(stream));
+  if (rc == contract::kNotEligible)
+    return fail(BNN_ERR_UNSUPPORTED, "bnn_sampled_conv2d_dgrad: needs stride 1, Cout %% 32 == 0, C %% 4 == 0 and 16-byte "
+                                     "aligned tensors (use bnn_sampled_gemm_dgrad + bnn_col2im_nhwc)");
+  return rc;
+}
+
+int bnn_sampled_conv2d_wgrad(const float* dy, const float* x, int64_t x_sample_stride, const float* rho_w,
+                             const float* eps_w, float* dmu_w, float* drho_w, const bnn_conv2d_nhwc* g, int32_t S,
+                             uint32_t sample_begin, const bnn_rng* rng_w, void* stream) {
+  int rc = check_geom(g, "bnn_sampled_conv2d_wgrad");
+  if (rc != BNN_OK) return rc;
+  BNN_REQUIRE(dy && x && rho_w && dmu_w && drho_w && rng_w && S > 0 && S <= 65535, BNN_ERR_BAD_ARGUMENT,
+              "bnn_sampled_conv2d_wgrad: NULL pointer or bad sample count");
+  rc = check_device();
+  if (rc != BNN_OK) return rc;
+  rc = contract::tma_conv_wgrad(dy, x, x_sample_stride, rho_w, eps_w, dmu_w, drho_w, g, S, sample_begin, rng_w,
+                                static_cast<cudaStream_t>(stream));
+  if (rc == contract::kNotEligible)
+    return fail(BNN_ERR_UNSUPPORTED, "bnn_sampled_conv2d_wgrad: needs C %% 32 == 0, Cout %% 4 == 0 and 16-byte aligned "
+                                     "tensors (use bnn_im2col_nhwc + bnn_sampled_gemm_wgrad)");
+  return rc;
+}
+
+}  // extern "C"

@@ -92,13 +92,83 @@ int make_map(CUtensorMap* map, const float* base, int64_t cols, int64_t rows, in
   return BNN_OK;
 }
 
+// NHWC fp32 tensor [n_imgs][H][W][C] seen through the filter's bounding box (cuTensorMapEncodeIm2col): a load delivers
+// `box_pixels` base pixels (traversed w, h, n with the given stride, starting at the lower corner) x 32 channels, TF32
+// conversion, zero fill outside the image.  lower / upper corner: first base pixel and (last base pixel + 1 - extent).
+using EncodeIm2colFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+EncodeIm2colFn encode_im2col_fn() {
+  static EncodeIm2colFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  });
+  return fn;
+}
+
+int make_im2col_map(CUtensorMap* map, const float* base, int64_t C, int64_t W, int64_t H, int64_t n_imgs, int lower_w,
+                    int lower_h, int upper_w, int upper_h, int stride_w, int stride_h, int box_pixels, bool mn_major) {
+  EncodeIm2colFn fn = encode_im2col_fn();
+  if (fn == nullptr) return kNotEligible;
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                              static_cast<cuuint64_t>(n_imgs)};
+  const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4u, static_cast<cuuint64_t>(W * C) * 4u,
+                                 static_cast<cuuint64_t>(H * W * C) * 4u};
+  const int lower[2] = {lower_w, lower_h}, upper[2] = {upper_w, upper_h};
+  const cuuint32_t estr[4] = {1u, static_cast<cuuint32_t>(stride_w), static_cast<cuuint32_t>(stride_h), 1u};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(base), dims, strides, lower, upper,
+                        32u, static_cast<cuuint32_t>(box_pixels), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return kNotEligible;
+  // Known driver issue (CUDA <= 13.1, the workaround CUTLASS applies in cute/atom/copy_traits_sm90_im2col.hpp): for tensors
+  // smaller than 128 KiB the encoder sets bit 21 of the descriptor's second word, which makes the copy engine misread the
+  // extent; clear it.
+  int driver = 0;
+  if (cudaDriverGetVersion(&driver) == cudaSuccess && driver <= 13010 && n_imgs * H * W * C * 4 < 131072)
+    reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+  return BNN_OK;
+}
+
 bool tma_ok(const void* base, int64_t ld, int64_t ss) {
   return aligned16(base) && ld % 4 == 0 && ss % 4 == 0 && ld > 0;
 }
 
 // ---------------------------------------------------------------------------------------------- forward / dgrad
+// Implicit-GEMM addressing of the TMA-loaded operand (conv layers): the operand is never an im2col MATRIX, it is the NHWC
+// tensor itself seen through an im2col tensor map; row m of the GEMM is the pixel (img, p, q) of a P = rows x OW grid
+// (output pixels for forward / weight gradient, input pixels for the data gradient), k-block rb is (filter tap, 32
+// channels).  on == 0: plain row-major matrix.
+struct ConvCoords {
+  int on;
+  int P, OW;                // pixel grid of the GEMM rows
+  int imgs;                 // images per sample: n coordinate = sample * imgs + img
+  int sh, sw;               // traversal stride (the conv stride; 1 for the data gradient)
+  int lh, lw;               // lower corner: base pixel of grid pixel 0
+  int dh, dw;               // dilation
+  int KW, taps;             // filter width, KH * KW
+  int cblocks;              // 32-channel k-blocks per tap (channels of the LOADED tensor / 32)
+  int w_rows;               // data gradient: rows of the weight matrix (Cout); its row pitch is taps * K floats
+  int chans;                // channels of the loaded tensor (weight gradient: groups beyond K load channel `chans` = zeros)
+};
+__device__ __forceinline__ void conv_pixel(const ConvCoords& c, int m, int smp, int* w, int* h, int* n) {
+  const int img = m / c.P, rem = m - img * c.P;
+  const int ph = rem / c.OW, q = rem - ph * c.OW;
+  *w = q * c.sw + c.lw;
+  *h = ph * c.sh + c.lh;
+  *n = smp * c.imgs + img;
+}
+
 struct TmaContractParams {
-  CUtensorMap map_l;        // fwd: activations [S or 1][M][K]; dgrad: dY [S][M][N]
+  CUtensorMap map_l;        // fwd: activations [S or 1][M][K]; dgrad: dY [S][M][N]; conv: the NHWC tensor (im2col map)
+  ConvCoords conv;
+  int64_t w_numel;          // elements of the weight tensor (injected eps: stride between samples)
   View out;                 // fwd: y view; dgrad: da as a row-major view
   int64_t out_sample_stride;
   const float* mu_w;
@@ -144,9 +214,12 @@ __device__ __forceinline__ TmaPipe carve_tma(uint8_t* smem_raw) {
 // group (kGroupThreads threads, four float4 per thread and trip: all loads first, then the Philox chains).
 //   kMnMajor = false: K-major tile, tile rows = n (kRows of them), columns = k          (forward)
 //   kMnMajor = true : MN-major tile, K-rows = n (32), MN = k (kRows of them)            (data gradient)
+// Element (n, k) of the weight matrix lives at n * ldw + woff + k (ldw = K, woff = 0 for a plain [N][K] matrix; the
+// conv data gradient walks the (o, kh, kw, c) tensor with n = o, ldw = taps * C, woff = tap * C, k = c).
 template <int kRows, bool kMnMajor>
 __device__ __forceinline__ void gen_w_tile(uint32_t tile, const float* __restrict__ mu, const float* __restrict__ sigma,
-                                           const EpsSrc& eps, int n0, int N, int k0, int K, int tid) {
+                                           const EpsSrc& eps, int n0, int N, int k0, int K, int tid, int64_t ldw,
+                                           int64_t woff) {
   constexpr int kItems = kRows * 8;                       // float4 items
   constexpr int kTrips = kItems / (4 * kGroupThreads);
   static_assert(kItems % (4 * kGroupThreads) == 0, "tile does not divide over the generator group");
@@ -162,7 +235,7 @@ __device__ __forceinline__ void gen_w_tile(uint32_t tile, const float* __restric
       else { n = n0 + item / (kRows / 4); k = k0 + ((item % (kRows / 4)) << 2); }
       idx[u] = -1;
       if (n < N && k < K) {
-        idx[u] = static_cast<int64_t>(n) * K + k;
+        idx[u] = static_cast<int64_t>(n) * ldw + woff + k;
         m[u] = __ldg(reinterpret_cast<const float4*>(mu + idx[u]));
         sg[u] = __ldg(reinterpret_cast<const float4*>(sigma + idx[u]));
       }
@@ -231,7 +304,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
     for (int it = group; it < total; it += kGenGroups) {
       const int s = s_begin + it / red_blocks, rb = it - (it / red_blocks) * red_blocks;
       EpsSrc eps;
-      eps.inj = p.eps_w ? p.eps_w + static_cast<int64_t>(s) * p.N * p.K : nullptr;
+      eps.inj = p.eps_w ? p.eps_w + static_cast<int64_t>(s) * p.w_numel : nullptr;
       eps.key = key;
       eps.sample = p.sample_begin + s;
       { BNN_T0(); mbar_wait(pipe.empty_w + group, ((it >> 2) & 1) ^ 1); BNN_ACC(w_gen); }
@@ -240,9 +313,14 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
       if (p.exp_flags & 1) { /* skip */ } else
 #endif
       if (!kDgrad)
-        gen_w_tile<128, false>(tile, p.mu_w, p.sigma_w, eps, col0, p.N, rb * kBK, p.K, tid);
-      else
-        gen_w_tile<128, true>(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, col0, p.K, tid);
+        gen_w_tile<128, false>(tile, p.mu_w, p.sigma_w, eps, col0, p.N, rb * kBK, p.K, tid, p.K, 0);
+      else if (!p.conv.on)
+        gen_w_tile<128, true>(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, col0, p.K, tid, p.K, 0);
+      else {          // conv data gradient: k-block = (flipped tap, 32 output channels o0 ..)
+        const int tapf = rb / p.conv.cblocks, o0 = (rb - tapf * p.conv.cblocks) * kBK;
+        gen_w_tile<128, true>(tile, p.mu_w, p.sigma_w, eps, o0, p.conv.w_rows, col0, p.K, tid,
+                              static_cast<int64_t>(p.conv.taps) * p.K, static_cast<int64_t>(p.conv.taps - 1 - tapf) * p.K);
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pipe.full_w + group);
@@ -260,8 +338,19 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
           if (p.exp_flags & 2) { mbar_arrive(pipe.full_a + g); continue; }
 #endif
           mbar_arrive_expect_tx(pipe.full_a + g, mb_used * kTileBytes);
-          for (int mb = 0; mb < mb_used; ++mb)
-            tma_load_3d(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, rb * kBK, row0 + mb * 128, smp, pipe.full_a + g);
+          if (!p.conv.on) {
+            for (int mb = 0; mb < mb_used; ++mb)
+              tma_load_3d(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, rb * kBK, row0 + mb * 128, smp, pipe.full_a + g);
+          } else {
+            const int tap = rb / p.conv.cblocks, c0 = (rb - tap * p.conv.cblocks) * kBK;
+            const int kh = tap / p.conv.KW, kw = tap - kh * p.conv.KW;
+            for (int mb = 0; mb < mb_used; ++mb) {
+              int w, h, n;
+              conv_pixel(p.conv, row0 + mb * 128, smp, &w, &h, &n);
+              tma_load_im2col_4d(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, c0, w, h, n,
+                                 static_cast<uint16_t>(kw * p.conv.dw), static_cast<uint16_t>(kh * p.conv.dh), pipe.full_a + g);
+            }
+          }
         }
       }
     }
@@ -447,15 +536,20 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
     for (int it = group; it < total; it += kGenGroups) {
       const int s = s_begin + it / red_blocks, rb = it - (it / red_blocks) * red_blocks;
       EpsSrc eps;
-      eps.inj = p.eps_w ? p.eps_w + static_cast<int64_t>(s) * p.N * p.K : nullptr;
+      eps.inj = p.eps_w ? p.eps_w + static_cast<int64_t>(s) * p.w_numel : nullptr;
       eps.key = key;
       eps.sample = p.sample_begin + s;
       { BNN_T0(); mbar_wait(pipe.empty_w + group, ((it >> 2) & 1) ^ 1); BNN_ACC(w_gen); }
       const uint32_t tile = pipe.ring_w + group * kHalfTileBytes;
       if (!kDgrad)
-        gen_w_tile<64, false>(tile, p.mu_w, p.sigma_w, eps, half0, p.N, rb * kBK, p.K, tid);
-      else
-        gen_w_tile<64, true>(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, half0, p.K, tid);
+        gen_w_tile<64, false>(tile, p.mu_w, p.sigma_w, eps, half0, p.N, rb * kBK, p.K, tid, p.K, 0);
+      else if (!p.conv.on)
+        gen_w_tile<64, true>(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, half0, p.K, tid, p.K, 0);
+      else {
+        const int tapf = rb / p.conv.cblocks, o0 = (rb - tapf * p.conv.cblocks) * kBK;
+        gen_w_tile<64, true>(tile, p.mu_w, p.sigma_w, eps, o0, p.conv.w_rows, half0, p.K, tid,
+                             static_cast<int64_t>(p.conv.taps) * p.K, static_cast<int64_t>(p.conv.taps - 1 - tapf) * p.K);
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(lead_full_w);
@@ -471,9 +565,21 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
           const int g = it & 1;
           if (it >= 2) { BNN_T0(); mbar_wait(pipe.empty_w + ((it - 2) & 3), ((it - 2) >> 2) & 1); BNN_ACC(w_tma); }
           if (rank == 0) mbar_arrive_expect_tx(pipe.full_a + g, 2 * mb_pair * kTileBytes);
-          for (int mb = 0; mb < mb_pair; ++mb)
-            tma_load_3d_pair(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, rb * kBK, row0 + mb * 128, smp,
-                             lead_full_a + g * 8);
+          if (!p.conv.on) {
+            for (int mb = 0; mb < mb_pair; ++mb)
+              tma_load_3d_pair(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, rb * kBK, row0 + mb * 128, smp,
+                               lead_full_a + g * 8);
+          } else {
+            const int tap = rb / p.conv.cblocks, c0 = (rb - tap * p.conv.cblocks) * kBK;
+            const int kh = tap / p.conv.KW, kw = tap - kh * p.conv.KW;
+            for (int mb = 0; mb < mb_pair; ++mb) {
+              int w, h, n;
+              conv_pixel(p.conv, row0 + mb * 128, smp, &w, &h, &n);
+              tma_load_im2col_4d_pair(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, c0, w, h, n,
+                                      static_cast<uint16_t>(kw * p.conv.dw), static_cast<uint16_t>(kh * p.conv.dh),
+                                      lead_full_a + g * 8);
+            }
+          }
         }
       }
     }
@@ -653,7 +759,8 @@ constexpr size_t kWgradSmem = kSmemAux + 1024 + static_cast<size_t>(kWgStages) *
 
 struct TmaWgradParams {
   CUtensorMap map_dy;       // dY [S][M][N], box 32 x 32
-  CUtensorMap map_a;        // A  [S or 1][M][K], box 32 x 32
+  CUtensorMap map_a;        // A  [S or 1][M][K], box 32 x 32; conv: the NHWC input (im2col map, 32 channels x 64 pixels)
+  ConvCoords conv;
   const float* rho_w;
   const float* eps_w;
   float* dmu_w;
@@ -724,12 +831,30 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
             const int stage = it % kWgStages;
             mbar_wait(empty + stage, ((it / kWgStages) & 1) ^ 1);
             const uint32_t base = ring + stage * 2 * kWgOperandBytes;
+            int cw = 0, ch = 0, cn = 0;
+            if (p.conv.on) conv_pixel(p.conv, mb * kWgRows, sa, &cw, &ch, &cn);
+            // conv: the 32-column group kc .. kc + 31 of the im2col matrix = (tap, channels c0 ..) of the NHWC input; groups
+            // beyond K read channel `chans` (outside the tensor: zeros, the transaction still completes)
+            auto conv_group = [&](int kc, int* c0, uint16_t* ow, uint16_t* oh) {
+              if (kc >= p.K) { *c0 = p.conv.chans; *ow = 0; *oh = 0; return; }
+              const int tap = kc / p.conv.chans;
+              *c0 = kc - tap * p.conv.chans;
+              const int kh = tap / p.conv.KW, kw = tap - kh * p.conv.KW;
+              *ow = static_cast<uint16_t>(kw * p.conv.dw);
+              *oh = static_cast<uint16_t>(kh * p.conv.dh);
+            };
             if (!kPair) {
               mbar_arrive_expect_tx(full + stage, 2 * kWgOperandBytes);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 tma_load_3d(base + g * kWgLbo, &p.map_dy, n0 + g * 32, mb * kWgRows, s, full + stage);
-                tma_load_3d(base + kWgOperandBytes + g * kWgLbo, &p.map_a, k0 + g * 32, mb * kWgRows, sa, full + stage);
+                if (!p.conv.on) {
+                  tma_load_3d(base + kWgOperandBytes + g * kWgLbo, &p.map_a, k0 + g * 32, mb * kWgRows, sa, full + stage);
+                } else {
+                  int c0; uint16_t ow, oh;
+                  conv_group(k0 + g * 32, &c0, &ow, &oh);
+                  tma_load_im2col_4d(base + kWgOperandBytes + g * kWgLbo, &p.map_a, c0, cw, ch, cn, ow, oh, full + stage);
+                }
               }
             } else {
               const uint32_t lead_full = mapa_u32(smem_u32(full + stage), 0);
@@ -738,9 +863,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
               for (int g = 0; g < 4; ++g)
                 tma_load_3d_pair(base + g * kWgLbo, &p.map_dy, n0 + g * 32, mb * kWgRows, s, lead_full);
 #pragma unroll
-              for (int g = 0; g < 2; ++g)       // this CTA's half (64 columns) of the shared A^T tile
-                tma_load_3d_pair(base + kWgOperandBytes + g * kWgLbo, &p.map_a, k0 + static_cast<int>(rank) * 64 + g * 32,
-                                 mb * kWgRows, sa, lead_full);
+              for (int g = 0; g < 2; ++g) {     // this CTA's half (64 columns) of the shared A^T tile
+                const int kc = k0 + static_cast<int>(rank) * 64 + g * 32;
+                if (!p.conv.on) {
+                  tma_load_3d_pair(base + kWgOperandBytes + g * kWgLbo, &p.map_a, kc, mb * kWgRows, sa, lead_full);
+                } else {
+                  int c0; uint16_t ow, oh;
+                  conv_group(kc, &c0, &ow, &oh);
+                  tma_load_im2col_4d_pair(base + kWgOperandBytes + g * kWgLbo, &p.map_a, c0, cw, ch, cn, ow, oh, lead_full);
+                }
+              }
             }
           }
         }
@@ -939,6 +1071,7 @@ int tma_fwd(const float* a, int64_t lda, int64_t a_sample_stride, const float* m
   p.out.base = y.base; p.out.bs = y.batch_stride; p.out.P = y.P; p.out_sample_stride = y_sample_stride;
   p.mu_w = mu_w; p.sigma_w = sigma_w; p.eps_w = eps_w; p.mu_b = mu_b; p.sigma_b = sigma_b; p.eps_b = eps_b;
   p.M = M; p.N = N; p.K = K; p.S = S; p.sample_begin = sample_begin;
+  p.w_numel = static_cast<int64_t>(N) * K;
   p.rng_w = *rng_w; p.rng_b = rng_b ? *rng_b : *rng_w;
   p.shared_l = shared ? 1 : 0;
   p.sum_samples = 0;
@@ -961,6 +1094,7 @@ int tma_dgrad(bnn_view dy, int64_t dy_sample_stride, const float* mu_w, const fl
   p.out.base = da; p.out.bs = lda; p.out.P = 1; p.out_sample_stride = a_sample_stride;
   p.mu_w = mu_w; p.sigma_w = sigma_w; p.eps_w = eps_w;
   p.M = M; p.N = N; p.K = K; p.S = S; p.sample_begin = sample_begin;
+  p.w_numel = static_cast<int64_t>(N) * K;
   p.rng_w = *rng_w; p.rng_b = *rng_w;
   p.shared_l = 0;
   p.sum_samples = (a_sample_stride == 0) ? 1 : 0;
@@ -968,23 +1102,9 @@ int tma_dgrad(bnn_view dy, int64_t dy_sample_stride, const float* mu_w, const fl
   return dispatch_tma_contract<true>(p, K, st);
 }
 
-int tma_wgrad(bnn_view dy, int64_t dy_sample_stride, const float* a, int64_t lda, int64_t a_sample_stride,
-              const float* rho_w, const float* eps_w, float* dmu_w, float* drho_w, int M, int N, int K, int S,
-              uint32_t sample_begin, const bnn_rng* rng_w, cudaStream_t st) {
-  const bool shared = a_sample_stride == 0;
-  if (dy.P != 1 || !tma_ok(dy.base, dy.batch_stride, dy_sample_stride) || !tma_ok(a, lda, a_sample_stride) ||
-      K % 4 != 0 || rng_w->elem_offset % 4 != 0 || !aligned16(rho_w) || !aligned16(dmu_w) || !aligned16(drho_w) ||
-      (eps_w != nullptr && !aligned16(eps_w)))
-    return kNotEligible;
-  TmaWgradParams p{};
-  int rc = make_map(&p.map_dy, dy.base, N, M, S, dy.batch_stride, dy_sample_stride, kWgRows, true);
-  if (rc != BNN_OK) return rc;
-  rc = make_map(&p.map_a, a, K, M, shared ? 1 : S, lda, a_sample_stride, kWgRows, true);
-  if (rc != BNN_OK) return rc;
-  p.rho_w = rho_w; p.eps_w = eps_w; p.dmu_w = dmu_w; p.drho_w = drho_w;
-  p.M = M; p.N = N; p.K = K; p.S = S; p.sample_begin = sample_begin;
-  p.rng_w = *rng_w;
-  p.shared_a = shared ? 1 : 0;
+// Work-unit plan + launch shared by the matrix and the implicit-GEMM (conv) weight gradient
+int wgrad_plan_and_launch(TmaWgradParams& p, int M, int N, int K, int S, cudaStream_t st) {
+  int rc = BNN_OK;
   const int tiles = ((N + 127) / 128) * ((K + 127) / 128);
   const int m_total = (M + kWgRows - 1) / kWgRows;         // 64-row stages
   // Work units = (sample, M-chunk); a CTA = (tile, group) walks `per` consecutive units, the epilogue of one unit
@@ -1041,6 +1161,126 @@ int tma_wgrad(bnn_view dy, int64_t dy_sample_stride, const float* a, int64_t lda
   }
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
+}
+
+
+int tma_wgrad(bnn_view dy, int64_t dy_sample_stride, const float* a, int64_t lda, int64_t a_sample_stride,
+              const float* rho_w, const float* eps_w, float* dmu_w, float* drho_w, int M, int N, int K, int S,
+              uint32_t sample_begin, const bnn_rng* rng_w, cudaStream_t st) {
+  const bool shared = a_sample_stride == 0;
+  if (dy.P != 1 || !tma_ok(dy.base, dy.batch_stride, dy_sample_stride) || !tma_ok(a, lda, a_sample_stride) ||
+      K % 4 != 0 || rng_w->elem_offset % 4 != 0 || !aligned16(rho_w) || !aligned16(dmu_w) || !aligned16(drho_w) ||
+      (eps_w != nullptr && !aligned16(eps_w)))
+    return kNotEligible;
+  TmaWgradParams p{};
+  int rc = make_map(&p.map_dy, dy.base, N, M, S, dy.batch_stride, dy_sample_stride, kWgRows, true);
+  if (rc != BNN_OK) return rc;
+  rc = make_map(&p.map_a, a, K, M, shared ? 1 : S, lda, a_sample_stride, kWgRows, true);
+  if (rc != BNN_OK) return rc;
+  p.rho_w = rho_w; p.eps_w = eps_w; p.dmu_w = dmu_w; p.drho_w = drho_w;
+  p.M = M; p.N = N; p.K = K; p.S = S; p.sample_begin = sample_begin;
+  p.rng_w = *rng_w;
+  p.shared_a = shared ? 1 : 0;
+  return wgrad_plan_and_launch(p, M, N, K, S, st);
+}
+
+// ---------------------------------------------------------------------------------------------- implicit-GEMM convolution
+// The same kernels with the activation operand addressed through an im2col tensor map over the NHWC tensor: no im2col
+// matrix exists.  Weights are [Cout][KH][KW][C] (k = (kh, kw, c), c fastest), so a 32-wide k-block is one filter tap and
+// 32 consecutive channels — C % 32 == 0 is the eligibility condition.
+namespace {
+ConvCoords conv_coords_fwd(const bnn_conv2d_nhwc& g) {
+  ConvCoords c{};
+  c.on = 1; c.P = g.OH * g.OW; c.OW = g.OW; c.imgs = g.B;
+  c.sh = g.sh; c.sw = g.sw; c.lh = -g.ph; c.lw = -g.pw; c.dh = g.dh; c.dw = g.dw;
+  c.KW = g.KW; c.taps = g.KH * g.KW; c.cblocks = g.C / kBK; c.w_rows = g.Cout; c.chans = g.C;
+  return c;
+}
+bool conv_ok(const bnn_conv2d_nhwc& g) {
+  const int lo_h = -g.ph, lo_w = -g.pw, up_h = g.ph - (g.KH - 1) * g.dh, up_w = g.pw - (g.KW - 1) * g.dw;
+  return g.C % kBK == 0 && lo_h >= -128 && lo_w >= -128 && up_h >= -128 && up_w >= -128 && up_h <= 127 && up_w <= 127 &&
+         (g.KH - 1) * g.dh < 256 && (g.KW - 1) * g.dw < 256 && g.sh >= 1 && g.sw >= 1 && g.sh <= 8 && g.sw <= 8;
+}
+}  // namespace
+
+int tma_conv_fwd(const float* x, int64_t x_sample_stride, const float* mu_w, const float* sigma_w, const float* mu_b,
+                 const float* sigma_b, const float* eps_w, const float* eps_b, bnn_view y, int64_t y_sample_stride,
+                 const bnn_conv2d_nhwc* g, int S, uint32_t sample_begin, const bnn_rng* rng_w, const bnn_rng* rng_b,
+                 cudaStream_t st) {
+  const bool shared = x_sample_stride == 0;
+  if (!conv_ok(*g) || !aligned16(x) || rng_w->elem_offset % 4 != 0 || !aligned16(mu_w) || !aligned16(sigma_w) ||
+      (eps_w != nullptr && !aligned16(eps_w)))
+    return kNotEligible;
+  TmaContractParams p{};
+  int rc = make_im2col_map(&p.map_l, x, g->C, g->W, g->H, static_cast<int64_t>(shared ? 1 : S) * g->B, -g->pw, -g->ph,
+                           g->pw - (g->KW - 1) * g->dw, g->ph - (g->KH - 1) * g->dh, g->sw, g->sh, 128, false);
+  if (rc != BNN_OK) return rc;
+  p.conv = conv_coords_fwd(*g);
+  p.out.base = y.base; p.out.bs = y.batch_stride; p.out.P = y.P; p.out_sample_stride = y_sample_stride;
+  p.mu_w = mu_w; p.sigma_w = sigma_w; p.eps_w = eps_w; p.mu_b = mu_b; p.sigma_b = sigma_b; p.eps_b = eps_b;
+  p.M = g->B * g->OH * g->OW; p.N = g->Cout; p.K = g->KH * g->KW * g->C; p.S = S; p.sample_begin = sample_begin;
+  p.w_numel = static_cast<int64_t>(p.N) * p.K;
+  p.rng_w = *rng_w; p.rng_b = rng_b ? *rng_b : *rng_w;
+  p.shared_l = shared ? 1 : 0;
+  p.sum_samples = 0;
+  p.vec_out = (y.P == 1) && (y.batch_stride % 4 == 0) && (y_sample_stride % 4 == 0) && aligned16(y.base);
+  return dispatch_tma_contract<false>(p, p.N, st);
+}
+
+// dX[n][h][w][c] = sum_{kh, kw, o} dY[n][h + ph - kh dh][w + pw - kw dw][o] W[o][kh][kw][c]   (stride 1): the transposed-
+// filter form — an im2col load of dY with lower corner p - (K - 1) d, taps walked in flipped order — so the input gradient
+// is a gather like the forward pass: no column matrix, no scatter.
+int tma_conv_dgrad(const float* dy, const float* mu_w, const float* sigma_w, const float* eps_w, float* dx,
+                   int64_t x_sample_stride, const bnn_conv2d_nhwc* g, int S, uint32_t sample_begin, const bnn_rng* rng_w,
+                   cudaStream_t st) {
+  if (g->sh != 1 || g->sw != 1 || g->Cout % kBK != 0 || g->C % 4 != 0 || !aligned16(dy) || !aligned16(dx) ||
+      rng_w->elem_offset % 4 != 0 || !aligned16(mu_w) || !aligned16(sigma_w) || (eps_w != nullptr && !aligned16(eps_w)))
+    return kNotEligible;
+  const int lo_w = g->pw - (g->KW - 1) * g->dw, lo_h = g->ph - (g->KH - 1) * g->dh;
+  const int up_w = lo_w + g->W - g->OW, up_h = lo_h + g->H - g->OH;
+  if (lo_w < -128 || lo_h < -128 || lo_w > 127 || lo_h > 127 || up_w < -128 || up_h < -128 || up_w > 127 || up_h > 127 ||
+      (g->KH - 1) * g->dh >= 256 || (g->KW - 1) * g->dw >= 256)
+    return kNotEligible;
+  TmaContractParams p{};
+  int rc = make_im2col_map(&p.map_l, dy, g->Cout, g->OW, g->OH, static_cast<int64_t>(S) * g->B, lo_w, lo_h, up_w, up_h, 1,
+                           1, 128, false);
+  if (rc != BNN_OK) return rc;
+  ConvCoords c{};
+  c.on = 1; c.P = g->H * g->W; c.OW = g->W; c.imgs = g->B; c.sh = 1; c.sw = 1; c.lh = lo_h; c.lw = lo_w;
+  c.dh = g->dh; c.dw = g->dw; c.KW = g->KW; c.taps = g->KH * g->KW; c.cblocks = g->Cout / kBK; c.w_rows = g->Cout;
+  c.chans = g->Cout;
+  p.conv = c;
+  p.out.base = dx; p.out.bs = g->C; p.out.P = 1; p.out_sample_stride = x_sample_stride;
+  p.mu_w = mu_w; p.sigma_w = sigma_w; p.eps_w = eps_w;
+  p.M = g->B * g->H * g->W; p.N = c.taps * g->Cout; p.K = g->C; p.S = S; p.sample_begin = sample_begin;
+  p.w_numel = static_cast<int64_t>(g->Cout) * c.taps * g->C;
+  p.rng_w = *rng_w; p.rng_b = *rng_w;
+  p.shared_l = 0;
+  p.sum_samples = (x_sample_stride == 0) ? 1 : 0;
+  p.vec_out = (x_sample_stride % 4 == 0);
+  return dispatch_tma_contract<true>(p, p.K, st);
+}
+
+int tma_conv_wgrad(const float* dy, const float* x, int64_t x_sample_stride, const float* rho_w, const float* eps_w,
+                   float* dmu_w, float* drho_w, const bnn_conv2d_nhwc* g, int S, uint32_t sample_begin,
+                   const bnn_rng* rng_w, cudaStream_t st) {
+  const bool shared = x_sample_stride == 0;
+  const int M = g->B * g->OH * g->OW, N = g->Cout, K = g->KH * g->KW * g->C;
+  if (!conv_ok(*g) || N % 4 != 0 || !aligned16(dy) || !aligned16(x) || rng_w->elem_offset % 4 != 0 || !aligned16(rho_w) ||
+      !aligned16(dmu_w) || !aligned16(drho_w) || (eps_w != nullptr && !aligned16(eps_w)))
+    return kNotEligible;
+  TmaWgradParams p{};
+  int rc = make_map(&p.map_dy, dy, N, M, S, N, static_cast<int64_t>(M) * N, kWgRows, true);
+  if (rc != BNN_OK) return rc;
+  rc = make_im2col_map(&p.map_a, x, g->C, g->W, g->H, static_cast<int64_t>(shared ? 1 : S) * g->B, -g->pw, -g->ph,
+                       g->pw - (g->KW - 1) * g->dw, g->ph - (g->KH - 1) * g->dh, g->sw, g->sh, kWgRows, true);
+  if (rc != BNN_OK) return rc;
+  p.conv = conv_coords_fwd(*g);
+  p.rho_w = rho_w; p.eps_w = eps_w; p.dmu_w = dmu_w; p.drho_w = drho_w;
+  p.M = M; p.N = N; p.K = K; p.S = S; p.sample_begin = sample_begin;
+  p.rng_w = *rng_w;
+  p.shared_a = shared ? 1 : 0;
+  return wgrad_plan_and_launch(p, M, N, K, S, st);
 }
 
 int tma_wait_counters(unsigned long long* out8, int reset) {

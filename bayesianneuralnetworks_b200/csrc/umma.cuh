@@ -280,6 +280,33 @@ __device__ __forceinline__ void tma_load_3d_pair(uint32_t smem_dst, const void* 
       : "memory");
 }
 
+// ---- TMA im2col mode (implicit-GEMM convolution): the tensor map describes an NHWC activation tensor (dims C, W, H, N)
+// with the filter's bounding box; a load delivers `pixelsPerColumn` consecutive OUTPUT pixels (traversed w, then h, then
+// n, with the convolution stride) x `channelsPerPixel` channels, read at (base pixel + filter-tap offset), zero outside
+// the image — i.e. one (rows x 32) tile of the im2col matrix for the k-block (tap, c0 .. c0 + 31) without the matrix.
+// (w, h, n) = the first base pixel = output pixel * stride + lower corner; (off_w, off_h) = tap * dilation.
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t smem_dst, const void* tmap, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2], {%7, %8};"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
+        "h"(off_w), "h"(off_h)
+      : "memory");
+}
+// CTA-pair form: data lands in THIS CTA's shared memory, the bytes complete on the barrier at `mbar_cluster_addr`
+__device__ __forceinline__ void tma_load_im2col_4d_pair(uint32_t smem_dst, const void* tmap, int c, int w, int h, int n,
+                                                        uint16_t off_w, uint16_t off_h, uint32_t mbar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], "
+      "[%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar_cluster_addr), "r"(c), "r"(w), "r"(h), "r"(n),
+        "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
 __host__ __device__ constexpr uint32_t tmem_cols_pow2(uint32_t need) {
   return need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u;
 }

@@ -245,6 +245,122 @@ class SampledConv2d(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+def conv_implicit_eligible(in_channels, groups):
+    """Layers whose eps stream is keyed in (o, kh, kw, c) order and that run the implicit-GEMM path (a STATIC property of
+    the layer, so that forward, backward and `.sampled` agree whatever the precision mode or the input layout)."""
+    return groups == 1 and in_channels % 32 == 0
+
+
+def _nhwc(t):
+    """(tensor whose memory is NHWC-contiguous, copied?) for a logical NCHW tensor."""
+    if t.permute(0, 2, 3, 1).is_contiguous():
+        return t
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+class SampledConv2dImplicit(torch.autograd.Function):
+    """y[s] = conv2d(x[s], W_s, b_s) for S samples (conv.py:65-73,112-119) WITHOUT an im2col matrix: channels-last
+    activations reach the tensor cores through a TMA im2col tensor map, the weights are presented in (o, kh, kw, c) order
+    (one small layout kernel per step, which also produces sigma), the input gradient of stride-1 layers is the
+    transposed-filter gather, the weight gradient reads dY and x through tensor maps and is returned in OIHW order.
+    TF32 mode; fp32 (3xTF32) mode and the input gradient of strided layers lower explicitly in the same column order
+    (bnn_im2col_nhwc / bnn_col2im_nhwc + the register-staged / TMA GEMM kernels).
+
+    x: logical [S*B, C, H, W] (sample-major) or, when `shared`, [B, C, H, W]; any memory format — channels_last input gives
+    a channels_last result without a copy (torch's own convention), a contiguous NCHW input is converted once and gives an
+    NCHW-contiguous result."""
+
+    @staticmethod
+    def forward(ctx, x, mu_w, rho_w, mu_b, rho_b, S, shared, spec_w, spec_b, precision, stride, padding, dilation):
+        for n, t in (("input", x), ("weight.mean", mu_w), ("weight.scale", rho_w), ("bias.mean", mu_b),
+                     ("bias.scale", rho_b)):
+            _check_f32_cuda(n, t)
+        Cout, C, KH, KW = mu_w.shape
+        if x.dim() != 4 or x.shape[1] != C:
+            raise RuntimeError(f"sampled conv2d: input {tuple(x.shape)} does not match weight {tuple(mu_w.shape)}")
+        rows, _, H, W = x.shape
+        B = rows if shared else rows // S
+        if not shared and B * S != rows:
+            raise RuntimeError(f"sampled conv2d: batch {rows} is not divisible by {S} Monte-Carlo samples")
+        OH = _conv_out(H, KH, stride[0], padding[0], dilation[0])
+        OW = _conv_out(W, KW, stride[1], padding[1], dilation[1])
+        if OH <= 0 or OW <= 0:
+            raise RuntimeError("sampled conv2d: empty output")
+        nchw_out = x.is_contiguous() and not (C == 1 or H * W == 1)      # follow the input's memory format
+        x_cl = _nhwc(x)
+        geom = _C.conv_geom(B, H, W, C, OH, OW, Cout, KH, KW, stride, padding, dilation)
+        wl = _C.conv_weight_layout(mu_w.contiguous(), rho_w.contiguous())          # [3, numel]: mean, sigma, scale
+        has_bias = mu_b is not None
+        mu_b_c = mu_b.contiguous() if has_bias else None
+        sigma_b = _C.stddev(rho_b.contiguous()) if has_bias else None
+        P, K = OH * OW, KH * KW * C
+        M = B * P
+        y = torch.empty((S * B, Cout, OH, OW), device=x.device, dtype=torch.float32,
+                        memory_format=torch.contiguous_format if nchw_out else torch.channels_last)
+        if nchw_out:
+            y_view, y_ss = _C.make_view(y.data_ptr(), Cout * P, P), B * Cout * P
+        else:
+            y_view, y_ss = _C.make_view(y.data_ptr(), Cout, 1), M * Cout
+        eps_w = _eps_slice(spec_w, S, Cout * K)
+        eps_b = _eps_slice(spec_b, S, Cout) if has_bias else None
+        x_ss = 0 if shared else B * H * W * C
+        if precision == _C.PREC_TF32:
+            _C.sampled_conv2d_fwd(x_cl, x_ss, wl[0], wl[1], mu_b_c, sigma_b, eps_w, eps_b, y_view, y_ss, geom, S,
+                                  spec_w.sample_begin, spec_w.rng(), spec_b.rng() if has_bias else None)
+        else:
+            col = _C.im2col_nhwc(x_cl, geom, rows)
+            _C.sampled_gemm_fwd(col, K, 0 if shared else M * K, wl[0], wl[1], mu_b_c, sigma_b, eps_w, eps_b, y_view, y_ss,
+                                M, Cout, K, S, spec_w.sample_begin, spec_w.rng(), spec_b.rng() if has_bias else None,
+                                precision)
+        ctx.save_for_backward(x_cl, wl, rho_b)
+        ctx.meta = (S, shared, spec_w, spec_b, precision, geom, tuple(mu_w.shape), rows)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_cl, wl, rho_b = ctx.saved_tensors
+        S, shared, spec_w, spec_b, precision, geom, w_shape, rows = ctx.meta
+        Cout, C, KH, KW = w_shape
+        B, H, W, OH, OW = geom.B, geom.H, geom.W, geom.OH, geom.OW
+        P, K = OH * OW, KH * KW * C
+        M = B * P
+        dy_cl = _nhwc(dy)                               # rows [S*B*OH*OW, Cout]: free for a channels_last gradient
+        dy_view, dy_ss = _C.make_view(dy_cl.data_ptr(), Cout, 1), M * Cout
+        eps_w = _eps_slice(spec_w, S, Cout * K)
+        x_ss = 0 if shared else B * H * W * C
+        tf32 = precision == _C.PREC_TF32
+        need_x = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        need_b = rho_b is not None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
+        dx = None
+        if need_x:
+            dx = torch.empty(x_cl.shape, device=dy.device, dtype=torch.float32, memory_format=torch.channels_last)
+            if tf32 and geom.sh == 1 and geom.sw == 1 and Cout % 32 == 0:
+                _C.sampled_conv2d_dgrad(dy_cl, wl[0], wl[1], eps_w, dx, x_ss, geom, S, spec_w.sample_begin, spec_w.rng())
+            else:                                       # strided layers / fp32 mode: column gradients + gather
+                dcol = torch.empty((rows * P, K), device=dy.device, dtype=torch.float32)
+                _C.sampled_gemm_dgrad(dy_view, dy_ss, wl[0], wl[1], eps_w, dcol, K, 0 if shared else M * K, M, Cout, K, S,
+                                      spec_w.sample_begin, spec_w.rng(), precision)
+                _C.col2im_nhwc(dcol, dx, geom, rows)
+        grads_p, bg = _zero_grads((Cout * K,) if need_w else None, Cout if need_b else None, dy.device)
+        dmu = drho = None
+        if need_w:
+            if tf32 and Cout % 4 == 0:
+                _C.sampled_conv2d_wgrad(dy_cl, x_cl, x_ss, wl[2], eps_w, grads_p[0], grads_p[1], geom, S,
+                                        spec_w.sample_begin, spec_w.rng())
+            else:
+                col = _C.im2col_nhwc(x_cl, geom, rows)
+                _C.sampled_gemm_wgrad(dy_view, dy_ss, col, K, 0 if shared else M * K, wl[2], eps_w, grads_p[0], grads_p[1],
+                                      M, Cout, K, S, spec_w.sample_begin, spec_w.rng(), precision)
+            g = _C.conv_weight_unlayout(grads_p, w_shape)
+            dmu, drho = g[0], g[1]
+        if need_b:
+            _C.bias_grad(dy_view, dy_ss, rho_b.contiguous(), _eps_slice(spec_b, S, Cout), bg[0], bg[1], M, Cout, S,
+                         spec_b.sample_begin, spec_b.rng())
+        return (dx, dmu, drho, bg[0] if need_b else None, bg[1] if need_b else None) + (None,) * 8
+
+
+# ------------------------------------------------------------------------------------------------
 class Materialize(torch.autograd.Function):
     """W_s = mean + stddev * eps_s for s in [0, S) as a tensor [S, *shape] (core.py:44-45); used by
     `.sampled` and by layers without a fused contraction (NormalConv3d)."""

@@ -155,7 +155,8 @@ class BayesianNetworkModule(Module):
                 h.remove()
             for bn, sv in zip(tracked, saved):
                 bn.momentum = sv[3]
-        if not plan.verified and not torch.cuda.is_current_stream_capturing():
+        if (not plan.verified and not torch.cuda.is_current_stream_capturing()
+                and getattr(runtime._tls, "eps", None) is None):      # (injected eps tensors are sized for S samples)
             # once per plan: ONE reference-loop pass with the first sample's draws must reproduce the first row block
             # (catches functional code in `_forward` that mixes rows, which no module inspection can see)
             if not self._verify_batched(x, out, rows, draws, tracked, args, kwargs):
@@ -175,10 +176,14 @@ class BayesianNetworkModule(Module):
         same Philox draw indices, hence the same eps) and compares it with the first row block of `out`."""
         rank, world = runtime.sample_partition()
         after = [(w, (w._draw, w._last)) for w, _ in draws_before]
-        bn_state = [(bn.running_mean.clone(), bn.running_var.clone(), bn.num_batches_tracked.clone()) for bn in tracked]
         composites = [m for m in self.modules() if getattr(m, '_mc_composite', False)]
         if composites:
             return True         # torch-RNG composites (Flipout signs, full covariance) cannot replay their draws
+        # the check pass must not touch the running statistics IN PLACE: the batched pass saved them for its backward
+        # (an in-place write would invalidate that graph) — it runs on throw-away copies of the buffers instead
+        real = [(bn, bn.running_mean, bn.running_var, bn.num_batches_tracked) for bn in tracked]
+        for bn, m0, v0, n0 in real:
+            bn.running_mean, bn.running_var, bn.num_batches_tracked = m0.clone(), v0.clone(), n0.clone()
         for w, state in draws_before:
             w._draw, w._last = state
         try:
@@ -194,9 +199,8 @@ class BayesianNetworkModule(Module):
         finally:
             for w, state in after:
                 w._draw, w._last = state
-            with torch.no_grad():
-                for bn, (m0, v0, n0) in zip(tracked, bn_state):
-                    bn.running_mean.copy_(m0), bn.running_var.copy_(v0), bn.num_batches_tracked.copy_(n0)
+            for bn, m0, v0, n0 in real:
+                bn.running_mean, bn.running_var, bn.num_batches_tracked = m0, v0, n0
         return same
 
     def forward(self, x, samples=None, *args, **kwargs):

@@ -12,7 +12,7 @@ from torch.distributions.normal import Normal
 from torch.nn import init
 
 from .. import runtime
-from ..functional import SampledConv2d, SampledLinear
+from ..functional import SampledConv2d, SampledConv2dImplicit, SampledLinear, conv_implicit_eligible
 from ..utils.traversal import _pair, _single, _triple
 from .container import BayesianModule
 from .variational import WeightNormal
@@ -170,6 +170,27 @@ class NormalConvNd(BayesianConvNd):
         return (self.weight.sampled, self.bias.sampled if self.bias is not None else None)
 
 
+def _mark_implicit(layer):
+    """Layers with groups == 1 and in_channels % 32 == 0 run the implicit-GEMM path; their weight's eps stream is keyed in
+    (o, kh, kw, c) order (variational.WeightNormal._eps_layout)."""
+    w = layer.weight.mean
+    layer._implicit = conv_implicit_eligible(layer.in_channels, layer.groups) and not layer.transposed
+    if layer._implicit:
+        layer.weight._eps_layout = (w.shape[0], w.shape[1], w.numel() // (w.shape[0] * w.shape[1]))
+
+
+def _sampled_conv2d(layer, x, w_shape, S, shared, spec_w, spec_b, stride, padding, dilation):
+    bias = layer.bias
+    mean, scale = layer.weight.mean.view(w_shape), layer.weight.scale.view(w_shape)
+    if layer._implicit:
+        return SampledConv2dImplicit.apply(x, mean, scale, bias.mean if bias is not None else None,
+                                           bias.scale if bias is not None else None, S, shared, spec_w, spec_b,
+                                           runtime.precision(), stride, padding, dilation)
+    return SampledConv2d.apply(x, mean, scale, bias.mean if bias is not None else None,
+                               bias.scale if bias is not None else None, S, shared, spec_w, spec_b, runtime.precision(),
+                               stride, padding, dilation, layer.groups)
+
+
 class NormalConv2d(_FusedBayesianLayer, NormalConvNd):
     """conv.py:99-119."""
 
@@ -177,15 +198,13 @@ class NormalConv2d(_FusedBayesianLayer, NormalConvNd):
                  bias=True, prior=Normal(0, .1)):
         super(NormalConv2d, self).__init__(in_channels, out_channels, _pair(kernel_size), _pair(stride),
                                            _pair(padding), _pair(dilation), False, groups, bias, prior)
+        _mark_implicit(self)
 
     def forward(self, x, sample=True):
         S, shared, offset, total, ctx = self._mc_shape(x)
         spec_w, spec_b = self._draws(sample, S, offset, total)
-        y = SampledConv2d.apply(x, self.weight.mean, self.weight.scale,
-                                self.bias.mean if self.bias is not None else None,
-                                self.bias.scale if self.bias is not None else None,
-                                S, shared, spec_w, spec_b, runtime.precision(),
-                                tuple(self.stride), tuple(self.padding), tuple(self.dilation), self.groups)
+        y = _sampled_conv2d(self, x, tuple(self.weight.mean.shape), S, shared, spec_w, spec_b, tuple(self.stride),
+                            tuple(self.padding), tuple(self.dilation))
         if ctx is not None:
             ctx.expanded = True
         return y
@@ -198,17 +217,14 @@ class NormalConv1d(_FusedBayesianLayer, NormalConvNd):
                  bias=True, prior=Normal(0, .1)):
         super(NormalConv1d, self).__init__(in_channels, out_channels, _single(kernel_size), _single(stride),
                                            _single(padding), _single(dilation), False, groups, bias, prior)
+        _mark_implicit(self)
 
     def forward(self, x, sample=True):
         S, shared, offset, total, ctx = self._mc_shape(x)
         spec_w, spec_b = self._draws(sample, S, offset, total)
         w_shape = (self.weight.mean.shape[0], self.weight.mean.shape[1], 1, self.weight.mean.shape[2])
-        y = SampledConv2d.apply(x.unsqueeze(2), self.weight.mean.view(w_shape), self.weight.scale.view(w_shape),
-                                self.bias.mean if self.bias is not None else None,
-                                self.bias.scale if self.bias is not None else None,
-                                S, shared, spec_w, spec_b, runtime.precision(),
-                                (1, tuple(self.stride)[0]), (0, tuple(self.padding)[0]),
-                                (1, tuple(self.dilation)[0]), self.groups)
+        y = _sampled_conv2d(self, x.unsqueeze(2), w_shape, S, shared, spec_w, spec_b, (1, tuple(self.stride)[0]),
+                            (0, tuple(self.padding)[0]), (1, tuple(self.dilation)[0]))
         if ctx is not None:
             ctx.expanded = True
         return y.squeeze(2)

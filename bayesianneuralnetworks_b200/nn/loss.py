@@ -50,9 +50,19 @@ class KLDivergence(Module):
             key = (type, param.device)
             hit = cache.get(key)
             if hit is None or hit[0] is not prior:
+                standard = bool((prior.mean == 0).all()) and bool(
+                    (prior.scale_tril == torch.eye(prior.scale_tril.shape[-1]).expand_as(prior.scale_tril)).all())
                 hit = (prior, MultivariateNormal(prior.mean.to(param.device), scale_tril=prior.scale_tril.to(param.device),
-                                                 validate_args=False))
+                                                 validate_args=False), standard)
                 cache[key] = hit
+            if hit[2]:
+                # standard-normal prior (the layer's default, dense.py:91-96): _kl_multivariatenormal_multivariatenormal
+                # (torch/distributions/kl.py) reduces to  0.5 (tr(L L^T) + |mu|^2 - k) - sum_i log L_ii  — the same value
+                # without the batched triangular solves (C3 step: ~40 small launches fewer)
+                tril = param.variance
+                k = tril.shape[-1]
+                half = 0.5 * (tril.pow(2).sum((-2, -1)) + param.mean.pow(2).sum(-1) - k)
+                return (half - tril.diagonal(dim1=-2, dim2=-1).log().sum(-1)).mean()
             posterior = MultivariateNormal(param.mean, scale_tril=param.variance, validate_args=False)
             return kl_divergence(posterior, hit[1]).mean()
         if not isinstance(param, WeightNormal):

@@ -15,6 +15,11 @@ from ..functional import DrawSpec, Materialize
 
 
 class WeightNormal(Module):
+    # (Cout, Cg, taps) for conv weights whose eps stream is keyed by the element index in (o, kh, kw, c) order — the order
+    # the implicit-GEMM conv kernels walk the tensor in (functional.SampledConv2dImplicit); None: storage order.  eps is
+    # i.i.d., so this only decides WHICH standard-normal draw meets which weight; `.sampled`, the kernels and injected eps
+    # (given in storage order, like the reference's randn_like tensors) all go through the same mapping.
+    _eps_layout = None
 
     def __init__(self, *channels):
         super(WeightNormal, self).__init__()
@@ -72,6 +77,9 @@ class WeightNormal(Module):
                 raise ValueError(f"injected eps must have shape [{count}, {tuple(self.mean.shape)}], got "
                                  f"{tuple(eps.shape)}")
             eps = eps.to(device=self.mean.device, dtype=torch.float32).contiguous()
+            if self._eps_layout is not None:
+                O, Cg, taps = self._eps_layout
+                eps = eps.reshape(count, O, Cg, taps).transpose(2, 3).contiguous()
         return DrawSpec(runtime.seed(), self._tensor_id, begin, eps, runtime.step_counter(self.mean.device)
                         if self.mean.is_cuda else None)
 
@@ -84,6 +92,12 @@ class WeightNormal(Module):
         if begin is None:
             begin, count = self._last
         _C.require_cuda(self.mean)
+        if self._eps_layout is not None:
+            O, Cg, taps = self._eps_layout
+            def perm(t):
+                return t.reshape(O, Cg, taps).transpose(1, 2).contiguous()
+            out = Materialize.apply(perm(self.mean), perm(self.scale), count, self.draw_spec(begin, count))
+            return out.reshape(count, O, taps, Cg).transpose(2, 3).reshape((count,) + tuple(self.mean.shape))
         return Materialize.apply(self.mean, self.scale, count, self.draw_spec(begin, count))
 
     @property

@@ -152,6 +152,50 @@ int bnn_im2col(const float* x, float* col, const bnn_conv2d_geom* g, void* strea
 int bnn_col2im(const float* dcol, float* dx, const bnn_conv2d_geom* g, int32_t accumulate,
                void* stream);
 
+/* ---- implicit-GEMM convolution (no im2col matrix) ----
+ * NormalConv2d.forward — pytorch_bayesian/nn/conv.py:65-73,112-119 (F.conv2d(x, W_s, b_s, stride, padding, dilation)
+ * for S Monte-Carlo samples) — and its autograd, for groups == 1 layers with in_channels % 32 == 0, TF32.
+ * Layouts: activations NHWC (torch.channels_last memory) [S or 1][B][H][W][C] (x_sample_stride = 0: all samples share x,
+ * else B*H*W*C); weights, sigma, rho, injected eps and the weight gradients in (o, kh, kw, c) order [Cout][KH][KW][C] —
+ * bnn_conv2d_weight_layout / _unlayout convert from / to the reference's OIHW parameters; the eps stream of the tensor is
+ * keyed by the element index in THAT order.  The activation operand reaches the tensor cores through an im2col tensor
+ * map (cuTensorMapEncodeIm2col): a k-block is one filter tap x 32 channels.
+ *   fwd    y[s] = conv2d(x[s], W_s) + b_s; y: view of [B*OH*OW][Cout] per sample (P = 1, batch_stride = Cout: NHWC;
+ *          P = OH*OW, batch_stride = Cout*OH*OW: NCHW), y_sample_stride floats between samples
+ *   dgrad  dx[s] = conv2d_transpose(dy[s], W_s) in the transposed-filter (gather) form, stride 1 only, Cout % 32 == 0;
+ *          dy NHWC [S][B][OH][OW][Cout], dx NHWC; x_sample_stride = 0 sums the S contributions into one dx
+ *   wgrad  G_s = dy[s]^T im2col(x[s]); dmu_w += sum_s G_s; drho_w += (sum_s G_s o eps_s) o sigmoid(rho_w) (accumulated)
+ * BNN_ERR_UNSUPPORTED when a requirement is not met (callers then lower explicitly: bnn_im2col_nhwc + bnn_sampled_gemm_*). */
+typedef struct bnn_conv2d_nhwc {
+  int32_t B;                 /* images per Monte-Carlo sample */
+  int32_t H, W, C;           /* input height, width, channels */
+  int32_t OH, OW, Cout;
+  int32_t KH, KW;
+  int32_t sh, sw, ph, pw, dh, dw;
+  int32_t reserved;
+} bnn_conv2d_nhwc;
+int bnn_sampled_conv2d_fwd(const float* x, int64_t x_sample_stride, const float* mu_w, const float* sigma_w,
+                           const float* mu_b, const float* sigma_b, const float* eps_w, const float* eps_b, bnn_view y,
+                           int64_t y_sample_stride, const bnn_conv2d_nhwc* g, int32_t S, uint32_t sample_begin,
+                           const bnn_rng* rng_w, const bnn_rng* rng_b, void* stream);
+int bnn_sampled_conv2d_dgrad(const float* dy, const float* mu_w, const float* sigma_w, const float* eps_w, float* dx,
+                             int64_t x_sample_stride, const bnn_conv2d_nhwc* g, int32_t S, uint32_t sample_begin,
+                             const bnn_rng* rng_w, void* stream);
+int bnn_sampled_conv2d_wgrad(const float* dy, const float* x, int64_t x_sample_stride, const float* rho_w,
+                             const float* eps_w, float* dmu_w, float* drho_w, const bnn_conv2d_nhwc* g, int32_t S,
+                             uint32_t sample_begin, const bnn_rng* rng_w, void* stream);
+/* OIHW parameters [Cout][Cg][taps] -> (o, kh, kw, c) order: mu_p, and optionally sigma_p = 1e-10 + softplus(rho) and
+ * rho_p (NULL to skip); the inverse for `n_arrays` arrays stored back to back (gradients of mean and scale). */
+int bnn_conv2d_weight_layout(const float* mu, const float* rho, float* mu_p, float* sigma_p, float* rho_p, int32_t Cout,
+                             int32_t Cg, int32_t taps, void* stream);
+int bnn_conv2d_weight_unlayout(const float* in, float* out, int32_t n_arrays, int32_t Cout, int32_t Cg, int32_t taps,
+                               void* stream);
+/* explicit lowering in the same column order (kh, kw, c), NHWC tensors of n_imgs images, C % 4 == 0:
+ *   col[(n, oh, ow)][(kh*KW + kw)*C + c] = x[n][oh*sh - ph + kh*dh][ow*sw - pw + kw*dw][c]  (0 outside)
+ *   dx[n][h][w][c] = sum of the dcol entries that read (n, h, w, c)  (gather form, overwrites dx) */
+int bnn_im2col_nhwc(const float* x, float* col, const bnn_conv2d_nhwc* g, int64_t n_imgs, void* stream);
+int bnn_col2im_nhwc(const float* dcol, float* dx, const bnn_conv2d_nhwc* g, int64_t n_imgs, void* stream);
+
 /* ---- KL divergence, closed form, many tensors per launch ----
  * For tensor t with posterior N(mu, sigma = 1e-10 + softplus(rho)) and scalar prior N(loc, scale):
  *   kl_sum[t] = sum_i 0.5*[(sigma/scale)^2 + ((mu-loc)/scale)^2 - 1 - log((sigma/scale)^2)]

@@ -81,10 +81,26 @@ def test_conv_layer_at_configuration_scale_matches_torch_conv2d(shape, shared, p
     ref.backward(dy.double())
     assert rel_err(y, ref) < tol
     assert rel_err(x.grad, xd.grad) < tol
-    assert rel_err(layer.weight.mean.grad, mw.grad) < tol
-    assert rel_err(layer.weight.scale.grad, rw.grad) < tol
-    assert rel_err(layer.bias.mean.grad, mb.grad) < 1e-5
-    assert rel_err(layer.bias.scale.grad, rb.grad) < 1e-5
+    # The weight gradient reduces over B*OH*OW rows per sample (131 072 products per element at C3, S = 16): fp32
+    # accumulation itself is then no longer in the 1e-5 class.  The yardstick in fp32 mode is what the reference's own
+    # arithmetic — torch's fp32 conv2d backward, TF32 off — achieves against the same float64 result.
+    w_tol = tol
+    if prec == "fp32":
+        prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+        m32 = layer.weight.mean.detach().clone().requires_grad_(True)
+        r32 = layer.weight.scale.detach().clone().requires_grad_(True)
+        x32 = x.detach()
+        for s in range(S):
+            w = m32 + (1e-10 + F.softplus(r32)) * eps[layer.weight][s]
+            xs = x32 if shared else x32[s * B:(s + 1) * B]
+            F.conv2d(xs, w, None, stride, 1).backward(dy[s * B:(s + 1) * B])
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+        w_tol = max(tol, 3 * rel_err(m32.grad, mw.grad), 3 * rel_err(r32.grad, rw.grad))
+    assert rel_err(layer.weight.mean.grad, mw.grad) < w_tol
+    assert rel_err(layer.weight.scale.grad, rw.grad) < w_tol
+    assert rel_err(layer.bias.mean.grad, mb.grad) < 1e-4          # sums of S*B*OH*OW fp32 terms
+    assert rel_err(layer.bias.scale.grad, rb.grad) < 1e-4
 
 
 # ------------------------------------------------------------------------------------------------ (b) the bench step
@@ -240,3 +256,82 @@ def test_c3_example_model_trains_on_the_batched_graph_path():
     assert all(np.isfinite(losses)) and losses[-1] < losses[0] - 0.05, (losses[0], losses[-1])
     assert not torch.equal(before, head.weight.scale.detach())
     trainer.release()
+
+
+# ------------------------------------------------------------------------------------------------ implicit-GEMM conv, ragged
+@pytest.mark.parametrize("cfg", [
+    # (B, S, Cin, Cout, H, W, k, stride, padding, dilation)
+    (3, 2, 32, 40, 7, 5, 3, 1, 1, 1),          # ragged rows (105 per sample), Cout not a multiple of 16, K = 288
+    (5, 3, 64, 64, 6, 6, 3, 2, 1, 1),          # the C2 layer geometry at a small batch (strided: explicit input gradient)
+    (2, 2, 96, 32, 9, 8, (3, 2), 1, (2, 0), (2, 1)),   # dilation, asymmetric filter and padding, K = 576
+    (4, 1, 32, 136, 5, 5, 1, 1, 0, 1),         # 1x1 filter, two column tiles
+    (70, 2, 32, 32, 4, 4, 3, 1, 1, 1),         # 1120 rows per sample: several row blocks, CTA-pair eligible
+])
+@pytest.mark.parametrize("shared", [True, False])
+@pytest.mark.parametrize("layout", ["nchw", "channels_last"])
+@pytest.mark.parametrize("prec,tol", [("tf32", 2e-3), ("fp32", 2e-5)])
+def test_implicit_gemm_conv_matches_torch_on_ragged_geometries(cfg, shared, layout, prec, tol):
+    """NormalConv2d layers with in_channels % 32 == 0 (no im2col matrix in TF32 mode; conv.py:65-73,112-119) against
+    torch's float64 conv2d with injected eps: outputs and every gradient, for ragged row counts, strides, dilation,
+    asymmetric padding, narrow / wide Cout, shared and per-sample activations, both input memory formats (the result
+    follows the input's format, as torch's conv does)."""
+    import bayesianneuralnetworks_b200 as bnn
+    from bayesianneuralnetworks_b200 import runtime
+    from bayesianneuralnetworks_b200.nn import NormalConv2d
+    B, S, Cin, Cout, H, W, k, stride, padding, dilation = cfg
+    bnn.set_precision(prec)
+    torch.manual_seed(41)
+    layer = NormalConv2d(Cin, Cout, k, stride=stride, padding=padding, dilation=dilation).cuda()
+    assert layer._implicit
+    g = torch.Generator(device="cuda").manual_seed(42)
+    x = torch.randn(B if shared else S * B, Cin, H, W, device="cuda", generator=g)
+    if layout == "channels_last":
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    eps = {layer.weight: torch.randn((S,) + tuple(layer.weight.shape), device="cuda", generator=g),
+           layer.bias: torch.randn((S,) + tuple(layer.bias.shape), device="cuda", generator=g)}
+    ctx = runtime.MCContext(S, B)
+    ctx.expanded = not shared
+    with bnn.injected_eps(eps), runtime.mc_batch(ctx):
+        y = layer(x)
+    if layout == "channels_last":
+        assert y.permute(0, 2, 3, 1).is_contiguous()
+    else:
+        assert y.is_contiguous()
+    dy = torch.randn(y.shape, device="cuda", generator=g)
+    y.backward(dy)
+    xd = x.detach().double().requires_grad_(True)
+    mw, rw = layer.weight.mean.detach().double().requires_grad_(True), layer.weight.scale.detach().double().requires_grad_(True)
+    mb, rb = layer.bias.mean.detach().double().requires_grad_(True), layer.bias.scale.detach().double().requires_grad_(True)
+    outs = []
+    for s in range(S):
+        w = mw + (1e-10 + F.softplus(rw)) * eps[layer.weight][s].double()
+        b = mb + (1e-10 + F.softplus(rb)) * eps[layer.bias][s].double()
+        outs.append(F.conv2d(xd if shared else xd[s * B:(s + 1) * B], w, b, stride, padding, dilation))
+    ref = torch.cat(outs)
+    assert ref.shape == y.shape
+    ref.backward(dy.double())
+    assert rel_err(y, ref) < tol
+    assert rel_err(x.grad, xd.grad) < tol
+    assert rel_err(layer.weight.mean.grad, mw.grad) < tol
+    assert rel_err(layer.weight.scale.grad, rw.grad) < tol
+    assert rel_err(layer.bias.mean.grad, mb.grad) < 1e-5
+    assert rel_err(layer.bias.scale.grad, rb.grad) < 1e-5
+
+
+def test_implicit_conv_sampled_attribute_matches_the_forward_pass():
+    """`.sampled` of an implicit-GEMM layer (eps keyed in (o, kh, kw, c) order) is the weight the forward pass used:
+    conv2d with the materialised sample reproduces forward(sample=False) (dense.py:56-60 semantics for conv.py:112-119),
+    also with the in-kernel Philox stream."""
+    import bayesianneuralnetworks_b200 as bnn
+    from bayesianneuralnetworks_b200.nn import NormalConv2d
+    bnn.set_precision("fp32")
+    torch.manual_seed(5)
+    layer = NormalConv2d(32, 16, 3, padding=1).cuda()
+    x = torch.randn(4, 32, 6, 6, device="cuda")
+    y = layer(x)
+    w, b = layer.sampled
+    assert w.shape == layer.weight.mean.shape
+    assert rel_err(y, F.conv2d(x.double(), w.double(), b.double(), 1, 1)) < 2e-5
+    assert rel_err(layer(x, sample=False), y) < 1e-6
+    assert not torch.equal(layer(x), y)            # a fresh draw differs
