@@ -59,6 +59,12 @@ class bnn_prune_tensor(ctypes.Structure):
                 ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
+class bnn_prune_into_tensor(ctypes.Structure):
+    _fields_ = [("mu", ctypes.c_void_p), ("rho", ctypes.c_void_p), ("mu_out", ctypes.c_void_p), ("rho_out", ctypes.c_void_p),
+                ("mask_out", ctypes.c_void_p), ("numel", ctypes.c_int64), ("k", ctypes.c_int64),
+                ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
 class bnn_adam_tensor(ctypes.Structure):
     _fields_ = [("mu", ctypes.c_void_p), ("rho", ctypes.c_void_p), ("g_mu", ctypes.c_void_p), ("g_rho", ctypes.c_void_p),
                 ("m_mu", ctypes.c_void_p), ("v_mu", ctypes.c_void_p), ("m_rho", ctypes.c_void_p), ("v_rho", ctypes.c_void_p),
@@ -122,6 +128,9 @@ _SIGNATURES = {
     "bnn_prune_workspace_size": (ctypes.c_size_t, [ctypes.POINTER(bnn_prune_tensor), ctypes.c_int32]),
     "bnn_prune": (ctypes.c_int, [ctypes.POINTER(bnn_prune_tensor), ctypes.c_int32, ctypes.c_void_p,
                                  ctypes.c_size_t, ctypes.c_void_p]),
+    "bnn_prune_into_workspace_size": (ctypes.c_size_t, [ctypes.POINTER(bnn_prune_into_tensor), ctypes.c_int32]),
+    "bnn_prune_into": (ctypes.c_int, [ctypes.POINTER(bnn_prune_into_tensor), ctypes.c_int32, ctypes.c_void_p,
+                                      ctypes.c_size_t, ctypes.c_void_p]),
     "bnn_adam_kl_step": (ctypes.c_int, [ctypes.POINTER(bnn_adam_tensor), ctypes.c_int32, ctypes.c_float, ctypes.c_float,
                                         ctypes.c_float, ctypes.c_float, _c_f32p, ctypes.c_int64, ctypes.c_void_p]),
     "bnn_adam_kl_step_peers": (ctypes.c_int, [ctypes.POINTER(bnn_adam_tensor), ctypes.c_int32, ctypes.c_float, ctypes.c_float,
@@ -490,6 +499,36 @@ def prune(entries, flags=0):
     with torch.cuda.device(device):
         _call("bnn_prune", table, n, ctypes.c_void_p(base), nbytes, _stream())
     _count(15 * ((n + 23) // 24))
+
+
+def prune_into(entries, flags=0):
+    """Out-of-place pruning in one sweep (bnn_prune_into).  entries: list of (mu, rho, k, mask_out|None); returns the list
+    of (mu_out, rho_out) tensors — the inputs are not modified."""
+    n = len(entries)
+    if n == 0:
+        return []
+    table = (bnn_prune_into_tensor * n)()
+    device = entries[0][0].device
+    outs = []
+    for i, (mu, rho, k, mask) in enumerate(entries):
+        require_cuda(mu, rho, mask)
+        _f32c(mu, "mu"), _f32c(rho, "rho")
+        if mask is not None and (mask.dtype not in (torch.uint8, torch.bool) or not mask.is_contiguous()):
+            raise TypeError("mask_out must be a contiguous uint8/bool tensor")
+        mu_out, rho_out = torch.empty_like(mu), torch.empty_like(rho)
+        outs.append((mu_out, rho_out))
+        t = table[i]
+        t.mu, t.rho, t.mu_out, t.rho_out = mu.data_ptr(), rho.data_ptr(), mu_out.data_ptr(), rho_out.data_ptr()
+        t.mask_out = None if mask is None else mask.data_ptr()
+        t.numel, t.k = mu.numel(), int(k)
+        t.flags, t.reserved = flags, 0
+    nbytes = lib().bnn_prune_into_workspace_size(table, n)
+    ws = _workspace(_prune_ws, device, nbytes + 256)
+    base = (ws.data_ptr() + 255) & ~255
+    with torch.cuda.device(device):
+        _call("bnn_prune_into", table, n, ctypes.c_void_p(base), nbytes, _stream())
+    _count(15 * ((n + 23) // 24))
+    return outs
 
 
 def adam_kl_step(entries, lr, beta1, beta2, eps, step_dev=None, step=0, peers=None):

@@ -82,6 +82,19 @@ __device__ __forceinline__ void red_add4(float* dst, float a, float b, float c, 
                : "memory");
 }
 
+// the same chunk ADDED to a row-major output (several CTAs contribute partial sums over the samples)
+__device__ __forceinline__ void add_chunk(const View& out, int m, int n, int N, const float* v, bool vec) {
+  float* dst = out.base + static_cast<int64_t>(m) * out.bs + n;
+  if (vec && n + 16 <= N) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) red_add4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (n + j < N) atomicAdd(dst + j, v[j]);
+  }
+}
+
 
 // ---- TMA-fed TF32 kernels (sampled_gemm_tma.cu).  Each returns kNotEligible when the request does not meet
 // its alignment / layout requirements; the caller then takes the register-staged kernels.

@@ -23,6 +23,17 @@
 //    which also serves BNN_PRUNE_GENERAL and keys_out requests.  Its kernels return at once for tensors
 //    that the sampled path has finished.
 // All tensors of a call share the launches (table of <= 24 descriptors by value in the kernel parameters).
+//
+//  * bnn_prune_into — the same selection OUT OF PLACE in ONE sweep (8 B read + 8 B written per pair instead of two reads
+//    and a write).  In place nothing may be modified before the bracket is proven, which costs the read-only sweep 1;
+//    with a separate output the sweep can commit at once to what lies outside the sample's grid — above: pruned, below:
+//    copied — copies the ~3 % inside the grid unchanged while histogramming and listing them, and the bracket step then
+//    runs on the histograms as before: a resolve kernel walks the listed elements (certainly above the bracket ->
+//    scattered prune in the output, overlapping it -> the short exact list), finish as before.  If the sample's grid turns
+//    out wrong (or anything else surprises) the INPUT is intact: the tensor is copied and goes through the general path
+//    on the output.  The Python layer swaps the parameters' storage for the output (prune/prune.py).
+#include <vector>
+
 #include "common.cuh"
 
 namespace bnn {
@@ -79,7 +90,8 @@ struct PruneState {
   uint32_t defer_all;        // small tensor: every element is deferred (exact select over the whole tensor)
   uint32_t n_take;           // how many of the deferred elements are pruned
   uint32_t expect_deferred;  // size of the deferred list, known from the histograms before sweep 2
-  uint32_t n_deferred;       // entries appended by sweep 2
+  uint32_t n_deferred;       // entries appended by sweep 2 (bnn_prune_into: in-grid elements listed by the single sweep)
+  uint32_t n_deferred2;      // bnn_prune_into: entries the resolve kernel passed on to the exact select
 };
 
 struct PruneDesc {
@@ -101,6 +113,11 @@ struct PruneDesc {
   uint32_t force_general;
   int vec;                   // mu / rho (and mask) aligned for 128-bit access
   int pad;
+  float* mu_w;               // where results are written: mu / rho themselves (in place) or the output tensors
+  float* rho_w;
+  uint32_t* list2;           // bnn_prune_into: the exact-select list [index | mu | rho] x cap2, then (key, index) pairs x cap2
+  uint32_t cap2;
+  uint32_t pad2;
 };
 struct PruneTable {
   PruneDesc t[kMaxTensors];
@@ -530,7 +547,10 @@ __global__ void __launch_bounds__(kThreads) prune_bracket_kernel(const __grid_co
     const bool top_open = j_hi >= kBins, bottom_open = j_lo < 0;
     const uint64_t certain = top_open ? 0 : n_above + s_cnt[2];            // pruned by sweep 2 without an exact key
     const uint64_t deferred = s_cnt[3] - s_cnt[2] + (top_open ? n_above : 0) + (bottom_open ? n_below : 0);
-    ok = j_lo <= j_hi && certain < k && deferred <= d.defer_cap && k - certain <= deferred;
+    ok = j_lo <= j_hi && certain < k && deferred <= (d.list2 != nullptr ? d.cap2 : d.defer_cap) && k - certain <= deferred;
+    // bnn_prune_into has already committed to everything outside the grid: the bracket must lie inside it, and the list
+    // of in-grid elements must be complete
+    if (d.list2 != nullptr && (top_open || bottom_open || st.n_deferred > d.defer_cap)) ok = false;
     if (ok) {
       st.a_thr = top_open ? INFINITY : static_cast<float>(j_hi + 1);
       st.b_thr = bottom_open ? -INFINITY : static_cast<float>(j_lo);
@@ -665,6 +685,216 @@ __global__ void __launch_bounds__(kThreads, 4) prune_apply_sampled_kernel(const 
   }
 }
 
+// ---- bnn_prune_into: the single out-of-place sweep.  Per element: interval in grid coordinates; above the grid ->
+// (0, -30) in the output and counted; inside the grid -> copied, both histograms updated, (index, mu, rho) listed; below ->
+// copied.  Same warp-private queue as the bin kernel for the histogram updates; the list append is one reservation per
+// warp and 512-element unit (a warp-wide prefix sum of the lanes' counts), not one per element.
+__global__ void __launch_bounds__(kThreads) prune_sweep_into_kernel(const __grid_constant__ PruneTable tab) {
+  __shared__ int64_t s_begin[kMaxTensors];
+  __shared__ float2 s_queue[(4 * kVecPerThread + 1) * kThreads];
+  if (threadIdx.x < tab.n) s_begin[threadIdx.x] = tab.t[threadIdx.x].chunk_begin;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int cur = -1;
+  int mode = 0;            // 0 general (left to the fallback), 1 copy, 2 all pruned, 3 select, 4 defer all (small tensor)
+  Grid g = {0.f, 0.f, 0.f, 0.f, 0.f};
+  unsigned int above = 0;
+  auto flush = [&]() {
+    const unsigned int v = warp_sum(above);
+    if (lane == 0 && v != 0u) atomicAdd(&tab.t[cur].state->count_above, static_cast<unsigned long long>(v));
+    above = 0;
+  };
+  for (int64_t chunk = blockIdx.x; chunk < tab.total_chunks; chunk += gridDim.x) {
+    const int t = find_tensor(s_begin, tab.n, chunk, cur < 0 ? 0 : cur);
+    if (t != cur) {
+      if (cur >= 0 && mode == 3) flush();
+      cur = t;
+      const PruneDesc& d0 = tab.t[t];
+      const PruneState* st = d0.state;
+      mode = st->general ? 0 : (d0.k <= 0 ? 1 : (d0.k >= d0.numel ? 2 : (st->defer_all ? 4 : 3)));
+      g = make_grid(st);
+    }
+    if (mode == 0) continue;
+    const PruneDesc& d = tab.t[t];
+    const int64_t ubase = (chunk - d.chunk_begin) * kChunk + warp * kUnit;
+    if (ubase >= d.numel) continue;        // warp-uniform
+    float2* const q_lane = s_queue + threadIdx.x;          // slot s of this lane: q_lane[s * kThreads]
+    int qpos = 0;
+    uint32_t listed = 0;                   // bit e: element ordinal e of this lane lies inside the grid
+    const bool full = d.vec && ubase + kUnit <= d.numel;
+    if (full) {
+      float4 m[kVecPerThread], r[kVecPerThread];
+#pragma unroll
+      for (int j = 0; j < kVecPerThread; ++j) {
+        const int64_t i = ubase + (j * 32 + lane) * 4;
+        m[j] = ldg_stream4(d.mu + i);
+        r[j] = ldg_stream4(d.rho + i);
+      }
+#pragma unroll
+      for (int j = 0; j < kVecPerThread; ++j) {
+        const int64_t i = ubase + (j * 32 + lane) * 4;
+        const float mm[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
+        const float rr[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
+        bool tk[4] = {mode == 2, mode == 2, mode == 2, mode == 2};
+        if (mode == 3) {
+          float ym[4], yp[4];
+          if (fmaxf(fmaxf(rr[0], rr[1]), fmaxf(rr[2], rr[3])) <= -1.3862944f) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) key_interval<false>(mm[q], rr[q], g, ym[q], yp[q]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) key_interval<true>(mm[q], rr[q], g, ym[q], yp[q]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            // above = certified above the grid (NaN never is); in-grid = neither above nor certified below (NaN is)
+            tk[q] = ym[q] >= static_cast<float>(kBins);
+            const bool in_grid = !tk[q] && !(yp[q] < 0.0f);
+            q_lane[qpos * kThreads] = make_float2(ym[q], yp[q]);
+            if (in_grid) { ++qpos; listed |= 1u << (j * 4 + q); }
+            above += tk[q] ? 1u : 0u;
+          }
+        } else if (mode == 4) {
+          listed |= 0xfu << (j * 4);
+        }
+        *reinterpret_cast<float4*>(d.mu_w + i) =
+            make_float4(tk[0] ? 0.f : mm[0], tk[1] ? 0.f : mm[1], tk[2] ? 0.f : mm[2], tk[3] ? 0.f : mm[3]);
+        *reinterpret_cast<float4*>(d.rho_w + i) = make_float4(tk[0] ? -30.f : rr[0], tk[1] ? -30.f : rr[1],
+                                                              tk[2] ? -30.f : rr[2], tk[3] ? -30.f : rr[3]);
+        if (d.mask != nullptr) *reinterpret_cast<uchar4*>(d.mask + i) = make_uchar4(tk[0], tk[1], tk[2], tk[3]);
+      }
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < 4 * kVecPerThread; ++j) {
+        const int64_t i = ubase + j * 32 + lane;
+        if (i >= d.numel) continue;
+        const float mu = d.mu[i], rho = d.rho[i];
+        bool take = mode == 2;
+        if (mode == 3) {
+          float ym, yp;
+          key_interval<true>(mu, rho, g, ym, yp);
+          take = ym >= static_cast<float>(kBins);
+          const bool in_grid = !take && !(yp < 0.0f);
+          q_lane[qpos * kThreads] = make_float2(ym, yp);
+          if (in_grid) { ++qpos; listed |= 1u << j; }
+          above += take ? 1u : 0u;
+        } else if (mode == 4) {
+          listed |= 1u << j;
+        }
+        d.mu_w[i] = take ? 0.0f : mu;
+        d.rho_w[i] = take ? -30.0f : rho;
+        if (d.mask != nullptr) d.mask[i] = take ? 1 : 0;
+      }
+    }
+    if (mode != 3 && mode != 4) continue;
+    // histogram updates of the queued intervals (bin kernel conventions)
+    for (int s = 0; s < qpos; ++s) {
+      const float2 y = q_lane[s * kThreads];
+      const int im = !(y.x >= 0.0f) ? 0 : __float2int_rd(y.x) + 1;
+      const int ip = !(y.y < static_cast<float>(kBins)) ? kBins : __float2int_rd(y.y);
+      atomicAdd(d.hist + im, 1u);
+      atomicAdd(d.hist_plus + ip, 1u);
+    }
+    // list append: one reservation per warp
+    const unsigned int mine = __popc(listed);
+    unsigned int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0u) continue;           // warp-uniform
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(&d.state->n_deferred, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    unsigned int slot = base + incl - mine;
+    while (listed != 0u) {
+      const int e = __ffs(listed) - 1;
+      listed &= listed - 1u;
+      const int64_t i = full ? ubase + ((e >> 2) * 32 + lane) * 4 + (e & 3) : ubase + e * 32 + lane;
+      if (slot < d.defer_cap) {
+        d.keys[slot] = static_cast<uint32_t>(i);                    // numel < 2^32 on this path
+        d.keys[d.defer_cap + slot] = __float_as_uint(__ldg(d.mu + i));
+        d.keys[2u * d.defer_cap + slot] = __float_as_uint(__ldg(d.rho + i));
+      }
+      ++slot;
+    }
+  }
+  if (cur >= 0 && mode == 3) flush();
+}
+
+// bnn_prune_into: after the bracket step, walk the listed in-grid elements of every tensor: certainly above the bracket ->
+// pruned in the output (scattered stores), overlapping it -> the exact-select list, below -> nothing (already copied)
+__global__ void __launch_bounds__(kThreads) prune_resolve_kernel(const __grid_constant__ PruneTable tab) {
+  const PruneDesc& d = tab.t[blockIdx.y];
+  const PruneState* stp = d.state;
+  if (stp->general || d.k <= 0 || d.k >= d.numel) return;
+  const uint32_t n = stp->n_deferred;
+  if (n > d.defer_cap) return;             // overflow: the bracket kernel has flagged the tensor (see there)
+  const Grid g = make_grid(stp);
+  const float a_thr = stp->a_thr, b_thr = stp->b_thr;
+  const int lane = threadIdx.x & 31;
+  for (uint32_t i0 = blockIdx.x * kThreads; i0 < n; i0 += gridDim.x * kThreads) {
+    const uint32_t i = i0 + threadIdx.x;
+    bool take = false, defer = false;
+    uint32_t idx = 0;
+    float mu = 0.f, rho = 0.f;
+    if (i < n) {
+      idx = d.keys[i];
+      mu = __uint_as_float(d.keys[d.defer_cap + i]);
+      rho = __uint_as_float(d.keys[2u * d.defer_cap + i]);
+      if (stp->defer_all) {
+        defer = true;
+      } else {
+        float ym, yp;
+        key_interval<true>(mu, rho, g, ym, yp);        // the same arithmetic as the sweep: identical intervals
+        take = ym >= a_thr;
+        defer = !take && !(yp < b_thr);
+      }
+    }
+    if (take) {
+      d.mu_w[idx] = 0.0f;
+      d.rho_w[idx] = -30.0f;
+      if (d.mask != nullptr) d.mask[idx] = 1;
+    }
+    const unsigned int bal = __ballot_sync(0xffffffffu, defer);
+    if (bal != 0u) {
+      const int leader = __ffs(bal) - 1;
+      unsigned int base = 0;
+      if (lane == leader) base = atomicAdd(&d.state->n_deferred2, static_cast<unsigned int>(__popc(bal)));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (defer) {
+        const unsigned int slot = base + __popc(bal & ((1u << lane) - 1u));
+        if (slot < d.cap2) {
+          d.list2[slot] = idx;
+          d.list2[d.cap2 + slot] = __float_as_uint(mu);
+          d.list2[2u * static_cast<size_t>(d.cap2) + slot] = __float_as_uint(rho);
+        }
+      }
+    }
+  }
+}
+
+// bnn_prune_into, fallback: tensors flagged for the general path are first copied to the output unchanged
+__global__ void __launch_bounds__(kThreads) prune_copy_general_kernel(const __grid_constant__ PruneTable tab) {
+  if (*reinterpret_cast<volatile uint32_t*>(tab.any_general) == 0u) return;
+  __shared__ int64_t s_begin[kMaxTensors];
+  if (threadIdx.x < tab.n) s_begin[threadIdx.x] = tab.t[threadIdx.x].chunk_begin;
+  __syncthreads();
+  int cur = -1;
+  for (int64_t chunk = blockIdx.x; chunk < tab.total_chunks; chunk += gridDim.x) {
+    cur = find_tensor(s_begin, tab.n, chunk, cur < 0 ? 0 : cur);
+    const PruneDesc& d = tab.t[cur];
+    if (d.state->general == 0u) continue;
+    const int64_t base = (chunk - d.chunk_begin) * kChunk;
+    for (int j = 0; j < 4 * kVecPerThread; ++j) {
+      const int64_t i = base + static_cast<int64_t>(j) * kThreads + threadIdx.x;
+      if (i < d.numel) { d.mu_w[i] = d.mu[i]; d.rho_w[i] = d.rho[i]; }
+    }
+  }
+}
+
 // rank-th (0-based) value of the `n` candidates' field (`field` 0 = key descending, 1 = index ascending), restricted
 // to entries with key == only_key when field == 1.  Digits are taken relative to the minimum so that a narrow
 // bracket still spreads over the 2048 bins.  Returns the value; *count_before = entries strictly before it in the
@@ -789,11 +1019,15 @@ __global__ void __launch_bounds__(kResolveThreads) prune_finish_kernel(const __g
   const PruneDesc& d = tab.t[blockIdx.x];
   const PruneState st = *d.state;
   if (st.general || d.k <= 0 || d.k >= d.numel) return;
-  uint32_t n = st.n_deferred < d.defer_cap ? st.n_deferred : d.defer_cap;     // == expect_deferred by construction
-  const uint32_t* e_idx = d.keys;
-  const uint32_t* e_mu = d.keys + d.defer_cap;
-  const uint32_t* e_rho = d.keys + 2u * static_cast<size_t>(d.defer_cap);
-  uint32_t* pairs = n <= kResolveList ? s_list : d.keys + 3u * static_cast<size_t>(d.defer_cap);
+  const bool two_level = d.list2 != nullptr;                 // bnn_prune_into: the list the resolve kernel wrote
+  const uint32_t cap = two_level ? d.cap2 : d.defer_cap;
+  const uint32_t listed = two_level ? st.n_deferred2 : st.n_deferred;
+  uint32_t n = listed < cap ? listed : cap;                   // == expect_deferred by construction
+  const uint32_t* base = two_level ? d.list2 : d.keys;
+  const uint32_t* e_idx = base;
+  const uint32_t* e_mu = base + cap;
+  const uint32_t* e_rho = base + 2u * static_cast<size_t>(cap);
+  uint32_t* pairs = n <= kResolveList ? s_list : const_cast<uint32_t*>(base) + 3u * static_cast<size_t>(cap);
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     pairs[2 * static_cast<size_t>(i)] = order_key(prune_key(__uint_as_float(e_mu[i]), __uint_as_float(e_rho[i])));
     pairs[2 * static_cast<size_t>(i) + 1] = e_idx[i];
@@ -815,8 +1049,8 @@ __global__ void __launch_bounds__(kResolveThreads) prune_finish_kernel(const __g
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     const uint32_t key = pairs[2 * static_cast<size_t>(i)], idx = pairs[2 * static_cast<size_t>(i) + 1];
     if (key > T || (key == T && (all_eq || idx <= idx_bound))) {
-      d.mu[idx] = 0.0f;
-      d.rho[idx] = -30.0f;
+      d.mu_w[idx] = 0.0f;
+      d.rho_w[idx] = -30.0f;
       if (d.mask != nullptr) d.mask[idx] = 1;
     }
   }
@@ -1048,6 +1282,10 @@ uint32_t defer_cap_for(int64_t numel) {
   if (cap > (int64_t(1) << 28)) cap = int64_t(1) << 28;
   return static_cast<uint32_t>(cap);
 }
+uint32_t cap2_for(int64_t numel) {            // bnn_prune_into: capacity of the exact-select list
+  const uint32_t cap = defer_cap_for(numel);
+  return cap < 262144u ? cap : 262144u;
+}
 size_t keys_bytes(int64_t numel) {
   const size_t general = static_cast<size_t>(numel) * 4, sampled = static_cast<size_t>(defer_cap_for(numel)) * 20;
   return align_up(general > sampled ? general : sampled, 256);
@@ -1091,25 +1329,18 @@ int bnn_selftest_prune_interval(const float* mu, const float* rho, int64_t numel
   return BNN_OK;
 }
 
-int bnn_prune(const bnn_prune_tensor* tensors, int32_t n_tensors, void* workspace,
-              size_t workspace_bytes, void* stream) {
-  BNN_REQUIRE(n_tensors >= 0, BNN_ERR_BAD_ARGUMENT, "n_tensors < 0");
-  if (n_tensors == 0) return BNN_OK;
-  BNN_REQUIRE(tensors != nullptr, BNN_ERR_BAD_ARGUMENT, "bnn_prune: tensor table is NULL");
-  BNN_REQUIRE(workspace != nullptr && workspace_bytes >= bnn_prune_workspace_size(tensors, n_tensors),
-              BNN_ERR_WORKSPACE, "bnn_prune: workspace too small (%zu < %zu)", workspace_bytes,
-              bnn_prune_workspace_size(tensors, n_tensors));
-  BNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, BNN_ERR_MISALIGNED,
-              "bnn_prune: workspace must be 256-byte aligned");
-  for (int i = 0; i < n_tensors; ++i) {
-    BNN_REQUIRE(tensors[i].numel >= 0 && tensors[i].k >= 0 && tensors[i].k <= tensors[i].numel,
-                BNN_ERR_BAD_ARGUMENT, "bnn_prune: tensor %d needs 0 <= k <= numel", i);
-    BNN_REQUIRE(tensors[i].numel == 0 || (tensors[i].mu && tensors[i].rho), BNN_ERR_BAD_ARGUMENT,
-                "bnn_prune: tensor %d has NULL mu/rho", i);
-  }
-  int rc = check_device();
-  if (rc != BNN_OK) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+namespace {
+struct PruneIo {                       // one tensor of either entry point
+  float* mu; float* rho; float* mu_out; float* rho_out; uint8_t* mask; float* keys_out;
+  int64_t numel, k;
+  uint32_t flags;
+};
+
+size_t into_extra_bytes(int64_t numel) {       // the exact-select list of bnn_prune_into: 20 bytes per entry
+  return align_up(static_cast<size_t>(cap2_for(numel)) * 20, 256);
+}
+
+int prune_run(const PruneIo* io, int32_t n_tensors, bool into, void* workspace, cudaStream_t st) {
   uint32_t* group_flags = reinterpret_cast<uint32_t*>(workspace);
   char* small = static_cast<char*>(workspace) + header_bytes(n_tensors);
   char* ws = small + static_cast<size_t>(n_tensors) * kSmallBytes;
@@ -1117,7 +1348,7 @@ int bnn_prune(const bnn_prune_tensor* tensors, int32_t n_tensors, void* workspac
   const int max_grid = sm_count() * 8;
   static SmemOptIn sample_opt_in;
   const size_t sample_smem = static_cast<size_t>(kSample) * sizeof(uint32_t);
-  rc = allow_dynamic_smem(prune_sample_kernel, sample_smem, &sample_opt_in);
+  int rc = allow_dynamic_smem(prune_sample_kernel, sample_smem, &sample_opt_in);
   if (rc != BNN_OK) return rc;
 
   for (int first = 0; first < n_tensors; first += kMaxTensors) {
@@ -1128,12 +1359,13 @@ int bnn_prune(const bnn_prune_tensor* tensors, int32_t n_tensors, void* workspac
     tab.any_general = group_flags + first / kMaxTensors;
     int64_t chunks = 0;
     for (int i = 0; i < n; ++i) {
-      const bnn_prune_tensor& t = tensors[first + i];
+      const PruneIo& t = io[first + i];
       if (t.numel == 0) continue;
       PruneDesc& d = tab.t[tab.n++];
       const int64_t nch = (t.numel + kChunk - 1) / kChunk;
       char* mine = small + static_cast<size_t>(first + i) * kSmallBytes;
-      d.mu = t.mu; d.rho = t.rho; d.mask = t.mask_out; d.keys_out = t.keys_out;
+      d.mu = t.mu; d.rho = t.rho; d.mask = t.mask; d.keys_out = t.keys_out;
+      d.mu_w = into ? t.mu_out : t.mu; d.rho_w = into ? t.rho_out : t.rho;
       d.numel = t.numel; d.k = t.k; d.chunk_begin = chunks; d.n_chunks = nch;
       d.state = reinterpret_cast<PruneState*>(mine);
       d.hist = reinterpret_cast<uint32_t*>(mine + kStateBytes);
@@ -1141,8 +1373,11 @@ int bnn_prune(const bnn_prune_tensor* tensors, int32_t n_tensors, void* workspac
       d.keys = reinterpret_cast<uint32_t*>(ws); ws += keys_bytes(t.numel);
       d.defer_cap = defer_cap_for(t.numel);
       d.chunk_cnt = reinterpret_cast<int64_t*>(ws); ws += align_up(static_cast<size_t>(nch) * 8, 256);
+      d.list2 = nullptr; d.cap2 = 0; d.pad2 = 0;
+      if (into) { d.list2 = reinterpret_cast<uint32_t*>(ws); d.cap2 = cap2_for(t.numel); ws += into_extra_bytes(t.numel); }
       d.force_general = ((t.flags & BNN_PRUNE_GENERAL) != 0u || t.keys_out != nullptr) ? 1u : 0u;
-      d.vec = aligned16(t.mu) && aligned16(t.rho) && (t.mask_out == nullptr || (reinterpret_cast<uintptr_t>(t.mask_out) & 3u) == 0);
+      d.vec = aligned16(t.mu) && aligned16(t.rho) && aligned16(d.mu_w) && aligned16(d.rho_w) &&
+              (t.mask == nullptr || (reinterpret_cast<uintptr_t>(t.mask) & 3u) == 0);
       d.pad = 0;
       chunks += nch;
     }
@@ -1152,15 +1387,26 @@ int bnn_prune(const bnn_prune_tensor* tensors, int32_t n_tensors, void* workspac
     // sampled path
     prune_sample_keys_kernel<<<dim3(kSample / (4 * kResolveThreads), tab.n), kResolveThreads, 0, st>>>(tab);
     prune_sample_kernel<<<tab.n, kResolveThreads, sample_smem, st>>>(tab);
-    prune_bin_kernel<<<grid, kThreads, 0, st>>>(tab);
-    prune_bracket_kernel<<<tab.n, kThreads, 0, st>>>(tab);
-    prune_apply_sampled_kernel<<<grid, kThreads, 0, st>>>(tab);
+    if (!into) {
+      prune_bin_kernel<<<grid, kThreads, 0, st>>>(tab);
+      prune_bracket_kernel<<<tab.n, kThreads, 0, st>>>(tab);
+      prune_apply_sampled_kernel<<<grid, kThreads, 0, st>>>(tab);
+    } else {
+      prune_sweep_into_kernel<<<grid, kThreads, 0, st>>>(tab);
+      prune_bracket_kernel<<<tab.n, kThreads, 0, st>>>(tab);
+      prune_resolve_kernel<<<dim3(64, tab.n), kThreads, 0, st>>>(tab);
+    }
     prune_finish_kernel<<<tab.n, kResolveThreads, 0, st>>>(tab);
     // general path (kernels return immediately unless a tensor asked for it; when no tensor is known to need it they
     // are launched with one block per SM — all of them loop over the chunks — so that the idle launches stay cheap)
     bool forced = false;
     for (int i = 0; i < tab.n; ++i) forced = forced || tab.t[i].force_general != 0u || tab.t[i].numel >= (int64_t(1) << 32);
     const int ggrid = forced ? grid : (grid < sm_count() ? grid : sm_count());
+    if (into) {
+      // the input is intact: flagged tensors are copied, then selected in place on the OUTPUT
+      prune_copy_general_kernel<<<ggrid, kThreads, 0, st>>>(tab);
+      for (int i = 0; i < tab.n; ++i) { tab.t[i].mu = tab.t[i].mu_w; tab.t[i].rho = tab.t[i].rho_w; }
+    }
     prune_hist_kernel<0><<<ggrid, kThreads, 0, st>>>(tab);
     prune_select_kernel<0><<<tab.n, kThreads, 0, st>>>(tab);
     prune_hist_kernel<1><<<ggrid, kThreads, 0, st>>>(tab);
@@ -1173,6 +1419,68 @@ int bnn_prune(const bnn_prune_tensor* tensors, int32_t n_tensors, void* workspac
     BNN_CUDA_OK(cudaGetLastError());
   }
   return BNN_OK;
+}
+}  // namespace
+
+int bnn_prune(const bnn_prune_tensor* tensors, int32_t n_tensors, void* workspace,
+              size_t workspace_bytes, void* stream) {
+  BNN_REQUIRE(n_tensors >= 0, BNN_ERR_BAD_ARGUMENT, "n_tensors < 0");
+  if (n_tensors == 0) return BNN_OK;
+  BNN_REQUIRE(tensors != nullptr, BNN_ERR_BAD_ARGUMENT, "bnn_prune: tensor table is NULL");
+  BNN_REQUIRE(workspace != nullptr && workspace_bytes >= bnn_prune_workspace_size(tensors, n_tensors),
+              BNN_ERR_WORKSPACE, "bnn_prune: workspace too small (%zu < %zu)", workspace_bytes,
+              bnn_prune_workspace_size(tensors, n_tensors));
+  BNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, BNN_ERR_MISALIGNED,
+              "bnn_prune: workspace must be 256-byte aligned");
+  std::vector<PruneIo> io(static_cast<size_t>(n_tensors));
+  for (int i = 0; i < n_tensors; ++i) {
+    BNN_REQUIRE(tensors[i].numel >= 0 && tensors[i].k >= 0 && tensors[i].k <= tensors[i].numel,
+                BNN_ERR_BAD_ARGUMENT, "bnn_prune: tensor %d needs 0 <= k <= numel", i);
+    BNN_REQUIRE(tensors[i].numel == 0 || (tensors[i].mu && tensors[i].rho), BNN_ERR_BAD_ARGUMENT,
+                "bnn_prune: tensor %d has NULL mu/rho", i);
+    io[i] = PruneIo{tensors[i].mu, tensors[i].rho, nullptr, nullptr, tensors[i].mask_out, tensors[i].keys_out,
+                    tensors[i].numel, tensors[i].k, tensors[i].flags};
+  }
+  int rc = check_device();
+  if (rc != BNN_OK) return rc;
+  return prune_run(io.data(), n_tensors, false, workspace, static_cast<cudaStream_t>(stream));
+}
+
+size_t bnn_prune_into_workspace_size(const bnn_prune_into_tensor* tensors, int32_t n_tensors) {
+  if (tensors == nullptr || n_tensors <= 0) return 256;
+  size_t total = header_bytes(n_tensors) + static_cast<size_t>(n_tensors) * kSmallBytes;
+  for (int i = 0; i < n_tensors; ++i) {
+    const int64_t numel = tensors[i].numel > 0 ? tensors[i].numel : 0;
+    total += prune_ws_one(numel) + into_extra_bytes(numel);
+  }
+  return total;
+}
+
+int bnn_prune_into(const bnn_prune_into_tensor* tensors, int32_t n_tensors, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  BNN_REQUIRE(n_tensors >= 0, BNN_ERR_BAD_ARGUMENT, "n_tensors < 0");
+  if (n_tensors == 0) return BNN_OK;
+  BNN_REQUIRE(tensors != nullptr, BNN_ERR_BAD_ARGUMENT, "bnn_prune_into: tensor table is NULL");
+  BNN_REQUIRE(workspace != nullptr && workspace_bytes >= bnn_prune_into_workspace_size(tensors, n_tensors),
+              BNN_ERR_WORKSPACE, "bnn_prune_into: workspace too small (%zu < %zu)", workspace_bytes,
+              bnn_prune_into_workspace_size(tensors, n_tensors));
+  BNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, BNN_ERR_MISALIGNED,
+              "bnn_prune_into: workspace must be 256-byte aligned");
+  std::vector<PruneIo> io(static_cast<size_t>(n_tensors));
+  for (int i = 0; i < n_tensors; ++i) {
+    const bnn_prune_into_tensor& t = tensors[i];
+    BNN_REQUIRE(t.numel >= 0 && t.k >= 0 && t.k <= t.numel, BNN_ERR_BAD_ARGUMENT,
+                "bnn_prune_into: tensor %d needs 0 <= k <= numel", i);
+    BNN_REQUIRE(t.numel == 0 || (t.mu && t.rho && t.mu_out && t.rho_out), BNN_ERR_BAD_ARGUMENT,
+                "bnn_prune_into: tensor %d has a NULL pointer", i);
+    BNN_REQUIRE(t.numel == 0 || (t.mu != t.mu_out && t.rho != t.rho_out), BNN_ERR_BAD_ARGUMENT,
+                "bnn_prune_into: tensor %d: outputs must not alias the inputs (use bnn_prune in place)", i);
+    io[i] = PruneIo{const_cast<float*>(t.mu), const_cast<float*>(t.rho), t.mu_out, t.rho_out, t.mask_out, nullptr,
+                    t.numel, t.k, t.flags};
+  }
+  int rc = check_device();
+  if (rc != BNN_OK) return rc;
+  return prune_run(io.data(), n_tensors, true, workspace, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

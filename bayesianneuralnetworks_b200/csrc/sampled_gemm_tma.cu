@@ -182,6 +182,8 @@ struct TmaContractParams {
   bnn_rng rng_w, rng_b;
   int shared_l;             // all samples read sample 0 of the L operand (shared activations)
   int sum_samples;          // dgrad with shared activations: one output, summed over the samples
+  int z_per;                // sum_samples: samples per CTA (grid.z = sample groups); more than one group -> the partial
+  int atomic_out;           //   sums are ADDED to the (zeroed) output
   int vec_out;
   int exp_flags;            // profiling builds: 1 = skip weight generation, 2 = skip TMA loads, 4 = skip MMA issue
 };
@@ -290,8 +292,8 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
   const int row0 = blockIdx.y * (MB * 128);            // output rows (m)
   const int n_cols = kDgrad ? p.K : p.N;
   const int n_red = kDgrad ? p.N : p.K;
-  const int s_begin = p.sum_samples ? 0 : blockIdx.z;
-  const int s_end = p.sum_samples ? p.S : blockIdx.z + 1;
+  const int s_begin = p.sum_samples ? static_cast<int>(blockIdx.z) * p.z_per : blockIdx.z;
+  const int s_end = p.sum_samples ? (s_begin + p.z_per < p.S ? s_begin + p.z_per : p.S) : blockIdx.z + 1;
   const int red_blocks = (n_red + kBK - 1) / kBK;
   int mb_used = (p.M - row0 + 127) / 128;
   if (mb_used > MB) mb_used = MB;
@@ -331,6 +333,12 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
       int it = 0;
       for (int s = s_begin; s < s_end; ++s) {
         const int smp = p.shared_l ? 0 : s;
+        int cw[MB], ch[MB], cn[MB];                // conv: first pixel of each row block (fixed over the k-blocks)
+        if (p.conv.on) {
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) conv_pixel(p.conv, row0 + mb * 128, smp, &cw[mb], &ch[mb], &cn[mb]);
+        }
+        int tap = 0, cb = 0;                       // conv: k-block rb = (tap, 32-channel block cb), walked incrementally
         for (int rb = 0; rb < red_blocks; ++rb, ++it) {
           const int g = it & 1;
           if (it >= 2) { BNN_T0(); mbar_wait(pipe.empty_w + ((it - 2) & 3), ((it - 2) >> 2) & 1); BNN_ACC(w_tma); }
@@ -342,14 +350,13 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
             for (int mb = 0; mb < mb_used; ++mb)
               tma_load_3d(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, rb * kBK, row0 + mb * 128, smp, pipe.full_a + g);
           } else {
-            const int tap = rb / p.conv.cblocks, c0 = (rb - tap * p.conv.cblocks) * kBK;
             const int kh = tap / p.conv.KW, kw = tap - kh * p.conv.KW;
-            for (int mb = 0; mb < mb_used; ++mb) {
-              int w, h, n;
-              conv_pixel(p.conv, row0 + mb * 128, smp, &w, &h, &n);
-              tma_load_im2col_4d(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, c0, w, h, n,
-                                 static_cast<uint16_t>(kw * p.conv.dw), static_cast<uint16_t>(kh * p.conv.dh), pipe.full_a + g);
-            }
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+              if (mb < mb_used)
+                tma_load_im2col_4d(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, cb * kBK, cw[mb], ch[mb], cn[mb],
+                                   static_cast<uint16_t>(kw * p.conv.dw), static_cast<uint16_t>(kh * p.conv.dh), pipe.full_a + g);
+            if (++cb == p.conv.cblocks) { cb = 0; ++tap; }
           }
         }
       }
@@ -415,7 +422,10 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] += pipe.aux[c * 16 + j];
         }
-        if (m < p.M) store_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+        if (m < p.M) {
+          if (kDgrad && p.atomic_out) add_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+          else store_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+        }
       }
     }
   }
@@ -517,8 +527,8 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
   const int row0 = blockIdx.x * (MB * 128);            // output rows of THIS CTA (the pair is adjacent in x)
   const int n_cols = kDgrad ? p.K : p.N;
   const int n_red = kDgrad ? p.N : p.K;
-  const int s_begin = p.sum_samples ? 0 : blockIdx.z;
-  const int s_end = p.sum_samples ? p.S : blockIdx.z + 1;
+  const int s_begin = p.sum_samples ? static_cast<int>(blockIdx.z) * p.z_per : blockIdx.z;
+  const int s_end = p.sum_samples ? (s_begin + p.z_per < p.S ? s_begin + p.z_per : p.S) : blockIdx.z + 1;
   const int red_blocks = (n_red + kBK - 1) / kBK;
   // both CTAs walk the same number of M-blocks (the leader holds the lower rows, so its count is the larger one);
   // tiles beyond M are zero-filled by TMA and never stored
@@ -561,6 +571,12 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
       const uint32_t lead_full_a = mapa_u32(smem_u32(pipe.full_a), 0);
       for (int s = s_begin; s < s_end; ++s) {
         const int smp = p.shared_l ? 0 : s;
+        int cw[MB], ch[MB], cn[MB];
+        if (p.conv.on) {
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) conv_pixel(p.conv, row0 + mb * 128, smp, &cw[mb], &ch[mb], &cn[mb]);
+        }
+        int tap = 0, cb = 0;
         for (int rb = 0; rb < red_blocks; ++rb, ++it) {
           const int g = it & 1;
           if (it >= 2) { BNN_T0(); mbar_wait(pipe.empty_w + ((it - 2) & 3), ((it - 2) >> 2) & 1); BNN_ACC(w_tma); }
@@ -570,15 +586,14 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
               tma_load_3d_pair(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, rb * kBK, row0 + mb * 128, smp,
                                lead_full_a + g * 8);
           } else {
-            const int tap = rb / p.conv.cblocks, c0 = (rb - tap * p.conv.cblocks) * kBK;
             const int kh = tap / p.conv.KW, kw = tap - kh * p.conv.KW;
-            for (int mb = 0; mb < mb_pair; ++mb) {
-              int w, h, n;
-              conv_pixel(p.conv, row0 + mb * 128, smp, &w, &h, &n);
-              tma_load_im2col_4d_pair(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, c0, w, h, n,
-                                      static_cast<uint16_t>(kw * p.conv.dw), static_cast<uint16_t>(kh * p.conv.dh),
-                                      lead_full_a + g * 8);
-            }
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+              if (mb < mb_pair)
+                tma_load_im2col_4d_pair(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, cb * kBK, cw[mb], ch[mb], cn[mb],
+                                        static_cast<uint16_t>(kw * p.conv.dw), static_cast<uint16_t>(kh * p.conv.dh),
+                                        lead_full_a + g * 8);
+            if (++cb == p.conv.cblocks) { cb = 0; ++tap; }
           }
         }
       }
@@ -643,7 +658,10 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] += pipe.aux[c * 16 + j];
         }
-        if (m < p.M) store_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+        if (m < p.M) {
+          if (kDgrad && p.atomic_out) add_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+          else store_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+        }
       }
     }
   }
@@ -700,18 +718,33 @@ int forced_variant() {
 }
 
 template <bool kDgrad>
-int dispatch_tma_contract(const TmaContractParams& p, int n_cols, cudaStream_t st) {
+int dispatch_tma_contract(TmaContractParams& p, int n_cols, cudaStream_t st) {
   const int m_blocks = (p.M + 127) / 128;
-  const int gx = (n_cols + 127) / 128, gz = p.sum_samples ? 1 : p.S;
+  const int gx = (n_cols + 127) / 128;
   const int sms = sm_count();
   const int n_red = kDgrad ? p.N : p.K;
+  // Shared activations (one output summed over the samples): a CTA walks `z_per` samples; when the output has too few
+  // tiles to fill the machine the samples are split over grid.z and the partial sums are added to the zeroed output.
+  int gz = p.S;
+  if (p.sum_samples) {
+    const int64_t tiles = static_cast<int64_t>(gx) * ((m_blocks + 3) / 4);
+    int groups = static_cast<int>((sms + tiles - 1) / tiles);
+    if (groups > p.S) groups = p.S;
+    if (groups < 1 || p.out.P != 1) groups = 1;
+    p.z_per = (p.S + groups - 1) / groups;
+    gz = (p.S + p.z_per - 1) / p.z_per;
+    p.atomic_out = gz > 1 ? 1 : 0;
+    if (p.atomic_out)
+      BNN_CUDA_OK(cudaMemset2DAsync(p.out.base, static_cast<size_t>(p.out.bs) * 4, 0, static_cast<size_t>(n_cols) * 4,
+                                    static_cast<size_t>(p.M), st));
+  }
   // Rows per CTA by a cost model of the measured kernels, in cycles per 32-wide k-block: a CTA generates
   // its weight tile at ~1.86 weights/clk whatever the number of 128-row blocks that reuse it (128 x 32 tile: ~2200
   // cycles; half of it per CTA of a pair), its MMAs + operand delivery cost ~425 cycles per block (~468 per block pair
   // with cta_group::2), so a k-block takes the larger of the two; a launch takes waves x (fixed cost + k-blocks x that).
   // Small problems thereby keep few rows per CTA (every SM gets a short k-loop) and large ones share each generated
   // tile between 1024 rows — without insisting on a CTA for every SM: 144 busy SMs with 4x the reuse beat 148.
-  const double iters = static_cast<double>((n_red + kBK - 1) / kBK) * (p.sum_samples ? p.S : 1);
+  const double iters = static_cast<double>((n_red + kBK - 1) / kBK) * (p.sum_samples ? p.z_per : 1);
   const double w_rows = n_cols < 128 ? n_cols : 128;
   auto cost_single = [&](int mb) {
     const int64_t ctas = static_cast<int64_t>(gx) * ((m_blocks + mb - 1) / mb) * gz;
@@ -822,6 +855,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
     if (warp == 0) {
       if (lane == 0) {
         int it = 0;
+        // conv: the 32-column group kc .. kc + 31 of the im2col matrix = (tap, channels c0 ..) of the NHWC input — fixed per
+        // CTA; groups beyond K read channel `chans` (outside the tensor: zeros, the transaction still completes)
+        int g_c0[4] = {0, 0, 0, 0};
+        uint16_t g_ow[4] = {0, 0, 0, 0}, g_oh[4] = {0, 0, 0, 0};
+        if (p.conv.on) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int kc = k0 + g * 32;
+            if (kc >= p.K) { g_c0[g] = p.conv.chans; continue; }
+            const int tap = kc / p.conv.chans;
+            g_c0[g] = kc - tap * p.conv.chans;
+            const int kh = tap / p.conv.KW, kw = tap - kh * p.conv.KW;
+            g_ow[g] = static_cast<uint16_t>(kw * p.conv.dw);
+            g_oh[g] = static_cast<uint16_t>(kh * p.conv.dh);
+          }
+        }
         for (int u = s_begin; u < s_end; ++u) {
           const int s = u / p.n_chunks;
           const int sa = p.shared_a ? 0 : s;
@@ -833,16 +882,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
             const uint32_t base = ring + stage * 2 * kWgOperandBytes;
             int cw = 0, ch = 0, cn = 0;
             if (p.conv.on) conv_pixel(p.conv, mb * kWgRows, sa, &cw, &ch, &cn);
-            // conv: the 32-column group kc .. kc + 31 of the im2col matrix = (tap, channels c0 ..) of the NHWC input; groups
-            // beyond K read channel `chans` (outside the tensor: zeros, the transaction still completes)
-            auto conv_group = [&](int kc, int* c0, uint16_t* ow, uint16_t* oh) {
-              if (kc >= p.K) { *c0 = p.conv.chans; *ow = 0; *oh = 0; return; }
-              const int tap = kc / p.conv.chans;
-              *c0 = kc - tap * p.conv.chans;
-              const int kh = tap / p.conv.KW, kw = tap - kh * p.conv.KW;
-              *ow = static_cast<uint16_t>(kw * p.conv.dw);
-              *oh = static_cast<uint16_t>(kh * p.conv.dh);
-            };
             if (!kPair) {
               mbar_arrive_expect_tx(full + stage, 2 * kWgOperandBytes);
 #pragma unroll
@@ -851,9 +890,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
                 if (!p.conv.on) {
                   tma_load_3d(base + kWgOperandBytes + g * kWgLbo, &p.map_a, k0 + g * 32, mb * kWgRows, sa, full + stage);
                 } else {
-                  int c0; uint16_t ow, oh;
-                  conv_group(k0 + g * 32, &c0, &ow, &oh);
-                  tma_load_im2col_4d(base + kWgOperandBytes + g * kWgLbo, &p.map_a, c0, cw, ch, cn, ow, oh, full + stage);
+                  tma_load_im2col_4d(base + kWgOperandBytes + g * kWgLbo, &p.map_a, g_c0[g], cw, ch, cn, g_ow[g], g_oh[g],
+                                     full + stage);
                 }
               }
             } else {
@@ -868,9 +906,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
                 if (!p.conv.on) {
                   tma_load_3d_pair(base + kWgOperandBytes + g * kWgLbo, &p.map_a, kc, mb * kWgRows, sa, lead_full);
                 } else {
-                  int c0; uint16_t ow, oh;
-                  conv_group(kc, &c0, &ow, &oh);
-                  tma_load_im2col_4d_pair(base + kWgOperandBytes + g * kWgLbo, &p.map_a, c0, cw, ch, cn, ow, oh, lead_full);
+                  const int gi = static_cast<int>(rank) * 2 + g;
+                  tma_load_im2col_4d_pair(base + kWgOperandBytes + g * kWgLbo, &p.map_a, g_c0[gi], cw, ch, cn, g_ow[gi],
+                                          g_oh[gi], lead_full);
                 }
               }
             }

@@ -1,9 +1,16 @@
 """PruneNormal (mirror of pytorch_bayesian/prune/prune.py:5-22).
 
 Per variational tensor, independently: key = log N(0; mean, stddev), the k = int(percentage * numel)
-largest keys get mean <- 0, scale <- -30, in place and without autograd.  All tensors of the model
-go through the same launches of libbnn_b200's exact select (keys bit-identical to torch's
-Normal.log_prob on the device; ties at the k-th key resolved towards the lowest index).
+largest keys get mean <- 0, scale <- -30, without autograd.  All tensors of the model go through the
+same launches of libbnn_b200's exact select (keys bit-identical to torch's Normal.log_prob on the
+device; ties at the k-th key resolved towards the lowest index).
+
+Large tensors take the ONE-SWEEP out-of-place path (bnn_prune_into: 8 bytes read + 8 written per pair
+instead of two reads and a write): the pruned values land in fresh tensors whose storage then replaces
+the Parameters' (`param.data = out`; the Parameter objects, their `.grad` and every optimizer state keyed
+by them stay).  That is observably the reference's in-place update unless other tensors alias the
+parameter's storage — views taken earlier, or a captured CUDA graph that bakes the address in; for those
+`PruneNormal(in_place=True)` (or `bnn.prune.set_in_place(True)`) keeps the strictly in-place kernel.
 """
 import torch
 
@@ -12,7 +19,19 @@ from ..nn.variational import WeightNormal
 from ..utils.traversal import apply_wb
 
 
+_IN_PLACE = {"always": False}
+_SWAP_MIN_NUMEL = 1 << 20       # below this the in-place kernel's second read comes out of L2 anyway
+
+
+def set_in_place(flag=True):
+    """Process-wide default of PruneNormal(in_place=None)."""
+    _IN_PLACE["always"] = bool(flag)
+
+
 class PruneNormal():
+
+    def __init__(self, in_place=None):
+        self.in_place = in_place
 
     def __call__(self, module, percentage=0.5):
         self.prune(module, percentage)
@@ -21,9 +40,9 @@ class PruneNormal():
         """prune.py:10-17 for one tensor."""
         self._launch([param], percentage)
 
-    @staticmethod
-    def _launch(params, percentage):
-        entries = []
+    def _launch(self, params, percentage):
+        in_place = _IN_PLACE["always"] if self.in_place is None else self.in_place
+        entries, swap = [], []
         for p in params:
             if not isinstance(p, WeightNormal):
                 raise NotImplementedError(f"PruneNormal: unsupported variational tensor {p.__class__.__name__}")
@@ -34,8 +53,15 @@ class PruneNormal():
                 raise RuntimeError(f"selected index k out of range: k={k}, numel={n}")
             if not (p.mean.is_contiguous() and p.scale.is_contiguous()):
                 raise ValueError("PruneNormal needs contiguous mean/scale parameters")
-            entries.append((p.mean.data, p.scale.data, k, None, None))
+            if not in_place and n >= _SWAP_MIN_NUMEL:
+                swap.append((p, k))
+            else:
+                entries.append((p.mean.data, p.scale.data, k, None, None))
         _C.prune(entries)
+        if swap:
+            outs = _C.prune_into([(p.mean.data, p.scale.data, k, None) for p, k in swap])
+            for (p, _), (mu_out, rho_out) in zip(swap, outs):
+                p.mean.data, p.scale.data = mu_out, rho_out
 
     def prune(self, module, percentage=0.5):
         """prune.py:19-22 — every tensor the traversal finds, weights and biases alike."""

@@ -753,7 +753,10 @@ def run_b200(args):
     _C.lib()                          # fails loudly when the CUDA library is missing
     rank, world, device = env.rank, env.world, env.device
     env.clocks.start()
-    tf32_peak = measure_tf32_peak(device)
+    if args.tf32_peak > 0:           # profiling runs: do not spend the profiler's launch budget on 1400 cuBLAS calls
+        tf32_peak = {"burst_tflops": args.tf32_peak, "sustained_tflops": args.tf32_peak, "how": "given on the command line"}
+    else:
+        tf32_peak = measure_tf32_peak(device)
     env.pk.update(tf32_burst=tf32_peak["burst_tflops"], tf32_sustained=tf32_peak["sustained_tflops"])
     main_mode = {"c4": "sample"}.get(args.workload, "grid") if args.parallel == "auto" else args.parallel
     main = measure_step(env, args.workload, args.steps, args.warmup, args.precision, main_mode,
@@ -835,6 +838,8 @@ def main():
                     help="leave the deterministic torch trunk in torch's default NCHW memory format (the examples' setting)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="only the main workload (profiling runs)")
+    ap.add_argument("--tf32-peak", type=float, default=0.0,
+                    help="skip the in-run cuBLAS TF32 peak measurement and use this TFLOP/s figure (runs under a profiler)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -327,6 +327,25 @@ size_t bnn_prune_workspace_size(const bnn_prune_tensor* tensors, int32_t n_tenso
 int bnn_prune(const bnn_prune_tensor* tensors /* HOST array */, int32_t n_tensors,
               void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same selection OUT OF PLACE, in ONE sweep over (mu, rho): 8 bytes read + 8 bytes written per pair, against two
+ * reads and a write in place (where nothing may be modified before the selection is proven).  mu_out / rho_out receive
+ * the pruned tensors (every element is written); the inputs are read only.  Same keys, same tie rule, same masks as
+ * bnn_prune.  Callers that own the parameters swap their storage for the outputs (prune/prune.py does). */
+typedef struct bnn_prune_into_tensor {
+  const float* mu;
+  const float* rho;
+  float* mu_out;
+  float* rho_out;
+  uint8_t* mask_out;   /* optional */
+  int64_t numel;
+  int64_t k;
+  uint32_t flags;      /* BNN_PRUNE_GENERAL: force the general path (on a copy in the outputs) */
+  uint32_t reserved;
+} bnn_prune_into_tensor;
+size_t bnn_prune_into_workspace_size(const bnn_prune_into_tensor* tensors, int32_t n_tensors);
+int bnn_prune_into(const bnn_prune_into_tensor* tensors /* HOST array */, int32_t n_tensors, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* ---- self test of the prune path's certified key intervals: for every element writes the interval [lo, hi] that the
  * two sweeps of bnn_prune use to classify it, in "key2" units: key2 = (log N(0; mu, sigma) + log sqrt(2 pi)) * log2(e).
  * The exact fp32 key that torch computes (prune.py:11) must lie inside.  variant 0: the fast path taken when every

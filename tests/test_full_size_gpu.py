@@ -73,7 +73,7 @@ def test_kl_additivity_and_torch_value_at_c5_tensor_size(C):
 
 
 @pytest.mark.parametrize("p", [0.75, 0.9])
-def test_prune_properties_at_c5_tensor_size(C, p):
+def test_prune_properties_at_c5_tensor_size(C, prune_mode, p):
     torch.distributions.Distribution.set_default_validate_args(False)
     g = torch.Generator(device="cuda").manual_seed(2)
     mu = (torch.rand(4096, 4096, device="cuda", generator=g) * 2 - 1) / 64

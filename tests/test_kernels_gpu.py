@@ -163,7 +163,7 @@ def torch_keys_same_device(mu, rho):
 
 @pytest.mark.parametrize("shape,p", [((64, 64, 3, 3), 0.75), ((10, 576), 0.9), ((10,), 0.5), ((4099,), 0.0),
                                      ((4099,), 1.0), ((1000, 333), 0.3)])
-def test_prune_bit_exact(C, shape, p):
+def test_prune_bit_exact(C, prune_mode, shape, p):
     g = torch.Generator().manual_seed(3)
     mu, rho = init_params(shape, g)
     k = orc.prune_count(p, mu.numel())
@@ -197,7 +197,7 @@ def test_prune_bit_exact(C, shape, p):
 
 @pytest.mark.parametrize("numel,p", [(333000, 0.3), (333000, 0.75), (1 << 20, 0.9), (1 << 20, 0.999), (70001, 0.5),
                                      (200000, 1e-5), (200000, 0.99999)])
-def test_prune_sampled_path_equals_general_path(C, numel, p):
+def test_prune_sampled_path_equals_general_path(C, prune_mode, numel, p):
     """The sampled two-sweep path and the general radix-select path are both exact: identical masks, and
     identical to the stable descending sort of torch's keys on the device."""
     g = torch.Generator().manual_seed(12)
@@ -257,7 +257,7 @@ def test_prune_certified_intervals_contain_the_exact_key(C, variant):
 
 @pytest.mark.parametrize("kind", ["wide_rho", "pruned_mix", "strided_structure", "outliers", "nonfinite_free_extremes",
                                   "nan_entries"])
-def test_prune_sampled_path_hard_distributions(C, kind):
+def test_prune_sampled_path_hard_distributions(C, prune_mode, kind):
     """Inputs that stress the certified-interval arithmetic of the sampled path (every softplus regime, rho above
     torch's threshold of 20, keys of very different magnitude, already pruned entries) or defeat its strided sample
     (structure with the sample's period: the bracket misses and the tensor must fall back to the general path).
@@ -301,7 +301,7 @@ def test_prune_sampled_path_hard_distributions(C, kind):
 
 
 @pytest.mark.parametrize("classes", [1, 2, 3])
-def test_prune_large_tie_classes(C, classes):
+def test_prune_large_tie_classes(C, prune_mode, classes):
     """Huge tie classes on a tensor large enough for the sampled path: the bracket collapses onto one key
     (candidate-heavy resolve, index bound) or overflows the candidate buffer (device-side fallback)."""
     n = 300000
@@ -317,7 +317,7 @@ def test_prune_large_tie_classes(C, classes):
         assert torch.equal(mask.bool(), orc.prune_mask_from_keys(keys, k))
 
 
-def test_prune_ties_lowest_index_first(C):
+def test_prune_ties_lowest_index_first(C, prune_mode):
     # 3 distinct (mu, rho) pairs repeated: massive ties at the threshold
     base_mu = torch.tensor([0.0, 0.5, 1.0]).repeat(5000)
     base_rho = torch.full((15000,), -2.0)
@@ -337,7 +337,7 @@ def test_prune_ties_lowest_index_first(C):
             assert bool(sel[:n].all()) and not bool(sel[n:].any())
 
 
-def test_prune_many_tensors_and_idempotent_order(C):
+def test_prune_many_tensors_and_idempotent_order(C, prune_mode):
     g = torch.Generator().manual_seed(4)
     shapes = [(64, 64, 3, 3), (64,), (10, 576), (10,)] * 8        # 32 tensors: two launches' worth
     dev = [tuple(t.cuda() for t in init_params(s, g)) for s in shapes]
@@ -641,7 +641,7 @@ def test_conv2d_forward_through_gemm_view(C, case, prec):
         assert rel_err(y[smp], ref) < TOL[prec]
 
 
-def test_golden_checkpoint_prune_fingerprints(C):
+def test_golden_checkpoint_prune_fingerprints(C, prune_mode):
     """masks of PruneNormal on the reference's shipped MNIST checkpoint (bit-exact)."""
     import os
     path = os.path.join(os.path.dirname(__file__), "golden", "mnist_ckpt_bayes_layers.npz")
