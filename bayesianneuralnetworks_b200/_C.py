@@ -120,6 +120,9 @@ _SIGNATURES = {
                                                 ctypes.c_int32, ctypes.c_void_p]),
     "bnn_conv2d_weight_unlayout": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                   ctypes.c_int32, ctypes.c_void_p]),
+    "bnn_nchw_to_nhwc_bias_grad": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                                  ctypes.c_int32, _c_f32p, _c_f32p, _c_f32p, _c_f32p, ctypes.c_uint32,
+                                                  ctypes.POINTER(bnn_rng), ctypes.c_void_p]),
     "bnn_im2col_nhwc": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.POINTER(bnn_conv2d_nhwc), ctypes.c_int64, ctypes.c_void_p]),
     "bnn_col2im_nhwc": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.POINTER(bnn_conv2d_nhwc), ctypes.c_int64, ctypes.c_void_p]),
     "bnn_kl_workspace_size": (ctypes.c_size_t, [ctypes.c_int32]),
@@ -381,6 +384,21 @@ def conv_weight_unlayout(grads_p, shape):
     out = torch.empty((grads_p.shape[0],) + tuple(shape), device=grads_p.device, dtype=torch.float32)
     with torch.cuda.device(grads_p.device):
         _call("bnn_conv2d_weight_unlayout", _ptr(grads_p), _ptr(out), grads_p.shape[0], Cout, Cg, taps, _stream())
+    _count()
+    return out
+
+
+def nchw_to_nhwc_bias_grad(dy, B, rho_b=None, eps_b=None, dmu_b=None, drho_b=None, sample_begin=0, rng_b=None):
+    """dy: NCHW-contiguous [S*B, N, OH, OW] -> the same tensor in channels_last memory (returned as a logical NCHW tensor);
+    optionally accumulates the bias gradient in the same pass.  None when the shape is not supported."""
+    R, N = dy.shape[0], dy.shape[1]
+    P = dy.shape[2] * dy.shape[3]
+    if (N + 1) * P * 4 > 48 * 1024 or (dmu_b is not None and N > 256):
+        return None
+    out = torch.empty(dy.shape, device=dy.device, dtype=torch.float32, memory_format=torch.channels_last)
+    with torch.cuda.device(dy.device):
+        _call("bnn_nchw_to_nhwc_bias_grad", _ptr(dy), _ptr(out), R, B, N, P, _ptr(rho_b), _ptr(eps_b), _ptr(dmu_b),
+              _ptr(drho_b), sample_begin, ctypes.byref(rng_b) if rng_b is not None else None, _stream())
     _count()
     return out
 

@@ -106,6 +106,61 @@ __global__ void __launch_bounds__(kThreads) col2im_nhwc_kernel(const float* __re
   }
 }
 
+// dY of a conv layer arrives from autograd NCHW-contiguous ([R][N][P], P = OH*OW) whenever the layer's output was; the
+// implicit-GEMM kernels want it as rows [R*P][N] (NHWC).  One block transposes `ipb` images through shared memory — an
+// image's N*P block is contiguous on both sides, so reads and writes are fully coalesced — and, while the values are
+// there, sums every column: the reparameterised bias gradient (c_s[n] = sum_m dY[s][m][n]; dmu_b += sum_s
+// c_s; drho_b += sum_s c_s eps_b(s, n) sigmoid(rho_b[n])) costs no second pass over dY.
+__global__ void __launch_bounds__(kThreads) nchw_to_nhwc_bias_kernel(const float* __restrict__ dy, float* __restrict__ out,
+                                                                     int64_t n_imgs, int B, int N, int P, int ipb,
+                                                                     const float* __restrict__ rho_b,
+                                                                     const float* __restrict__ eps_b, float* __restrict__ dmu_b,
+                                                                     float* __restrict__ drho_b, uint32_t sample_begin,
+                                                                     bnn_rng rng) {
+  extern __shared__ float s_tile[];          // [P][N + 1]
+  const int pitch = N + 1, NP = N * P;
+  const bool want_bias = dmu_b != nullptr;
+  const RngKey key = resolve_rng(rng);
+  const int64_t img0 = static_cast<int64_t>(blockIdx.x) * ipb;
+  float acc = 0.f;                           // column sum of thread n = threadIdx.x over the images of one sample
+  int cur_s = -1;
+  auto flush = [&](int s) {
+    if (!want_bias || s < 0) return;
+    const int n = threadIdx.x;               // N <= kThreads on this path (checked by the host)
+    if (n < N) {
+      const float e = eps_b != nullptr ? __ldg(eps_b + static_cast<int64_t>(s) * N + n)
+                                       : eps1(key, sample_begin + s, static_cast<uint64_t>(n));
+      atomicAdd(dmu_b + n, acc);
+      atomicAdd(drho_b + n, acc * e * sigmoid_fast(__ldg(rho_b + n)));
+    }
+    acc = 0.f;
+  };
+  for (int k = 0; k < ipb; ++k) {
+    const int64_t img = img0 + k;
+    if (img >= n_imgs) break;
+    const int s = static_cast<int>(img / B);
+    if (s != cur_s) { flush(cur_s); cur_s = s; }
+    const float* src = dy + img * NP;
+    __syncthreads();
+    for (int i = threadIdx.x; i < NP; i += kThreads) {
+      const int n = i / P, pp = i - n * P;
+      s_tile[pp * pitch + n] = __ldg(src + i);
+    }
+    __syncthreads();
+    float* dst = out + img * NP;
+    for (int i = threadIdx.x; i < NP; i += kThreads) {
+      const int pp = i / N, n = i - pp * N;
+      dst[i] = s_tile[pp * pitch + n];
+    }
+    if (want_bias && static_cast<int>(threadIdx.x) < N) {
+      float c = 0.f;
+      for (int pp = 0; pp < P; ++pp) c += s_tile[pp * pitch + threadIdx.x];
+      acc += c;
+    }
+  }
+  flush(cur_s);
+}
+
 int grid_for(int64_t items) {
   const int64_t blocks = (items + kThreads - 1) / kThreads;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
@@ -180,6 +235,32 @@ int bnn_col2im_nhwc(const float* dcol, float* dx, const bnn_conv2d_nhwc* g, int6
   if (rc != BNN_OK) return rc;
   const int64_t total = n_imgs * g->H * g->W * (g->C / 4);
   col2im_nhwc_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(dcol, dx, *g, n_imgs);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+
+int bnn_nchw_to_nhwc_bias_grad(const float* dy, float* dy_nhwc, int64_t n_imgs, int32_t B, int32_t N, int32_t P,
+                               const float* rho_b, const float* eps_b, float* dmu_b, float* drho_b, uint32_t sample_begin,
+                               const bnn_rng* rng_b, void* stream) {
+  BNN_REQUIRE(dy && dy_nhwc && n_imgs > 0 && B > 0 && N > 0 && P > 0, BNN_ERR_BAD_ARGUMENT,
+              "bnn_nchw_to_nhwc_bias_grad: NULL pointer or bad shape");
+  BNN_REQUIRE((dmu_b == nullptr) == (drho_b == nullptr) && (dmu_b == nullptr || (rho_b != nullptr && rng_b != nullptr)),
+              BNN_ERR_BAD_ARGUMENT, "bnn_nchw_to_nhwc_bias_grad: the bias gradient needs dmu_b, drho_b, rho_b and rng_b");
+  const size_t smem = static_cast<size_t>(N + 1) * P * sizeof(float);
+  BNN_REQUIRE(smem <= 48 * 1024 && (dmu_b == nullptr || N <= kThreads), BNN_ERR_UNSUPPORTED,
+              "bnn_nchw_to_nhwc_bias_grad: one image's (N + 1) x P block must fit 48 KiB of shared memory (and N <= 256 with "
+              "the bias gradient)");
+  int rc = check_device();
+  if (rc != BNN_OK) return rc;
+  const int64_t per_img = static_cast<int64_t>(N) * P;
+  int ipb = static_cast<int>(16384 / per_img);         // ~64 KiB of traffic per block
+  if (ipb < 1) ipb = 1;
+  if (ipb > 64) ipb = 64;
+  const int64_t blocks = (n_imgs + ipb - 1) / ipb;
+  BNN_REQUIRE(blocks <= 0x7fffffff, BNN_ERR_UNSUPPORTED, "bnn_nchw_to_nhwc_bias_grad: too many images");
+  bnn_rng rng = rng_b ? *rng_b : bnn_rng{};
+  nchw_to_nhwc_bias_kernel<<<static_cast<int>(blocks), kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      dy, dy_nhwc, n_imgs, B, N, P, ipb, rho_b, eps_b, dmu_b, drho_b, sample_begin, rng);
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
 }

@@ -251,6 +251,19 @@ def conv_implicit_eligible(in_channels, groups):
     return groups == 1 and in_channels % 32 == 0
 
 
+_CONV_OUTPUT = {"format": "contiguous"}
+
+
+def set_conv_output_format(fmt):
+    """Memory format of the implicit-GEMM conv layers' OUTPUT: 'contiguous' (default: NCHW-contiguous, what the reference
+    produces and what a following Flatten / view wants; the gradient that comes back is transposed to channels-last by one
+    fused pass that also forms the bias gradient) or 'preserve' (torch's convention: a channels_last input gives a
+    channels_last result — the choice for conv -> conv stacks kept in channels_last)."""
+    if fmt not in ("contiguous", "preserve"):
+        raise ValueError("conv output format must be 'contiguous' or 'preserve'")
+    _CONV_OUTPUT["format"] = fmt
+
+
 def _nhwc(t):
     """(tensor whose memory is NHWC-contiguous, copied?) for a logical NCHW tensor."""
     if t.permute(0, 2, 3, 1).is_contiguous():
@@ -267,8 +280,8 @@ class SampledConv2dImplicit(torch.autograd.Function):
     (bnn_im2col_nhwc / bnn_col2im_nhwc + the register-staged / TMA GEMM kernels).
 
     x: logical [S*B, C, H, W] (sample-major) or, when `shared`, [B, C, H, W]; any memory format — channels_last input gives
-    a channels_last result without a copy (torch's own convention), a contiguous NCHW input is converted once and gives an
-    NCHW-contiguous result."""
+    a channels_last result under set_conv_output_format('preserve'); by default the result is NCHW-contiguous (written
+    through the kernel's strided epilogue) and a contiguous NCHW input is converted once."""
 
     @staticmethod
     def forward(ctx, x, mu_w, rho_w, mu_b, rho_b, S, shared, spec_w, spec_b, precision, stride, padding, dilation):
@@ -286,7 +299,7 @@ class SampledConv2dImplicit(torch.autograd.Function):
         OW = _conv_out(W, KW, stride[1], padding[1], dilation[1])
         if OH <= 0 or OW <= 0:
             raise RuntimeError("sampled conv2d: empty output")
-        nchw_out = x.is_contiguous() and not (C == 1 or H * W == 1)      # follow the input's memory format
+        nchw_out = _CONV_OUTPUT["format"] == "contiguous" or x.is_contiguous()
         x_cl = _nhwc(x)
         geom = _C.conv_geom(B, H, W, C, OH, OW, Cout, KH, KW, stride, padding, dilation)
         wl = _C.conv_weight_layout(mu_w.contiguous(), rho_w.contiguous())          # [3, numel]: mean, sigma, scale
@@ -324,14 +337,31 @@ class SampledConv2dImplicit(torch.autograd.Function):
         B, H, W, OH, OW = geom.B, geom.H, geom.W, geom.OH, geom.OW
         P, K = OH * OW, KH * KW * C
         M = B * P
-        dy_cl = _nhwc(dy)                               # rows [S*B*OH*OW, Cout]: free for a channels_last gradient
-        dy_view, dy_ss = _C.make_view(dy_cl.data_ptr(), Cout, 1), M * Cout
         eps_w = _eps_slice(spec_w, S, Cout * K)
         x_ss = 0 if shared else B * H * W * C
         tf32 = precision == _C.PREC_TF32
         need_x = ctx.needs_input_grad[0]
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         need_b = rho_b is not None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
+        # the gradient kernels read dY as rows [S*B*OH*OW, Cout]: free for a channels_last gradient; an NCHW-contiguous
+        # one goes through ONE transposing pass that forms the bias gradient on the way
+        bias_done = False
+        bg_fused = None
+        if dy.permute(0, 2, 3, 1).is_contiguous():
+            dy_cl = dy
+        else:
+            dy_cl = None
+            if dy.is_contiguous():
+                if need_b:
+                    bg_fused = torch.zeros((2, Cout), device=dy.device, dtype=torch.float32)
+                dy_cl = _C.nchw_to_nhwc_bias_grad(dy, B, rho_b.contiguous() if need_b else None,
+                                                  _eps_slice(spec_b, S, Cout) if need_b else None,
+                                                  bg_fused[0] if need_b else None, bg_fused[1] if need_b else None,
+                                                  spec_b.sample_begin if need_b else 0, spec_b.rng() if need_b else None)
+                bias_done = dy_cl is not None and need_b
+            if dy_cl is None:
+                dy_cl = dy.contiguous(memory_format=torch.channels_last)
+        dy_view, dy_ss = _C.make_view(dy_cl.data_ptr(), Cout, 1), M * Cout
         dx = None
         if need_x:
             dx = torch.empty(x_cl.shape, device=dy.device, dtype=torch.float32, memory_format=torch.channels_last)
@@ -342,7 +372,9 @@ class SampledConv2dImplicit(torch.autograd.Function):
                 _C.sampled_gemm_dgrad(dy_view, dy_ss, wl[0], wl[1], eps_w, dcol, K, 0 if shared else M * K, M, Cout, K, S,
                                       spec_w.sample_begin, spec_w.rng(), precision)
                 _C.col2im_nhwc(dcol, dx, geom, rows)
-        grads_p, bg = _zero_grads((Cout * K,) if need_w else None, Cout if need_b else None, dy.device)
+        grads_p, bg = _zero_grads((Cout * K,) if need_w else None, Cout if (need_b and not bias_done) else None, dy.device)
+        if bias_done:
+            bg = bg_fused
         dmu = drho = None
         if need_w:
             if tf32 and Cout % 4 == 0:
@@ -354,7 +386,7 @@ class SampledConv2dImplicit(torch.autograd.Function):
                                       M, Cout, K, S, spec_w.sample_begin, spec_w.rng(), precision)
             g = _C.conv_weight_unlayout(grads_p, w_shape)
             dmu, drho = g[0], g[1]
-        if need_b:
+        if need_b and not bias_done:
             _C.bias_grad(dy_view, dy_ss, rho_b.contiguous(), _eps_slice(spec_b, S, Cout), bg[0], bg[1], M, Cout, S,
                          spec_b.sample_begin, spec_b.rng())
         return (dx, dmu, drho, bg[0] if need_b else None, bg[1] if need_b else None) + (None,) * 8

@@ -190,6 +190,13 @@ int bnn_conv2d_weight_layout(const float* mu, const float* rho, float* mu_p, flo
                              int32_t Cg, int32_t taps, void* stream);
 int bnn_conv2d_weight_unlayout(const float* in, float* out, int32_t n_arrays, int32_t Cout, int32_t Cg, int32_t taps,
                                void* stream);
+/* dY of a conv layer as autograd delivers it for an NCHW-contiguous output ([n_imgs][N][P], P = OH*OW, n_imgs = S*B
+ * sample-major) -> the row-major [n_imgs*P][N] (NHWC) matrix the gradient kernels read, one coalesced pass through shared
+ * memory; with dmu_b / drho_b non-NULL the same pass accumulates the reparameterised bias gradient (see bnn_bias_grad;
+ * eps_b [S][N] optional injected eps).  BNN_ERR_UNSUPPORTED when an image's (N + 1) x P floats exceed 48 KiB. */
+int bnn_nchw_to_nhwc_bias_grad(const float* dy, float* dy_nhwc, int64_t n_imgs, int32_t B, int32_t N, int32_t P,
+                               const float* rho_b, const float* eps_b, float* dmu_b, float* drho_b, uint32_t sample_begin,
+                               const bnn_rng* rng_b, void* stream);
 /* explicit lowering in the same column order (kh, kw, c), NHWC tensors of n_imgs images, C % 4 == 0:
  *   col[(n, oh, ow)][(kh*KW + kw)*C + c] = x[n][oh*sh - ph + kh*dh][ow*sw - pw + kw*dw][c]  (0 outside)
  *   dx[n][h][w][c] = sum of the dcol entries that read (n, h, w, c)  (gather form, overwrites dx) */

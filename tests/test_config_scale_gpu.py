@@ -33,6 +33,7 @@ def _reset_knobs():
     bnn.set_mc_batching("auto")
     bnn.graph_safe_rng(False)
     bnn.set_sample_partition(0, 1)
+    bnn.set_conv_output_format("contiguous")
 
 
 # ------------------------------------------------------------------------------------------------ (a) C3 / C2 conv layer
@@ -138,6 +139,9 @@ def test_replayed_cuda_graph_bench_step_matches_the_oracle(prec, tol):
         torch.manual_seed(0)
         model = bench.build_model("c2", S)
         stages, eps_order = _oracle_stages(model)
+        initial = []
+        for st in stages:
+            initial += [q.detach().clone().double() for q in (st[1].parameters() if st[0] == 'torch' else st[1:5])]
         gen = torch.Generator().manual_seed(1)
         x, y = bench.synthetic_batch("c2", B, gen)
         eps_cpu = {w: torch.randn((S,) + tuple(w.shape), generator=gen) for w in eps_order}
@@ -164,7 +168,10 @@ def test_replayed_cuda_graph_bench_step_matches_the_oracle(prec, tol):
                 loss = trainer.step(x.cuda(), y.cuda())
         torch.cuda.synchronize()
         assert float(loss) == pytest.approx(float(ref_loss), rel=tol)
-        # parameters after five Adam steps: every update is at most lr = 1e-3 per step; agreement far below that
+        # Parameters after five Adam steps.  Adam's first updates are lr * g / |g|: an element whose gradient is at rounding
+        # level takes a full +-lr step in a direction that rounding decides, so the maximum deviation is not a parity
+        # measure.  Measured instead: the relative L2 error of the whole update (after - before) and the 99th percentile
+        # of the element deviations, per parameter tensor.
         ref_params = []
         for st in stages:
             ref_params += list(st[1].parameters()) if st[0] == 'torch' else list(st[1:5])
@@ -174,12 +181,18 @@ def test_replayed_cuda_graph_bench_step_matches_the_oracle(prec, tol):
                 got_params += [m.weight.mean, m.weight.scale, m.bias.mean, m.bias.scale]
             else:
                 got_params += list(m.parameters())
-        assert len(ref_params) == len(got_params)
-        worst = 0.0
-        for a, b in zip(got_params, ref_params):
+        assert len(ref_params) == len(got_params) == len(initial)
+        num = den = 0.0
+        worst_q = 0.0
+        for a, b, p0 in zip(got_params, ref_params, initial):
             assert a.shape == b.shape
-            worst = max(worst, float((a.detach().cpu() - b.detach()).abs().max()))
-        assert worst < (5e-5 if prec == "fp32" else 1e-3), worst
+            a, b = a.detach().cpu().double(), b.detach().double()
+            num += float(((a - p0) - (b - p0)).pow(2).sum())
+            den += float((b - p0).pow(2).sum())
+            worst_q = max(worst_q, float((a - b).abs().flatten().quantile(0.99)) if a.numel() > 100 else 0.0)
+        update_err = (num / den) ** 0.5
+        assert update_err < (5e-3 if prec == "fp32" else 8e-2), (update_err, worst_q)
+        assert worst_q < (2e-5 if prec == "fp32" else 5e-4), (update_err, worst_q)
         bn, bn_ref = model.layers[1], stages[0][1][1]
         assert int(bn.num_batches_tracked) == int(bn_ref.num_batches_tracked) == n_steps * S
         assert rel_err(bn.running_mean, bn_ref.running_mean) < 1e-4 and rel_err(bn.running_var, bn_ref.running_var) < 1e-4
@@ -239,7 +252,7 @@ def test_c3_example_model_trains_on_the_batched_graph_path():
     assert len(trainer.opt.composite) == 2                      # weight and bias of the full-covariance head
     x, y = bench.synthetic_batch("c3", 512, torch.Generator().manual_seed(1))
     x, y = x.cuda(), y.cuda()
-    head, conv = model.layers[-2], model.layers[10]
+    head, conv = model.layers[-2], model.layers[11]
     before = [t.detach().clone() for t in (head.weight.scale, head.weight.mean, conv.weight.mean, conv.weight.scale,
                                            model.layers[0].weight)]
     trainer.capture(x, y)
@@ -310,7 +323,10 @@ def test_implicit_gemm_conv_matches_torch_on_ragged_geometries(cfg, shared, layo
     assert layer._implicit
     g = torch.Generator(device="cuda").manual_seed(42)
     x = torch.randn(B if shared else S * B, Cin, H, W, device="cuda", generator=g)
+    bnn.set_conv_output_format("preserve" if layout == "channels_last" else "contiguous")
     if layout == "channels_last":
+        x = x.contiguous(memory_format=torch.channels_last)
+    elif cfg[0] == 5:                      # a channels_last input with the default NCHW result (the bench's configuration)
         x = x.contiguous(memory_format=torch.channels_last)
     x.requires_grad_(True)
     eps = {layer.weight: torch.randn((S,) + tuple(layer.weight.shape), device="cuda", generator=g),
@@ -319,11 +335,13 @@ def test_implicit_gemm_conv_matches_torch_on_ragged_geometries(cfg, shared, layo
     ctx.expanded = not shared
     with bnn.injected_eps(eps), runtime.mc_batch(ctx):
         y = layer(x)
-    if layout == "channels_last":
+    if layout == "channels_last":          # 'preserve': the result follows the input's format, as torch's conv does
         assert y.permute(0, 2, 3, 1).is_contiguous()
-    else:
+    else:                                  # default: NCHW-contiguous result; its gradient takes the fused transposing pass
         assert y.is_contiguous()
     dy = torch.randn(y.shape, device="cuda", generator=g)
+    if layout == "channels_last":
+        dy = dy.contiguous(memory_format=torch.channels_last)
     y.backward(dy)
     xd = x.detach().double().requires_grad_(True)
     mw, rw = layer.weight.mean.detach().double().requires_grad_(True), layer.weight.scale.detach().double().requires_grad_(True)
