@@ -112,16 +112,15 @@ __global__ void __launch_bounds__(kThreads) col2im_nhwc_kernel(const float* __re
 // there, sums every column: the reparameterised bias gradient (c_s[n] = sum_m dY[s][m][n]; dmu_b += sum_s
 // c_s; drho_b += sum_s c_s eps_b(s, n) sigmoid(rho_b[n])) costs no second pass over dY.
 __global__ void __launch_bounds__(kThreads) nchw_to_nhwc_bias_kernel(const float* __restrict__ dy, float* __restrict__ out,
-                                                                     int64_t n_imgs, int B, int N, int P, int ipb,
+                                                                     int64_t n_imgs, int B, int N, int P, int ipt, int passes,
                                                                      const float* __restrict__ rho_b,
                                                                      const float* __restrict__ eps_b, float* __restrict__ dmu_b,
                                                                      float* __restrict__ drho_b, uint32_t sample_begin,
-                                                                     bnn_rng rng) {
-  extern __shared__ float s_tile[];          // [P][N + 1]
-  const int pitch = N + 1, NP = N * P;
+                                                                     bnn_rng rng, int vec) {
+  extern __shared__ float s_tile[];          // ipt images x [P][N + 1]
+  const int pitch = N + 1, NP = N * P, img_smem = P * pitch;
   const bool want_bias = dmu_b != nullptr;
   const RngKey key = resolve_rng(rng);
-  const int64_t img0 = static_cast<int64_t>(blockIdx.x) * ipb;
   float acc = 0.f;                           // column sum of thread n = threadIdx.x over the images of one sample
   int cur_s = -1;
   auto flush = [&](int s) {
@@ -135,27 +134,55 @@ __global__ void __launch_bounds__(kThreads) nchw_to_nhwc_bias_kernel(const float
     }
     acc = 0.f;
   };
-  for (int k = 0; k < ipb; ++k) {
-    const int64_t img = img0 + k;
-    if (img >= n_imgs) break;
-    const int s = static_cast<int>(img / B);
-    if (s != cur_s) { flush(cur_s); cur_s = s; }
-    const float* src = dy + img * NP;
+  for (int pass = 0; pass < passes; ++pass) {
+    const int64_t img0 = (static_cast<int64_t>(blockIdx.x) * passes + pass) * ipt;
+    if (img0 >= n_imgs) break;
+    const int here = n_imgs - img0 < ipt ? static_cast<int>(n_imgs - img0) : ipt;
+    const int total = here * NP;
+    const float* src = dy + img0 * NP;
+    float* dst = out + img0 * NP;
     __syncthreads();
-    for (int i = threadIdx.x; i < NP; i += kThreads) {
-      const int n = i / P, pp = i - n * P;
-      s_tile[pp * pitch + n] = __ldg(src + i);
+    if (vec) {                               // P % 4 == 0: a float4 holds (n, p .. p + 3)
+      for (int i = threadIdx.x * 4; i < total; i += kThreads * 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+        const int im = i / NP, r = i - im * NP;
+        const int n = r / P, pp = r - n * P;
+        float* t = s_tile + im * img_smem + pp * pitch + n;
+        t[0] = v.x; t[pitch] = v.y; t[2 * pitch] = v.z; t[3 * pitch] = v.w;
+      }
+    } else {
+      for (int i = threadIdx.x; i < total; i += kThreads) {
+        const int im = i / NP, r = i - im * NP;
+        const int n = r / P, pp = r - n * P;
+        s_tile[im * img_smem + pp * pitch + n] = __ldg(src + i);
+      }
     }
     __syncthreads();
-    float* dst = out + img * NP;
-    for (int i = threadIdx.x; i < NP; i += kThreads) {
-      const int pp = i / N, n = i - pp * N;
-      dst[i] = s_tile[pp * pitch + n];
+    if (vec && N % 4 == 0) {
+      for (int i = threadIdx.x * 4; i < total; i += kThreads * 4) {
+        const int im = i / NP, r = i - im * NP;
+        const int pp = r / N, n = r - pp * N;
+        const float* t = s_tile + im * img_smem + pp * pitch + n;
+        *reinterpret_cast<float4*>(dst + i) = make_float4(t[0], t[1], t[2], t[3]);
+      }
+    } else {
+      for (int i = threadIdx.x; i < total; i += kThreads) {
+        const int im = i / NP, r = i - im * NP;
+        const int pp = r / N, n = r - pp * N;
+        dst[i] = s_tile[im * img_smem + pp * pitch + n];
+      }
     }
-    if (want_bias && static_cast<int>(threadIdx.x) < N) {
-      float c = 0.f;
-      for (int pp = 0; pp < P; ++pp) c += s_tile[pp * pitch + threadIdx.x];
-      acc += c;
+    if (want_bias) {
+      for (int im = 0; im < here; ++im) {
+        const int s = static_cast<int>((img0 + im) / B);
+        if (s != cur_s) { flush(cur_s); cur_s = s; }
+        if (static_cast<int>(threadIdx.x) < N) {
+          const float* t = s_tile + im * img_smem + threadIdx.x;
+          float c = 0.f;
+          for (int pp = 0; pp < P; ++pp) c += t[pp * pitch];
+          acc += c;
+        }
+      }
     }
   }
   flush(cur_s);
@@ -246,21 +273,27 @@ int bnn_nchw_to_nhwc_bias_grad(const float* dy, float* dy_nhwc, int64_t n_imgs, 
               "bnn_nchw_to_nhwc_bias_grad: NULL pointer or bad shape");
   BNN_REQUIRE((dmu_b == nullptr) == (drho_b == nullptr) && (dmu_b == nullptr || (rho_b != nullptr && rng_b != nullptr)),
               BNN_ERR_BAD_ARGUMENT, "bnn_nchw_to_nhwc_bias_grad: the bias gradient needs dmu_b, drho_b, rho_b and rng_b");
-  const size_t smem = static_cast<size_t>(N + 1) * P * sizeof(float);
-  BNN_REQUIRE(smem <= 48 * 1024 && (dmu_b == nullptr || N <= kThreads), BNN_ERR_UNSUPPORTED,
+  const size_t img_smem = static_cast<size_t>(N + 1) * P * sizeof(float);
+  BNN_REQUIRE(img_smem <= 48 * 1024 && (dmu_b == nullptr || N <= kThreads), BNN_ERR_UNSUPPORTED,
               "bnn_nchw_to_nhwc_bias_grad: one image's (N + 1) x P block must fit 48 KiB of shared memory (and N <= 256 with "
               "the bias gradient)");
   int rc = check_device();
   if (rc != BNN_OK) return rc;
-  const int64_t per_img = static_cast<int64_t>(N) * P;
-  int ipb = static_cast<int>(16384 / per_img);         // ~64 KiB of traffic per block
-  if (ipb < 1) ipb = 1;
-  if (ipb > 64) ipb = 64;
-  const int64_t blocks = (n_imgs + ipb - 1) / ipb;
+  int ipt = static_cast<int>((32 * 1024) / img_smem);      // images per pass: ~32 KiB of shared memory per block
+  if (ipt < 1) ipt = 1;
+  if (ipt > 64) ipt = 64;
+  // a few passes per block keep the number of (atomic) bias flushes down without starving the machine of blocks
+  const int64_t tiles = (n_imgs + ipt - 1) / ipt;
+  int passes = static_cast<int>(tiles / (static_cast<int64_t>(sm_count()) * 4));
+  if (passes < 1) passes = 1;
+  if (passes > 8) passes = 8;
+  const int64_t blocks = (tiles + passes - 1) / passes;
   BNN_REQUIRE(blocks <= 0x7fffffff, BNN_ERR_UNSUPPORTED, "bnn_nchw_to_nhwc_bias_grad: too many images");
+  const int vec = (P % 4 == 0) && aligned16(dy) && aligned16(dy_nhwc) && ((static_cast<int64_t>(N) * P) % 4 == 0);
   bnn_rng rng = rng_b ? *rng_b : bnn_rng{};
-  nchw_to_nhwc_bias_kernel<<<static_cast<int>(blocks), kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      dy, dy_nhwc, n_imgs, B, N, P, ipb, rho_b, eps_b, dmu_b, drho_b, sample_begin, rng);
+  nchw_to_nhwc_bias_kernel<<<static_cast<int>(blocks), kThreads, static_cast<size_t>(ipt) * img_smem,
+                             static_cast<cudaStream_t>(stream)>>>(dy, dy_nhwc, n_imgs, B, N, P, ipt, passes, rho_b, eps_b, dmu_b,
+                                                                  drho_b, sample_begin, rng, vec);
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
 }

@@ -124,7 +124,7 @@ class BucketedAllReduce:
         self._bucket_of = {}
         off, begin, count = 0, 0, 0
         for p in order:
-            p.grad = torch.as_strided(self.flat, p.size(), p.stride(), off)
+            p.grad = torch.as_strided(self.flat, p.size(), p.stride(), self.flat.storage_offset() + off)
             self._bucket_of[id(p)] = len(self.buckets)
             off += p.numel()
             count += 1

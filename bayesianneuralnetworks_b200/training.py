@@ -63,6 +63,7 @@ class ElboTrainer:
         self.peers = None
         self.buckets = None
         if self.world > 1:
+            self.exchange_note = ""
             mode = exchange
             if mode == "auto":
                 mode = "peer" if (optimizer == "elbo-adam" and grad_bytes <= peer_limit_bytes) else "bucketed"
@@ -107,7 +108,7 @@ class ElboTrainer:
         dense permutations of their storage), so that the exchange sees static addresses and a single range."""
         off = 0
         for p in self.params:
-            p.grad = torch.as_strided(self.flat, p.size(), p.stride(), off)
+            p.grad = torch.as_strided(self.flat, p.size(), p.stride(), self.flat.storage_offset() + off)
             off += p.numel()
 
     # ------------------------------------------------------------------------------------------------ one step

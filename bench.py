@@ -532,44 +532,57 @@ def bench_kl_prune(device, pk, world=1, tensors=64):
             best = min(best, a.elapsed_time(b) * 1e-3)
         return over_ranks(best)
 
-    def prune_once():
+    # PruneNormal on tensors of this size (prune/prune.py): the ONE-sweep out-of-place kernel (bnn_prune_into: 8 B read +
+    # 8 B written per pair), the outputs then replace the parameters' storage
+    state = {"mus": mus, "rhos": rhos}
+
+    def prune_swap(kk=k):
+        outs = _C.prune_into([(m, r, kk, None) for m, r in zip(state["mus"], state["rhos"])])
+        state["mus"], state["rhos"] = [o[0] for o in outs], [o[1] for o in outs]
+
+    def prune_in_place():
         _C.prune([(m, r, k, None, None) for m, r in zip(mus, rhos)])
-    prune_once()
-    res["prune_p0.75"] = entry(8 + 8 * p, best_of(prune_once))
-    res["prune_p0.75"]["what"] = "stand-alone PruneNormal sweep (prune.py:10-17): sample + interval histogram sweep + apply sweep"
-    if hasattr(_C, "kl_with_prune_plan"):
-        # north_star: "the pruning mask reuses that same pass" — the KL pass also histograms the certified key intervals
-        # (bnn_kl_prune_plan), the prune that follows is ONE read + write sweep (fused sweep 8 + 8p B/pair)
-        plan = {}
 
-        def kl_plan():
-            plan["p"] = _C.kl_with_prune_plan(fwd)
+    def restore_swap():
+        restore()
+        state["mus"], state["rhos"] = mus, rhos
 
-        def prune_planned():
-            _C.prune_with_plan(plan["p"], [(m, r, k, None, None) for m, r in zip(mus, rhos)])
-        res["kl_fwd_with_prune_plan"] = entry(8, time_it(kl_plan, reps=3, inner=2))
-        res["prune_p0.75_after_kl"] = entry(8 + 8 * p, best_of(prune_planned, prepare=kl_plan))
-        res["prune_p0.75_after_kl"]["what"] = ("PruneNormal sweep that reuses the histograms of the preceding KL pass: "
-                                               "bracket + ONE apply sweep + exact finish")
-
-        def both_legs():
-            kl_plan()
-            prune_planned()
-        res["kl_plus_prune_p0.75"] = entry(8 + 8 * p, best_of(both_legs))
-        res["kl_plus_prune_p0.75"]["what"] = "KL forward (with plan) + prune, together, against the fused-sweep figure 8 + 8p B/pair"
+    def best_swap(reps=3):
+        best = 1e30
+        for _ in range(reps):
+            restore_swap()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            prune_swap()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b) * 1e-3)
+        return over_ranks(best)
+    prune_swap()                              # warm-up: the caching allocator now holds the output blocks
+    torch.cuda.synchronize()
+    res["prune_p0.75"] = entry(8 + 8 * p, best_swap())
+    res["prune_p0.75"]["what"] = ("PruneNormal sweep (prune.py:10-17) as the package runs it on tensors of this size: sample + ONE "
+                                  "out-of-place sweep (bnn_prune_into: read 8 B, write 8 B per pair) + bracket + resolve + exact "
+                                  "finish; the outputs replace the parameters' storage")
+    restore_swap()
+    prune_in_place()
+    res["prune_p0.75_in_place"] = entry(8 + 8 * p, best_of(prune_in_place))
+    res["prune_p0.75_in_place"]["what"] = ("strictly in-place kernel (bnn_prune): sample + read-only interval-histogram sweep + "
+                                           "apply sweep (two reads and a write: 24 B/pair of traffic)")
     # the example's sweep (examples/MNIST/prune.py:49-50): successive levels on the SAME tensors — what was pruned at
     # one level (mu = 0, rho = -30: the largest key there is) is re-selected first at the next
-    restore()
+    restore_swap()
     sweep = []
     for level in torch.linspace(.75, 1, 6).tolist():
         kk = int(level * 4096 * 4096)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        _C.prune([(m, r, kk, None, None) for m, r in zip(mus, rhos)])
+        prune_swap(kk)
         b.record()
         torch.cuda.synchronize()
         t = over_ranks(a.elapsed_time(b) * 1e-3)
         sweep.append(dict(entry(8 if kk == 4096 * 4096 else 8 + 8 * level, t), p=round(level, 2)))      # p = 1 writes only
+    rhos = state["rhos"]
     pruned = sum(int((r == -30).sum()) for r in rhos)
     res["prune_sweep"] = {"levels": sweep, "all_pruned_after_p1": pruned == n_t * 4096 * 4096}
     return res

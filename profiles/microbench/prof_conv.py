@@ -1,0 +1,56 @@
+"""Profiling driver: the C3 (default) or C2 Bayesian conv layer through the implicit-GEMM path — forward, input gradient,
+weight gradient — with CUDA-event times per call.  `python profiles/microbench/prof_conv.py [c3|c2] [shared|per]`.
+Under ncu: `-k regex:"contract_|wgrad_tma"`."""
+import sys
+
+import torch
+
+sys.path.insert(0, '.')
+from bayesianneuralnetworks_b200 import _C as C  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "c3"
+shared = (sys.argv[2] if len(sys.argv) > 2 else "shared") == "shared"
+B, S, Cn, HW, stride = (512, 16, 128, 4, 1) if which == "c3" else (256, 8, 64, 6, 2)
+OH = (HW + 2 - 3) // stride + 1
+g = torch.Generator(device='cuda').manual_seed(0)
+x = torch.randn((B if shared else S * B), HW, HW, Cn, device='cuda', generator=g)          # NHWC memory
+mu = (torch.rand(Cn, Cn, 3, 3, device='cuda', generator=g) * 2 - 1) / 34
+rho = torch.randn(Cn, Cn, 3, 3, device='cuda', generator=g) * 0.15 - 2
+wl = C.conv_weight_layout(mu, rho)
+mub = torch.zeros(Cn, device='cuda')
+sigb = C.stddev(torch.full((Cn,), -2.0, device='cuda'))
+geom = C.conv_geom(B, HW, HW, Cn, OH, OH, Cn, 3, 3, (stride, stride), (1, 1), (1, 1))
+M, K = B * OH * OH, 9 * Cn
+y = torch.empty(S * M, Cn, device='cuda')
+dy = torch.randn(S * M, Cn, device='cuda', generator=g)
+dx = torch.empty_like(x)
+gr = torch.zeros(2, Cn * K, device='cuda')
+rw, rb = C.make_rng(1, 0, 1), C.make_rng(1, 0, 2)
+xss = 0 if shared else B * HW * HW * Cn
+
+
+def fwd():
+    C.sampled_conv2d_fwd(x, xss, wl[0], wl[1], mub, sigb, None, None, C.make_view(y.data_ptr(), Cn, 1), M * Cn, geom, S, 0, rw, rb)
+
+
+def dgrad():
+    if stride == 1:
+        C.sampled_conv2d_dgrad(dy, wl[0], wl[1], None, dx, xss, geom, S, 0, rw)
+
+
+def wgrad():
+    C.sampled_conv2d_wgrad(dy, x, xss, wl[2], None, gr[0], gr[1], geom, S, 0, rw)
+
+
+for _ in range(3):
+    fwd(), dgrad(), wgrad()
+torch.cuda.synchronize()
+flops = 2.0 * M * Cn * K * S
+for name, fn in (("fwd", fwd), ("dgrad", dgrad), ("wgrad", wgrad)):
+    best = 1e9
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    print(f"{which} {'shared' if shared else 'per-sample'} {name}: {best * 1e3:.1f} us  {flops / best / 1e9:.1f} TFLOP/s")
