@@ -79,6 +79,10 @@ class bnn_peer_grads(ctypes.Structure):
     _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("base", ctypes.c_void_p * MAX_PEERS)]
 
 
+class bnn_pack_item(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_void_p), ("dst_offset", ctypes.c_int64), ("numel", ctypes.c_int64)]
+
+
 _SIGNATURES = {
     "bnn_abi_version": (ctypes.c_int, []),
     "bnn_last_error_string": (ctypes.c_char_p, []),
@@ -139,6 +143,7 @@ _SIGNATURES = {
     "bnn_adam_kl_step_peers": (ctypes.c_int, [ctypes.POINTER(bnn_adam_tensor), ctypes.c_int32, ctypes.c_float, ctypes.c_float,
                                               ctypes.c_float, ctypes.c_float, _c_f32p, ctypes.c_int64,
                                               ctypes.POINTER(bnn_peer_grads), ctypes.c_void_p]),
+    "bnn_pack_gradients": (ctypes.c_int, [ctypes.POINTER(bnn_pack_item), ctypes.c_int32, _c_f32p, ctypes.c_void_p]),
     "bnn_peer_barrier": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                         ctypes.c_void_p]),
     "bnn_mc_cross_entropy_workspace_size": (ctypes.c_size_t, []),
@@ -602,6 +607,21 @@ def _dense(t):
             return False
         expect *= sz
     return True
+
+
+def pack_gradients(items, flat):
+    """items: list of (gradient tensor | None, offset in `flat` (floats), numel); the gradients must be dense in their
+    parameter's memory order (the caller checks) — they are copied as raw memory."""
+    n = len(items)
+    if n == 0:
+        return
+    table = (bnn_pack_item * n)()
+    for i, (g, off, numel) in enumerate(items):
+        table[i].src = None if g is None else g.data_ptr()
+        table[i].dst_offset, table[i].numel = off, numel
+    with torch.cuda.device(flat.device):
+        _call("bnn_pack_gradients", table, n, _ptr(flat), _stream())
+    _count((n + 31) // 32)
 
 
 def peer_barrier(flag_ptrs, rank, epoch, device):

@@ -268,10 +268,73 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant_
   if (t == 0) *p.epoch = e;
 }
 
+// ---- bnn_pack_gradients: the gradients autograd left in separate tensors -> one flat (peer-visible) buffer, one launch.
+// Replaces "gradients are views of the flat buffer" (a fill of the buffer plus one accumulation kernel per parameter
+// in every backward pass) by a single gather after the backward pass.
+constexpr int kPackMax = 32;
+struct PackItem { const float* src; int64_t dst; int64_t numel; int64_t chunk_begin; };
+struct PackTable {
+  PackItem t[kPackMax];
+  int n;
+  int pad;
+  int64_t total_chunks;
+  float* dst_base;
+};
+__global__ void __launch_bounds__(kThreads) pack_kernel(const __grid_constant__ PackTable tab) {
+  __shared__ int64_t s_begin[kPackMax];
+  if (threadIdx.x < tab.n) s_begin[threadIdx.x] = tab.t[threadIdx.x].chunk_begin;
+  __syncthreads();
+  int t = 0;
+  for (int64_t chunk = blockIdx.x; chunk < tab.total_chunks; chunk += gridDim.x) {
+    while (t + 1 < tab.n && chunk >= s_begin[t + 1]) ++t;
+    const PackItem& it = tab.t[t];
+    const int64_t i0 = (chunk - it.chunk_begin) * kChunk + threadIdx.x * kPerThread;
+    if (i0 >= it.numel) continue;
+    float* dst = tab.dst_base + it.dst + i0;
+    const bool vec = it.src != nullptr ? ((reinterpret_cast<uintptr_t>(it.src + i0) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0
+                                       : (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+    if (vec && i0 + kPerThread <= it.numel) {
+      *reinterpret_cast<float4*>(dst) = it.src != nullptr ? ldg_stream4(it.src + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int e = 0; e < kPerThread && i0 + e < it.numel; ++e) dst[e] = it.src != nullptr ? it.src[i0 + e] : 0.f;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace bnn
 
 using namespace bnn;
+
+extern "C" int bnn_pack_gradients(const bnn_pack_item* items, int32_t n_items, float* dst, void* stream) {
+  BNN_REQUIRE(n_items >= 0, BNN_ERR_BAD_ARGUMENT, "bnn_pack_gradients: n_items < 0");
+  if (n_items == 0) return BNN_OK;
+  BNN_REQUIRE(items != nullptr && dst != nullptr, BNN_ERR_BAD_ARGUMENT, "bnn_pack_gradients: NULL pointer");
+  for (int i = 0; i < n_items; ++i)
+    BNN_REQUIRE(items[i].numel >= 0 && items[i].dst_offset >= 0, BNN_ERR_BAD_ARGUMENT,
+                "bnn_pack_gradients: item %d has a negative size or offset", i);
+  int rc = check_device();
+  if (rc != BNN_OK) return rc;
+  const int max_grid = sm_count() * 4;
+  for (int first = 0; first < n_items; first += kPackMax) {
+    const int n = n_items - first < kPackMax ? n_items - first : kPackMax;
+    PackTable tab;
+    tab.n = 0; tab.pad = 0; tab.dst_base = dst;
+    int64_t chunks = 0;
+    for (int i = 0; i < n; ++i) {
+      const bnn_pack_item& it = items[first + i];
+      if (it.numel == 0) continue;
+      tab.t[tab.n++] = PackItem{it.src, it.dst_offset, it.numel, chunks};
+      chunks += (it.numel + kChunk - 1) / kChunk;
+    }
+    if (tab.n == 0) continue;
+    tab.total_chunks = chunks;
+    const int grid = static_cast<int>(chunks < max_grid ? chunks : max_grid);
+    pack_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(tab);
+    BNN_CUDA_OK(cudaGetLastError());
+  }
+  return BNN_OK;
+}
 
 extern "C" int bnn_adam_kl_step(const bnn_adam_tensor* tensors, int32_t n_tensors, float lr, float beta1, float beta2,
                                 float eps, const float* step_dev, int64_t step_host, void* stream) {

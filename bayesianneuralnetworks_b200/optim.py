@@ -69,11 +69,15 @@ class ELBOAdam(torch.optim.Optimizer):
         self._step_dev = {}               # device -> 0-dim float32 step count (device-resident: graph replays advance it)
         self._torch_adam = None           # for parameters the kernel does not take (non-CUDA / non-float32)
         self._peers = None
+        self._views = None
 
     # ---------------------------------------------------------------------------------------------------------------
-    def attach_peers(self, peers):
-        """`peers`: a parallel.PeerGradients whose flat buffer holds every gradient of this optimizer (see module doc)."""
+    def attach_peers(self, peers, views=None):
+        """`peers`: a parallel.PeerGradients whose flat buffer holds every gradient of this optimizer (see module doc).
+        `views` ({id(param): view of peers.flat}): where each parameter's gradient sits in the flat buffer when the
+        gradients are gathered into it after the backward pass (training.ElboTrainer) instead of being views of it."""
         self._peers = peers
+        self._views = views
 
     def _moments(self, p):
         st = self.state[p]
@@ -86,6 +90,8 @@ class ELBOAdam(torch.optim.Optimizer):
         return p.is_cuda and p.dtype == torch.float32 and _C._dense(p)
 
     def _grad(self, p):
+        if self._peers is not None and self._views is not None:
+            return self._views[id(p)]
         g = p.grad
         if g is None:
             return None
@@ -117,7 +123,7 @@ class ELBOAdam(torch.optim.Optimizer):
                          e["loc"], e["scale"], e["coeff"]))
             else:
                 for p in group["params"]:
-                    if not p.requires_grad or p.grad is None:
+                    if not p.requires_grad or (p.grad is None and not (self._peers is not None and self._views is not None)):
                         continue
                     if self._kernel_ok(p):
                         m, v = self._moments(p)

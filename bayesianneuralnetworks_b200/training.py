@@ -78,9 +78,14 @@ class ElboTrainer:
                     self.exchange_note = f"peer memory unavailable ({type(exc).__name__}: {exc}); "
                     mode = "flat"
             if mode == "peer":
-                self.flat = self.peers.flat
-                self._bind_flat()
-                self.opt.attach_peers(self.peers)
+                # gradients stay where autograd puts them (set_to_none each step, no accumulation kernels); ONE gather
+                # launch copies them into the peer-visible flat buffer after the backward pass
+                self._peer_views, off = {}, 0
+                for p in self.params:
+                    self._peer_views[id(p)] = torch.as_strided(self.peers.flat, p.size(), p.stride(),
+                                                               self.peers.flat.storage_offset() + off)
+                    off += p.numel()
+                self.opt.attach_peers(self.peers, self._peer_views)
                 self.exchange_note = ("gradients averaged inside the optimizer kernel over NVLink peer memory "
                                       "(bnn_adam_kl_step_peers + bnn_peer_barrier); no NCCL call; one CUDA graph")
             elif mode == "bucketed":
@@ -141,13 +146,27 @@ class ElboTrainer:
         loss.backward()
         return loss
 
+    def _pack(self):
+        """'peer' exchange: every gradient -> its slot of the peer-visible flat buffer, one launch."""
+        items, off = [], 0
+        for p in self.params:
+            g = p.grad
+            if g is not None and g.stride() != p.stride():      # not in the parameter's memory order: through the view
+                self._peer_views[id(p)].copy_(g)
+            else:
+                items.append((g, off, p.numel()))
+            off += p.numel()
+        _C.pack_gradients(items, self.peers.flat)
+
     def _exchange(self):
         import torch.distributed as dist
-        if self.exchange == "flat":
+        if self.exchange == "peer":
+            self._pack()
+        elif self.exchange == "flat":
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
         elif self.exchange == "bucketed":
             self.buckets.finish()
-        # 'peer': inside opt.step()
+        # 'peer': the averaging itself happens inside opt.step()
 
     def _body(self, x, y):
         loss = self._forward_backward(x, y)
@@ -179,6 +198,8 @@ class ElboTrainer:
         with torch.cuda.graph(self.graph):
             self.static_loss = self._forward_backward(self.sx, self.sy)
             if not two_graphs:
+                if self.world > 1:
+                    self._exchange()
                 self.opt.step()
         if two_graphs:
             self.graph_opt = torch.cuda.CUDAGraph()

@@ -278,6 +278,15 @@ typedef struct bnn_peer_grads {
 int bnn_adam_kl_step_peers(const bnn_adam_tensor* tensors /* HOST array */, int32_t n_tensors, float lr, float beta1,
                            float beta2, float eps, const float* step_dev, int64_t step_host,
                            const bnn_peer_grads* peers, void* stream);
+/* Gathers separately stored gradients into the flat (peer-visible) buffer in one launch: dst[dst_offset .. + numel) =
+ * src[0 .. numel) (src NULL: zeros).  The alternative — gradients as views of the flat buffer — costs a fill plus one
+ * accumulation kernel per parameter in every backward pass. */
+typedef struct bnn_pack_item {
+  const float* src;
+  int64_t dst_offset;      /* in floats */
+  int64_t numel;
+} bnn_pack_item;
+int bnn_pack_gradients(const bnn_pack_item* items /* HOST array */, int32_t n_items, float* dst, void* stream);
 /* Flag barrier between the ranks (one launch per rank, same point of every rank's stream; a rank that never arrives
  * traps the waiting kernels after 10 s instead of hanging).  flags[r] (HOST array of `world` pointers): rank r's flag
  * block — BNN_MAX_PEERS uint32 words in peer-visible memory, zero before first use — as mapped into this process.

@@ -29,6 +29,17 @@ def _worker(rank, world, port, results):
         dist.all_gather_object(got, (b, e))
         assert sorted(got) == [(0, 4), (4, 8)]
         assert parallel.grid_coordinates(rank, world, 2) == (0, rank)
+        # --- the data x sample grid bench.py / training.ElboTrainer use by default: 2 = 1 x 2, 4 = 2 x 2, 8 = 2 x 4;
+        #     every rank of a data group sees the same batch slice, the sample blocks of a data group tile [0, S)
+        assert [parallel.default_grid(w) for w in (1, 2, 4, 8)] == [(1, 1), (1, 2), (2, 2), (2, 4)]
+        for w in (2, 4, 8):
+            dg, sg = parallel.default_grid(w)
+            cells = [parallel.grid_coordinates(r, w, sg) for r in range(w)]
+            assert sorted(cells) == [(d, s) for d in range(dg) for s in range(sg)]
+            for d in range(dg):
+                blocks = sorted(parallel.sample_range(16 * sg, s, sg) for dd, s in cells if dd == d)
+                assert blocks[0][0] == 0 and blocks[-1][1] == 16 * sg
+                assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
         # --- tensor-sharded KL with one small all-reduce == the oracle's mean-of-means
         g = torch.Generator().manual_seed(0)
         tensors = [(torch.rand(n, generator=g) - 0.5, torch.randn(n, generator=g) * 0.15 - 2.0, 0.0, 0.1)

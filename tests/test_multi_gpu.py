@@ -1,0 +1,85 @@
+"""Two-GPU tests (skipped on a single-GPU box): the gradient exchange folded into the optimizer kernel over NVLink peer
+memory (bnn_adam_kl_step_peers + bnn_peer_barrier, training.ElboTrainer(exchange='peer')) against the NCCL all-reduce of
+the flat gradient buffer (exchange='flat') — same parameters after three steps, bit-identical across ranks — and the
+data x sample grid against a single process that evaluates all samples of both batch slices."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, results):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    device = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    try:
+        sys.path.insert(0, ROOT)
+        import bench
+        import bayesianneuralnetworks_b200 as bnn
+        from bayesianneuralnetworks_b200.training import ElboTrainer
+        bnn.set_precision("fp32")
+        S, B = 4, 32
+        finals = {}
+        for mode in ("peer", "flat", "bucketed"):
+            torch.manual_seed(0)
+            model = bench.build_model("c2", S).to(device)            # S = global samples; grid 1 data x 2 sample groups
+            trainer = ElboTrainer(model, 10, lr=1e-2, graph=(mode != "bucketed"), exchange=mode, sample_groups=2)
+            assert trainer.exchange == mode and (trainer.data_index, trainer.sample_index) == (0, rank)
+            gen = torch.Generator().manual_seed(7)
+            x, y = bench.synthetic_batch("c2", B, gen)
+            x, y = x.to(device), y.to(device)
+            # injected eps (the same in every mode; each rank draws for ITS two samples of the four)
+            ge = torch.Generator().manual_seed(100 + rank)
+            eps = {w: torch.randn((S // world,) + tuple(w.shape), generator=ge).to(device)
+                   for w in model.modules() if isinstance(w, bnn.nn.WeightNormal)}
+            with bnn.injected_eps(eps):
+                if trainer.use_graph:
+                    trainer.capture(x, y)                             # three eager steps
+                else:
+                    for _ in range(3):
+                        trainer.step(x, y)
+                for _ in range(2):
+                    loss = trainer.step(x, y)
+            torch.cuda.synchronize()
+            finals[mode] = torch.cat([p.detach().flatten() for p in model.parameters()]).clone()
+            assert torch.isfinite(loss)
+            trainer.release()
+            del trainer, model
+        # every rank holds the same parameters (the peer kernel sums the ranks in a fixed order: bit-identical)
+        gathered = [torch.empty_like(finals["peer"]) for _ in range(world)]
+        dist.all_gather(gathered, finals["peer"])
+        assert torch.equal(gathered[0], gathered[1]), "ranks diverged under the peer exchange"
+        # and they are the parameters the NCCL exchanges produce (different summation order: rounding only)
+        for other in ("flat", "bucketed"):
+            diff = (finals["peer"] - finals[other]).abs()
+            assert float(diff.flatten().quantile(0.999)) < 2e-5 and float(diff.mean()) < 1e-6, (
+                other, float(diff.max()), float(diff.mean()))
+        results[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_memory_gradient_exchange_matches_nccl_on_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    with mp.Manager() as m:
+        results = m.dict()
+        mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
+        assert dict(results) == {0: "ok", 1: "ok"}
