@@ -47,7 +47,11 @@ constexpr int kChunk = kThreads * 4 * kVecPerThread;           // 4096 elements
 constexpr int kMaxTensors = 24;
 constexpr int kBins = 2048;
 constexpr int kHistStride = kBins + 64;                        // a histogram slot: 2049 used entries, 256-byte multiple
-constexpr int kSample = 32768;                                 // sampled keys per tensor (128 KiB of smem)
+constexpr int kSample = 32768;                                 // sampled keys per tensor: single elements at a fixed stride
+constexpr int kSampleBig = 262144;                             // tensors of >= 4 * kSampleBig elements: 2048 runs of 128
+constexpr int kSampleRun = 128;                                //   consecutive elements (whole sectors; the bracket is
+                                                               //   2.8x narrower: fewer elements to defer / list)
+__host__ __device__ inline int sample_size(int64_t numel) { return numel >= 4 * static_cast<int64_t>(kSampleBig) ? kSampleBig : kSample; }
 constexpr int kSmallTensor = 65536;                            // at or below: every element is deferred to the exact select
 constexpr int kResolveThreads = 1024;
 constexpr int kUnit = 512;                                     // elements one warp handles per pass (8 units per chunk)
@@ -234,17 +238,26 @@ __device__ __forceinline__ float key2_fast(float mu, float rho) {
 
 // 1a. the sample: kSample strided elements per tensor, spread over the whole machine (one SM cannot keep enough of
 // these scattered sector reads in flight), ordered fast keys into the tensor's (still unused) keys region
-static_assert((kSample & (kSample - 1)) == 0, "kSample must be a power of two");
+static_assert((kSample & (kSample - 1)) == 0 && (kSampleBig & (kSampleBig - 1)) == 0, "sample sizes must be powers of two");
 __global__ void __launch_bounds__(kResolveThreads) prune_sample_keys_kernel(const __grid_constant__ PruneTable tab) {
   const PruneDesc& d = tab.t[blockIdx.y];
   if (d.k <= 0 || d.k >= d.numel || d.force_general || d.numel >= (int64_t(1) << 32) || d.numel <= kSmallTensor) return;
+  const int m = sample_size(d.numel);
   constexpr int kPer = 4;
-  float mv[kPer], rv[kPer];
   const int j0 = blockIdx.x * (kPer * kResolveThreads) + threadIdx.x;
+  if (j0 >= m) return;                                   // the grid is sized for the large sample
+  float mv[kPer], rv[kPer];
 #pragma unroll
   for (int u = 0; u < kPer; ++u) {
     const uint64_t j = static_cast<uint64_t>(j0 + u * kResolveThreads);
-    const int64_t i = static_cast<int64_t>((j * static_cast<uint64_t>(d.numel)) / kSample);      // a shift; numel < 2^32
+    int64_t i;
+    if (m == kSample) {
+      i = static_cast<int64_t>((j * static_cast<uint64_t>(d.numel)) / kSample);      // a shift; numel < 2^32
+    } else {                                             // run j / 128 starts at run * numel / 2048 (4-element aligned)
+      const uint64_t run = j / kSampleRun, within = j % kSampleRun;
+      i = static_cast<int64_t>(((run * static_cast<uint64_t>(d.numel)) / (kSampleBig / kSampleRun)) & ~uint64_t(3)) +
+          static_cast<int64_t>(within);
+    }
     mv[u] = __ldg(d.mu + i);
     rv[u] = __ldg(d.rho + i);
   }
@@ -254,7 +267,6 @@ __global__ void __launch_bounds__(kResolveThreads) prune_sample_keys_kernel(cons
 
 // 1b. one block per tensor: bracket of the k-th largest key from the sample -> the grid
 __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __grid_constant__ PruneTable tab) {
-  extern __shared__ uint32_t s_keys[];          // kSample keys
   __shared__ uint32_t s_hist[kBins], s_hist2[kBins];
   __shared__ uint32_t s_bcast[2], s_sel[6];
   const PruneDesc& d = tab.t[blockIdx.x];
@@ -271,10 +283,8 @@ __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __g
     st.expect_deferred = static_cast<uint32_t>(d.numel);
   }
   if (!trivial && !st.general && d.numel > kSmallTensor) {
-    const int m = kSample;
-    for (int j = threadIdx.x * 4; j < m; j += 4 * kResolveThreads)       // keys written by prune_sample_keys_kernel
-      *reinterpret_cast<uint4*>(s_keys + j) = *reinterpret_cast<const uint4*>(d.keys + j);
-    __syncthreads();
+    const int m = sample_size(d.numel);
+    const uint32_t* __restrict__ s_keys = d.keys;          // written by prune_sample_keys_kernel; 128 KiB / 1 MiB: L2
     const double p = static_cast<double>(d.k) / static_cast<double>(d.numel);
     const int r = static_cast<int>(p * m);                              // descending rank of the k-th key
     const int margin = static_cast<int>(6.0 * sqrt(m * p * (1.0 - p))) + 8;
@@ -1346,10 +1356,7 @@ int prune_run(const PruneIo* io, int32_t n_tensors, bool into, void* workspace, 
   char* ws = small + static_cast<size_t>(n_tensors) * kSmallBytes;
   BNN_CUDA_OK(cudaMemsetAsync(workspace, 0, static_cast<size_t>(ws - static_cast<char*>(workspace)), st));
   const int max_grid = sm_count() * 8;
-  static SmemOptIn sample_opt_in;
-  const size_t sample_smem = static_cast<size_t>(kSample) * sizeof(uint32_t);
-  int rc = allow_dynamic_smem(prune_sample_kernel, sample_smem, &sample_opt_in);
-  if (rc != BNN_OK) return rc;
+  int rc = BNN_OK;
 
   for (int first = 0; first < n_tensors; first += kMaxTensors) {
     const int n = (n_tensors - first < kMaxTensors) ? n_tensors - first : kMaxTensors;
@@ -1385,8 +1392,8 @@ int prune_run(const PruneIo* io, int32_t n_tensors, bool into, void* workspace, 
     tab.total_chunks = chunks;
     const int grid = static_cast<int>(chunks < max_grid ? chunks : max_grid);
     // sampled path
-    prune_sample_keys_kernel<<<dim3(kSample / (4 * kResolveThreads), tab.n), kResolveThreads, 0, st>>>(tab);
-    prune_sample_kernel<<<tab.n, kResolveThreads, sample_smem, st>>>(tab);
+    prune_sample_keys_kernel<<<dim3(kSampleBig / (4 * kResolveThreads), tab.n), kResolveThreads, 0, st>>>(tab);
+    prune_sample_kernel<<<tab.n, kResolveThreads, 0, st>>>(tab);
     if (!into) {
       prune_bin_kernel<<<grid, kThreads, 0, st>>>(tab);
       prune_bracket_kernel<<<tab.n, kThreads, 0, st>>>(tab);
