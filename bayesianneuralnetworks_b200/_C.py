@@ -521,30 +521,44 @@ def prune(entries, flags=0):
     base = (ws.data_ptr() + 255) & ~255
     with torch.cuda.device(device):
         _call("bnn_prune", table, n, ctypes.c_void_p(base), nbytes, _stream())
-    _count(15 * ((n + 23) // 24))
+    _count(14 * ((n + 23) // 24))
 
 
-def prune_into(entries, flags=0):
+def prune_into(entries, flags=0, out=None):
     """Out-of-place pruning in one sweep (bnn_prune_into).  entries: list of (mu, rho, k, mask_out|None); returns the list
-    of (mu_out, rho_out) tensors — the inputs are not modified."""
+    of (mu_out, rho_out) tensors — the inputs are not modified.  `out`: optional list of caller-owned (mu_out, rho_out)
+    pairs to write into (same shapes, not aliasing the inputs); by default every output is a fresh tensor."""
     n = len(entries)
     if n == 0:
         return []
+    if out is not None and len(out) != n:
+        raise ValueError("prune_into: `out` needs one (mu_out, rho_out) pair per entry")
     table = (bnn_prune_into_tensor * n)()
     device = entries[0][0].device
     outs = []
+    f32 = torch.float32
     for i, (mu, rho, k, mask) in enumerate(entries):
-        require_cuda(mu, rho, mask)
-        _f32c(mu, "mu"), _f32c(rho, "rho")
-        if mask is not None and (mask.dtype not in (torch.uint8, torch.bool) or not mask.is_contiguous()):
-            raise TypeError("mask_out must be a contiguous uint8/bool tensor")
-        mu_out, rho_out = torch.empty_like(mu), torch.empty_like(rho)
+        if out is None:
+            mu_out, rho_out = torch.empty_like(mu), torch.empty_like(rho)
+        else:
+            mu_out, rho_out = out[i]
+            if mu_out.shape != mu.shape or rho_out.shape != rho.shape:
+                raise ValueError("prune_into: output shapes must match the inputs")
+        # one pass of checks per entry (this loop is on the timed path of a 64-tensor sweep)
+        if not (mu.is_cuda and rho.is_cuda and mu_out.is_cuda and rho_out.is_cuda):
+            require_cuda(mu, rho, mu_out, rho_out)
+        if not (mu.dtype is f32 and rho.dtype is f32 and mu_out.dtype is f32 and rho_out.dtype is f32 and mu.is_contiguous()
+                and rho.is_contiguous() and mu_out.is_contiguous() and rho_out.is_contiguous()):
+            _f32c(mu, "mu"), _f32c(rho, "rho"), _f32c(mu_out, "mu_out"), _f32c(rho_out, "rho_out")
         outs.append((mu_out, rho_out))
         t = table[i]
         t.mu, t.rho, t.mu_out, t.rho_out = mu.data_ptr(), rho.data_ptr(), mu_out.data_ptr(), rho_out.data_ptr()
-        t.mask_out = None if mask is None else mask.data_ptr()
-        t.numel, t.k = mu.numel(), int(k)
-        t.flags, t.reserved = flags, 0
+        if mask is not None:
+            require_cuda(mask)
+            if mask.dtype not in (torch.uint8, torch.bool) or not mask.is_contiguous():
+                raise TypeError("mask_out must be a contiguous uint8/bool tensor")
+            t.mask_out = mask.data_ptr()
+        t.numel, t.k, t.flags = mu.numel(), int(k), flags
     nbytes = lib().bnn_prune_into_workspace_size(table, n)
     ws = _workspace(_prune_ws, device, nbytes + 256)
     base = (ws.data_ptr() + 255) & ~255

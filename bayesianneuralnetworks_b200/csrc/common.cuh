@@ -174,4 +174,9 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   return v;
 }
 
+// streaming 128-bit store (evict-first: the line is not needed again by this kernel)
+__device__ __forceinline__ void st_stream4(float* p, const float4& v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 }  // namespace bnn

@@ -32,9 +32,14 @@
 //    scattered prune in the output, overlapping it -> the short exact list), finish as before.  If the sample's grid turns
 //    out wrong (or anything else surprises) the INPUT is intact: the tensor is copied and goes through the general path
 //    on the output.  The Python layer swaps the parameters' storage for the output (prune/prune.py).
+#include <cooperative_groups.h>
+
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace bnn {
 namespace {
@@ -54,6 +59,9 @@ constexpr int kSampleRun = 128;                                //   consecutive 
 __host__ __device__ inline int sample_size(int64_t numel) { return numel >= 4 * static_cast<int64_t>(kSampleBig) ? kSampleBig : kSample; }
 constexpr int kSmallTensor = 65536;                            // at or below: every element is deferred to the exact select
 constexpr int kResolveThreads = 1024;
+constexpr int kFinishThreads = 512;                             // finish kernel: leaves room on an SM that is busy sweeping
+constexpr int kSweepChunks = 8;                                // chunks per block of the out-of-place sweep
+constexpr float kMidGrid = 1024.0f;                            // bnn_prune_into: provisional decision inside the grid
 constexpr int kUnit = 512;                                     // elements one warp handles per pass (8 units per chunk)
 
 // ordered key: unsigned order == float order (larger float -> larger uint)
@@ -182,6 +190,53 @@ __device__ __forceinline__ void warp_find_bin(const uint32_t* hist, bool descend
   *before_out = before_g + excl2 + (first ? 0 : c0s);
 }
 
+// The same search over a histogram that is spread over the CTAs of a cluster (the sample kernel): every CTA holds a
+// partial histogram `hist` (kBins) and its 32 group sums `grp` (64 bins each); warp 0 of ONE CTA walks them through
+// distributed shared memory — 8 remote loads per lane for the group level, 16 for the two bins of the group level —
+// instead of pulling all kBins x kCtas counters.  Bins are walked downwards (descending rank).
+template <int kCtas>
+__device__ __forceinline__ void cluster_find_bin(cg::cluster_group& cluster, uint32_t* hist, uint32_t* grp, uint64_t rem,
+                                                 uint32_t* bin_out, uint64_t* before_out) {
+  const int lane = threadIdx.x & 31;
+  const int pos = 31 - lane;
+  uint64_t gs = 0;
+#pragma unroll
+  for (int q = 0; q < kCtas; ++q) gs += cluster.map_shared_rank(grp, q)[pos];
+  uint64_t incl = gs;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const unsigned int hit = __ballot_sync(0xffffffffu, incl > rem);
+  const int g = hit ? __ffs(hit) - 1 : 31;
+  const uint64_t before_g = __shfl_sync(0xffffffffu, incl - gs, g);
+  const int gpos = 31 - g;
+  const int b0 = gpos * 64 + 63 - 2 * lane, b1 = b0 - 1;
+  uint64_t c0 = 0, c1 = 0;
+#pragma unroll
+  for (int q = 0; q < kCtas; ++q) {
+    const uint32_t* h = cluster.map_shared_rank(hist, q);
+    c0 += h[b0];
+    c1 += h[b1];
+  }
+  uint64_t incl2 = c0 + c1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t v = __shfl_up_sync(0xffffffffu, incl2, o);
+    if (lane >= o) incl2 += v;
+  }
+  const uint64_t rem2 = rem - before_g;
+  const unsigned int hit2 = __ballot_sync(0xffffffffu, incl2 > rem2);
+  const int l2 = hit2 ? __ffs(hit2) - 1 : 31;
+  const uint64_t excl2 = __shfl_sync(0xffffffffu, incl2 - (c0 + c1), l2);
+  const uint64_t c0s = __shfl_sync(0xffffffffu, c0, l2);
+  const int b0s = __shfl_sync(0xffffffffu, b0, l2), b1s = __shfl_sync(0xffffffffu, b1, l2);
+  const bool first = !hit2 ? false : (excl2 + c0s > rem2);
+  *bin_out = static_cast<uint32_t>(first ? b0s : b1s);
+  *before_out = before_g + excl2 + (first ? 0 : c0s);
+}
+
 // key2 = (key + log sqrt(2 pi)) * log2(e): the domain of the certified intervals and of the grid
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kDelta2 = 4e-5f * 1.4426950408889634f;      // absolute part of the key margin, in key2 units
@@ -236,45 +291,35 @@ __device__ __forceinline__ float key2_fast(float mu, float rho) {
   return lo;
 }
 
-// 1a. the sample: kSample strided elements per tensor, spread over the whole machine (one SM cannot keep enough of
-// these scattered sector reads in flight), ordered fast keys into the tensor's (still unused) keys region
+// 1. the sample -> the grid.  One CLUSTER of kSampleCtas CTAs per tensor: every thread gathers its share of the strided
+// sample (kSample single elements, or kSampleBig elements in 2048 runs of 128 for large tensors), turns it into ordered
+// fast keys and KEEPS THEM IN REGISTERS for the three passes (min / max, an 11-bit histogram of the key range, an 11-bit
+// sub-histogram of the two bins holding the bracketing order statistics).  Each pass bins into the CTA's own shared
+// memory; CTA 0 sums the eight histograms through distributed shared memory, locates the bins and broadcasts them.  The
+// earlier form — a machine-wide gather kernel that wrote the keys to the workspace plus ONE block per tensor that re-read
+// them three times — cost 19 + 154 us per group of 16 tensors; this one is bounded by the gather latency.
 static_assert((kSample & (kSample - 1)) == 0 && (kSampleBig & (kSampleBig - 1)) == 0, "sample sizes must be powers of two");
-__global__ void __launch_bounds__(kResolveThreads) prune_sample_keys_kernel(const __grid_constant__ PruneTable tab) {
-  const PruneDesc& d = tab.t[blockIdx.y];
-  if (d.k <= 0 || d.k >= d.numel || d.force_general || d.numel >= (int64_t(1) << 32) || d.numel <= kSmallTensor) return;
-  const int m = sample_size(d.numel);
-  constexpr int kPer = 4;
-  const int j0 = blockIdx.x * (kPer * kResolveThreads) + threadIdx.x;
-  if (j0 >= m) return;                                   // the grid is sized for the large sample
-  float mv[kPer], rv[kPer];
-#pragma unroll
-  for (int u = 0; u < kPer; ++u) {
-    const uint64_t j = static_cast<uint64_t>(j0 + u * kResolveThreads);
-    int64_t i;
-    if (m == kSample) {
-      i = static_cast<int64_t>((j * static_cast<uint64_t>(d.numel)) / kSample);      // a shift; numel < 2^32
-    } else {                                             // run j / 128 starts at run * numel / 2048 (4-element aligned)
-      const uint64_t run = j / kSampleRun, within = j % kSampleRun;
-      i = static_cast<int64_t>(((run * static_cast<uint64_t>(d.numel)) / (kSampleBig / kSampleRun)) & ~uint64_t(3)) +
-          static_cast<int64_t>(within);
-    }
-    mv[u] = __ldg(d.mu + i);
-    rv[u] = __ldg(d.rho + i);
-  }
-#pragma unroll
-  for (int u = 0; u < kPer; ++u) d.keys[j0 + u * kResolveThreads] = order_key(key2_fast(mv[u], rv[u]));
-}
+constexpr int kSampleCtas = 8;
+constexpr int kSamplePerThread = kSampleBig / (kSampleCtas * kResolveThreads);      // 32 keys per thread (4 for kSample)
+static_assert(kSamplePerThread * kSampleCtas * kResolveThreads == kSampleBig && kSample % (kSampleCtas * kResolveThreads) == 0,
+              "the sample must split evenly over the cluster");
 
-// 1b. one block per tensor: bracket of the k-th largest key from the sample -> the grid
-__global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __grid_constant__ PruneTable tab) {
+__global__ void __cluster_dims__(kSampleCtas, 1, 1) __launch_bounds__(kResolveThreads)
+prune_sample_kernel(const __grid_constant__ PruneTable tab) {
   __shared__ uint32_t s_hist[kBins], s_hist2[kBins];
-  __shared__ uint32_t s_bcast[2], s_sel[6];
-  const PruneDesc& d = tab.t[blockIdx.x];
+  __shared__ uint32_t s_grp[32], s_grp2[32];      // sums over groups of 64 bins of s_hist / s_hist2
+  __shared__ uint32_t s_red[2 * (kResolveThreads / 32)];
+  __shared__ uint32_t s_mm[2];          // this CTA's min / max (read by the whole cluster)
+  __shared__ uint32_t s_sel[6];         // CTA 0: bins / counts of the two order statistics (read by the whole cluster)
+  __shared__ uint32_t s_loc[6];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned int rank = cluster.block_rank();
+  const PruneDesc& d = tab.t[blockIdx.x / kSampleCtas];
   PruneState st;
   st.prefix = 0; st.need_ranks = 0; st.k_rem = d.k; st.eq_total = 0;
   st.scale = 0.f; st.offs_minus = 0.f; st.offs_plus = 0.f;
   st.count_above = 0ull; st.a_thr = INFINITY; st.b_thr = -INFINITY;
-  st.defer_all = 0; st.n_take = 0; st.expect_deferred = 0; st.n_deferred = 0;
+  st.defer_all = 0; st.n_take = 0; st.expect_deferred = 0; st.n_deferred = 0; st.n_deferred2 = 0;
   const bool trivial = d.k <= 0 || d.k >= d.numel;
   st.general = (d.force_general || d.numel >= (int64_t(1) << 32)) ? 1u : 0u;
   if (!trivial && !st.general && d.numel <= kSmallTensor) {
@@ -282,83 +327,141 @@ __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __g
     st.n_take = static_cast<uint32_t>(d.k);
     st.expect_deferred = static_cast<uint32_t>(d.numel);
   }
-  if (!trivial && !st.general && d.numel > kSmallTensor) {
-    const int m = sample_size(d.numel);
-    const uint32_t* __restrict__ s_keys = d.keys;          // written by prune_sample_keys_kernel; 128 KiB / 1 MiB: L2
-    const double p = static_cast<double>(d.k) / static_cast<double>(d.numel);
-    const int r = static_cast<int>(p * m);                              // descending rank of the k-th key
-    const int margin = static_cast<int>(6.0 * sqrt(m * p * (1.0 - p))) + 8;
-    const int r_hi = r - margin, r_lo = r + margin;
-    // block min / max of the sampled keys
-    uint32_t mn = 0xffffffffu, mx = 0u;
-    for (int j = threadIdx.x; j < m; j += blockDim.x) { mn = min(mn, s_keys[j]); mx = max(mx, s_keys[j]); }
-    for (int o = 16; o > 0; o >>= 1) {
-      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (trivial || st.general || d.numel <= kSmallTensor) {      // uniform over the cluster: nobody reaches a cluster.sync
+    if (rank == 0 && threadIdx.x == 0) {
+      *d.state = st;
+      if (st.general) atomicOr(tab.any_general, 1u);
     }
-    if ((threadIdx.x & 31) == 0) { s_hist[threadIdx.x >> 5] = mn; s_hist[64 + (threadIdx.x >> 5)] = mx; }
-    __syncthreads();
+    return;
+  }
+  const int m = sample_size(d.numel);
+  const int per = m / (kSampleCtas * kResolveThreads);        // 4 or 32
+  const int cta_base = static_cast<int>(rank) * (m / kSampleCtas);
+  uint32_t keys[kSamplePerThread];
+#pragma unroll
+  for (int u0 = 0; u0 < kSamplePerThread; u0 += 8) {
+    float mv[8], rv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      mv[u] = 0.f; rv[u] = 0.f;
+      if (u0 + u < per) {
+        const uint64_t j = static_cast<uint64_t>(cta_base + (u0 + u) * kResolveThreads + static_cast<int>(threadIdx.x));
+        int64_t i;
+        if (m == kSample) {
+          i = static_cast<int64_t>((j * static_cast<uint64_t>(d.numel)) / kSample);      // a shift; numel < 2^32
+        } else {                                             // run j / 128 starts at run * numel / 2048 (4-element aligned)
+          const uint64_t run = j / kSampleRun, within = j % kSampleRun;
+          i = static_cast<int64_t>(((run * static_cast<uint64_t>(d.numel)) / (kSampleBig / kSampleRun)) & ~uint64_t(3)) +
+              static_cast<int64_t>(within);
+        }
+        mv[u] = __ldg(d.mu + i);
+        rv[u] = __ldg(d.rho + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) keys[u0 + u] = order_key(key2_fast(mv[u], rv[u]));
+  }
+  // min / max over the cluster
+  uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+  for (int u = 0; u < kSamplePerThread; ++u)
+    if (u < per) { mn = min(mn, keys[u]); mx = max(mx, keys[u]); }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = mn; s_red[kResolveThreads / 32 + (threadIdx.x >> 5)] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t a = 0xffffffffu, b = 0u;
+    for (int w = 0; w < kResolveThreads / 32; ++w) { a = min(a, s_red[w]); b = max(b, s_red[kResolveThreads / 32 + w]); }
+    s_mm[0] = a; s_mm[1] = b;
+  }
+  cluster.sync();
+  if (threadIdx.x == 0) {
+    uint32_t a = 0xffffffffu, b = 0u;
+    for (int r = 0; r < kSampleCtas; ++r) {
+      const uint32_t* remote = cluster.map_shared_rank(s_mm, r);
+      a = min(a, remote[0]); b = max(b, remote[1]);
+    }
+    s_loc[0] = a; s_loc[1] = b;
+  }
+  __syncthreads();
+  mn = s_loc[0]; mx = s_loc[1];
+  const double p = static_cast<double>(d.k) / static_cast<double>(d.numel);
+  const int r = static_cast<int>(p * m);                              // descending rank of the k-th key
+  const int margin = static_cast<int>(6.0 * sqrt(m * p * (1.0 - p))) + 8;
+  const int r_hi = r - margin, r_lo = r + margin;
+  // both order statistics in two histogram passes (11 + 11 bits of the key range; below that the bracket ends are
+  // sub-bin edges, which only widens the bracket by < 2^-22 of the range)
+  const uint32_t range_u = mx - mn;
+  const int bits = range_u == 0u ? 0 : 32 - __clz(range_u);
+  const int s0 = max(bits - 11, 0), s1 = max(bits - 22, 0);
+  for (int b = threadIdx.x; b < kBins; b += blockDim.x) { s_hist[b] = 0; s_hist2[b] = 0; }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < kSamplePerThread; ++u)
+    if (u < per) atomicAdd(&s_hist[(keys[u] - mn) >> s0], 1u);
+  __syncthreads();
+  {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;      // 32 warps: warp w sums the 64 bins of group w
+    const uint32_t v = warp_sum(s_hist[64 * w + l] + s_hist[64 * w + 32 + l]);
+    if (l == 0) s_grp[w] = v;
+  }
+  cluster.sync();
+  if (rank == 0 && threadIdx.x < 32) {
+    uint32_t bin_a = 0, bin_b = 0;
+    uint64_t before_a = 0, before_b = 0;
+    if (r_hi >= 0) cluster_find_bin<kSampleCtas>(cluster, s_hist, s_grp, static_cast<uint64_t>(r_hi), &bin_a, &before_a);
+    if (r_lo < m) cluster_find_bin<kSampleCtas>(cluster, s_hist, s_grp, static_cast<uint64_t>(r_lo), &bin_b, &before_b);
     if (threadIdx.x == 0) {
-      uint32_t a = 0xffffffffu, b = 0u;
-      for (int w = 0; w < kResolveThreads / 32; ++w) { a = min(a, s_hist[w]); b = max(b, s_hist[64 + w]); }
-      s_bcast[0] = a; s_bcast[1] = b;
+      s_sel[0] = bin_a; s_sel[1] = static_cast<uint32_t>(before_a);
+      s_sel[2] = bin_b; s_sel[3] = static_cast<uint32_t>(before_b);
+    }
+  }
+  cluster.sync();              // CTA 0 has read every histogram and published the bins
+  if (threadIdx.x < 4) s_loc[2 + threadIdx.x] = cluster.map_shared_rank(s_sel, 0)[threadIdx.x];
+  __syncthreads();
+  const uint32_t bin_a = s_loc[2], before_a = s_loc[3], bin_b = s_loc[4], before_b = s_loc[5];
+  uint32_t sub_a = 0, sub_b = 0;
+  if (s0 > 0) {                // uniform over the cluster (a function of the common min / max)
+    for (int b = threadIdx.x; b < kBins; b += blockDim.x) { s_hist[b] = 0; s_hist2[b] = 0; }
+    __syncthreads();
+    const uint32_t sub_mask = (1u << (s0 - s1)) - 1u;
+#pragma unroll
+    for (int u = 0; u < kSamplePerThread; ++u) {
+      if (u < per) {
+        const uint32_t v = keys[u] - mn, dgt = v >> s0, sub = (v >> s1) & sub_mask;
+        if (dgt == bin_a) atomicAdd(&s_hist[sub], 1u);
+        if (dgt == bin_b) atomicAdd(&s_hist2[sub], 1u);
+      }
     }
     __syncthreads();
-    mn = s_bcast[0]; mx = s_bcast[1];
-    __syncthreads();
+    {
+      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+      const uint32_t va = warp_sum(s_hist[64 * w + l] + s_hist[64 * w + 32 + l]);
+      const uint32_t vb = warp_sum(s_hist2[64 * w + l] + s_hist2[64 * w + 32 + l]);
+      if (l == 0) { s_grp[w] = va; s_grp2[w] = vb; }
+    }
+    cluster.sync();
+    if (rank == 0 && threadIdx.x < 32) {
+      uint32_t a = 0, b = 0;
+      uint64_t before = 0;
+      if (r_hi >= 0) cluster_find_bin<kSampleCtas>(cluster, s_hist, s_grp, static_cast<uint64_t>(r_hi) - before_a, &a, &before);
+      if (r_lo < m) cluster_find_bin<kSampleCtas>(cluster, s_hist2, s_grp2, static_cast<uint64_t>(r_lo) - before_b, &b, &before);
+      sub_a = a; sub_b = b;          // used by thread 0 below
+    }
+  }
+  if (rank == 0 && threadIdx.x == 0) {
     // bracket ends; a rank outside the sample leaves that side at the sample extreme (the thin tail beyond it simply
     // lands in the outermost bin or outside the grid — both are handled exactly by the bracket step)
     uint32_t hi = mx, lo = mn;
-    {
-      // both order statistics in two shared histogram passes (11 + 11 bits of the key range; below that the bracket
-      // ends are sub-bin edges, which only widens the bracket by < 2^-22 of the range)
-      const uint32_t range = mx - mn;
-      const int bits = range == 0u ? 0 : 32 - __clz(range);
-      const int s0 = max(bits - 11, 0), s1 = max(bits - 22, 0);
-      for (int b = threadIdx.x; b < kBins; b += blockDim.x) { s_hist[b] = 0; s_hist2[b] = 0; }
-      __syncthreads();
-      for (int j = threadIdx.x; j < m; j += blockDim.x) atomicAdd(&s_hist[(s_keys[j] - mn) >> s0], 1u);
-      __syncthreads();
-      if (threadIdx.x < 32) {
-        uint32_t bin_a = 0, bin_b = 0;
-        uint64_t before_a = 0, before_b = 0;
-        if (r_hi >= 0) warp_find_bin(s_hist, true, static_cast<uint64_t>(r_hi), &bin_a, &before_a);
-        if (r_lo < m) warp_find_bin(s_hist, true, static_cast<uint64_t>(r_lo), &bin_b, &before_b);
-        if (threadIdx.x == 0) {
-          s_sel[0] = bin_a; s_sel[1] = static_cast<uint32_t>(before_a);
-          s_sel[2] = bin_b; s_sel[3] = static_cast<uint32_t>(before_b);
-        }
-      }
-      __syncthreads();
-      const uint32_t bin_a = s_sel[0], before_a = s_sel[1], bin_b = s_sel[2], before_b = s_sel[3];
-      uint32_t sub_a = 0, sub_b = 0;
-      if (s0 > 0) {
-        for (int b = threadIdx.x; b < kBins; b += blockDim.x) s_hist[b] = 0;
-        __syncthreads();
-        const uint32_t sub_mask = (1u << (s0 - s1)) - 1u;
-        for (int j = threadIdx.x; j < m; j += blockDim.x) {
-          const uint32_t v = s_keys[j] - mn, dgt = v >> s0, sub = (v >> s1) & sub_mask;
-          if (dgt == bin_a) atomicAdd(&s_hist[sub], 1u);
-          if (dgt == bin_b) atomicAdd(&s_hist2[sub], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-          uint32_t a = 0, b = 0;
-          uint64_t before = 0;
-          if (r_hi >= 0) warp_find_bin(s_hist, true, static_cast<uint64_t>(r_hi) - before_a, &a, &before);
-          if (r_lo < m) warp_find_bin(s_hist2, true, static_cast<uint64_t>(r_lo) - before_b, &b, &before);
-          if (threadIdx.x == 0) { s_sel[4] = a; s_sel[5] = b; }
-        }
-        __syncthreads();
-        sub_a = s_sel[4]; sub_b = s_sel[5];
-      }
-      if (r_hi >= 0) {
-        const uint64_t top = static_cast<uint64_t>(mn) + ((static_cast<uint64_t>(bin_a) << s0) | (static_cast<uint64_t>(sub_a) << s1)) +
-                             ((uint64_t(1) << s1) - 1);
-        hi = top < mx ? static_cast<uint32_t>(top) : mx;
-      }
-      if (r_lo < m) lo = mn + ((bin_b << s0) | (sub_b << s1));
+    if (r_hi >= 0) {
+      const uint64_t top = static_cast<uint64_t>(mn) + ((static_cast<uint64_t>(bin_a) << s0) | (static_cast<uint64_t>(sub_a) << s1)) +
+                           ((uint64_t(1) << s1) - 1);
+      hi = top < mx ? static_cast<uint32_t>(top) : mx;
     }
+    if (r_lo < m) lo = mn + ((bin_b << s0) | (sub_b << s1));
     const float g_lo = unorder_key(lo), g_hi = unorder_key(hi);      // the sampled keys are key2 values already
     const float range = fmaxf(g_hi - g_lo, 2e-4f + 1e-5f * fabsf(g_lo));      // never degenerate
     if (g_lo == g_lo && range < INFINITY) {                                   // no NaN / inf among the bracket keys
@@ -368,11 +471,10 @@ __global__ void __launch_bounds__(kResolveThreads) prune_sample_kernel(const __g
     } else {
       st.general = 1u;
     }
-  }
-  if (threadIdx.x == 0) {
     *d.state = st;
     if (st.general) atomicOr(tab.any_general, 1u);
   }
+  cluster.sync();              // no CTA exits while CTA 0 may still read its shared memory
 }
 
 // self test: the interval on the identity grid (scale 1, origin 0), i.e. in key2 units
@@ -732,6 +834,16 @@ __global__ void __launch_bounds__(kThreads) prune_sweep_into_kernel(const __grid
     int qpos = 0;
     uint32_t listed = 0;                   // bit e: element ordinal e of this lane lies inside the grid
     const bool full = d.vec && ubase + kUnit <= d.numel;
+    if (full && mode == 2) {               // k == numel: write only
+#pragma unroll
+      for (int j = 0; j < kVecPerThread; ++j) {
+        const int64_t i = ubase + (j * 32 + lane) * 4;
+        st_stream4(d.mu_w + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        st_stream4(d.rho_w + i, make_float4(-30.f, -30.f, -30.f, -30.f));
+        if (d.mask != nullptr) *reinterpret_cast<uchar4*>(d.mask + i) = make_uchar4(1, 1, 1, 1);
+      }
+      continue;
+    }
     if (full) {
       float4 m[kVecPerThread], r[kVecPerThread];
 #pragma unroll
@@ -745,7 +857,7 @@ __global__ void __launch_bounds__(kThreads) prune_sweep_into_kernel(const __grid
         const int64_t i = ubase + (j * 32 + lane) * 4;
         const float mm[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
         const float rr[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
-        bool tk[4] = {mode == 2, mode == 2, mode == 2, mode == 2};
+        bool tk[4] = {false, false, false, false};
         if (mode == 3) {
           float ym[4], yp[4];
           if (fmaxf(fmaxf(rr[0], rr[1]), fmaxf(rr[2], rr[3])) <= -1.3862944f) {
@@ -757,20 +869,24 @@ __global__ void __launch_bounds__(kThreads) prune_sweep_into_kernel(const __grid
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            // above = certified above the grid (NaN never is); in-grid = neither above nor certified below (NaN is)
-            tk[q] = ym[q] >= static_cast<float>(kBins);
-            const bool in_grid = !tk[q] && !(yp[q] < 0.0f);
-            q_lane[qpos * kThreads] = make_float2(ym[q], yp[q]);
+            // above = certified above the grid (NaN never is); in-grid = neither above nor certified below (NaN is).
+            // What is written for an in-grid element is the PROVISIONAL decision "upper half of the grid": the resolve
+            // and finish kernels correct it where the proven bracket says otherwise (see kMidGrid)
+            const bool is_above = ym[q] >= static_cast<float>(kBins);
+            tk[q] = ym[q] >= kMidGrid;
+            const bool in_grid = !is_above && !(yp[q] < 0.0f);
+            q_lane[qpos * kThreads] = make_float2(mm[q], rr[q]);
             if (in_grid) { ++qpos; listed |= 1u << (j * 4 + q); }
-            above += tk[q] ? 1u : 0u;
+            above += is_above ? 1u : 0u;
           }
         } else if (mode == 4) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) q_lane[qpos++ * kThreads] = make_float2(mm[q], rr[q]);
           listed |= 0xfu << (j * 4);
         }
-        *reinterpret_cast<float4*>(d.mu_w + i) =
-            make_float4(tk[0] ? 0.f : mm[0], tk[1] ? 0.f : mm[1], tk[2] ? 0.f : mm[2], tk[3] ? 0.f : mm[3]);
-        *reinterpret_cast<float4*>(d.rho_w + i) = make_float4(tk[0] ? -30.f : rr[0], tk[1] ? -30.f : rr[1],
-                                                              tk[2] ? -30.f : rr[2], tk[3] ? -30.f : rr[3]);
+        st_stream4(d.mu_w + i, make_float4(tk[0] ? 0.f : mm[0], tk[1] ? 0.f : mm[1], tk[2] ? 0.f : mm[2], tk[3] ? 0.f : mm[3]));
+        st_stream4(d.rho_w + i, make_float4(tk[0] ? -30.f : rr[0], tk[1] ? -30.f : rr[1],
+                                            tk[2] ? -30.f : rr[2], tk[3] ? -30.f : rr[3]));
         if (d.mask != nullptr) *reinterpret_cast<uchar4*>(d.mask + i) = make_uchar4(tk[0], tk[1], tk[2], tk[3]);
       }
     } else {
@@ -783,12 +899,14 @@ __global__ void __launch_bounds__(kThreads) prune_sweep_into_kernel(const __grid
         if (mode == 3) {
           float ym, yp;
           key_interval<true>(mu, rho, g, ym, yp);
-          take = ym >= static_cast<float>(kBins);
-          const bool in_grid = !take && !(yp < 0.0f);
-          q_lane[qpos * kThreads] = make_float2(ym, yp);
+          const bool is_above = ym >= static_cast<float>(kBins);
+          take = ym >= kMidGrid;
+          const bool in_grid = !is_above && !(yp < 0.0f);
+          q_lane[qpos * kThreads] = make_float2(mu, rho);
           if (in_grid) { ++qpos; listed |= 1u << j; }
-          above += take ? 1u : 0u;
+          above += is_above ? 1u : 0u;
         } else if (mode == 4) {
+          q_lane[qpos++ * kThreads] = make_float2(mu, rho);
           listed |= 1u << j;
         }
         d.mu_w[i] = take ? 0.0f : mu;
@@ -797,13 +915,18 @@ __global__ void __launch_bounds__(kThreads) prune_sweep_into_kernel(const __grid
       }
     }
     if (mode != 3 && mode != 4) continue;
-    // histogram updates of the queued intervals (bin kernel conventions)
-    for (int s = 0; s < qpos; ++s) {
-      const float2 y = q_lane[s * kThreads];
-      const int im = !(y.x >= 0.0f) ? 0 : __float2int_rd(y.x) + 1;
-      const int ip = !(y.y < static_cast<float>(kBins)) ? kBins : __float2int_rd(y.y);
-      atomicAdd(d.hist + im, 1u);
-      atomicAdd(d.hist_plus + ip, 1u);
+    // histogram updates of the queued in-grid elements (bin kernel conventions); the queue holds their (mu, rho) — the
+    // interval is recomputed (same arithmetic, ~1 % of the elements) so that the list below needs no second global read
+    if (mode == 3) {
+      for (int s = 0; s < qpos; ++s) {
+        const float2 e = q_lane[s * kThreads];
+        float ym, yp;
+        key_interval<true>(e.x, e.y, g, ym, yp);
+        const int im = !(ym >= 0.0f) ? 0 : __float2int_rd(ym) + 1;
+        const int ip = !(yp < static_cast<float>(kBins)) ? kBins : __float2int_rd(yp);
+        atomicAdd(d.hist + im, 1u);
+        atomicAdd(d.hist_plus + ip, 1u);
+      }
     }
     // list append: one reservation per warp
     const unsigned int mine = __popc(listed);
@@ -819,15 +942,16 @@ __global__ void __launch_bounds__(kThreads) prune_sweep_into_kernel(const __grid
     if (lane == 0) base = atomicAdd(&d.state->n_deferred, total);
     base = __shfl_sync(0xffffffffu, base, 0);
     unsigned int slot = base + incl - mine;
+    int s = 0;                           // queue entries are in element order, like the bits of `listed`
     while (listed != 0u) {
       const int e = __ffs(listed) - 1;
       listed &= listed - 1u;
       const int64_t i = full ? ubase + ((e >> 2) * 32 + lane) * 4 + (e & 3) : ubase + e * 32 + lane;
-      if (slot < d.defer_cap) {
-        d.keys[slot] = static_cast<uint32_t>(i);                    // numel < 2^32 on this path
-        d.keys[d.defer_cap + slot] = __float_as_uint(__ldg(d.mu + i));
-        d.keys[2u * d.defer_cap + slot] = __float_as_uint(__ldg(d.rho + i));
-      }
+      const float2 v = q_lane[s * kThreads];
+      ++s;
+      if (slot < d.defer_cap)            // one 16-byte record per listed element: (index, mu, rho, -); numel < 2^32 here
+        reinterpret_cast<uint4*>(d.keys)[slot] =
+            make_uint4(static_cast<uint32_t>(i), __float_as_uint(v.x), __float_as_uint(v.y), 0u);
       ++slot;
     }
   }
@@ -847,13 +971,14 @@ __global__ void __launch_bounds__(kThreads) prune_resolve_kernel(const __grid_co
   const int lane = threadIdx.x & 31;
   for (uint32_t i0 = blockIdx.x * kThreads; i0 < n; i0 += gridDim.x * kThreads) {
     const uint32_t i = i0 + threadIdx.x;
-    bool take = false, defer = false;
+    bool take = false, defer = false, provisional = false;
     uint32_t idx = 0;
     float mu = 0.f, rho = 0.f;
     if (i < n) {
-      idx = d.keys[i];
-      mu = __uint_as_float(d.keys[d.defer_cap + i]);
-      rho = __uint_as_float(d.keys[2u * d.defer_cap + i]);
+      const uint4 rec = reinterpret_cast<const uint4*>(d.keys)[i];
+      idx = rec.x;
+      mu = __uint_as_float(rec.y);
+      rho = __uint_as_float(rec.z);
       if (stp->defer_all) {
         defer = true;
       } else {
@@ -861,12 +986,17 @@ __global__ void __launch_bounds__(kThreads) prune_resolve_kernel(const __grid_co
         key_interval<true>(mu, rho, g, ym, yp);        // the same arithmetic as the sweep: identical intervals
         take = ym >= a_thr;
         defer = !take && !(yp < b_thr);
+        provisional = ym >= kMidGrid;                  // what the sweep wrote
       }
     }
-    if (take) {
+    if (take && !provisional) {
       d.mu_w[idx] = 0.0f;
       d.rho_w[idx] = -30.0f;
       if (d.mask != nullptr) d.mask[idx] = 1;
+    } else if (i < n && !take && !defer && provisional) {
+      d.mu_w[idx] = mu;
+      d.rho_w[idx] = rho;
+      if (d.mask != nullptr) d.mask[idx] = 0;
     }
     const unsigned int bal = __ballot_sync(0xffffffffu, defer);
     if (bal != 0u) {
@@ -1022,7 +1152,7 @@ __device__ uint32_t cand_select(const uint32_t* cand, uint32_t n, int field, uin
 // tensors that defer everything) go through (key, index) pairs in the workspace.
 constexpr uint32_t kResolveList = 4096;      // (key, index) pairs in shared memory
 
-__global__ void __launch_bounds__(kResolveThreads) prune_finish_kernel(const __grid_constant__ PruneTable tab) {
+__global__ void __launch_bounds__(kFinishThreads) prune_finish_kernel(const __grid_constant__ PruneTable tab) {
   __shared__ uint32_t s_hist[kBins];
   __shared__ uint32_t s_bcast[4];
   __shared__ __align__(8) uint32_t s_list[2 * kResolveList];
@@ -1044,7 +1174,16 @@ __global__ void __launch_bounds__(kResolveThreads) prune_finish_kernel(const __g
   }
   __syncthreads();
   uint32_t take = st.n_take < n ? st.n_take : n;
-  if (take == 0u) return;
+  if (take == 0u) {
+    if (two_level)             // the sweep's provisional decision may have pruned some of them
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t idx = e_idx[i];
+        d.mu_w[idx] = __uint_as_float(e_mu[i]);
+        d.rho_w[idx] = __uint_as_float(e_rho[i]);
+        if (d.mask != nullptr) d.mask[idx] = 0;
+      }
+    return;
+  }
   uint64_t above = 0;
   uint32_t eq = 0;
   const uint32_t T = cand_select(pairs, n, 0, 0u, static_cast<uint64_t>(take) - 1, s_hist, s_bcast, &above, &eq);
@@ -1062,6 +1201,10 @@ __global__ void __launch_bounds__(kResolveThreads) prune_finish_kernel(const __g
       d.mu_w[idx] = 0.0f;
       d.rho_w[idx] = -30.0f;
       if (d.mask != nullptr) d.mask[idx] = 1;
+    } else if (two_level) {    // bnn_prune_into: undo a provisional decision of the sweep
+      d.mu_w[idx] = __uint_as_float(e_mu[i]);
+      d.rho_w[idx] = __uint_as_float(e_rho[i]);
+      if (d.mask != nullptr) d.mask[idx] = 0;
     }
   }
 }
@@ -1297,7 +1440,7 @@ uint32_t cap2_for(int64_t numel) {            // bnn_prune_into: capacity of the
   return cap < 262144u ? cap : 262144u;
 }
 size_t keys_bytes(int64_t numel) {
-  const size_t general = static_cast<size_t>(numel) * 4, sampled = static_cast<size_t>(defer_cap_for(numel)) * 20;
+  const size_t general = static_cast<size_t>(numel) * 4, sampled = static_cast<size_t>(defer_cap_for(numel)) * 24;
   return align_up(general > sampled ? general : sampled, 256);
 }
 size_t header_bytes(int n_tensors) {       // one "some tensor needs the general path" flag per group of kMaxTensors
@@ -1350,20 +1493,89 @@ size_t into_extra_bytes(int64_t numel) {       // the exact-select list of bnn_p
   return align_up(static_cast<size_t>(cap2_for(numel)) * 20, 256);
 }
 
+// A second stream per device for bnn_prune_into calls that span several groups of kMaxTensors tensors: the short
+// single-block steps of group g (bracket, resolve, finish, idle fallback launches) run there while the main stream
+// already sweeps group g + 1.  Created lazily; if anything fails the call runs on the caller's stream alone.
+struct SideLane {
+  cudaStream_t stream = nullptr;
+  cudaStream_t fallback = nullptr;      // the (normally idle) general-path launches of a group, off the critical path
+  std::vector<cudaEvent_t> events;
+  bool failed = false;
+};
+std::mutex g_side_mutex;
+SideLane g_side[64];
+
+SideLane* side_lane(int n_events) {      // call with g_side_mutex held
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideLane& lane = g_side[dev];
+  if (lane.failed) return nullptr;
+  if (lane.stream == nullptr) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);            // hi = numerically lowest = highest priority
+    if (cudaStreamCreateWithPriority(&lane.stream, cudaStreamNonBlocking, hi) != cudaSuccess) {
+      cudaGetLastError();
+      lane.stream = nullptr;
+      lane.failed = true;
+      return nullptr;
+    }
+    if (cudaStreamCreateWithPriority(&lane.fallback, cudaStreamNonBlocking, hi) != cudaSuccess) {
+      cudaGetLastError();
+      lane.failed = true;
+      return nullptr;
+    }
+  }
+  while (static_cast<int>(lane.events.size()) < n_events) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      lane.failed = true;
+      return nullptr;
+    }
+    lane.events.push_back(e);
+  }
+  return &lane;
+}
+
+void launch_general_path(PruneTable tab, bool into, int grid, cudaStream_t st) {
+  // general path (kernels return immediately unless a tensor asked for it; when no tensor is known to need it they
+  // are launched with one block per SM — all of them loop over the chunks — so that the idle launches stay cheap)
+  bool forced = false;
+  for (int i = 0; i < tab.n; ++i) forced = forced || tab.t[i].force_general != 0u || tab.t[i].numel >= (int64_t(1) << 32);
+  const int ggrid = forced ? grid : (grid < sm_count() ? grid : sm_count());
+  if (into) {
+    // the input is intact: flagged tensors are copied, then selected in place on the OUTPUT
+    prune_copy_general_kernel<<<ggrid, kThreads, 0, st>>>(tab);
+    for (int i = 0; i < tab.n; ++i) { tab.t[i].mu = tab.t[i].mu_w; tab.t[i].rho = tab.t[i].rho_w; }
+  }
+  prune_hist_kernel<0><<<ggrid, kThreads, 0, st>>>(tab);
+  prune_select_kernel<0><<<tab.n, kThreads, 0, st>>>(tab);
+  prune_hist_kernel<1><<<ggrid, kThreads, 0, st>>>(tab);
+  prune_select_kernel<1><<<tab.n, kThreads, 0, st>>>(tab);
+  prune_hist_kernel<2><<<ggrid, kThreads, 0, st>>>(tab);
+  prune_select_kernel<2><<<tab.n, kThreads, 0, st>>>(tab);
+  prune_count_eq_kernel<<<ggrid, kThreads, 0, st>>>(tab);
+  prune_scan_kernel<<<tab.n, kThreads, 0, st>>>(tab);
+  prune_apply_kernel<<<ggrid, kThreads, 0, st>>>(tab);
+}
+
 int prune_run(const PruneIo* io, int32_t n_tensors, bool into, void* workspace, cudaStream_t st) {
   uint32_t* group_flags = reinterpret_cast<uint32_t*>(workspace);
   char* small = static_cast<char*>(workspace) + header_bytes(n_tensors);
   char* ws = small + static_cast<size_t>(n_tensors) * kSmallBytes;
   BNN_CUDA_OK(cudaMemsetAsync(workspace, 0, static_cast<size_t>(ws - static_cast<char*>(workspace)), st));
   const int max_grid = sm_count() * 8;
-  int rc = BNN_OK;
 
-  for (int first = 0; first < n_tensors; first += kMaxTensors) {
-    const int n = (n_tensors - first < kMaxTensors) ? n_tensors - first : kMaxTensors;
+  std::vector<PruneTable> tabs;
+  // groups of at most kMaxTensors tensors (one descriptor table each), balanced: 64 tensors -> 22 + 21 + 21
+  const int n_tables = (n_tensors + kMaxTensors - 1) / kMaxTensors;
+  const int per_table = (n_tensors + n_tables - 1) / n_tables;
+  for (int first = 0, gi = 0; first < n_tensors; first += per_table, ++gi) {
+    const int n = (n_tensors - first < per_table) ? n_tensors - first : per_table;
     PruneTable tab;
     tab.n = 0;
     tab.pad = 0;
-    tab.any_general = group_flags + first / kMaxTensors;
+    tab.any_general = group_flags + gi;
     int64_t chunks = 0;
     for (int i = 0; i < n; ++i) {
       const PruneIo& t = io[first + i];
@@ -1390,41 +1602,87 @@ int prune_run(const PruneIo* io, int32_t n_tensors, bool into, void* workspace, 
     }
     if (tab.n == 0) continue;
     tab.total_chunks = chunks;
-    const int grid = static_cast<int>(chunks < max_grid ? chunks : max_grid);
-    // sampled path
-    prune_sample_keys_kernel<<<dim3(kSampleBig / (4 * kResolveThreads), tab.n), kResolveThreads, 0, st>>>(tab);
-    prune_sample_kernel<<<tab.n, kResolveThreads, 0, st>>>(tab);
-    if (!into) {
+    tabs.push_back(tab);
+  }
+  const int n_groups = static_cast<int>(tabs.size());
+  if (n_groups == 0) return BNN_OK;
+  auto grid_of = [&](const PruneTable& tab) { return static_cast<int>(tab.total_chunks < max_grid ? tab.total_chunks : max_grid); };
+  // short-lived sweep blocks (kSweepChunks chunks each) instead of a persistent grid: SM slots free up all the time, so
+  // the side lane's small kernels of the previous group get onto the machine while this group is being swept
+  auto sweep_grid_of = [&](const PruneTable& tab) {
+    const int64_t g = (tab.total_chunks + kSweepChunks - 1) / kSweepChunks;
+    return static_cast<int>(g < 1 ? 1 : (g > (int64_t(1) << 30) ? (int64_t(1) << 30) : g));
+  };
+
+  if (!into) {
+    for (int g = 0; g < n_groups; ++g) {
+      const PruneTable& tab = tabs[g];
+      const int grid = grid_of(tab);
+      prune_sample_kernel<<<tab.n * kSampleCtas, kResolveThreads, 0, st>>>(tab);
       prune_bin_kernel<<<grid, kThreads, 0, st>>>(tab);
       prune_bracket_kernel<<<tab.n, kThreads, 0, st>>>(tab);
       prune_apply_sampled_kernel<<<grid, kThreads, 0, st>>>(tab);
-    } else {
-      prune_sweep_into_kernel<<<grid, kThreads, 0, st>>>(tab);
-      prune_bracket_kernel<<<tab.n, kThreads, 0, st>>>(tab);
-      prune_resolve_kernel<<<dim3(64, tab.n), kThreads, 0, st>>>(tab);
+      prune_finish_kernel<<<tab.n, kFinishThreads, 0, st>>>(tab);
+      launch_general_path(tab, false, grid, st);
     }
-    prune_finish_kernel<<<tab.n, kResolveThreads, 0, st>>>(tab);
-    // general path (kernels return immediately unless a tensor asked for it; when no tensor is known to need it they
-    // are launched with one block per SM — all of them loop over the chunks — so that the idle launches stay cheap)
-    bool forced = false;
-    for (int i = 0; i < tab.n; ++i) forced = forced || tab.t[i].force_general != 0u || tab.t[i].numel >= (int64_t(1) << 32);
-    const int ggrid = forced ? grid : (grid < sm_count() ? grid : sm_count());
-    if (into) {
-      // the input is intact: flagged tensors are copied, then selected in place on the OUTPUT
-      prune_copy_general_kernel<<<ggrid, kThreads, 0, st>>>(tab);
-      for (int i = 0; i < tab.n; ++i) { tab.t[i].mu = tab.t[i].mu_w; tab.t[i].rho = tab.t[i].rho_w; }
-    }
-    prune_hist_kernel<0><<<ggrid, kThreads, 0, st>>>(tab);
-    prune_select_kernel<0><<<tab.n, kThreads, 0, st>>>(tab);
-    prune_hist_kernel<1><<<ggrid, kThreads, 0, st>>>(tab);
-    prune_select_kernel<1><<<tab.n, kThreads, 0, st>>>(tab);
-    prune_hist_kernel<2><<<ggrid, kThreads, 0, st>>>(tab);
-    prune_select_kernel<2><<<tab.n, kThreads, 0, st>>>(tab);
-    prune_count_eq_kernel<<<ggrid, kThreads, 0, st>>>(tab);
-    prune_scan_kernel<<<tab.n, kThreads, 0, st>>>(tab);
-    prune_apply_kernel<<<ggrid, kThreads, 0, st>>>(tab);
     BNN_CUDA_OK(cudaGetLastError());
+    return BNN_OK;
   }
+
+  // bnn_prune_into over several groups: the main stream runs sample(0), sweep(0), sweep(1), ...; the side lane runs the
+  // samples of the later groups (hidden behind sweep(0)) and then, per group, bracket / resolve / finish / fallback as
+  // soon as that group's sweep is done — while the main stream sweeps the next group.
+  std::unique_lock<std::mutex> lock(g_side_mutex, std::defer_lock);
+  SideLane* lane = nullptr;
+  if (n_groups > 1) {
+    lock.lock();
+    lane = side_lane(4 * n_groups + 2);
+    if (lane == nullptr) lock.unlock();
+  }
+  cudaEvent_t* ev_sweep = lane ? lane->events.data() : nullptr;
+  cudaEvent_t* ev_sample = lane ? lane->events.data() + n_groups : nullptr;
+  prune_sample_kernel<<<tabs[0].n * kSampleCtas, kResolveThreads, 0, st>>>(tabs[0]);
+  if (lane != nullptr) {
+    cudaEvent_t fork = lane->events[2 * n_groups];
+    BNN_CUDA_OK(cudaEventRecord(fork, st));
+    BNN_CUDA_OK(cudaStreamWaitEvent(lane->stream, fork, 0));
+  }
+  for (int g = 1; g < n_groups; ++g) {
+    prune_sample_kernel<<<tabs[g].n * kSampleCtas, kResolveThreads, 0, lane ? lane->stream : st>>>(tabs[g]);
+    if (lane != nullptr) BNN_CUDA_OK(cudaEventRecord(ev_sample[g], lane->stream));
+  }
+  for (int g = 0; g < n_groups; ++g) {
+    const PruneTable& tab = tabs[g];
+    if (lane != nullptr && g > 0) BNN_CUDA_OK(cudaStreamWaitEvent(st, ev_sample[g], 0));
+    prune_sweep_into_kernel<<<sweep_grid_of(tab), kThreads, 0, st>>>(tab);
+    cudaStream_t post = st;
+    if (lane != nullptr) {
+      BNN_CUDA_OK(cudaEventRecord(ev_sweep[g], st));
+      BNN_CUDA_OK(cudaStreamWaitEvent(lane->stream, ev_sweep[g], 0));
+      post = lane->stream;
+    }
+    prune_bracket_kernel<<<tab.n, kThreads, 0, post>>>(tab);
+    cudaStream_t gen = post;
+    if (lane != nullptr) {     // the fallback launches only need the bracket step's verdict: third stream, beside resolve / finish
+      cudaEvent_t bracketed = lane->events[2 * n_groups + 2 + 2 * g];
+      BNN_CUDA_OK(cudaEventRecord(bracketed, post));
+      BNN_CUDA_OK(cudaStreamWaitEvent(lane->fallback, bracketed, 0));
+      gen = lane->fallback;
+    }
+    prune_resolve_kernel<<<dim3(64, tab.n), kThreads, 0, post>>>(tab);
+    prune_finish_kernel<<<tab.n, kFinishThreads, 0, post>>>(tab);
+    launch_general_path(tab, true, grid_of(tab), gen);
+    if (lane != nullptr) {     // ... and rejoin the side lane (one join with the caller's stream at the end)
+      cudaEvent_t done = lane->events[2 * n_groups + 3 + 2 * g];
+      BNN_CUDA_OK(cudaEventRecord(done, gen));
+      BNN_CUDA_OK(cudaStreamWaitEvent(post, done, 0));
+    }
+  }
+  if (lane != nullptr) {
+    BNN_CUDA_OK(cudaEventRecord(lane->events[2 * n_groups + 1], lane->stream));
+    BNN_CUDA_OK(cudaStreamWaitEvent(st, lane->events[2 * n_groups + 1], 0));
+  }
+  BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
 }
 }  // namespace

@@ -533,11 +533,15 @@ def bench_kl_prune(device, pk, world=1, tensors=64):
         return over_ranks(best)
 
     # PruneNormal on tensors of this size (prune/prune.py): the ONE-sweep out-of-place kernel (bnn_prune_into: 8 B read +
-    # 8 B written per pair), the outputs then replace the parameters' storage
-    state = {"mus": mus, "rhos": rhos}
+    # 8 B written per pair), the outputs then replace the parameters' storage.  The output buffers are caller-owned
+    # (C ABI: the library never allocates); here two spare sets alternate, allocated outside the timed region.
+    state = {"mus": mus, "rhos": rhos, "turn": 0}
+    spare = [[(torch.empty_like(m), torch.empty_like(r)) for m, r in zip(mus, rhos)] for _ in range(2)]
 
     def prune_swap(kk=k):
-        outs = _C.prune_into([(m, r, kk, None) for m, r in zip(state["mus"], state["rhos"])])
+        out = spare[state["turn"]]
+        state["turn"] ^= 1
+        outs = _C.prune_into([(m, r, kk, None) for m, r in zip(state["mus"], state["rhos"])], out=out)
         state["mus"], state["rhos"] = [o[0] for o in outs], [o[1] for o in outs]
 
     def prune_in_place():
@@ -547,23 +551,28 @@ def bench_kl_prune(device, pk, world=1, tensors=64):
         restore()
         state["mus"], state["rhos"] = mus, rhos
 
-    def best_swap(reps=3):
+    def best_swap(reps=3, inner=1):
+        """`inner` back-to-back calls on the (unmodified) inputs between one event pair, outputs alternating between the
+        two spare sets: with inner > 1 the host-side preparation of a call overlaps the previous call's kernels, the
+        protocol of the KL legs.  Every call streams the whole 8 GiB / N working set."""
         best = 1e30
         for _ in range(reps):
             restore_swap()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            prune_swap()
+            for _ in range(inner):
+                prune_swap()
+                state["mus"], state["rhos"] = mus, rhos
             b.record()
             torch.cuda.synchronize()
-            best = min(best, a.elapsed_time(b) * 1e-3)
+            best = min(best, a.elapsed_time(b) * 1e-3 / inner)
         return over_ranks(best)
-    prune_swap()                              # warm-up: the caching allocator now holds the output blocks
+    prune_swap()                              # warm-up (workspace allocation)
     torch.cuda.synchronize()
-    res["prune_p0.75"] = entry(8 + 8 * p, best_swap())
-    res["prune_p0.75"]["what"] = ("PruneNormal sweep (prune.py:10-17) as the package runs it on tensors of this size: sample + ONE "
-                                  "out-of-place sweep (bnn_prune_into: read 8 B, write 8 B per pair) + bracket + resolve + exact "
-                                  "finish; the outputs replace the parameters' storage")
+    res["prune_p0.75"] = entry(8 + 8 * p, best_swap(inner=2))
+    res["prune_p0.75"]["single_call"] = entry(8 + 8 * p, best_swap(inner=1))
+    res["prune_p0.75"]["timing"] = ("average of 2 back-to-back calls (best of 3), as for the KL legs; `single_call` = one call "
+                                    "bracketed on an idle stream, including the host-side preparation of the 64-entry table")
     restore_swap()
     prune_in_place()
     res["prune_p0.75_in_place"] = entry(8 + 8 * p, best_of(prune_in_place))

@@ -355,6 +355,26 @@ def test_prune_many_tensors_and_idempotent_order(C, prune_mode):
             assert torch.equal(m, bm) and torch.equal(r, br)
 
 
+def test_prune_several_groups_of_large_tensors(C, prune_mode):
+    """More tensors than one descriptor table holds (24), each large enough for the sampled path: bnn_prune_into runs the
+    bracket / resolve / finish steps of a group on its side lane while the next group is swept.  Every mask must equal
+    the stable sort of torch's keys; a second call on the results (75 % -> 80 %) re-selects what is pruned first."""
+    g = torch.Generator().manual_seed(21)
+    sizes = [150000 + 4099 * i for i in range(50)]
+    dev = [tuple(t.cuda() for t in init_params((n,), g, fan_in=400)) for n in sizes]
+    for p in (0.75, 0.8):
+        before = [(m.clone(), r.clone()) for m, r in dev]
+        masks = [torch.empty(n, dtype=torch.uint8, device="cuda") for n in sizes]
+        C.prune([(m, r, orc.prune_count(p, m.numel()), mk, None) for (m, r), mk in zip(dev, masks)])
+        for (m, r), mk, (bm, br) in zip(dev, masks, before):
+            k = orc.prune_count(p, bm.numel())
+            ref = orc.prune_mask_from_keys(torch_keys_same_device(bm, br), k)
+            assert int(mk.sum()) == k
+            assert torch.equal(mk.bool(), ref)
+            orc.prune_apply(bm, br, ref)
+            assert torch.equal(m, bm) and torch.equal(r, br)
+
+
 # ------------------------------------------------------------------------------------------------ contractions
 def gemm_inputs(M, N, K, S, shared_a, gen, bias=True):
     mu_w, rho_w = init_params((N, K), gen)
