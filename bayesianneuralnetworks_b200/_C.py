@@ -143,6 +143,7 @@ _SIGNATURES = {
     "bnn_adam_kl_step_peers": (ctypes.c_int, [ctypes.POINTER(bnn_adam_tensor), ctypes.c_int32, ctypes.c_float, ctypes.c_float,
                                               ctypes.c_float, ctypes.c_float, _c_f32p, ctypes.c_int64,
                                               ctypes.POINTER(bnn_peer_grads), ctypes.c_void_p]),
+    "bnn_peer_average": (ctypes.c_int, [ctypes.POINTER(bnn_peer_grads), ctypes.c_int64, ctypes.c_void_p]),
     "bnn_pack_gradients": (ctypes.c_int, [ctypes.POINTER(bnn_pack_item), ctypes.c_int32, _c_f32p, ctypes.c_void_p]),
     "bnn_peer_barrier": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                         ctypes.c_void_p]),
@@ -636,6 +637,17 @@ def pack_gradients(items, flat):
     with torch.cuda.device(flat.device):
         _call("bnn_pack_gradients", table, n, _ptr(flat), _stream())
     _count((n + 31) // 32)
+
+
+def peer_average(bases, rank, numel, device):
+    """bnn_peer_average: in-place average of the ranks' flat gradient buffers (bases = every rank's buffer as mapped here)."""
+    pg = bnn_peer_grads()
+    pg.world, pg.rank = len(bases), rank
+    for r, b in enumerate(bases):
+        pg.base[r] = b
+    with torch.cuda.device(device):
+        _call("bnn_peer_average", ctypes.byref(pg), int(numel), _stream())
+    _count()
 
 
 def peer_barrier(flag_ptrs, rank, epoch, device):

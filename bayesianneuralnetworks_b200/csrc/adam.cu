@@ -268,6 +268,48 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant_
   if (t == 0) *p.epoch = e;
 }
 
+// ---- bnn_peer_average: in-place average of the ranks' flat gradient buffers in two hops instead of R - 1 reads of
+// everything by everyone: rank r owns the r-th slice of the buffer, reads that slice from every rank (all R loads of an
+// element are in flight together), averages in rank order and writes the result back into EVERY rank's buffer
+// (reduce-scatter + all-gather over NVLink peer memory, (R - 1) / R of the buffer in each direction per rank instead of
+// R - 1 buffers inbound).  An element is read and rewritten by its owner only, so the update is safe in place.  Between
+// two bnn_peer_barrier launches; afterwards every rank holds the same averaged gradients locally and the plain
+// optimizer kernel runs on them.
+struct AverageParams {
+  float* peer[BNN_MAX_PEERS];
+  int world, rank;
+  int64_t begin, end;        // this rank's slice [begin, end) in floats, multiples of 4 (except the very end of the buffer)
+};
+__global__ void __launch_bounds__(kThreads) peer_average_kernel(const __grid_constant__ AverageParams p) {
+  const float inv = 1.0f / static_cast<float>(p.world);
+  const int64_t n4 = (p.end - p.begin) / 4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const int64_t off = p.begin + 4 * i;
+    float4 v[BNN_MAX_PEERS];
+#pragma unroll
+    for (int r = 0; r < BNN_MAX_PEERS; ++r)
+      if (r < p.world) v[r] = ld_peer4(p.peer[r] + off);
+    float4 acc = v[0];
+#pragma unroll
+    for (int r = 1; r < BNN_MAX_PEERS; ++r)
+      if (r < p.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+#pragma unroll
+    for (int r = 0; r < BNN_MAX_PEERS; ++r)
+      if (r < p.world) *reinterpret_cast<float4*>(p.peer[r] + off) = acc;
+  }
+  // tail of the buffer (numel not a multiple of 4): the last rank's slice ends there
+  const int64_t tail = p.begin + 4 * n4;
+  if (blockIdx.x == 0 && threadIdx.x < p.end - tail) {
+    const int64_t off = tail + threadIdx.x;
+    float acc = 0.f;
+    for (int r = 0; r < p.world; ++r) acc += ld_peer1(p.peer[r] + off);
+    acc *= inv;
+    for (int r = 0; r < p.world; ++r) p.peer[r][off] = acc;
+  }
+}
+
 // ---- bnn_pack_gradients: the gradients autograd left in separate tensors -> one flat (peer-visible) buffer, one launch.
 // Replaces "gradients are views of the flat buffer" (a fill of the buffer plus one accumulation kernel per parameter
 // in every backward pass) by a single gather after the backward pass.
@@ -347,6 +389,32 @@ extern "C" int bnn_adam_kl_step_peers(const bnn_adam_tensor* tensors, int32_t n_
   BNN_REQUIRE(peers != nullptr, BNN_ERR_BAD_ARGUMENT, "bnn_adam_kl_step_peers: peers is NULL");
   return adam_launch(tensors, n_tensors, lr, beta1, beta2, eps, step_dev, step_host, peers, stream,
                      "bnn_adam_kl_step_peers");
+}
+
+extern "C" int bnn_peer_average(const bnn_peer_grads* peers, int64_t numel, void* stream) {
+  BNN_REQUIRE(peers != nullptr && numel >= 0, BNN_ERR_BAD_ARGUMENT, "bnn_peer_average: NULL table or negative size");
+  BNN_REQUIRE(peers->world >= 1 && peers->world <= BNN_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
+              BNN_ERR_BAD_ARGUMENT, "bnn_peer_average: need 1 <= world <= %d and 0 <= rank < world", BNN_MAX_PEERS);
+  if (numel == 0 || peers->world == 1) return BNN_OK;
+  int rc = check_device();
+  if (rc != BNN_OK) return rc;
+  AverageParams p;
+  for (int r = 0; r < BNN_MAX_PEERS; ++r) {
+    p.peer[r] = r < peers->world ? const_cast<float*>(peers->base[r]) : nullptr;
+    BNN_REQUIRE(r >= peers->world || (p.peer[r] != nullptr && aligned16(p.peer[r])), BNN_ERR_BAD_ARGUMENT,
+                "bnn_peer_average: peer gradient buffer %d is NULL or not 16-byte aligned", r);
+  }
+  p.world = peers->world; p.rank = peers->rank;
+  const int64_t per = ((numel + peers->world - 1) / peers->world + 3) / 4 * 4;      // slice length, a multiple of 4
+  p.begin = per * peers->rank < numel ? per * peers->rank : numel;
+  p.end = p.begin + per < numel ? p.begin + per : numel;
+  if (p.end <= p.begin) return BNN_OK;
+  const int64_t n4 = (p.end - p.begin + 3) / 4;
+  const int64_t blocks = (n4 + kThreads - 1) / kThreads;
+  const int grid = static_cast<int>(blocks < sm_count() * 8 ? blocks : sm_count() * 8);
+  peer_average_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
 }
 
 extern "C" int bnn_peer_barrier(uint32_t* const* flags, int32_t world, int32_t rank, uint32_t* epoch_dev, void* stream) {

@@ -70,6 +70,7 @@ class ELBOAdam(torch.optim.Optimizer):
         self._torch_adam = None           # for parameters the kernel does not take (non-CUDA / non-float32)
         self._peers = None
         self._views = None
+        self.two_hop_above = 2            # peer exchange: ranks above this count average the buffers in two hops first
 
     # ---------------------------------------------------------------------------------------------------------------
     def attach_peers(self, peers, views=None):
@@ -138,12 +139,18 @@ class ELBOAdam(torch.optim.Optimizer):
         for step_dev in self._step_dev.values():
             step_dev += 1                                 # device-resident: a captured graph replays it
         peers = self._peers
+        two_hop = peers is not None and peers.world > self.two_hop_above
         if peers is not None:
             peers.barrier()                               # every rank's gradients are complete
+        if two_hop:
+            # more than two ranks: average the flat buffers in place (every rank reduces its slice and writes it back to
+            # all: (R-1)/R of the buffer per direction instead of R-1 whole buffers inbound), then the local kernel
+            _C.peer_average(peers.bases, peers.rank, peers.flat.numel(), peers.device)
+            peers.barrier()                               # every slice has landed in every buffer
         for (device, hyper), entries in by_device.items():
             _C.adam_kl_step(entries, *hyper, step_dev=self._step_dev[device],
-                            peers=None if peers is None else (peers.rank, peers.bases))
-        if peers is not None:
+                            peers=None if (peers is None or two_hop) else (peers.rank, peers.bases))
+        if peers is not None and not two_hop:
             peers.barrier()                               # every rank has read: the buffers may be overwritten
         if leftovers:
             self._step_leftovers(leftovers)

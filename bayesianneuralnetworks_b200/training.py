@@ -86,8 +86,14 @@ class ElboTrainer:
                                                                self.peers.flat.storage_offset() + off)
                     off += p.numel()
                 self.opt.attach_peers(self.peers, self._peer_views)
-                self.exchange_note = ("gradients averaged inside the optimizer kernel over NVLink peer memory "
-                                      "(bnn_adam_kl_step_peers + bnn_peer_barrier); no NCCL call; one CUDA graph")
+                if self.world > self.opt.two_hop_above:
+                    self.exchange_note = ("flat gradient buffers averaged in place over NVLink peer memory in two hops (every "
+                                          "rank reduces its slice and writes it to all: bnn_peer_average between two "
+                                          "bnn_peer_barrier launches), then the local optimizer kernel; no NCCL call; one CUDA "
+                                          "graph")
+                else:
+                    self.exchange_note = ("gradients averaged inside the optimizer kernel over NVLink peer memory "
+                                          "(bnn_adam_kl_step_peers + bnn_peer_barrier); no NCCL call; one CUDA graph")
             elif mode == "bucketed":
                 self.buckets = parallel.BucketedAllReduce(self.params, group=group)
                 self.flat = self.buckets.flat

@@ -278,6 +278,12 @@ typedef struct bnn_peer_grads {
 int bnn_adam_kl_step_peers(const bnn_adam_tensor* tensors /* HOST array */, int32_t n_tensors, float lr, float beta1,
                            float beta2, float eps, const float* step_dev, int64_t step_host,
                            const bnn_peer_grads* peers, void* stream);
+/* In-place average of the ranks' flat gradient buffers (numel floats each) in two hops: every rank averages ITS slice
+ * of the buffer over all ranks and writes the result into every rank's buffer (reduce-scatter + all-gather over peer
+ * memory).  Launch between two bnn_peer_barrier calls; afterwards bnn_adam_kl_step runs on the local buffer.  Moves
+ * (R - 1) / R of the buffer per direction and rank where bnn_adam_kl_step_peers pulls R - 1 whole buffers: the choice for
+ * more than two ranks.  Replaces the same call site (the gradient all-reduce of SURVEY 8e). */
+int bnn_peer_average(const bnn_peer_grads* peers, int64_t numel, void* stream);
 /* Gathers separately stored gradients into the flat (peer-visible) buffer in one launch: dst[dst_offset .. + numel) =
  * src[0 .. numel) (src NULL: zeros).  The alternative — gradients as views of the flat buffer — costs a fill plus one
  * accumulation kernel per parameter in every backward pass. */

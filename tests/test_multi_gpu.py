@@ -35,12 +35,15 @@ def _worker(rank, world, port, results):
         bnn.set_precision("fp32")
         S, B = 4, 32
         finals = {}
-        for mode in ("peer", "flat", "bucketed"):
+        for mode in ("peer", "peer2hop", "flat", "bucketed"):
+            two_hop, mode = mode == "peer2hop", "peer" if mode == "peer2hop" else mode
             torch.manual_seed(0)
             model = bench.build_model("c2", S).to(device)            # S = global samples; grid 1 data x 2 sample groups
             initial = torch.cat([p.detach().flatten() for p in model.parameters()]).clone()
             trainer = ElboTrainer(model, 10, lr=1e-2, graph=(mode != "bucketed"), exchange=mode, sample_groups=2)
             assert trainer.exchange == mode and (trainer.data_index, trainer.sample_index) == (0, rank)
+            if two_hop:          # the exchange of more than two ranks (bnn_peer_average: reduce-scatter + all-gather in place)
+                trainer.opt.two_hop_above = 1
             gen = torch.Generator().manual_seed(7)
             x, y = bench.synthetic_batch("c2", B, gen)
             x, y = x.to(device), y.to(device)
@@ -57,7 +60,7 @@ def _worker(rank, world, port, results):
                 for _ in range(2):
                     loss = trainer.step(x, y)
             torch.cuda.synchronize()
-            finals[mode] = torch.cat([p.detach().flatten() for p in model.parameters()]).clone()
+            finals["peer2hop" if two_hop else mode] = torch.cat([p.detach().flatten() for p in model.parameters()]).clone()
             assert torch.isfinite(loss)
             trainer.release()
             del trainer, model
@@ -65,11 +68,25 @@ def _worker(rank, world, port, results):
         gathered = [torch.empty_like(finals["peer"]) for _ in range(world)]
         dist.all_gather(gathered, finals["peer"])
         assert torch.equal(gathered[0], gathered[1]), "ranks diverged under the peer exchange"
+        # the two-hop kernel on its own: in-place average of the ranks' flat buffers == NCCL's average of the same
+        # values, bit for bit with two ranks (one addition and an exact halving), on a length that is not a multiple of 4
+        from bayesianneuralnetworks_b200 import _C, parallel
+        pg = parallel.PeerGradients(100003, device)
+        vals = torch.randn(100003, generator=torch.Generator().manual_seed(50 + rank)).to(device)
+        for _ in range(2):
+            pg.flat.copy_(vals)
+            ref = vals.clone()
+            dist.all_reduce(ref, op=dist.ReduceOp.AVG)
+            pg.barrier()
+            _C.peer_average(pg.bases, pg.rank, pg.flat.numel(), device)
+            pg.barrier()
+            torch.cuda.synchronize()
+            assert torch.equal(pg.flat, ref), "bnn_peer_average differs from the all-reduce average"
         # and they are the parameters the NCCL exchanges produce.  The summation order differs, i.e. the gradients differ by
         # rounding; Adam's first steps are lr * g / |g|, so an element whose gradient is at rounding level can take a full
         # step the other way (max deviation ~ lr) — the measure is the relative L2 error of the whole update and the 99th
         # percentile of the element deviations
-        for other in ("flat", "bucketed"):
+        for other in ("flat", "bucketed", "peer2hop"):
             diff = (finals["peer"] - finals[other]).abs()
             upd = (finals[other] - initial).norm()
             assert float(diff.norm() / upd) < 2e-2 and float(diff.flatten().quantile(0.99)) < 1e-4, (
