@@ -62,7 +62,8 @@ class bnn_prune_tensor(ctypes.Structure):
 class bnn_prune_into_tensor(ctypes.Structure):
     _fields_ = [("mu", ctypes.c_void_p), ("rho", ctypes.c_void_p), ("mu_out", ctypes.c_void_p), ("rho_out", ctypes.c_void_p),
                 ("mask_out", ctypes.c_void_p), ("numel", ctypes.c_int64), ("k", ctypes.c_int64),
-                ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32), ("kl_sum_out", ctypes.c_void_p),
+                ("prior_loc", ctypes.c_float), ("prior_scale", ctypes.c_float)]
 
 
 class bnn_adam_tensor(ctypes.Structure):
@@ -525,19 +526,24 @@ def prune(entries, flags=0):
     _count(14 * ((n + 23) // 24))
 
 
-def prune_into(entries, flags=0, out=None):
+def prune_into(entries, flags=0, out=None, kl_priors=None):
     """Out-of-place pruning in one sweep (bnn_prune_into).  entries: list of (mu, rho, k, mask_out|None); returns the list
     of (mu_out, rho_out) tensors — the inputs are not modified.  `out`: optional list of caller-owned (mu_out, rho_out)
-    pairs to write into (same shapes, not aliasing the inputs); by default every output is a fresh tensor."""
+    pairs to write into (same shapes, not aliasing the inputs); by default every output is a fresh tensor.
+    `kl_priors`: optional list of (prior_loc, prior_scale) per entry — the same sweep then also accumulates every INPUT
+    tensor's KL element sum; returns (outs, sums) with sums a float64 [n] tensor (what _C.kl returns per tensor)."""
     n = len(entries)
     if n == 0:
-        return []
+        return [] if kl_priors is None else ([], torch.zeros(0, dtype=torch.float64))
+    if kl_priors is not None and len(kl_priors) != n:
+        raise ValueError("prune_into: `kl_priors` needs one (loc, scale) pair per entry")
     if out is not None and len(out) != n:
         raise ValueError("prune_into: `out` needs one (mu_out, rho_out) pair per entry")
     table = (bnn_prune_into_tensor * n)()
     device = entries[0][0].device
     outs = []
     f32 = torch.float32
+    kl_sums, kl_base = None, 0
     for i, (mu, rho, k, mask) in enumerate(entries):
         if out is None:
             mu_out, rho_out = torch.empty_like(mu), torch.empty_like(rho)
@@ -560,13 +566,18 @@ def prune_into(entries, flags=0, out=None):
                 raise TypeError("mask_out must be a contiguous uint8/bool tensor")
             t.mask_out = mask.data_ptr()
         t.numel, t.k, t.flags = mu.numel(), int(k), flags
+        if kl_priors is not None:
+            if kl_sums is None:
+                kl_sums = torch.zeros(n, dtype=torch.float64, device=device)
+                kl_base = kl_sums.data_ptr()
+            t.kl_sum_out, t.prior_loc, t.prior_scale = kl_base + 8 * i, float(kl_priors[i][0]), float(kl_priors[i][1])
     nbytes = lib().bnn_prune_into_workspace_size(table, n)
     ws = _workspace(_prune_ws, device, nbytes + 256)
     base = (ws.data_ptr() + 255) & ~255
     with torch.cuda.device(device):
         _call("bnn_prune_into", table, n, ctypes.c_void_p(base), nbytes, _stream())
     _count(15 * ((n + 23) // 24))
-    return outs
+    return outs if kl_priors is None else (outs, kl_sums)
 
 
 def adam_kl_step(entries, lr, beta1, beta2, eps, step_dev=None, step=0, peers=None):

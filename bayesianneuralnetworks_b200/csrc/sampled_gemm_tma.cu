@@ -261,7 +261,7 @@ __device__ __forceinline__ void gen_w_tile(uint32_t tile, const float* __restric
   }
 }
 
-template <int MB, bool kDgrad>
+template <int MB, bool kDgrad, bool kConv>
 __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __grid_constant__ TmaContractParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   long long w_kernel = 0, w_mma_w = 0, w_mma_a = 0, w_gen = 0, w_tma = 0;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
 #endif
       if (!kDgrad)
         gen_w_tile<128, false>(tile, p.mu_w, p.sigma_w, eps, col0, p.N, rb * kBK, p.K, tid, p.K, 0);
-      else if (!p.conv.on)
+      else if (!kConv)
         gen_w_tile<128, true>(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, col0, p.K, tid, p.K, 0);
       else {          // conv data gradient: k-block = (flipped tap, 32 output channels o0 ..)
         const int tapf = rb / p.conv.cblocks, o0 = (rb - tapf * p.conv.cblocks) * kBK;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
       for (int s = s_begin; s < s_end; ++s) {
         const int smp = p.shared_l ? 0 : s;
         int cw[MB], ch[MB], cn[MB];                // conv: first pixel of each row block (fixed over the k-blocks)
-        if (p.conv.on) {
+        if (kConv) {
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb) conv_pixel(p.conv, row0 + mb * 128, smp, &cw[mb], &ch[mb], &cn[mb]);
         }
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
           if (p.exp_flags & 2) { mbar_arrive(pipe.full_a + g); continue; }
 #endif
           mbar_arrive_expect_tx(pipe.full_a + g, mb_used * kTileBytes);
-          if (!p.conv.on) {
+          if (!kConv) {
             for (int mb = 0; mb < mb_used; ++mb)
               tma_load_3d(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, rb * kBK, row0 + mb * 128, smp, pipe.full_a + g);
           } else {
@@ -449,14 +449,21 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
 
 constexpr size_t kContractSmem = kSmemAux + 1024 + static_cast<size_t>(kASlots + kWSlots) * kTileBytes;
 
-template <int MB, bool kDgrad>
-int launch_tma_contract(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
+// The conv variants (im2col tensor maps, tap-major weight rows) are separate instantiations: folded into one kernel, the
+// conv state kept live across the generator loop pushed every input-gradient variant over its register budget (116-152
+// bytes of spill stores in the hot loop: C4 input gradient 2.33 -> 2.86 ms).
+template <int MB, bool kDgrad, bool kConv>
+int launch_tma_contract_v(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
   static SmemOptIn opt_in;
-  const int rc = allow_dynamic_smem(contract_tma_kernel<MB, kDgrad>, kContractSmem, &opt_in);
+  const int rc = allow_dynamic_smem(contract_tma_kernel<MB, kDgrad, kConv>, kContractSmem, &opt_in);
   if (rc != BNN_OK) return rc;
-  contract_tma_kernel<MB, kDgrad><<<grid, kThreadsTma, kContractSmem, st>>>(p);
+  contract_tma_kernel<MB, kDgrad, kConv><<<grid, kThreadsTma, kContractSmem, st>>>(p);
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
+}
+template <int MB, bool kDgrad>
+int launch_tma_contract(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
+  return p.conv.on ? launch_tma_contract_v<MB, kDgrad, true>(p, grid, st) : launch_tma_contract_v<MB, kDgrad, false>(p, grid, st);
 }
 
 // ---------------------------------------------------------------------------------------------- CTA-pair forward / dgrad
@@ -494,7 +501,7 @@ __device__ __forceinline__ PairPipe carve_pair(uint8_t* smem_raw) {
   return p;
 }
 
-template <int MB, bool kDgrad>
+template <int MB, bool kDgrad, bool kConv>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTma, 1)
 contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -553,7 +560,7 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
       const uint32_t tile = pipe.ring_w + group * kHalfTileBytes;
       if (!kDgrad)
         gen_w_tile<64, false>(tile, p.mu_w, p.sigma_w, eps, half0, p.N, rb * kBK, p.K, tid, p.K, 0);
-      else if (!p.conv.on)
+      else if (!kConv)
         gen_w_tile<64, true>(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, half0, p.K, tid, p.K, 0);
       else {
         const int tapf = rb / p.conv.cblocks, o0 = (rb - tapf * p.conv.cblocks) * kBK;
@@ -572,7 +579,7 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
       for (int s = s_begin; s < s_end; ++s) {
         const int smp = p.shared_l ? 0 : s;
         int cw[MB], ch[MB], cn[MB];
-        if (p.conv.on) {
+        if (kConv) {
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb) conv_pixel(p.conv, row0 + mb * 128, smp, &cw[mb], &ch[mb], &cn[mb]);
         }
@@ -581,7 +588,7 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
           const int g = it & 1;
           if (it >= 2) { BNN_T0(); mbar_wait(pipe.empty_w + ((it - 2) & 3), ((it - 2) >> 2) & 1); BNN_ACC(w_tma); }
           if (rank == 0) mbar_arrive_expect_tx(pipe.full_a + g, 2 * mb_pair * kTileBytes);
-          if (!p.conv.on) {
+          if (!kConv) {
             for (int mb = 0; mb < mb_pair; ++mb)
               tma_load_3d_pair(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, rb * kBK, row0 + mb * 128, smp,
                                lead_full_a + g * 8);
@@ -683,14 +690,18 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
   }
 }
 
-template <int MB, bool kDgrad>
-int launch_pair_contract(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
+template <int MB, bool kDgrad, bool kConv>
+int launch_pair_contract_v(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
   static SmemOptIn opt_in;
-  const int rc = allow_dynamic_smem(contract_pair_kernel<MB, kDgrad>, kPairSmem, &opt_in);
+  const int rc = allow_dynamic_smem(contract_pair_kernel<MB, kDgrad, kConv>, kPairSmem, &opt_in);
   if (rc != BNN_OK) return rc;
-  contract_pair_kernel<MB, kDgrad><<<grid, kThreadsTma, kPairSmem, st>>>(p);
+  contract_pair_kernel<MB, kDgrad, kConv><<<grid, kThreadsTma, kPairSmem, st>>>(p);
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
+}
+template <int MB, bool kDgrad>
+int launch_pair_contract(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
+  return p.conv.on ? launch_pair_contract_v<MB, kDgrad, true>(p, grid, st) : launch_pair_contract_v<MB, kDgrad, false>(p, grid, st);
 }
 
 bool pair_enabled() {

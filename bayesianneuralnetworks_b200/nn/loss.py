@@ -32,6 +32,22 @@ def _scalar_prior(prior, what):
     return float(prior.loc), float(prior.scale)
 
 
+def fused_kl_entries(model):
+    """[(WeightNormal, prior_loc, prior_scale)] of every variational tensor the traversal finds, in its order (weights
+    before biases, loss.py:17-20) — for callers that need the KL of each tensor from a fused sweep (prune.kl_and_prune).
+    Raises NotImplementedError for tensors without a fused form (full covariance, tensor-valued priors)."""
+    def visit(param, module, type):
+        if not isinstance(param, WeightNormal):
+            raise NotImplementedError(f"no fused KL for {param.__class__.__name__}")
+        loc, scale = _scalar_prior(module.weight_prior if type == 'w' else module.bias_prior,
+                                   f"{module.__class__.__name__}.{'weight' if type == 'w' else 'bias'}")
+        return (param, loc, scale)
+    found = model.traverse(lambda m: apply_wb(m, visit, pass_module=True, pass_type=True))
+    if found is None:
+        raise ValueError('KLDivergence was not able to find BayasianModules')    # loss.py:34-36
+    return found
+
+
 class KLDivergence(Module):
     def __init__(self, number_of_batches=1):
         super(KLDivergence, self).__init__()

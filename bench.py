@@ -573,6 +573,31 @@ def bench_kl_prune(device, pk, world=1, tensors=64):
     res["prune_p0.75"]["single_call"] = entry(8 + 8 * p, best_swap(inner=1))
     res["prune_p0.75"]["timing"] = ("average of 2 back-to-back calls (best of 3), as for the KL legs; `single_call` = one call "
                                     "bracketed on an idle stream, including the host-side preparation of the 64-entry table")
+    # the fused sweep SURVEY §8d counts at 8 + 8p B/pair: KL element sums of the (unpruned) tensors AND the pruned tensors
+    # from ONE pass over (mu, rho) (bnn_prune_into with kl_sum_out)
+    priors = [(0.0, 0.1)] * n_t
+
+    def kl_prune_swap():
+        out = spare[state["turn"]]
+        state["turn"] ^= 1
+        _C.prune_into([(m, r, k, None) for m, r in zip(mus, rhos)], out=out, kl_priors=priors)
+
+    def time_fused(reps=3, inner=2):
+        best = 1e30
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(inner):
+                kl_prune_swap()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b) * 1e-3 / inner)
+        return over_ranks(best)
+    restore_swap()
+    kl_prune_swap()
+    res["kl_prune_fused_p0.75"] = entry(8 + 8 * p, time_fused())
+    res["kl_prune_fused_p0.75"]["what"] = ("KL sums of the unpruned tensors + pruned outputs from one sweep (the pruning pass "
+                                           "reuses the KL pass, north_star); per-GPU sums only (no all-reduce in this leg)")
     restore_swap()
     prune_in_place()
     res["prune_p0.75_in_place"] = entry(8 + 8 * p, best_of(prune_in_place))

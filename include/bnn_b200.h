@@ -363,6 +363,13 @@ typedef struct bnn_prune_into_tensor {
   int64_t k;
   uint32_t flags;      /* BNN_PRUNE_GENERAL: force the general path (on a copy in the outputs) */
   uint32_t reserved;
+  /* optional by-product of the same sweep (north_star: "the pruning mask reuses that same pass"): the element sum of
+   * KL(N(mu, sigma) || N(prior_loc, prior_scale)) over the INPUT tensor, i.e. the per-tensor sum bnn_kl reports
+   * (loss.py:16-38), formed from the sigma / log sigma the key arithmetic computes anyway.  Agrees with bnn_kl to a few
+   * 1e-6 relative (approximate softplus / log2).  NULL: not computed.  numel == 0 leaves it untouched. */
+  double* kl_sum_out;
+  float prior_loc;
+  float prior_scale;
 } bnn_prune_into_tensor;
 size_t bnn_prune_into_workspace_size(const bnn_prune_into_tensor* tensors, int32_t n_tensors);
 int bnn_prune_into(const bnn_prune_into_tensor* tensors /* HOST array */, int32_t n_tensors, void* workspace,

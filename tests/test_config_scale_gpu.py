@@ -379,3 +379,27 @@ def test_implicit_conv_sampled_attribute_matches_the_forward_pass():
     assert rel_err(y, F.conv2d(x.double(), w.double(), b.double(), 1, 1)) < 2e-5
     assert rel_err(layer(x, sample=False), y) < 1e-6
     assert not torch.equal(layer(x), y)            # a fresh draw differs
+
+
+def test_kl_and_prune_returns_the_divergence_before_pruning_and_prunes_identically():
+    """PruneNormal.kl_and_prune: KLDivergence(n)(model) of the unpruned model as a by-product of the pruning sweep (large
+    tensors: bnn_prune_into's kl_sum_out; small ones: bnn_kl), same parameters afterwards as PruneNormal()(model, p)."""
+    import copy
+    import bayesianneuralnetworks_b200 as bnn
+    torch.manual_seed(3)
+
+    class Net(bnn.nn.BayesianNetworkModule):
+        def __init__(self):
+            super().__init__(1200, 10, 2)
+            self.layers = torch.nn.Sequential(bnn.nn.NormalLinear(1200, 1100), torch.nn.ELU(), bnn.nn.NormalLinear(1100, 10))
+
+        def _forward(self, x):
+            return self.layers(x)
+    a = Net().cuda()
+    b = copy.deepcopy(a)
+    want = bnn.nn.KLDivergence(number_of_batches=7)(a)
+    got = bnn.prune.PruneNormal().kl_and_prune(a, 0.6, number_of_batches=7)
+    assert float(got) == pytest.approx(float(want), rel=1e-5)
+    bnn.prune.PruneNormal()(b, 0.6)
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.equal(pa, pb)

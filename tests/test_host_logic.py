@@ -48,6 +48,7 @@ def test_binding_struct_sizes_match_the_header():
     assert ctypes.sizeof(_C.bnn_conv2d_geom) == 64
     assert ctypes.sizeof(_C.bnn_kl_tensor) == 56
     assert ctypes.sizeof(_C.bnn_prune_tensor) == 56
+    assert ctypes.sizeof(_C.bnn_prune_into_tensor) == 80
     assert ctypes.sizeof(_C.bnn_adam_tensor) == 88
 
 

@@ -375,6 +375,34 @@ def test_prune_several_groups_of_large_tensors(C, prune_mode):
             assert torch.equal(m, bm) and torch.equal(r, br)
 
 
+def test_prune_into_reports_the_kl_sums_of_the_same_sweep(C):
+    """north_star: "the pruning mask reuses that same pass".  bnn_prune_into's optional by-product — the KL element sum of
+    every INPUT tensor, formed from the sigma / log sigma of the key arithmetic — against bnn_kl on the same tensors, for
+    every kind of tensor the sweep distinguishes (sampled path, small tensor, k = 0, k = numel, forced general path,
+    ragged length, rho above the fast-math regime); the masks are the ones the plain call produces."""
+    g = torch.Generator().manual_seed(31)
+    shapes = [(700001,), (1 << 20,), (64, 64, 3, 3), (10,), (300007,), (300007,), (500000,)]
+    ks = [0.75, 0.9, 0.5, 0.5, 0.0, 1.0, 0.6]
+    params = [init_params(sh, g, fan_in=400) for sh in shapes]
+    params[6][1].mul_(-1.0).add_(-1.0)                     # rho around +1: the general softplus regime
+    dev = [(m.cuda(), r.cuda()) for m, r in params]
+    entries = [(m, r, orc.prune_count(p, m.numel()), None) for (m, r), p in zip(dev, ks)]
+    priors = [(0.0, 0.1), (0.05, 0.2), (0.0, 0.1), (0.0, 1.0), (0.0, 0.1), (-0.1, 0.3), (0.0, 0.5)]
+    ref = C.kl([(m, r, None, None, loc, sc, 1.0) for (m, r), (loc, sc) in zip(dev, priors)])
+    plain = C.prune_into(entries)
+    outs, sums = C.prune_into(entries, kl_priors=priors)
+    torch.cuda.synchronize()
+    assert sums.dtype == torch.float64 and sums.shape == (len(shapes),)
+    for i in range(len(shapes)):
+        assert float(sums[i]) == pytest.approx(float(ref[i]), rel=1e-5), (i, float(sums[i]), float(ref[i]))
+        assert torch.equal(outs[i][0], plain[i][0]) and torch.equal(outs[i][1], plain[i][1])
+    # forced general path: the sweep leaves the tensor to the fallback but still sums its KL
+    outs_g, sums_g = C.prune_into(entries[:2], flags=C.PRUNE_GENERAL, kl_priors=priors[:2])
+    for i in range(2):
+        assert float(sums_g[i]) == pytest.approx(float(ref[i]), rel=1e-5)
+        assert torch.equal(outs_g[i][0], plain[i][0]) and torch.equal(outs_g[i][1], plain[i][1])
+
+
 # ------------------------------------------------------------------------------------------------ contractions
 def gemm_inputs(M, N, K, S, shared_a, gen, bias=True):
     mu_w, rho_w = init_params((N, K), gen)
