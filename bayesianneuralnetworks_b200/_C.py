@@ -28,7 +28,9 @@ class BnnError(RuntimeError):
 class bnn_rng(ctypes.Structure):
     _fields_ = [("seed", ctypes.c_uint64), ("step", ctypes.c_uint64),
                 ("step_dev", ctypes.c_void_p), ("elem_offset", ctypes.c_uint64),
-                ("tensor_id", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("tensor_id", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+                ("row_sign", ctypes.c_void_p), ("col_sign", ctypes.c_void_p), ("rows", ctypes.c_int32),
+                ("cols", ctypes.c_int32)]
 
 
 class bnn_view(ctypes.Structure):
@@ -260,8 +262,17 @@ def _f32c(t, name):
     return t
 
 
-def make_rng(seed, step, tensor_id, elem_offset=0, step_dev=None):
+def make_rng(seed, step, tensor_id, elem_offset=0, step_dev=None, signs=None, sample_begin=0):
+    """signs = (row_sign [S, rows], col_sign [S, cols]) float32 CUDA tensors of +-1: rank-one sign noise (Flipout) for
+    the local samples [sample_begin, sample_begin + S) — the kernels index by the global sample number."""
     r = bnn_rng()
+    if signs is not None:
+        row, col = signs
+        require_cuda(row, col)
+        _f32c(row, "row_sign"), _f32c(col, "col_sign")
+        r.rows, r.cols = row.shape[-1], col.shape[-1]
+        r.row_sign = row.data_ptr() - 4 * sample_begin * r.rows
+        r.col_sign = col.data_ptr() - 4 * sample_begin * r.cols
     r.seed = seed & 0xFFFFFFFFFFFFFFFF
     r.step = step & 0xFFFFFFFFFFFFFFFF
     r.step_dev = None if step_dev is None else step_dev.data_ptr()

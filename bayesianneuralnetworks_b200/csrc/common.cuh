@@ -70,6 +70,9 @@ struct RngKey {        // resolved on the device at kernel entry (adds *step_dev
   uint32_t tensor_id;  // counter word 2
   uint32_t step_lo;    // counter word 3
   uint64_t elem_offset;  // added to the element index (slice of a larger tensor)
+  const float* row_sign; // rank-one sign noise (Flipout): eps(n, k) = row_sign[s * rows + n] * col_sign[s * cols + k]
+  const float* col_sign;
+  int rows, cols;
 };
 
 __device__ __forceinline__ RngKey resolve_rng(const bnn_rng& r) {
@@ -81,6 +84,7 @@ __device__ __forceinline__ RngKey resolve_rng(const bnn_rng& r) {
   k.tensor_id = r.tensor_id;
   k.step_lo = static_cast<uint32_t>(step);
   k.elem_offset = r.elem_offset;
+  k.row_sign = r.row_sign; k.col_sign = r.col_sign; k.rows = r.rows; k.cols = r.cols;
   return k;
 }
 

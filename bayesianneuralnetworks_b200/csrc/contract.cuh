@@ -40,12 +40,36 @@ struct EpsSrc {
   RngKey key;
   uint32_t sample;
 };
+// rank-one sign noise (Flipout): element idx = (n, k) of a [rows][cols] weight matrix (plus the slice offset)
+__device__ __forceinline__ float eps_rank_one(const EpsSrc& e, int64_t idx) {
+  const int64_t el = idx + static_cast<int64_t>(e.key.elem_offset);
+  const int64_t n = el / e.key.cols;
+  const int k = static_cast<int>(el - n * e.key.cols);
+  return __ldg(e.key.row_sign + static_cast<int64_t>(e.sample) * e.key.rows + n) *
+         __ldg(e.key.col_sign + static_cast<int64_t>(e.sample) * e.key.cols + k);
+}
+// kSigns: 1 = the launch uses rank-one sign noise, 0 = it does not (the TMA kernels are instantiated per case: the sign
+// vectors' pointers kept live across the generator loop cost registers those kernels do not have), -1 = decided at run time
+template <int kSigns = -1>
 __device__ __forceinline__ float4 eps_vec4(const EpsSrc& e, int64_t idx) {   // idx % 4 == 0
   if (e.inj != nullptr) return __ldg(reinterpret_cast<const float4*>(e.inj + idx));
+  if (kSigns == 1 || (kSigns == -1 && e.key.row_sign != nullptr)) {
+    if ((e.key.cols & 3) == 0 && (e.key.elem_offset & 3u) == 0) {      // the four elements share a row
+      const int64_t el = idx + static_cast<int64_t>(e.key.elem_offset);
+      const int64_t n = el / e.key.cols;
+      const int k = static_cast<int>(el - n * e.key.cols);
+      const float r = __ldg(e.key.row_sign + static_cast<int64_t>(e.sample) * e.key.rows + n);
+      const float* c = e.key.col_sign + static_cast<int64_t>(e.sample) * e.key.cols + k;
+      return make_float4(r * __ldg(c), r * __ldg(c + 1), r * __ldg(c + 2), r * __ldg(c + 3));
+    }
+    return make_float4(eps_rank_one(e, idx), eps_rank_one(e, idx + 1), eps_rank_one(e, idx + 2), eps_rank_one(e, idx + 3));
+  }
   return eps4(e.key, e.sample, static_cast<uint32_t>(idx >> 2));
 }
+template <int kSigns = -1>
 __device__ __forceinline__ float eps_one(const EpsSrc& e, int64_t idx) {
   if (e.inj != nullptr) return __ldg(e.inj + idx);
+  if (kSigns == 1 || (kSigns == -1 && e.key.row_sign != nullptr)) return eps_rank_one(e, idx);
   return eps1(e.key, e.sample, static_cast<uint64_t>(idx));
 }
 

@@ -218,7 +218,7 @@ __device__ __forceinline__ TmaPipe carve_tma(uint8_t* smem_raw) {
 //   kMnMajor = true : MN-major tile, K-rows = n (32), MN = k (kRows of them)            (data gradient)
 // Element (n, k) of the weight matrix lives at n * ldw + woff + k (ldw = K, woff = 0 for a plain [N][K] matrix; the
 // conv data gradient walks the (o, kh, kw, c) tensor with n = o, ldw = taps * C, woff = tap * C, k = c).
-template <int kRows, bool kMnMajor>
+template <int kRows, bool kMnMajor, int kSigns>
 __device__ __forceinline__ void gen_w_tile(uint32_t tile, const float* __restrict__ mu, const float* __restrict__ sigma,
                                            const EpsSrc& eps, int n0, int N, int k0, int K, int tid, int64_t ldw,
                                            int64_t woff) {
@@ -247,7 +247,7 @@ __device__ __forceinline__ void gen_w_tile(uint32_t tile, const float* __restric
       const int item = (trip * 4 + u) * kGroupThreads + tid;
       float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
       if (idx[u] >= 0) {
-        const float4 e = eps_vec4(eps, idx[u]);
+        const float4 e = eps_vec4<kSigns>(eps, idx[u]);
         w.x = fmaf(sg[u].x, e.x, m[u].x);
         w.y = fmaf(sg[u].y, e.y, m[u].y);
         w.z = fmaf(sg[u].z, e.z, m[u].z);
@@ -261,8 +261,10 @@ __device__ __forceinline__ void gen_w_tile(uint32_t tile, const float* __restric
   }
 }
 
-template <int MB, bool kDgrad, bool kConv>
+template <int MB, bool kDgrad, int kMode>      // kMode: 0 plain, 1 conv (im2col maps), 2 rank-one sign noise (Flipout)
 __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __grid_constant__ TmaContractParams p) {
+  constexpr bool kConv = kMode == 1;
+  constexpr int kSigns = kMode == 2 ? 1 : 0;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   long long w_kernel = 0, w_mma_w = 0, w_mma_a = 0, w_gen = 0, w_tma = 0;
   (void)w_kernel; (void)w_mma_w; (void)w_mma_a; (void)w_gen; (void)w_tma;
@@ -315,12 +317,12 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
       if (p.exp_flags & 1) { /* skip */ } else
 #endif
       if (!kDgrad)
-        gen_w_tile<128, false>(tile, p.mu_w, p.sigma_w, eps, col0, p.N, rb * kBK, p.K, tid, p.K, 0);
+        gen_w_tile<128, false, kSigns>(tile, p.mu_w, p.sigma_w, eps, col0, p.N, rb * kBK, p.K, tid, p.K, 0);
       else if (!kConv)
-        gen_w_tile<128, true>(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, col0, p.K, tid, p.K, 0);
+        gen_w_tile<128, true, kSigns>(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, col0, p.K, tid, p.K, 0);
       else {          // conv data gradient: k-block = (flipped tap, 32 output channels o0 ..)
         const int tapf = rb / p.conv.cblocks, o0 = (rb - tapf * p.conv.cblocks) * kBK;
-        gen_w_tile<128, true>(tile, p.mu_w, p.sigma_w, eps, o0, p.conv.w_rows, col0, p.K, tid,
+        gen_w_tile<128, true, kSigns>(tile, p.mu_w, p.sigma_w, eps, o0, p.conv.w_rows, col0, p.K, tid,
                               static_cast<int64_t>(p.conv.taps) * p.K, static_cast<int64_t>(p.conv.taps - 1 - tapf) * p.K);
       }
       fence_proxy_async_smem();
@@ -452,18 +454,20 @@ constexpr size_t kContractSmem = kSmemAux + 1024 + static_cast<size_t>(kASlots +
 // The conv variants (im2col tensor maps, tap-major weight rows) are separate instantiations: folded into one kernel, the
 // conv state kept live across the generator loop pushed every input-gradient variant over its register budget (116-152
 // bytes of spill stores in the hot loop: C4 input gradient 2.33 -> 2.86 ms).
-template <int MB, bool kDgrad, bool kConv>
+template <int MB, bool kDgrad, int kMode>
 int launch_tma_contract_v(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
   static SmemOptIn opt_in;
-  const int rc = allow_dynamic_smem(contract_tma_kernel<MB, kDgrad, kConv>, kContractSmem, &opt_in);
+  const int rc = allow_dynamic_smem(contract_tma_kernel<MB, kDgrad, kMode>, kContractSmem, &opt_in);
   if (rc != BNN_OK) return rc;
-  contract_tma_kernel<MB, kDgrad, kConv><<<grid, kThreadsTma, kContractSmem, st>>>(p);
+  contract_tma_kernel<MB, kDgrad, kMode><<<grid, kThreadsTma, kContractSmem, st>>>(p);
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
 }
 template <int MB, bool kDgrad>
 int launch_tma_contract(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
-  return p.conv.on ? launch_tma_contract_v<MB, kDgrad, true>(p, grid, st) : launch_tma_contract_v<MB, kDgrad, false>(p, grid, st);
+  if (p.conv.on) return launch_tma_contract_v<MB, kDgrad, 1>(p, grid, st);
+  if (p.rng_w.row_sign != nullptr) return launch_tma_contract_v<MB, kDgrad, 2>(p, grid, st);
+  return launch_tma_contract_v<MB, kDgrad, 0>(p, grid, st);
 }
 
 // ---------------------------------------------------------------------------------------------- CTA-pair forward / dgrad
@@ -501,9 +505,11 @@ __device__ __forceinline__ PairPipe carve_pair(uint8_t* smem_raw) {
   return p;
 }
 
-template <int MB, bool kDgrad, bool kConv>
+template <int MB, bool kDgrad, int kMode>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTma, 1)
 contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
+  constexpr bool kConv = kMode == 1;
+  constexpr int kSigns = kMode == 2 ? 1 : 0;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   long long w_kernel = 0, w_mma_w = 0, w_mma_a = 0, w_gen = 0, w_tma = 0;
   (void)w_kernel; (void)w_mma_w; (void)w_mma_a; (void)w_gen; (void)w_tma;
@@ -559,12 +565,12 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
       { BNN_T0(); mbar_wait(pipe.empty_w + group, ((it >> 2) & 1) ^ 1); BNN_ACC(w_gen); }
       const uint32_t tile = pipe.ring_w + group * kHalfTileBytes;
       if (!kDgrad)
-        gen_w_tile<64, false>(tile, p.mu_w, p.sigma_w, eps, half0, p.N, rb * kBK, p.K, tid, p.K, 0);
+        gen_w_tile<64, false, kSigns>(tile, p.mu_w, p.sigma_w, eps, half0, p.N, rb * kBK, p.K, tid, p.K, 0);
       else if (!kConv)
-        gen_w_tile<64, true>(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, half0, p.K, tid, p.K, 0);
+        gen_w_tile<64, true, kSigns>(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, half0, p.K, tid, p.K, 0);
       else {
         const int tapf = rb / p.conv.cblocks, o0 = (rb - tapf * p.conv.cblocks) * kBK;
-        gen_w_tile<64, true>(tile, p.mu_w, p.sigma_w, eps, o0, p.conv.w_rows, half0, p.K, tid,
+        gen_w_tile<64, true, kSigns>(tile, p.mu_w, p.sigma_w, eps, o0, p.conv.w_rows, half0, p.K, tid,
                              static_cast<int64_t>(p.conv.taps) * p.K, static_cast<int64_t>(p.conv.taps - 1 - tapf) * p.K);
       }
       fence_proxy_async_smem();
@@ -690,18 +696,20 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
   }
 }
 
-template <int MB, bool kDgrad, bool kConv>
+template <int MB, bool kDgrad, int kMode>
 int launch_pair_contract_v(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
   static SmemOptIn opt_in;
-  const int rc = allow_dynamic_smem(contract_pair_kernel<MB, kDgrad, kConv>, kPairSmem, &opt_in);
+  const int rc = allow_dynamic_smem(contract_pair_kernel<MB, kDgrad, kMode>, kPairSmem, &opt_in);
   if (rc != BNN_OK) return rc;
-  contract_pair_kernel<MB, kDgrad, kConv><<<grid, kThreadsTma, kPairSmem, st>>>(p);
+  contract_pair_kernel<MB, kDgrad, kMode><<<grid, kThreadsTma, kPairSmem, st>>>(p);
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
 }
 template <int MB, bool kDgrad>
 int launch_pair_contract(const TmaContractParams& p, dim3 grid, cudaStream_t st) {
-  return p.conv.on ? launch_pair_contract_v<MB, kDgrad, true>(p, grid, st) : launch_pair_contract_v<MB, kDgrad, false>(p, grid, st);
+  if (p.conv.on) return launch_pair_contract_v<MB, kDgrad, 1>(p, grid, st);
+  if (p.rng_w.row_sign != nullptr) return launch_pair_contract_v<MB, kDgrad, 2>(p, grid, st);
+  return launch_pair_contract_v<MB, kDgrad, 0>(p, grid, st);
 }
 
 bool pair_enabled() {
@@ -821,7 +829,7 @@ struct TmaWgradParams {
 // n-tiles and ONE k-tile, tcgen05.mma.cta_group::2 computes 256 (n) x 128 (k) per instruction, and each CTA loads its own
 // dY^T tile but only HALF of the shared A^T tile (48 instead of 64 KiB per stage and CTA: the kernel is paced by operand
 // delivery).  TMA bytes and the epilogue's buffer releases land on the leader's barriers; commits are multicast.
-template <bool kPair>
+template <bool kPair, bool kSignNoise>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_constant__ TmaWgradParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr uint32_t kTmemCols = 512;
@@ -994,7 +1002,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tma_kernel(const __grid_c
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (k + q * 4 < p.K) {
-                const float4 e = eps_vec4(eps, row + k + q * 4);
+                const float4 e = eps_vec4<kSignNoise ? 1 : 0>(eps, row + k + q * 4);
                 dm[q * 4 + 0] += g[q * 4 + 0]; dr[q * 4 + 0] = fmaf(g[q * 4 + 0], e.x, dr[q * 4 + 0]);
                 dm[q * 4 + 1] += g[q * 4 + 1]; dr[q * 4 + 1] = fmaf(g[q * 4 + 1], e.y, dr[q * 4 + 1]);
                 dm[q * 4 + 2] += g[q * 4 + 2]; dr[q * 4 + 2] = fmaf(g[q * 4 + 2], e.z, dr[q * 4 + 2]);
@@ -1186,10 +1194,12 @@ int wgrad_plan_and_launch(TmaWgradParams& p, int M, int N, int K, int S, cudaStr
   p.chunk_blocks = best_cb;
   p.n_chunks = best_n;
   const int groups = static_cast<int>((static_cast<int64_t>(S) * best_n + best_per - 1) / best_per);
-  static SmemOptIn opt_in_single, opt_in_pair;
-  rc = allow_dynamic_smem(wgrad_tma_kernel<false>, kWgradSmem, &opt_in_single);
-  if (rc != BNN_OK) return rc;
-  rc = allow_dynamic_smem(wgrad_tma_kernel<true>, kWgradSmem, &opt_in_pair);
+  static SmemOptIn opt_in[4];
+  const bool signs = p.rng_w.row_sign != nullptr;
+  rc = allow_dynamic_smem(wgrad_tma_kernel<false, false>, kWgradSmem, &opt_in[0]);
+  if (rc == BNN_OK) rc = allow_dynamic_smem(wgrad_tma_kernel<true, false>, kWgradSmem, &opt_in[1]);
+  if (rc == BNN_OK) rc = allow_dynamic_smem(wgrad_tma_kernel<false, true>, kWgradSmem, &opt_in[2]);
+  if (rc == BNN_OK) rc = allow_dynamic_smem(wgrad_tma_kernel<true, true>, kWgradSmem, &opt_in[3]);
   if (rc != BNN_OK) return rc;
   const int n_tiles = (N + 127) / 128, k_tiles = (K + 127) / 128;
   if (n_tiles >= 2 && pair_enabled() && static_cast<int64_t>(tiles) * groups >= 2 * sm_count()) {
@@ -1204,9 +1214,11 @@ int wgrad_plan_and_launch(TmaWgradParams& p, int M, int N, int K, int S, cudaStr
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    BNN_CUDA_OK(cudaLaunchKernelEx(&cfg, wgrad_tma_kernel<true>, p));
+    if (signs) BNN_CUDA_OK(cudaLaunchKernelEx(&cfg, wgrad_tma_kernel<true, true>, p));
+    else BNN_CUDA_OK(cudaLaunchKernelEx(&cfg, wgrad_tma_kernel<true, false>, p));
   } else {
-    wgrad_tma_kernel<false><<<dim3(n_tiles, k_tiles, groups), kWgThreads, kWgradSmem, st>>>(p);
+    if (signs) wgrad_tma_kernel<false, true><<<dim3(n_tiles, k_tiles, groups), kWgThreads, kWgradSmem, st>>>(p);
+    else wgrad_tma_kernel<false, false><<<dim3(n_tiles, k_tiles, groups), kWgThreads, kWgradSmem, st>>>(p);
   }
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;

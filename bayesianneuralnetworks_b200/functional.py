@@ -13,18 +13,20 @@ class DrawSpec:
     """Which eps a launch uses: Philox (seed, tensor_id, [sample_begin, sample_begin+S)) or an
     injected tensor [S, numel] (tests).  `step_dev` (optional int64[1] device tensor) is added to the
     Philox step word inside the kernels (CUDA-graph replays, runtime.graph_safe_rng)."""
-    __slots__ = ("seed", "tensor_id", "sample_begin", "step", "eps", "step_dev")
+    __slots__ = ("seed", "tensor_id", "sample_begin", "step", "eps", "step_dev", "signs")
 
-    def __init__(self, seed, tensor_id, draw_begin, eps=None, step_dev=None):
+    def __init__(self, seed, tensor_id, draw_begin, eps=None, step_dev=None, signs=None):
         self.seed = seed
         self.tensor_id = tensor_id
         self.sample_begin = draw_begin & 0xFFFFFFFF
         self.step = draw_begin >> 32
         self.eps = eps
         self.step_dev = step_dev
+        self.signs = signs            # (R [S, out], S [S, in]): rank-one sign noise instead of Philox normals (Flipout)
 
     def rng(self, elem_offset=0):
-        return _C.make_rng(self.seed, self.step, self.tensor_id, elem_offset=elem_offset, step_dev=self.step_dev)
+        return _C.make_rng(self.seed, self.step, self.tensor_id, elem_offset=elem_offset, step_dev=self.step_dev,
+                           signs=self.signs, sample_begin=self.sample_begin)
 
 
 def _check_f32_cuda(name, t):

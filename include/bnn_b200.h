@@ -60,6 +60,15 @@ typedef struct bnn_rng {
                              group) of a tensor and still draw the tensor-global stream */
   uint32_t tensor_id;
   uint32_t reserved;
+  /* Rank-one sign noise (Flipout, Wen et al. 2018; reference dense.py:63-83): when row_sign != NULL the eps of weight
+   * element (n, k) for sample index s is  row_sign[s * rows + n] * col_sign[s * cols + k]  (values +-1) instead of a Philox
+   * normal, so  y = x (mu + sigma o (r s^T))^T = x mu^T + ((x o s) sigma^T) o r  comes out of ONE sampled contraction and
+   * the backward kernels form d mu, d rho with the same eps.  s is the GLOBAL sample index (sample_begin + local index):
+   * pass pointers offset accordingly.  cols = row length of the weight matrix; rows = its row count. */
+  const float* row_sign;
+  const float* col_sign;
+  int32_t rows;
+  int32_t cols;
 } bnn_rng;
 
 /* A dense matrix operand seen through an NCHW window: logical element (m, n), m in [0, M),

@@ -176,3 +176,53 @@ def test_kl_of_mixed_model_with_full_covariance_layer_on_gpu():
     kl.backward()
     assert torch.allclose(mvn.weight.scale.grad.cpu(), T(z["g_w_scale"]), rtol=1e-4, atol=1e-7)
     assert torch.allclose(lin.weight.mean.grad.cpu(), T(z["g_lin_w_mean"]), rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", 2e-3)])
+@pytest.mark.parametrize("shape", [(64, 576, 10), (256, 128, 128), (33, 52, 7)])
+def test_fused_flipout_linear_equals_the_two_contraction_composite(shape, prec, tol):
+    """FlipoutNormalLinear on CUDA is ONE sampled contraction with the rank-one sign noise eps = R S^T (dense.py:63-83
+    rewritten as x (mean + stddev o R S^T)^T): output and the gradients of x, mean and scale against the reference's
+    two-contraction formula evaluated by torch in fp64 with the same signs — single pass and a batched pass of S = 5
+    Monte-Carlo samples."""
+    import bayesianneuralnetworks_b200 as bnn
+    from bayesianneuralnetworks_b200.nn import flipout
+    B, K, N = shape
+    torch.manual_seed(4)
+    bnn.set_precision(prec)
+    try:
+        lin = FlipoutNormalLinear(K, N).cuda()
+        x = torch.randn(B, K, device="cuda", requires_grad=True)
+        dy = torch.randn(B, N, device="cuda")
+        y = lin(x)
+        y.backward(dy)
+        R, S = lin.R.double(), lin.S.double()
+        xd = x.detach().double().requires_grad_(True)
+        mu = lin.weight.mean.detach().double().requires_grad_(True)
+        rho = lin.weight.scale.detach().double().requires_grad_(True)
+        sigma = 1e-10 + torch.nn.functional.softplus(rho)
+        ref = xd.matmul(mu.t()) + (xd * S).matmul(sigma.t()) * R
+        ref.backward(dy.double())
+
+        def close(a, b):
+            return float((a.double() - b).abs().max()) <= tol * float(b.abs().max()) + 1e-12
+        assert close(y, ref) and close(x.grad, xd.grad)
+        assert close(lin.weight.mean.grad, mu.grad) and close(lin.weight.scale.grad, rho.grad)
+        # sample=False reuses the draw
+        assert torch.equal(lin(x, sample=False), y)
+        # the composite (set_fused_flipout_linear(False)) gives the same numbers for the same signs
+        flipout.set_fused_flipout_linear(False)
+        assert close(lin(x, sample=False), ref)
+        flipout.set_fused_flipout_linear(True)
+        # batched Monte-Carlo pass: S sign pairs, one launch; every sample against the formula with ITS signs
+        net = Net(torch.nn.Sequential(lin), samples=5).cuda()
+        preds = net(x.detach())
+        assert len(preds) == 5
+        Rs, Ss = lin._signs
+        for s in range(5):
+            want = xd.detach().matmul(mu.detach().t()) + (xd.detach() * Ss[s].double()).matmul(sigma.detach().t()) * Rs[s].double()
+            assert close(preds[s], want)
+    finally:
+        bnn.set_precision("fp32")
+        flipout.set_fused_flipout_linear(True)

@@ -43,7 +43,7 @@ def test_header_symbols_are_exported_by_the_library():
 
 
 def test_binding_struct_sizes_match_the_header():
-    assert ctypes.sizeof(_C.bnn_rng) == 40
+    assert ctypes.sizeof(_C.bnn_rng) == 64
     assert ctypes.sizeof(_C.bnn_view) == 24
     assert ctypes.sizeof(_C.bnn_conv2d_geom) == 64
     assert ctypes.sizeof(_C.bnn_kl_tensor) == 56
