@@ -113,6 +113,8 @@ class ElboTrainer:
         self.graph_opt = None
         self.static_loss = None
         self.launches_per_step = None
+        self._copy_stream = None
+        self._prefetched = None
 
     def _bind_flat(self):
         """Gradients become views of ONE flat buffer (same strides as their parameter: channels_last trunk weights are
@@ -213,15 +215,69 @@ class ElboTrainer:
                 self.opt.step()
         self.launches_per_step = _C.launch_count - before
 
+    def prefetch(self, x, y):
+        """Start the host -> device copy of the NEXT step's (pinned) batch on a copy stream, so that it overlaps the step
+        that is running — what a DataLoader with pin_memory + non_blocking copies does for the reference loop
+        (train.py:52-56).  `step(x, y)` with the same tensors then only waits for that copy.  Two staging buffers
+        alternate; a buffer is rewritten only after the step that consumed it has picked it up."""
+        if x.is_cuda:
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staging = [None, None]
+            self._consumed = [None, None]
+            self._turn = 0
+        k = self._turn
+        self._turn ^= 1
+        with torch.cuda.stream(self._copy_stream):
+            if self._consumed[k] is not None:
+                self._copy_stream.wait_event(self._consumed[k])
+            if self._staging[k] is None or self._staging[k][0].shape != x.shape or self._staging[k][1].shape != y.shape:
+                self._staging[k] = (torch.empty(x.shape, dtype=x.dtype, device=self.device),
+                                    torch.empty(y.shape, dtype=y.dtype, device=self.device))
+            sx, sy = self._staging[k]
+            sx.copy_(x, non_blocking=True)
+            sy.copy_(y, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        self._prefetched = (x, y, k, ready)
+
+    def _take_prefetched(self, x, y):
+        """The staged device copy of (x, y) if prefetch() was called with exactly these tensors, else None."""
+        pf = self._prefetched
+        if pf is None or pf[0] is not x or pf[1] is not y:
+            return None
+        self._prefetched = None
+        _, _, k, ready = pf
+        torch.cuda.current_stream().wait_event(ready)
+        return k, self._staging[k]
+
+    def _release_staging(self, k):
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream())
+        self._consumed[k] = done
+
     def step(self, x, y):
         """One training step; returns the (device) loss tensor.  With a captured graph, x / y are copied into the
-        graph's static inputs (they may be pinned host tensors)."""
+        graph's static inputs (they may be pinned host tensors; `prefetch` overlaps that copy with the previous step)."""
+        staged = self._take_prefetched(x, y)
         if self.graph is None:
+            if staged is not None:
+                k, (dx, dy) = staged
+                loss = self._body(dx, dy)
+                self._release_staging(k)
+                return loss
             if not x.is_cuda:
                 x, y = x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
             return self._body(x, y)
-        self.sx.copy_(x, non_blocking=True)
-        self.sy.copy_(y, non_blocking=True)
+        if staged is not None:
+            k, (dx, dy) = staged
+            self.sx.copy_(dx, non_blocking=True)      # device -> device: microseconds
+            self.sy.copy_(dy, non_blocking=True)
+            self._release_staging(k)
+        else:
+            self.sx.copy_(x, non_blocking=True)
+            self.sy.copy_(y, non_blocking=True)
         self.graph.replay()
         if self.graph_opt is not None:
             self._exchange()

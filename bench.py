@@ -19,8 +19,8 @@ B = 1024, S = 32 on one GPU, sample-sharded S = 32 / N per GPU on N), `kl_prune`
 denominator), `reference_on_gpu` (N = 1: the unmodified reference classes on the same GPU through torch),
 `cpu_baseline`.
 
-One JSON line on stdout (rank 0).  `value`: inputs resident in HBM; `e2e`: the same step fed from pinned host memory with
-the loss read back every step; `roofline`: the dominant hot-path contraction timed live with CUDA events.
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM; `e2e`: the same step fed from pinned host memory (the next
+batch's copy overlaps the running step, as a pin_memory DataLoader does) with the loss read back every step; `roofline`: the dominant hot-path contraction timed live with CUDA events.
 `--impl reference` times the UNMODIFIED reference (baseline/_ref, installed by baseline/install_ref.py) on the host cores.
 
 Torch-side settings of the deterministic trunk (Conv2d / BatchNorm2d / ELU / Linear of the example models, outside the
@@ -300,12 +300,15 @@ def measure_step(env, workload, steps, warmup, precision, parallel_mode, with_e2
         env.barrier()
         t0, w0 = time.time(), time.perf_counter()
         last = None
+        if feed_from_host:
+            trainer.prefetch(*host[0])    # as a DataLoader does: the first batch is in flight before the loop starts
         for i in range(n_steps):
             env.flush.zero_()
             starts[i].record()
             x, y = host[i % n_host] if feed_from_host else dev[i % n_host]
-            loss = trainer.step(x, y)     # host-fed: pinned host -> the graph's static inputs, one async copy each
+            loss = trainer.step(x, y)     # host-fed: the step waits for ITS batch's pinned-host -> device copy ...
             if feed_from_host:
+                trainer.prefetch(*host[(i + 1) % n_host])   # ... and the next batch's copy overlaps this step
                 last = loss.item()        # device -> host read of the step's result, every step
             stops[i].record()
         env.barrier()
@@ -380,7 +383,10 @@ def measure_step(env, workload, steps, warmup, precision, parallel_mode, with_e2
         res["e2e"] = {"value": units / e2e_s, "unit": "samples*MC/s",
                       "h2d_bytes_per_step": x0.numel() * x0.element_size() + y0.numel() * y0.element_size(),
                       "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * e2e_s / steps, "last_loss": last_loss,
-                      "wall_s": e2e_wall}
+                      "wall_s": e2e_wall,
+                      "input_pipeline": "every step's batch is copied from pinned host memory (ElboTrainer.prefetch: a copy "
+                                        "stream, two staging buffers); the copy of batch i+1 is issued inside step i's timed "
+                                        "region and overlaps it, step i+1 waits for it; loss.item() every step"}
     if with_roofline:
         res["roofline"] = roof
         res["kernels_ms_per_step"] = per_kernel

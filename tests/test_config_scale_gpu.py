@@ -403,3 +403,33 @@ def test_kl_and_prune_returns_the_divergence_before_pruning_and_prunes_identical
     bnn.prune.PruneNormal()(b, 0.6)
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert torch.equal(pa, pb)
+
+
+def test_prefetched_batches_reach_the_captured_step():
+    """ElboTrainer.prefetch: the next batch's pinned-host -> device copy runs on a copy stream while the current step
+    replays; step() must then consume exactly that batch (the graph's static inputs hold it), in order, also when a
+    step is fed without a prefetch in between."""
+    import bayesianneuralnetworks_b200 as bnn
+    from bayesianneuralnetworks_b200.training import ElboTrainer
+    sys.path.insert(0, ROOT)
+    import bench
+    bnn.set_precision("tf32")
+    try:
+        torch.manual_seed(0)
+        model = bench.build_model("c2", 2).cuda()
+        tr = ElboTrainer(model, 10, graph=True)
+        gen = torch.Generator().manual_seed(1)
+        host = [tuple(t.pin_memory() for t in bench.synthetic_batch("c2", 32, gen)) for _ in range(5)]
+        tr.capture(host[0][0].cuda(), host[0][1].cuda())
+        tr.prefetch(*host[1])
+        for i in (1, 2, 3, 4, 0, 1):
+            loss = tr.step(*host[i])
+            nxt = host[(i + 1) % 5]
+            if i != 3:                      # one step without a prefetched batch: the direct copy path
+                tr.prefetch(*nxt)
+            torch.cuda.synchronize()
+            assert torch.equal(tr.sx.cpu(), host[i][0]) and torch.equal(tr.sy.cpu(), host[i][1])
+            assert torch.isfinite(loss)
+        tr.release()
+    finally:
+        bnn.set_precision("fp32")
