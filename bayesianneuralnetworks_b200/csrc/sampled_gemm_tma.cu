@@ -22,6 +22,10 @@
 #include <cstdlib>
 #include <mutex>
 
+#include <algorithm>
+#include <array>
+#include <vector>
+
 #include "contract.cuh"
 
 namespace bnn {
@@ -165,7 +169,18 @@ __device__ __forceinline__ void conv_pixel(const ConvCoords& c, int m, int smp, 
   *n = smp * c.imgs + img;
 }
 
+// Heterogeneous tile list of the CTA-pair kernel (narrow layers whose uniform 1024-row tiles need between one and two
+// waves): a sample's rows are cut into `a` tiles of 8 row blocks followed by `b` tiles of 6; samples [0, s1) use (a1, b1),
+// the others (a2, b2).  The grid lists every 8-block tile first, then the 6-block ones, so that a pair slot runs one of
+// each instead of two full ones (C3 conv forward: 74 + 72 tiles on 74 slots: 1.75 wave-equivalents instead of 2).
+struct TilePlan {
+  int on;
+  int n_a;                  // number of 8-block tiles of the launch
+  int s1, a1, b1, a2, b2;
+};
+
 struct TmaContractParams {
+  TilePlan plan;
   CUtensorMap map_l;        // fwd: activations [S or 1][M][K]; dgrad: dY [S][M][N]; conv: the NHWC tensor (im2col map)
   ConvCoords conv;
   int64_t w_numel;          // elements of the weight tensor (injected eps: stride between samples)
@@ -537,17 +552,36 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(pipe.tmem_slot);
 
   const int col0 = blockIdx.y * 128;                   // output columns of the PAIR (n for fwd, k for dgrad)
-  const int row0 = blockIdx.x * (MB * 128);            // output rows of THIS CTA (the pair is adjacent in x)
+  // the pair's tile: sample, first row of the leader, row blocks per CTA (uniform grid: MB; tile plan: 4 or 3)
+  int tile_s = blockIdx.z, lead_row0 = (blockIdx.x & ~1u) * (MB * 128), mb_cap = MB;
+  if (MB == 4 && p.plan.on) {
+    const TilePlan& pl = p.plan;
+    const int t = blockIdx.x >> 1;
+    if (t < pl.n_a) {
+      const int first = pl.s1 * pl.a1;
+      int j;
+      if (t < first) { tile_s = t / pl.a1; j = t - tile_s * pl.a1; }
+      else { const int u = t - first; tile_s = pl.s1 + u / pl.a2; j = u - (u / pl.a2) * pl.a2; }
+      lead_row0 = j * (8 * 128);
+    } else {
+      const int v = t - pl.n_a, first = pl.s1 * pl.b1;
+      int j, a;
+      if (v < first) { tile_s = v / pl.b1; j = v - tile_s * pl.b1; a = pl.a1; }
+      else { const int u = v - first; tile_s = pl.s1 + u / pl.b2; j = u - (u / pl.b2) * pl.b2; a = pl.a2; }
+      lead_row0 = (a * 8 + j * 6) * 128;
+      mb_cap = 3;
+    }
+  }
+  const int row0 = lead_row0 + static_cast<int>(blockIdx.x & 1u) * (mb_cap * 128);      // output rows of THIS CTA
   const int n_cols = kDgrad ? p.K : p.N;
   const int n_red = kDgrad ? p.N : p.K;
-  const int s_begin = p.sum_samples ? static_cast<int>(blockIdx.z) * p.z_per : blockIdx.z;
-  const int s_end = p.sum_samples ? (s_begin + p.z_per < p.S ? s_begin + p.z_per : p.S) : blockIdx.z + 1;
+  const int s_begin = p.sum_samples ? static_cast<int>(blockIdx.z) * p.z_per : tile_s;
+  const int s_end = p.sum_samples ? (s_begin + p.z_per < p.S ? s_begin + p.z_per : p.S) : tile_s + 1;
   const int red_blocks = (n_red + kBK - 1) / kBK;
   // both CTAs walk the same number of M-blocks (the leader holds the lower rows, so its count is the larger one);
   // tiles beyond M are zero-filled by TMA and never stored
-  const int lead_row0 = (blockIdx.x & ~1u) * (MB * 128);
   int mb_pair = (p.M - lead_row0 + 127) / 128;
-  if (mb_pair > MB) mb_pair = MB;
+  if (mb_pair > mb_cap) mb_pair = mb_cap;
 
   if (warp < kGenWarps) {
     // ------------------------------------------------------------------ weight generators (half tile per CTA, four groups)
@@ -648,7 +682,7 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
       float b = 0.f;
       const int n = col0 + et;
       if (p.mu_b != nullptr && n < p.N) {
-        const int s = blockIdx.z;
+        const int s = tile_s;
         const float e = p.eps_b ? __ldg(p.eps_b + static_cast<int64_t>(s) * p.N + n)
                                 : eps1(resolve_rng(p.rng_b), p.sample_begin + s, static_cast<uint64_t>(n));
         b = fmaf(__ldg(p.sigma_b + n), e, __ldg(p.mu_b + n));
@@ -659,7 +693,7 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
     mbar_wait(pipe.accum_full, 0);
     tc_fence_after_sync();
     View out = p.out;
-    out.base += (p.sum_samples ? 0 : static_cast<int64_t>(blockIdx.z) * p.out_sample_stride);
+    out.base += (p.sum_samples ? 0 : static_cast<int64_t>(tile_s) * p.out_sample_stride);
     const int cols_here = n_cols - col0 < 128 ? n_cols - col0 : 128;
     for (int mb = 0; mb < mb_pair; ++mb) {
       const int m = row0 + mb * 128 + quad * 32 + lane;
@@ -736,6 +770,66 @@ int forced_variant() {
   return v;
 }
 
+// Tile plan of the CTA-pair kernel (TilePlan): when the uniform grid needs a fraction of a wave more than a whole
+// number (1 < tiles / slots < 2 is the case that matters: the example conv layers), look for a cut of every sample into
+// 8- and 6-row-block tiles — at most two kinds of samples — whose list schedule (all 8-block tiles first) finishes
+// earlier.  Cost unit: one row block of MMAs per k-block; the fixed cost per tile is ignored, so a plan must win by 8 %.
+bool tile_plan_enabled() {                                     // BNN_TILE_PLAN=0 (read once) keeps the uniform grid: A/B runs
+  static const bool on = [] { const char* e = getenv("BNN_TILE_PLAN"); return !(e != nullptr && e[0] == '0'); }();
+  return on;
+}
+bool solve_pair_tiles(TilePlan* plan, int m_blocks, int S, int slots);
+bool plan_pair_tiles(TilePlan* plan, int m_blocks, int S, int gx, int gz, bool sum_samples, int slots) {
+  plan->on = 0;
+  if (!tile_plan_enabled() || sum_samples || gx != 1 || gz != S || S < 1 || slots < 1) return false;
+  // the search costs milliseconds: one result per (rows, samples, machine) for the life of the process
+  static std::mutex mu;
+  static std::vector<std::pair<std::array<int, 3>, TilePlan>> cache;
+  const std::array<int, 3> key = {m_blocks, S, slots};
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& e : cache)
+    if (e.first == key) { *plan = e.second; return plan->on != 0; }
+  TilePlan found{};
+  solve_pair_tiles(&found, m_blocks, S, slots);
+  cache.emplace_back(key, found);
+  *plan = found;
+  return plan->on != 0;
+}
+bool solve_pair_tiles(TilePlan* plan, int m_blocks, int S, int slots) {
+  plan->on = 0;
+  const int units = (m_blocks + 1) / 2;                        // row-block pairs per sample (one row block per CTA)
+  const int uniform_tiles = S * ((units + 3) / 4);
+  if (uniform_tiles <= slots || uniform_tiles > 4 * slots) return false;
+  auto makespan = [&](int n_a, int n_b) {                      // greedy list schedule on `slots` machines
+    std::vector<int> load(static_cast<size_t>(slots), 0);
+    auto place = [&](int cost) { auto it = std::min_element(load.begin(), load.end()); *it += cost; };
+    for (int i = 0; i < n_a; ++i) place(4);
+    for (int i = 0; i < n_b; ++i) place(3);
+    return *std::max_element(load.begin(), load.end());
+  };
+  const int base = makespan(uniform_tiles, 0);
+  struct Cut { int a, b; };
+  std::vector<Cut> cuts;                                       // 4 a + 3 b covers the units with at most 2 to spare
+  for (int a = 0; a * 4 <= units + 3; ++a)
+    for (int b = 0; b <= (units + 2) / 3 + 1; ++b) {
+      const int cover = 4 * a + 3 * b;
+      if (cover >= units && cover <= units + 2 && (a > 0 || b > 0)) cuts.push_back({a, b});
+    }
+  int best = base;
+  TilePlan found = *plan;
+  for (const Cut& c1 : cuts)
+    for (const Cut& c2 : cuts)
+      for (int s1 = 0; s1 <= S; ++s1) {
+        if ((s1 == 0 && (&c1 != &cuts[0])) || (s1 == S && (&c2 != &cuts[0]))) continue;      // unused class: one representative
+        const int n_a = s1 * c1.a + (S - s1) * c2.a, n_b = s1 * c1.b + (S - s1) * c2.b;
+        const int ms = makespan(n_a, n_b);
+        if (ms < best) { best = ms; found = TilePlan{1, n_a, s1, c1.a, c1.b, c2.a, c2.b}; }
+      }
+  if (best * 100 > base * 92) return false;
+  *plan = found;
+  return true;
+}
+
 template <bool kDgrad>
 int dispatch_tma_contract(TmaContractParams& p, int n_cols, cudaStream_t st) {
   const int m_blocks = (p.M + 127) / 128;
@@ -790,6 +884,8 @@ int dispatch_tma_contract(TmaContractParams& p, int n_cols, cudaStream_t st) {
   if (forced > 0 || (forced == 0 && m_blocks > 4)) best = forced;
   if (best == 0) {                                                // two CTAs (one cluster) per 1024 rows
     const int pairs = (m_blocks + 7) / 8;
+    if (plan_pair_tiles(&p.plan, m_blocks, p.S, gx, gz, p.sum_samples != 0, sms / 2))
+      return launch_pair_contract<4, kDgrad>(p, dim3(2 * (p.plan.n_a + p.plan.s1 * p.plan.b1 + (p.S - p.plan.s1) * p.plan.b2), 1, 1), st);
     return launch_pair_contract<4, kDgrad>(p, dim3(2 * pairs, gx, gz), st);
   }
   if (best == 4) return launch_tma_contract<4, kDgrad>(p, dim3(gx, (m_blocks + 3) / 4, gz), st);

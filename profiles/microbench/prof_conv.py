@@ -54,3 +54,21 @@ for name, fn in (("fwd", fwd), ("dgrad", dgrad), ("wgrad", wgrad)):
         torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b))
     print(f"{which} {'shared' if shared else 'per-sample'} {name}: {best * 1e3:.1f} us  {flops / best / 1e9:.1f} TFLOP/s")
+
+# profiling builds only (BNN_EXTRA_NVCC_FLAGS=-DBNN_PROFILE_WAITS): wait cycles of the contraction kernels' roles
+import ctypes  # noqa: E402
+try:
+    f = C.lib().bnn_debug_wait_counters
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
+    buf = (ctypes.c_ulonglong * 8)()
+    f(buf, 1)
+    for name, fn in (("fwd", fwd), ("dgrad", dgrad)):
+        fn()
+        torch.cuda.synchronize()
+        if f(buf, 1) == 0 and buf[5]:
+            n = buf[5]
+            print(f"{name}: CTAs {n}  kernel {buf[0] / n:.0f} cycles/CTA | MMA thread waits: weights {buf[1] / n * 2:.0f} (leader only) "
+                  f"activations {buf[2] / n * 2:.0f} | generators wait for a free slot {buf[3] / n:.0f} | TMA thread waits {buf[4] / n:.0f}")
+except AttributeError:
+    pass

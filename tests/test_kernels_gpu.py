@@ -546,6 +546,34 @@ def test_every_tma_contraction_variant_on_small_shapes(C, request, variant, M, N
     assert rel_err(da, d_a) < TOL[0]
 
 
+@pytest.mark.parametrize("M,N,K,S", [(2100, 128, 96, 30), (1300, 100, 64, 50), (3000, 128, 32, 19), (8192, 128, 64, 16),
+                                     (1050, 64, 64, 60)])
+def test_pair_kernel_tile_plan_covers_every_row_once(C, request, M, N, K, S):
+    """Narrow layers (one column tile) whose uniform 1024-row pair tiles need a fraction of a wave more than the machine
+    has slots are cut into 8- and 6-row-block tiles, two kinds of samples (sampled_gemm_tma.cu: TilePlan).  Forward and
+    per-sample input gradient on shapes whose plans differ (different cuts per sample, ragged last block, a sample count
+    that is not a multiple of anything): every output row must be written exactly once — NaN-filled outputs, torch fp64
+    reference with the injected eps."""
+    C.force_contract_variant("pair")
+    request.addfinalizer(lambda: C.force_contract_variant(None))
+    g = torch.Generator().manual_seed(33)
+    a, mu_w, rho_w, mu_b, rho_b, eps_w, eps_b = gemm_inputs(M, N, K, S, False, g)
+    y = run_fwd(C, a, mu_w, rho_w, mu_b, rho_b, eps_w, eps_b, S, 0)
+    assert bool(torch.isfinite(y).all())
+    sig = orc.stddev(rho_w.double())
+    w = mu_w.double().unsqueeze(0) + sig.unsqueeze(0) * eps_w.double()                     # [S, N, K]
+    b = mu_b.double().unsqueeze(0) + orc.stddev(rho_b.double()).unsqueeze(0) * eps_b.double()
+    ref = torch.bmm(a.double(), w.transpose(1, 2)) + b.unsqueeze(1)
+    assert rel_err(y, ref) < TOL[0]
+    dy = torch.randn(S, M, N, generator=g)
+    ddy = dy.cuda()
+    da = torch.full(tuple(a.shape), float("nan"), device="cuda")
+    C.sampled_gemm_dgrad(C.make_view(ddy.data_ptr(), N, 1), M * N, mu_w.cuda(), C.stddev(rho_w.cuda()), eps_w.cuda(), da,
+                         K, M * K, M, N, K, S, 0, C.make_rng(0, 0, 0), 0)
+    assert bool(torch.isfinite(da).all())
+    assert rel_err(da, torch.bmm(dy.double(), w)) < TOL[0]
+
+
 def test_wgrad_philox_equals_injected(C):
     g = torch.Generator().manual_seed(9)
     M, N, K, S = 96, 72, 136, 5
