@@ -230,16 +230,52 @@ class NormalConv1d(_FusedBayesianLayer, NormalConvNd):
         return y.squeeze(2)
 
 
-class NormalConv3d(NormalConvNd):
-    """conv.py:122-142 — no fused contraction: the sampled weights are materialised by the library
-    (autograd-tracked) and contracted by torch's conv3d, one MC sample per call."""
+_UNFOLD_LIMIT_BYTES = 1 << 30      # NormalConv3d: largest lowered activation matrix the fused path builds
+
+
+class NormalConv3d(_FusedBayesianLayer, NormalConvNd):
+    """conv.py:122-142.  CUDA, groups == 1: the input is lowered by torch (pad + three `unfold`s: a differentiable
+    strided view, one copy into a `[B·OD·OH·OW, C·kd·kh·kw]` matrix whose column order IS the weight's memory order) and
+    contracted by the sample-and-contract kernels (`SampledLinear`: all S Monte-Carlo samples in one launch, the sampled
+    weights never materialised, eps regenerated in the backward pass); autograd carries the input gradient back through
+    the lowering.  Grouped layers, CPU tensors and lowered matrices above 1 GiB keep the reference's form: the sampled
+    weights are materialised by the library (autograd-tracked) and contracted by torch's conv3d, one sample per call."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
                  bias=True, prior=Normal(0, .1)):
         super(NormalConv3d, self).__init__(in_channels, out_channels, _triple(kernel_size), _triple(stride),
                                            _triple(padding), _triple(dilation), False, groups, bias, prior)
+        self._fused = groups == 1
+
+    def _lowered_bytes(self, x):
+        k, s, p, d = (tuple(self.kernel_size), tuple(self.stride), tuple(self.padding), tuple(self.dilation))
+        out = [(x.shape[2 + i] + 2 * p[i] - d[i] * (k[i] - 1) - 1) // s[i] + 1 for i in range(3)]
+        return 4 * x.shape[0] * max(out[0], 0) * max(out[1], 0) * max(out[2], 0) * x.shape[1] * k[0] * k[1] * k[2]
 
     def forward(self, x, sample=True):
-        if sample:
-            self.sample()
-        return torch.nn.functional.conv3d(x, *self.sampled, self.stride, self.padding, self.dilation, self.groups)
+        fused = (self._fused and x.is_cuda and x.dim() == 5 and x.dtype == torch.float32
+                 and self._lowered_bytes(x) <= _UNFOLD_LIMIT_BYTES)
+        if not fused:
+            if runtime.current_mc() is not None:
+                raise RuntimeError("NormalConv3d: this call does not qualify for the batched Monte-Carlo forward")
+            if sample:
+                self.sample()
+            return torch.nn.functional.conv3d(x, *self.sampled, self.stride, self.padding, self.dilation, self.groups)
+        S, shared, offset, total, ctx = self._mc_shape(x)
+        spec_w, spec_b = self._draws(sample, S, offset, total)
+        k, s, p, d = (tuple(self.kernel_size), tuple(self.stride), tuple(self.padding), tuple(self.dilation))
+        cols = torch.nn.functional.pad(x, (p[2], p[2], p[1], p[1], p[0], p[0])) if any(p) else x
+        for i in range(3):                 # [rows, C, OD, OH, OW, kd, kh, kw]: window axes are appended in order
+            cols = cols.unfold(2 + i, (k[i] - 1) * d[i] + 1, s[i])
+            if d[i] > 1:
+                cols = cols[..., ::d[i]]
+        rows, C, OD, OH, OW = cols.shape[:5]
+        col = cols.permute(0, 2, 3, 4, 1, 5, 6, 7).reshape(rows * OD * OH * OW, C * k[0] * k[1] * k[2])
+        O = self.weight.mean.shape[0]
+        y = SampledLinear.apply(col, self.weight.mean.view(O, -1), self.weight.scale.view(O, -1),
+                                self.bias.mean if self.bias is not None else None,
+                                self.bias.scale if self.bias is not None else None,
+                                S, shared, spec_w, spec_b, runtime.precision())
+        if ctx is not None:
+            ctx.expanded = True
+        return y.view(-1, OD, OH, OW, O).permute(0, 4, 1, 2, 3).contiguous()

@@ -186,7 +186,8 @@ def test_mc_batching_plan():
         def forward(self, x):
             return x * self.w
     assert not Net(torch.nn.Sequential(Stateful(), NormalLinear(3, 3)))._mc_plan()[0]     # unknown code with state
-    assert not Net(torch.nn.Sequential(NormalConv3d(1, 1, 1)))._mc_plan()[0]              # no fused 3-d path
+    assert not Net(torch.nn.Sequential(NormalConv3d(2, 2, 1, groups=2)))._mc_plan()[0]    # grouped 3-d layers: no fused path
+    assert Net(torch.nn.Sequential(NormalConv3d(1, 1, 1)))._mc_plan()[0]                  # groups == 1: lowering + sampled GEMM
 
 
 # ------------------------------------------------------------------------------------------------ C ABI error behaviour

@@ -301,6 +301,42 @@ def test_normal_conv_known_answer(nd, cfg, bias):
     assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("cfg", [(3, 5, (2, 3, 3), (1, 1, 1), (0, 1, 1), (1, 1, 1)), (4, 8, 3, 2, 1, 1), (2, 4, (3, 1, 2), (1, 2, 1), (2, 0, 1), (2, 1, 1))])
+def test_normal_conv3d_fused_path_matches_torch_conv3d_on_injected_eps(cfg):
+    """NormalConv3d (conv.py:122-142) with groups == 1: torch lowers the input (pad + unfold, differentiable) and the
+    sample-and-contract kernels do the rest for all S samples in one launch.  Output and the gradients of the input, the
+    weight and the bias against torch's conv3d on mean + stddev * eps with the SAME eps, single pass and inside a batched
+    Monte-Carlo forward (fp32 mode, 1e-5 class)."""
+    import bayesianneuralnetworks_b200 as bnn
+    i, o, k, s, p, d = cfg
+    torch.manual_seed(5)
+    layer = NormalConv3d(i, o, k, s, p, d).cuda()
+    S, B = 3, 4
+    x = torch.randn(B, i, 7, 8, 9, device="cuda", requires_grad=True)
+    eps = {layer.weight: torch.randn((S,) + tuple(layer.weight.shape)), layer.bias: torch.randn(S, o)}
+    net = Net(torch.nn.Sequential(layer), samples=S).cuda()
+    with bnn.injected_eps(eps):
+        preds = net(x)
+    assert isinstance(preds, list) and len(preds) == S
+    dy = [torch.randn_like(q) for q in preds]
+    sum((q * g).sum() for q, g in zip(preds, dy)).backward()
+    xr = x.detach().double().requires_grad_(True)
+    mw, rw = (t.detach().double().requires_grad_(True) for t in (layer.weight.mean, layer.weight.scale))
+    mb, rb = (t.detach().double().requires_grad_(True) for t in (layer.bias.mean, layer.bias.scale))
+    total = 0
+    for smp in range(S):
+        w = mw + (1e-10 + F.softplus(rw)) * eps[layer.weight][smp].double().cuda()
+        b = mb + (1e-10 + F.softplus(rb)) * eps[layer.bias][smp].double().cuda()
+        ref = F.conv3d(xr, w, b, layer.stride, layer.padding, layer.dilation)
+        assert preds[smp].shape == ref.shape
+        assert float((preds[smp].double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+        total = total + (ref * dy[smp].double()).sum()
+    total.backward()
+    for got, want in ((x.grad, xr.grad), (layer.weight.mean.grad, mw.grad), (layer.weight.scale.grad, rw.grad),
+                      (layer.bias.mean.grad, mb.grad), (layer.bias.scale.grad, rb.grad)):
+        assert float((got.double() - want).abs().max()) <= 2e-5 * float(want.abs().max()) + 1e-9
+
+
 def test_forward_sample_false_reuses_draw():
     layer = NormalLinear(32, 16).cuda()
     x = torch.randn(8, 32, device="cuda")
