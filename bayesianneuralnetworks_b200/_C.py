@@ -160,6 +160,8 @@ _SIGNATURES = {
     "bnn_selftest_prune_interval": (ctypes.c_int, [_c_f32p, _c_f32p, ctypes.c_int64, _c_f32p, _c_f32p, ctypes.c_int32,
                                                    ctypes.c_void_p]),
     "bnn_debug_force_contract_variant": (ctypes.c_int, [ctypes.c_int32]),
+    "bnn_debug_pair_tile_plan": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                ctypes.POINTER(ctypes.c_int32)]),
     "bnn_selftest_umma": (ctypes.c_int, [_c_f32p, ctypes.c_void_p]),
     "bnn_selftest_umma_mn": (ctypes.c_int, [_c_f32p, ctypes.c_void_p]),
 }

@@ -145,6 +145,7 @@ int tma_conv_wgrad(const float* dy, const float* x, int64_t x_sample_stride, con
                    float* dmu_w, float* drho_w, const bnn_conv2d_nhwc* g, int S, uint32_t sample_begin,
                    const bnn_rng* rng_w, cudaStream_t st);
 int tma_selftest(float* max_err_dev, cudaStream_t st);
+int tma_pair_tile_plan(int m_blocks, int S, int slots, int32_t* out7);   // test aid: TilePlan fields {on, n_a, s1, a1, b1, a2, b2}
 int tma_force_variant(int variant);   // test aid: 0 = CTA pair, 1 / 2 / 4 = row blocks per CTA, -1 = cost model (default)
 int tma_wait_counters(unsigned long long* out8, int reset);   // profiling builds (-DBNN_PROFILE_WAITS) only
 

@@ -1454,6 +1454,13 @@ int tma_wait_counters(unsigned long long* out8, int reset) {
 #endif
 }
 
+int tma_pair_tile_plan(int m_blocks, int S, int slots, int32_t* out7) {      // host only: the plan the launcher would use
+  TilePlan plan{};
+  solve_pair_tiles(&plan, m_blocks, S, slots);
+  out7[0] = plan.on; out7[1] = plan.n_a; out7[2] = plan.s1; out7[3] = plan.a1; out7[4] = plan.b1; out7[5] = plan.a2; out7[6] = plan.b2;
+  return BNN_OK;
+}
+
 int tma_force_variant(int variant) {
   g_forced_variant.store(variant < -1 || variant > 4 || variant == 3 ? -1 : variant, std::memory_order_relaxed);
   return BNN_OK;

@@ -401,6 +401,11 @@ int bnn_selftest_umma_mn(float* max_err_dev, void* stream);
  * shapes reach all of them: 0 = CTA pair (needs more than four 128-row blocks), 1 / 2 / 4 = row blocks per CTA,
  * -1 = the launcher's cost model (default).  Process-wide; not for production use. */
 int bnn_debug_force_contract_variant(int32_t variant);
+/* test aid, host arithmetic only: the heterogeneous tile list of the CTA-pair kernel for `samples` samples of `m_blocks`
+ * 128-row blocks on `pair_slots` SM pairs (narrow layers: one column tile).  out7 = {on, n_a, s1, a1, b1, a2, b2}: samples
+ * [0, s1) are cut into a1 tiles of 8 row blocks followed by b1 tiles of 6, the others into a2 / b2; n_a = number of
+ * 8-block tiles; on = 0: the uniform grid is kept. */
+int bnn_debug_pair_tile_plan(int32_t m_blocks, int32_t samples, int32_t pair_slots, int32_t* out7);
 
 #ifdef __cplusplus
 }

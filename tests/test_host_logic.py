@@ -411,3 +411,62 @@ def test_elbo_adam_plans_the_same_tensors_and_coefficients_as_kl_divergence():
     net.layers[0].weight.grad = torch.ones_like(net.layers[0].weight)
     opt.zero_grad()
     assert net.layers[0].weight.grad is None
+
+
+def test_pair_kernel_tile_plans_cover_every_row_block_exactly_once():
+    """sampled_gemm_tma.cu: TilePlan.  For a sweep of (row blocks per sample, samples) the plan the launcher would use
+    (bnn_debug_pair_tile_plan, host arithmetic) is decoded exactly as the kernel decodes blockIdx.x and must (1) give
+    every sample a run of tiles that starts at row block 0, is contiguous and covers all of its row blocks, spilling at
+    most two block pairs past the end (those rows are masked), and (2) beat the uniform grid's list schedule."""
+    import ctypes
+    lib = _C.lib()
+    slots = 74
+    n_plans = 0
+    for m_blocks in list(range(5, 80)) + [128, 200]:
+        for S in (3, 8, 16, 19, 30, 50, 60):
+            out = (ctypes.c_int32 * 7)()
+            assert lib.bnn_debug_pair_tile_plan(m_blocks, S, slots, out) == 0
+            on, n_a, s1, a1, b1, a2, b2 = list(out)
+            if not on:
+                continue
+            n_plans += 1
+            n_b = s1 * b1 + (S - s1) * b2
+            assert n_a == s1 * a1 + (S - s1) * a2
+            tiles = {s: [] for s in range(S)}
+            for t in range(n_a + n_b):                      # the kernel's decode of t = blockIdx.x >> 1
+                if t < n_a:
+                    first = s1 * a1
+                    if t < first:
+                        s, j = divmod(t, a1)
+                    else:
+                        q, j = divmod(t - first, a2)
+                        s = s1 + q
+                    tiles[s].append((j * 8, 8))
+                else:
+                    v, first = t - n_a, s1 * b1
+                    if v < first:
+                        s, j = divmod(v, b1)
+                        a = a1
+                    else:
+                        q, j = divmod(v - first, b2)
+                        s, a = s1 + q, a2
+                    tiles[s].append((a * 8 + j * 6, 6))
+            for s in range(S):
+                run = sorted(tiles[s])
+                pos = 0
+                for start, size in run:
+                    assert start == pos, (m_blocks, S, s, run)
+                    pos += size
+                assert m_blocks <= pos <= m_blocks + 5, (m_blocks, S, s, pos)      # <= 2 block pairs (+ odd block) to spare
+            # list schedule: all 8-block tiles first, then the 6-block ones, against the uniform grid
+            def makespan(costs):
+                load = [0] * slots
+                for c in costs:
+                    load[load.index(min(load))] += c
+                return max(load)
+            uniform = S * ((((m_blocks + 1) // 2) + 3) // 4)
+            assert makespan([4] * n_a + [3] * n_b) * 100 <= makespan([4] * uniform) * 92
+    assert n_plans > 20
+    out = (ctypes.c_int32 * 7)()
+    lib.bnn_debug_pair_tile_plan(64, 16, 74, out)           # C3 conv forward: 74 + 72 tiles on 74 pair slots
+    assert out[0] == 1 and out[1] + out[2] * out[4] + (16 - out[2]) * out[6] <= 148
