@@ -403,6 +403,24 @@ def test_prune_into_reports_the_kl_sums_of_the_same_sweep(C):
         assert torch.equal(outs_g[i][0], plain[i][0]) and torch.equal(outs_g[i][1], plain[i][1])
 
 
+def test_prune_into_kl_sums_over_several_descriptor_groups(C):
+    """KL by-product + side-stream pipelining together: 53 tensors (three descriptor groups) with different priors; sums
+    against bnn_kl, outputs against the call without the by-product, twice in a row (the side lane's events are reused)."""
+    g = torch.Generator().manual_seed(41)
+    sizes = [70000 + 1111 * i for i in range(53)]
+    dev = [tuple(t.cuda() for t in init_params((n,), g, fan_in=300)) for n in sizes]
+    priors = [(0.01 * (i % 5), 0.1 + 0.05 * (i % 4)) for i in range(53)]
+    entries = [(m, r, orc.prune_count(0.7, m.numel()), None) for m, r in dev]
+    ref = C.kl([(m, r, None, None, loc, sc, 1.0) for (m, r), (loc, sc) in zip(dev, priors)])
+    plain = C.prune_into(entries)
+    for _ in range(2):
+        outs, sums = C.prune_into(entries, kl_priors=priors)
+        torch.cuda.synchronize()
+        assert torch.allclose(sums, ref, rtol=1e-5, atol=0)
+        for (a, b), (c, d) in zip(outs, plain):
+            assert torch.equal(a, c) and torch.equal(b, d)
+
+
 # ------------------------------------------------------------------------------------------------ contractions
 def gemm_inputs(M, N, K, S, shared_a, gen, bias=True):
     mu_w, rho_w = init_params((N, K), gen)
