@@ -111,12 +111,30 @@ __global__ void __launch_bounds__(kThreads) col2im_nhwc_kernel(const float* __re
 // image's N*P block is contiguous on both sides, so reads and writes are fully coalesced — and, while the values are
 // there, sums every column: the reparameterised bias gradient (c_s[n] = sum_m dY[s][m][n]; dmu_b += sum_s
 // c_s; drho_b += sum_s c_s eps_b(s, n) sigmoid(rho_b[n])) costs no second pass over dY.
+// division of a 32-bit index by a launch constant without the ~20-instruction integer divide (Granlund-Montgomery):
+// q = (umulhi(n, mul) + n) >> shift, exact for every n < 2^31 (the indices here are < 2^27)
+struct FastDiv {
+  uint32_t mul, shift, d;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((1u << s) < d) ++s;
+  f.shift = s;
+  f.mul = static_cast<uint32_t>(((uint64_t(1) << 32) * ((uint64_t(1) << s) - d)) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  return static_cast<uint32_t>((static_cast<uint64_t>(__umulhi(n, f.mul)) + n) >> f.shift);
+}
+
 __global__ void __launch_bounds__(kThreads) nchw_to_nhwc_bias_kernel(const float* __restrict__ dy, float* __restrict__ out,
                                                                      int64_t n_imgs, int B, int N, int P, int ipt, int passes,
                                                                      const float* __restrict__ rho_b,
                                                                      const float* __restrict__ eps_b, float* __restrict__ dmu_b,
                                                                      float* __restrict__ drho_b, uint32_t sample_begin,
-                                                                     bnn_rng rng, int vec) {
+                                                                     bnn_rng rng, int vec, FastDiv dNP, FastDiv dP, FastDiv dN) {
   extern __shared__ float s_tile[];          // ipt images x [P][N + 1]
   const int pitch = N + 1, NP = N * P, img_smem = P * pitch;
   const bool want_bias = dmu_b != nullptr;
@@ -134,6 +152,19 @@ __global__ void __launch_bounds__(kThreads) nchw_to_nhwc_bias_kernel(const float
     }
     acc = 0.f;
   };
+  // element i of the block's run of images -> (image, n, p) on the NCHW side, (image, p, n) on the NHWC side
+  auto split_nchw = [&](int i, int& im, int& n, int& pp) {
+    im = static_cast<int>(fdiv(i, dNP));
+    const int r = i - im * NP;
+    n = static_cast<int>(fdiv(r, dP));
+    pp = r - n * P;
+  };
+  auto split_nhwc = [&](int i, int& im, int& pp, int& n) {
+    im = static_cast<int>(fdiv(i, dNP));
+    const int r = i - im * NP;
+    pp = static_cast<int>(fdiv(r, dN));
+    n = r - pp * N;
+  };
   for (int pass = 0; pass < passes; ++pass) {
     const int64_t img0 = (static_cast<int64_t>(blockIdx.x) * passes + pass) * ipt;
     if (img0 >= n_imgs) break;
@@ -142,33 +173,57 @@ __global__ void __launch_bounds__(kThreads) nchw_to_nhwc_bias_kernel(const float
     const float* src = dy + img0 * NP;
     float* dst = out + img0 * NP;
     __syncthreads();
+    // several independent loads in flight per thread before the first (dependent) shared-memory store
     if (vec) {                               // P % 4 == 0: a float4 holds (n, p .. p + 3)
-      for (int i = threadIdx.x * 4; i < total; i += kThreads * 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
-        const int im = i / NP, r = i - im * NP;
-        const int n = r / P, pp = r - n * P;
-        float* t = s_tile + im * img_smem + pp * pitch + n;
-        t[0] = v.x; t[pitch] = v.y; t[2 * pitch] = v.z; t[3 * pitch] = v.w;
+      for (int i0 = threadIdx.x * 4; i0 < total; i0 += kThreads * 16) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * (kThreads * 4);
+          if (i < total) v[u] = ldg_stream4(src + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * (kThreads * 4);
+          if (i < total) {
+            int im, n, pp;
+            split_nchw(i, im, n, pp);
+            float* t = s_tile + im * img_smem + pp * pitch + n;
+            t[0] = v[u].x; t[pitch] = v[u].y; t[2 * pitch] = v[u].z; t[3 * pitch] = v[u].w;
+          }
+        }
       }
     } else {
-      for (int i = threadIdx.x; i < total; i += kThreads) {
-        const int im = i / NP, r = i - im * NP;
-        const int n = r / P, pp = r - n * P;
-        s_tile[im * img_smem + pp * pitch + n] = __ldg(src + i);
+      for (int i0 = threadIdx.x; i0 < total; i0 += kThreads * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * kThreads;
+          if (i < total) v[u] = __ldg(src + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * kThreads;
+          if (i < total) {
+            int im, n, pp;
+            split_nchw(i, im, n, pp);
+            s_tile[im * img_smem + pp * pitch + n] = v[u];
+          }
+        }
       }
     }
     __syncthreads();
     if (vec && N % 4 == 0) {
       for (int i = threadIdx.x * 4; i < total; i += kThreads * 4) {
-        const int im = i / NP, r = i - im * NP;
-        const int pp = r / N, n = r - pp * N;
+        int im, pp, n;
+        split_nhwc(i, im, pp, n);
         const float* t = s_tile + im * img_smem + pp * pitch + n;
         *reinterpret_cast<float4*>(dst + i) = make_float4(t[0], t[1], t[2], t[3]);
       }
     } else {
       for (int i = threadIdx.x; i < total; i += kThreads) {
-        const int im = i / NP, r = i - im * NP;
-        const int pp = r / N, n = r - pp * N;
+        int im, pp, n;
+        split_nhwc(i, im, pp, n);
         dst[i] = s_tile[im * img_smem + pp * pitch + n];
       }
     }
@@ -279,9 +334,11 @@ int bnn_nchw_to_nhwc_bias_grad(const float* dy, float* dy_nhwc, int64_t n_imgs, 
               "the bias gradient)");
   int rc = check_device();
   if (rc != BNN_OK) return rc;
-  int ipt = static_cast<int>((32 * 1024) / img_smem);      // images per pass: ~32 KiB of shared memory per block
+  int ipt = static_cast<int>((32 * 1024) / img_smem);      // images per pass: at most ~32 KiB of shared memory per block ...
   if (ipt < 1) ipt = 1;
   if (ipt > 64) ipt = 64;
+  const int64_t want_blocks = static_cast<int64_t>(sm_count()) * 4;      // ... but enough blocks to fill the machine
+  if (n_imgs / ipt < want_blocks) ipt = static_cast<int>(n_imgs / want_blocks > 1 ? n_imgs / want_blocks : 1);
   // a few passes per block keep the number of (atomic) bias flushes down without starving the machine of blocks
   const int64_t tiles = (n_imgs + ipt - 1) / ipt;
   int passes = static_cast<int>(tiles / (static_cast<int64_t>(sm_count()) * 4));
@@ -293,7 +350,10 @@ int bnn_nchw_to_nhwc_bias_grad(const float* dy, float* dy_nhwc, int64_t n_imgs, 
   bnn_rng rng = rng_b ? *rng_b : bnn_rng{};
   nchw_to_nhwc_bias_kernel<<<static_cast<int>(blocks), kThreads, static_cast<size_t>(ipt) * img_smem,
                              static_cast<cudaStream_t>(stream)>>>(dy, dy_nhwc, n_imgs, B, N, P, ipt, passes, rho_b, eps_b, dmu_b,
-                                                                  drho_b, sample_begin, rng, vec);
+                                                                  drho_b, sample_begin, rng, vec,
+                                                                  make_fastdiv(static_cast<uint32_t>(N) * P),
+                                                                  make_fastdiv(static_cast<uint32_t>(P)),
+                                                                  make_fastdiv(static_cast<uint32_t>(N)));
   BNN_CUDA_OK(cudaGetLastError());
   return BNN_OK;
 }
