@@ -23,12 +23,20 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     args = ap.parse_args()
     import bayesianneuralnetworks_b200 as bnn
+    from bayesianneuralnetworks_b200.training import ElboTrainer
     dev = torch.device("cuda", 0)
     wl = bench.WORKLOADS[args.workload]
     bnn.set_precision("tf32")
     torch.backends.cudnn.benchmark = True
     torch.backends.cuda.matmul.allow_tf32 = True
-    tr = bench.Trainer(args.workload, dev, 1, wl["samples"], graph=True, channels_last=not args.nchw)
+    torch.backends.cudnn.allow_tf32 = True
+    torch.manual_seed(0)
+    model = bench.build_model(args.workload, wl["samples"]).to(dev)
+    if not args.nchw:
+        for m in model.modules():
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.BatchNorm2d)):
+                m.to(memory_format=torch.channels_last)
+    tr = ElboTrainer(model, bench.N_BATCHES, graph=True)
     gen = torch.Generator().manual_seed(1)
     x, y = (t.to(dev) for t in bench.synthetic_batch(args.workload, wl["batch"], gen))
     tr.capture(x, y)
