@@ -243,6 +243,88 @@ __global__ void __launch_bounds__(kThreads) nchw_to_nhwc_bias_kernel(const float
   flush(cur_s);
 }
 
+// The same pass with ONE WARP PER IMAGE (images whose [P][N + 1] block fits 8 KiB-class shared-memory slices, i.e. the
+// example conv layers): no block-wide barrier, all of an image's 128-bit loads in flight before the first dependent
+// shared-memory store (16 per lane at C3), a warp walks `ipw` consecutive images and keeps the column sums of N <= 256
+// channels in registers.  The block-per-pass kernel above is sync bound at small images (3.4 TB/s at C3).
+constexpr int kWarpImgMaxN = 256;
+__global__ void __launch_bounds__(kThreads) nchw_to_nhwc_bias_warp_kernel(
+    const float* __restrict__ dy, float* __restrict__ out, int64_t n_imgs, int B, int N, int P, int ipw,
+    const float* __restrict__ rho_b, const float* __restrict__ eps_b, float* __restrict__ dmu_b, float* __restrict__ drho_b,
+    uint32_t sample_begin, bnn_rng rng, FastDiv dP, FastDiv dN) {
+  extern __shared__ float s_tile[];          // one [P][N + 1] block per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const int pitch = N + 1, NP = N * P;
+  float* const tile = s_tile + warp * (P * pitch);
+  const bool want_bias = dmu_b != nullptr;
+  const RngKey key = resolve_rng(rng);
+  float acc[kWarpImgMaxN / 32];              // column sums of channels lane, lane + 32, ... over the images of one sample
+#pragma unroll
+  for (int c = 0; c < kWarpImgMaxN / 32; ++c) acc[c] = 0.f;
+  int cur_s = -1;
+  auto flush = [&](int s) {
+    if (!want_bias || s < 0) return;
+#pragma unroll
+    for (int c = 0; c < kWarpImgMaxN / 32; ++c) {
+      const int n = c * 32 + lane;
+      if (n < N) {
+        const float e = eps_b != nullptr ? __ldg(eps_b + static_cast<int64_t>(s) * N + n)
+                                         : eps1(key, sample_begin + s, static_cast<uint64_t>(n));
+        atomicAdd(dmu_b + n, acc[c]);
+        atomicAdd(drho_b + n, acc[c] * e * sigmoid_fast(__ldg(rho_b + n)));
+      }
+      acc[c] = 0.f;
+    }
+  };
+  const int64_t img_begin = (static_cast<int64_t>(blockIdx.x) * warps + warp) * ipw;
+  for (int j = 0; j < ipw; ++j) {
+    const int64_t img = img_begin + j;
+    if (img >= n_imgs) break;
+    const float* src = dy + img * NP;
+    float* dst = out + img * NP;
+    // NCHW side: a float4 holds (n, p .. p + 3), P % 4 == 0 on this path
+    for (int i0 = lane * 4; i0 < NP; i0 += 32 * 4 * 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * 128;
+        if (i < NP) v[u] = ldg_stream4(src + i);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * 128;
+        if (i < NP) {
+          const int n = static_cast<int>(fdiv(i, dP)), pp = i - n * P;
+          float* t = tile + pp * pitch + n;
+          t[0] = v[u].x; t[pitch] = v[u].y; t[2 * pitch] = v[u].z; t[3 * pitch] = v[u].w;
+        }
+      }
+    }
+    __syncwarp();
+    // NHWC side: N % 4 == 0 on this path
+    for (int i = lane * 4; i < NP; i += 128) {
+      const int pp = static_cast<int>(fdiv(i, dN)), n = i - pp * N;
+      const float* t = tile + pp * pitch + n;
+      *reinterpret_cast<float4*>(dst + i) = make_float4(t[0], t[1], t[2], t[3]);      // read next by the gradient kernels: keep it in L2
+    }
+    if (want_bias) {
+      const int s = static_cast<int>(img / B);
+      if (s != cur_s) { flush(cur_s); cur_s = s; }
+#pragma unroll
+      for (int c = 0; c < kWarpImgMaxN / 32; ++c) {
+        const int n = c * 32 + lane;
+        if (n < N) {
+          float sum = 0.f;
+          for (int pp = 0; pp < P; ++pp) sum += tile[pp * pitch + n];
+          acc[c] += sum;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  flush(cur_s);
+}
+
 int grid_for(int64_t items) {
   const int64_t blocks = (items + kThreads - 1) / kThreads;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
@@ -348,6 +430,25 @@ int bnn_nchw_to_nhwc_bias_grad(const float* dy, float* dy_nhwc, int64_t n_imgs, 
   BNN_REQUIRE(blocks <= 0x7fffffff, BNN_ERR_UNSUPPORTED, "bnn_nchw_to_nhwc_bias_grad: too many images");
   const int vec = (P % 4 == 0) && aligned16(dy) && aligned16(dy_nhwc) && ((static_cast<int64_t>(N) * P) % 4 == 0);
   bnn_rng rng = rng_b ? *rng_b : bnn_rng{};
+  // one warp per image when an image's block is small and everything is 128-bit friendly
+  if (vec && N % 4 == 0 && N <= kWarpImgMaxN && img_smem <= 12 * 1024) {
+    int warps = static_cast<int>((64 * 1024) / img_smem);
+    if (warps > kThreads / 32) warps = kThreads / 32;
+    const int64_t want_warps = static_cast<int64_t>(sm_count()) * 24;
+    int ipw = static_cast<int>((n_imgs + want_warps - 1) / want_warps);
+    if (ipw < 1) ipw = 1;
+    if (ipw > 16) ipw = 16;
+    const int64_t wblocks = (n_imgs + static_cast<int64_t>(warps) * ipw - 1) / (static_cast<int64_t>(warps) * ipw);
+    const size_t smem = static_cast<size_t>(warps) * img_smem;
+    static SmemOptIn opt_in;
+    rc = allow_dynamic_smem(nchw_to_nhwc_bias_warp_kernel, 64 * 1024, &opt_in);
+    if (rc != BNN_OK) return rc;
+    nchw_to_nhwc_bias_warp_kernel<<<static_cast<int>(wblocks), warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+        dy, dy_nhwc, n_imgs, B, N, P, ipw, rho_b, eps_b, dmu_b, drho_b, sample_begin, rng,
+        make_fastdiv(static_cast<uint32_t>(P)), make_fastdiv(static_cast<uint32_t>(N)));
+    BNN_CUDA_OK(cudaGetLastError());
+    return BNN_OK;
+  }
   nchw_to_nhwc_bias_kernel<<<static_cast<int>(blocks), kThreads, static_cast<size_t>(ipt) * img_smem,
                              static_cast<cudaStream_t>(stream)>>>(dy, dy_nhwc, n_imgs, B, N, P, ipt, passes, rho_b, eps_b, dmu_b,
                                                                   drho_b, sample_begin, rng, vec,
