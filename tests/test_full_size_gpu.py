@@ -98,3 +98,22 @@ def test_prune_properties_at_c5_tensor_size(C, prune_mode, p):
     mask2 = torch.empty(mu.shape, dtype=torch.uint8, device="cuda")
     C.prune([(m2, r2, k, mask2, None)])
     assert torch.equal(mask2, mask)
+
+
+def test_prune_into_equals_the_in_place_kernel_on_large_tensors_with_different_fractions(C):
+    """Four tensors of 2^23 pairs with four different pruning fractions in one call: the one-sweep out-of-place kernel's
+    outputs must equal the strictly in-place kernel's, inputs stay intact."""
+    g = torch.Generator(device="cuda").manual_seed(8)
+    n = 1 << 23
+    mus = [(torch.rand(n, device="cuda", generator=g) * 2 - 1) / 64 for _ in range(4)]
+    rhos = [torch.randn(n, device="cuda", generator=g) * 0.15 - 2 for _ in range(4)]
+    ks = [int(p * n) for p in (0.75, 0.5, 0.9, 0.3)]
+    keep = [(m.clone(), r.clone()) for m, r in zip(mus, rhos)]
+    outs = C.prune_into([(m, r, k, None) for m, r, k in zip(mus, rhos, ks)])
+    ref = [(m.clone(), r.clone()) for m, r in keep]
+    C.prune([(m, r, k, None, None) for (m, r), k in zip(ref, ks)])
+    torch.cuda.synchronize()
+    for (mo, ro), (mr, rr), (m0, r0), (m, r), k in zip(outs, ref, keep, zip(mus, rhos), ks):
+        assert torch.equal(m, m0) and torch.equal(r, r0)
+        assert int((ro == -30).sum()) == k
+        assert torch.equal(mo, mr) and torch.equal(ro, rr)
