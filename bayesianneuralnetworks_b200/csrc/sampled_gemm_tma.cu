@@ -34,6 +34,11 @@ namespace contract {
 // profiling builds: cycles spent waiting, summed over CTAs: [0] kernel, [1] MMA on full_w, [2] MMA on full_a,
 // [3] generator warp 0 on empty_w, [4] TMA thread on the consumed barrier, [5] CTAs
 __device__ unsigned long long g_wait_cycles[8];
+// CTA timeline of the CTA-pair kernels, cycles since the CTA's first instruction summed over CTAs: [0] prologue done,
+// [1] generator warp 0 done, [2] accumulator complete (epilogue warp 0), [3] epilogue done, [4] CTA end, [5] CTAs;
+// [6] / [7] globaltimer (ns) of the first CTA start / last CTA end
+__device__ unsigned long long g_stage_cycles[8];
+#define BNN_STAGE(i, t0) atomicAdd(&g_stage_cycles[i], (unsigned long long)(clock64() - (t0)))
 #define BNN_T0() const long long _t0 = clock64()
 #define BNN_ACC(var) var += clock64() - _t0
 #else
@@ -201,6 +206,14 @@ struct TmaContractParams {
   int atomic_out;           //   sums are ADDED to the (zeroed) output
   int vec_out;
   int exp_flags;            // profiling builds: 1 = skip weight generation, 2 = skip TMA loads, 4 = skip MMA issue
+  // balanced schedule (contract_pair_sk_kernel): a line of sk_total items cut into sk_slots equal ranges, one per
+  // resident CTA pair.  sk_msplit: items = 256-row units of the (sample, column tile) columns, sk_mtiles units each;
+  // else items = k-block iterations of the 1024-row tiles (sk_its each; sk_mtiles tiles per column)
+  int sk_slots;             // > 0: pair slots (clusters) of the launch
+  int sk_msplit;
+  int sk_mtiles, sk_gx;     // column = z * sk_gx + y  (y: 128-column tile, z: sample)
+  int sk_its;               // k-block iterations per tile (reduction blocks x samples summed into the tile)
+  int sk_total;
 };
 
 struct TmaPipe {
@@ -276,6 +289,131 @@ __device__ __forceinline__ void gen_w_tile(uint32_t tile, const float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------- staged epilogue
+// A TMEM lane is an output row, so an epilogue thread that stores its own 16-column chunk writes 16 bytes of 32
+// different rows per warp instruction: 32 memory wavefronts per 512 bytes (measured: 25 k cycles to drain the 512 x 128
+// accumulator of one CTA, a quarter of a C3 conv tile's time).  Each epilogue warp therefore passes its 32 rows through
+// a private shared-memory buffer, 64 columns at a time, and writes whole row segments:
+//   row-major output (view P == 1): staging rows of 64 + 4 floats (float4 writes of a quarter warp hit 32 different
+//     banks); two rows per store instruction, 256 contiguous bytes each;
+//   NCHW output (P = OH*OW, P % 4 == 0): staging [column][32 rows + 4]; four rows of a lane's group are four consecutive
+//     pixels of one image, i.e. one aligned float4 of out[img][n][p..p+3]; a store instruction covers 4 columns x 8 row
+//     groups: for P = 16 two runs of 256 contiguous bytes (was: two runs of 64 bytes per scalar store).
+// kStageWarpBytes per warp; the uniform-grid kernels alias the operand ring (dead once the accumulator is complete), the
+// balanced schedule keeps its own region because its producers run ahead into the next segment.
+constexpr int kStageWarpBytes = 64 * 36 * 4;     // 9216: [64 columns][32 + 4] floats; the row-major form needs 32 x 68 x 4 = 8704
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool stage_eligible(const View& out, bool vec_out, int cols_here) {
+  if ((cols_here & 3) != 0 || (reinterpret_cast<uintptr_t>(out.base) & 15) != 0 || (out.bs & 3) != 0) return false;
+  return out.P == 1 ? vec_out : (out.P & 3) == 0;
+}
+// Halves [h_begin, h_end) (64 columns each) of one 128-row block, drained by one warp (TMEM lanes [32 quad, +32), rows
+// m0 .. m0 + 31 of the output, columns col0 .. col0 + cols_here): two tcgen05.ld per round trip, then (+ bias) ->
+// staging -> coalesced stores / adds.
+template <bool kBias>
+__device__ __forceinline__ void drain_block_staged(uint32_t taddr, uint32_t stage, const float* aux, const View& out,
+                                                   int m0, int M, int col0, int cols_here, int lane, bool add,
+                                                   int h_begin = 0, int h_end = 2) {
+  const bool nchw = out.P != 1;
+  // per-lane destination of the write-out phase
+  float* dst;
+  bool ok;
+  if (!nchw) {
+    dst = out.base + static_cast<int64_t>(m0 + (lane >> 4)) * out.bs + col0 + ((lane & 15) << 2);
+    ok = true;
+  } else {
+    const int m = m0 + ((lane & 7) << 2);                  // first of the lane's four rows (one image: P % 4 == 0)
+    const int b = m / out.P, px = m - b * out.P;
+    dst = out.base + static_cast<int64_t>(b) * out.bs + static_cast<int64_t>(col0 + (lane >> 3)) * out.P + px;
+    ok = m < M;
+  }
+  for (int h = h_begin; h < h_end && h * 64 < cols_here; ++h) {
+#pragma unroll 1
+    for (int pr = 0; pr < 2 && (h * 4 + pr * 2) * 16 < cols_here; ++pr) {      // two 16-column chunks per TMEM round trip
+      uint32_t r[2][16];
+      tmem_ld16_nowait(taddr + (h * 4 + pr * 2) * 16, r[0]);
+      if ((h * 4 + pr * 2 + 1) * 16 < cols_here) tmem_ld16_nowait(taddr + (h * 4 + pr * 2 + 1) * 16, r[1]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q2 = 0; q2 < 2; ++q2) {
+        const int cc = pr * 2 + q2;
+        if ((h * 4 + cc) * 16 >= cols_here) break;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[q2][j]);
+        if (kBias) {
+          const float4* a4 = reinterpret_cast<const float4*>(aux + (h * 4 + cc) * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 q = a4[j];
+            v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+          }
+        }
+        if (!nchw) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128(stage + lane * 272 + cc * 64 + j * 16, __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                   __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sts32(stage + ((cc * 16 + j) * 36 + lane) * 4, __float_as_uint(v[j]));
+        }
+      }
+    }
+    __syncwarp();
+    const int cols_half = cols_here - h * 64 < 64 ? cols_here - h * 64 : 64;
+    if (!nchw) {
+      const int c4 = lane & 15;
+#pragma unroll 8
+      for (int i = 0; i < 16; ++i) {
+        const int row = 2 * i + (lane >> 4);
+        if (c4 * 4 < cols_half && m0 + row < M) {
+          const float4 q = lds128(stage + row * 272 + c4 * 16);
+          float* d = dst + static_cast<int64_t>(2 * i) * out.bs + h * 64;
+          if (add) red_add4(d, q.x, q.y, q.z, q.w);
+          else *reinterpret_cast<float4*>(d) = q;
+        }
+      }
+    } else {
+      const int rg = lane & 7, ns = lane >> 3;
+#pragma unroll 8
+      for (int i = 0; i < 16; ++i) {
+        const int n = i * 4 + ns;
+        if (n < cols_half && ok) {
+          const float4 q = lds128(stage + (n * 36 + rg * 4) * 4);
+          float* d = dst + static_cast<int64_t>(h * 64 + i * 4) * out.P;
+          if (add) red_add4(d, q.x, q.y, q.z, q.w);
+          else *reinterpret_cast<float4*>(d) = q;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+// The accumulator of one CTA (mb_count row blocks of 128 rows x cols_here columns) drained by kDrainPerQuad warps per
+// TMEM lane quarter — the epilogue warp of the quarter (idx 0) and generator warps with the same warp % 4, idle once
+// their loop has ended: work items = (row block, 64-column half), item i goes to warp i % kDrainPerQuad.
+constexpr int kDrainPerQuad = 4;
+constexpr int kDrainThreads = 4 * kDrainPerQuad * 32;
+constexpr int kDrainBarrier = 2;
+template <bool kBias>
+__device__ __forceinline__ void drain_tile_shared(uint32_t tmem, uint32_t stage_base, const float* aux, const View& out,
+                                                  int row0, int M, int mb_count, int col0, int cols_here, int quad,
+                                                  int idx, int lane, bool add) {
+  const uint32_t stage = stage_base + static_cast<uint32_t>(idx * 4 + quad) * kStageWarpBytes;
+  const int halves = (cols_here + 63) / 64;
+  for (int item = idx; item < mb_count * halves; item += kDrainPerQuad) {
+    const int mb = item / halves, h = item - mb * halves;
+    if (row0 + mb * 128 >= M) break;
+    drain_block_staged<kBias>(tmem + (static_cast<uint32_t>(quad * 32) << 16) + mb * 128, stage, aux, out,
+                              row0 + mb * 128 + quad * 32, M, col0, cols_here, lane, add, h, h + 1);
+  }
+}
+
 template <int MB, bool kDgrad, int kMode>      // kMode: 0 plain, 1 conv (im2col maps), 2 rank-one sign noise (Flipout)
 __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __grid_constant__ TmaContractParams p) {
   constexpr bool kConv = kMode == 1;
@@ -315,6 +453,13 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
   int mb_used = (p.M - row0 + 127) / 128;
   if (mb_used > MB) mb_used = MB;
 
+  // the accumulator is drained by the epilogue warps AND, once their loop has ended, three generator warps per TMEM lane
+  // quarter (staged, coalesced write-out through the operand rings, which are dead by then); uniform per CTA
+  View out_tile = p.out;
+  out_tile.base += (p.sum_samples ? 0 : static_cast<int64_t>(blockIdx.z) * p.out_sample_stride);
+  const int cols_tile = n_cols - col0 < 128 ? n_cols - col0 : 128;
+  const bool staged = stage_eligible(out_tile, p.vec_out != 0, cols_tile) && (out_tile.P == 1 || (p.M & 3) == 0);
+
   if (warp < kGenWarps) {
     // ------------------------------------------------------------------ weight generators (four groups, slot = group)
     const int group = warp / kGroupWarps, tid = threadIdx.x - group * kGroupThreads;
@@ -343,6 +488,13 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pipe.full_w + group);
+    }
+    if (staged && (warp >> 2) < kDrainPerQuad - 1) {     // join the drain (TMEM lane quarter = warp % 4)
+      if (!kDgrad) named_bar_sync(kDrainBarrier, kDrainThreads);          // the bias row is in shared memory
+      mbar_wait(pipe.accum_full, 0);
+      tc_fence_after_sync();
+      drain_tile_shared<!kDgrad>(tmem, pipe.ring_a, pipe.aux, out_tile, row0, p.M, mb_used, col0, cols_tile, warp & 3,
+                                 1 + (warp >> 2), lane, kDgrad && p.atomic_out);
     }
   } else if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA issuer
@@ -424,24 +576,29 @@ __global__ void __launch_bounds__(kThreadsTma, 1) contract_tma_kernel(const __gr
       }
       pipe.aux[et] = b;
       named_bar_sync(kEpiBarrier, kEpiThreads);
+      if (staged) named_bar_sync(kDrainBarrier, kDrainThreads);
     }
     mbar_wait(pipe.accum_full, 0);
     tc_fence_after_sync();
-    View out = p.out;
-    out.base += (p.sum_samples ? 0 : static_cast<int64_t>(blockIdx.z) * p.out_sample_stride);
-    const int cols_here = n_cols - col0 < 128 ? n_cols - col0 : 128;
-    for (int mb = 0; mb < mb_used; ++mb) {
-      const int m = row0 + mb * 128 + quad * 32 + lane;
-      for (int c = 0; c * 16 < cols_here; ++c) {
-        float v[16];
-        tmem_ld16(tmem + (static_cast<uint32_t>(quad * 32) << 16) + mb * 128 + c * 16, v);
-        if (!kDgrad) {
+    if (staged) {
+      drain_tile_shared<!kDgrad>(tmem, pipe.ring_a, pipe.aux, out_tile, row0, p.M, mb_used, col0, cols_tile, quad, 0, lane,
+                                 kDgrad && p.atomic_out);
+    } else {
+      const View& out = out_tile;
+      const int cols_here = cols_tile;
+      for (int mb = 0; mb < mb_used; ++mb) {
+        const int m = row0 + mb * 128 + quad * 32 + lane;
+        for (int c = 0; c * 16 < cols_here; ++c) {
+          float v[16];
+          tmem_ld16(tmem + (static_cast<uint32_t>(quad * 32) << 16) + mb * 128 + c * 16, v);
+          if (!kDgrad) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += pipe.aux[c * 16 + j];
-        }
-        if (m < p.M) {
-          if (kDgrad && p.atomic_out) add_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
-          else store_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+            for (int j = 0; j < 16; ++j) v[j] += pipe.aux[c * 16 + j];
+          }
+          if (m < p.M) {
+            if (kDgrad && p.atomic_out) add_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+            else store_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+          }
         }
       }
     }
@@ -530,6 +687,11 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
   (void)w_kernel; (void)w_mma_w; (void)w_mma_a; (void)w_gen; (void)w_tma;
 #ifdef BNN_PROFILE_WAITS
   const long long t_kernel0 = clock64();
+  if (threadIdx.x == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    atomicMin(&g_stage_cycles[6], g);
+  }
 #endif
   constexpr uint32_t kTmemCols = tmem_cols_pow2(MB * 128);
   const PairPipe pipe = carve_pair(smem_raw);
@@ -550,6 +712,9 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
   cluster_sync_all();                                // barriers of both CTAs initialised before any remote arrive
   tc_fence_after_sync();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(pipe.tmem_slot);
+#ifdef BNN_PROFILE_WAITS
+  if (threadIdx.x == 0) { BNN_STAGE(0, t_kernel0); atomicAdd(&g_stage_cycles[5], 1ull); }
+#endif
 
   const int col0 = blockIdx.y * 128;                   // output columns of the PAIR (n for fwd, k for dgrad)
   // the pair's tile: sample, first row of the leader, row blocks per CTA (uniform grid: MB; tile plan: 4 or 3)
@@ -583,6 +748,13 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
   int mb_pair = (p.M - lead_row0 + 127) / 128;
   if (mb_pair > mb_cap) mb_pair = mb_cap;
 
+  // the accumulator is drained by the epilogue warps AND, once their loop has ended, three generator warps per TMEM lane
+  // quarter (staged, coalesced write-out through the operand rings, which are dead by then); uniform per CTA
+  View out_tile = p.out;
+  out_tile.base += (p.sum_samples ? 0 : static_cast<int64_t>(tile_s) * p.out_sample_stride);
+  const int cols_tile = n_cols - col0 < 128 ? n_cols - col0 : 128;
+  const bool staged = stage_eligible(out_tile, p.vec_out != 0, cols_tile) && (out_tile.P == 1 || (p.M & 3) == 0);
+
   if (warp < kGenWarps) {
     // ------------------------------------------------------------------ weight generators (half tile per CTA, four groups)
     const int group = warp / kGroupWarps, tid = threadIdx.x - group * kGroupThreads;
@@ -610,6 +782,13 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(lead_full_w);
+    }
+    if (staged && (warp >> 2) < kDrainPerQuad - 1) {     // join the drain (TMEM lane quarter = warp % 4)
+      if (!kDgrad) named_bar_sync(kDrainBarrier, kDrainThreads);          // the bias row is in shared memory
+      mbar_wait(pipe.accum_full, 0);
+      tc_fence_after_sync();
+      drain_tile_shared<!kDgrad>(tmem, pipe.ring_a, pipe.aux, out_tile, row0, p.M, mb_pair, col0, cols_tile, warp & 3,
+                                 1 + (warp >> 2), lane, kDgrad && p.atomic_out);
     }
   } else if (warp == kTmaWarp) {
     // ------------------------------------------------------------------ TMA issuer (own rows; bytes counted by the leader)
@@ -689,30 +868,40 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
       }
       pipe.aux[et] = b;
       named_bar_sync(kEpiBarrier, kEpiThreads);
+      if (staged) named_bar_sync(kDrainBarrier, kDrainThreads);
     }
     mbar_wait(pipe.accum_full, 0);
     tc_fence_after_sync();
-    View out = p.out;
-    out.base += (p.sum_samples ? 0 : static_cast<int64_t>(tile_s) * p.out_sample_stride);
-    const int cols_here = n_cols - col0 < 128 ? n_cols - col0 : 128;
-    for (int mb = 0; mb < mb_pair; ++mb) {
-      const int m = row0 + mb * 128 + quad * 32 + lane;
-      if (row0 + mb * 128 >= p.M) break;               // uniform per CTA
-      for (int c = 0; c * 16 < cols_here; ++c) {
-        float v[16];
-        tmem_ld16(tmem + (static_cast<uint32_t>(quad * 32) << 16) + mb * 128 + c * 16, v);
-        if (!kDgrad) {
+#ifdef BNN_PROFILE_WAITS
+    if (threadIdx.x == kEpiWarp0T * 32) BNN_STAGE(2, t_kernel0);
+#endif
+    if (staged) {
+      drain_tile_shared<!kDgrad>(tmem, pipe.ring_a, pipe.aux, out_tile, row0, p.M, mb_pair, col0, cols_tile, quad, 0, lane,
+                                 kDgrad && p.atomic_out);
+    } else {
+      const View& out = out_tile;
+      const int cols_here = cols_tile;
+      for (int mb = 0; mb < mb_pair; ++mb) {
+        const int m = row0 + mb * 128 + quad * 32 + lane;
+        if (row0 + mb * 128 >= p.M) break;               // uniform per CTA
+        for (int c = 0; c * 16 < cols_here; ++c) {
+          float v[16];
+          tmem_ld16(tmem + (static_cast<uint32_t>(quad * 32) << 16) + mb * 128 + c * 16, v);
+          if (!kDgrad) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += pipe.aux[c * 16 + j];
-        }
-        if (m < p.M) {
-          if (kDgrad && p.atomic_out) add_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
-          else store_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+            for (int j = 0; j < 16; ++j) v[j] += pipe.aux[c * 16 + j];
+          }
+          if (m < p.M) {
+            if (kDgrad && p.atomic_out) add_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+            else store_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+          }
         }
       }
     }
   }
 #ifdef BNN_PROFILE_WAITS
+  if (threadIdx.x == kEpiWarp0T * 32) BNN_STAGE(3, t_kernel0);
+  if (threadIdx.x == 0) BNN_STAGE(1, t_kernel0);
   {
     const int w_ = threadIdx.x >> 5, l_ = threadIdx.x & 31;
     if (l_ == 0) {
@@ -728,6 +917,14 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
     tc_fence_after_sync();
     tmem_dealloc_pair(tmem, kTmemCols);
   }
+#ifdef BNN_PROFILE_WAITS
+  if (threadIdx.x == 0) {
+    BNN_STAGE(4, t_kernel0);
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    atomicMax(&g_stage_cycles[7], g);
+  }
+#endif
 }
 
 template <int MB, bool kDgrad, int kMode>
@@ -746,6 +943,359 @@ int launch_pair_contract(const TmaContractParams& p, dim3 grid, cudaStream_t st)
   return launch_pair_contract_v<MB, kDgrad, 0>(p, grid, st);
 }
 
+// ---------------------------------------------------------------------------------------------- balanced schedule
+// contract_pair_sk_kernel: the CTA-pair kernel as a PERSISTENT grid of `sk_slots` clusters (one per resident SM pair).
+// The uniform grid runs whole 1024-row tiles, so a layer with 128 tiles on 74 pair slots (the example conv layers)
+// pays two full waves for 1.73 waves of work, and the shared-input data gradient (64 sample-group tiles) leaves 10 of
+// 74 slots idle.  Here all work forms one line of items that is cut into sk_slots equal ranges; a slot walks its
+// range segment by segment, keeping barriers, TMEM and the producer pipelines alive across segments — generators and
+// the TMA thread run ahead into the next segment while the epilogue warps drain the accumulator of the previous one
+// (the MMA thread waits on `tmem_empty`).  Two ways to cut, neither needs scratch memory or a hand-over between slots:
+//   sk_msplit == 1 (forward, per-sample data gradient): items are UNITS of 256 rows (one 128-row block per CTA) of the
+//     (sample, column tile) columns of the output; a segment is a tile of 1..4 consecutive units over the whole
+//     reduction, stored like a uniform tile (C3 conv forward: 512 units on 74 slots = 7 or 6 units per slot, run as
+//     4 + 3 / 3 + 3 instead of two waves of 4);
+//   sk_msplit == 0 (summed data gradient: one output for all samples, zeroed first): items are the k-block
+//     iterations (reduction blocks x samples) of the 1024-row tiles; every segment ADDS its partial sums
+//     (red.global.add), as the uniform grid does when it splits the samples over grid.z.
+struct SkPipe {
+  uint64_t* full_a;      // [2]  as PairPipe
+  uint64_t* full_w;      // [4]
+  uint64_t* empty_w;     // [4]
+  uint64_t* accum_full;  // both CTAs: one phase per segment
+  uint64_t* tmem_empty;  // leader: one arrival per epilogue warp of both CTAs, one phase per segment
+  uint32_t* tmem_slot;
+  float* aux;            // [2][128]: sampled bias rows, double buffered by segment parity
+  uint32_t ring_a, ring_w;
+  uint32_t stage;        // four staging buffers of the epilogue warps (the rings stay live across segments)
+};
+constexpr size_t kPairSkSmem = kPairSmem + 4 * static_cast<size_t>(kStageWarpBytes);
+__device__ __forceinline__ SkPipe carve_sk(uint8_t* smem_raw) {
+  SkPipe p;
+  p.full_a = reinterpret_cast<uint64_t*>(smem_raw);
+  p.full_w = p.full_a + 2;
+  p.empty_w = p.full_w + kPairWSlots;
+  p.accum_full = p.empty_w + kPairWSlots;
+  p.tmem_empty = p.accum_full + 1;
+  p.tmem_slot = reinterpret_cast<uint32_t*>(p.tmem_empty + 1);
+  p.aux = reinterpret_cast<float*>(smem_raw + 512);
+  const uint32_t base = smem_u32(smem_raw) + kSmemAux;
+  p.ring_a = (base + 1023u) & ~1023u;
+  p.ring_w = p.ring_a + kASlots * kTileBytes;
+  p.stage = p.ring_w + kPairWSlots * kHalfTileBytes;
+  return p;
+}
+struct SkSeg {
+  int lead_row0;         // first output row of the leader CTA
+  int mb_cap;            // row blocks per CTA of this tile (1..4); the peer's rows start mb_cap * 128 further
+  int y, z;              // column tile, sample (0 for a summed tile)
+  int i0, n;             // first k-block iteration inside the tile, iterations of this segment
+};
+// units of a tile that starts a run of `run` units: never a lone unit after a full tile (5 -> 3 + 2, 6 -> 3 + 3, 7 -> 4 + 3)
+__host__ __device__ __forceinline__ int sk_tile_units(int run) {
+  return (run >= 8 || run <= 4) ? (run < 4 ? run : 4) : (run + 1) / 2;
+}
+// next segment of the range [pos, end); advances pos
+__device__ __forceinline__ bool sk_next(const TmaContractParams& p, int& pos, int end, SkSeg* s) {
+  if (pos >= end) return false;
+  if (p.sk_msplit) {
+    const int col = pos / p.sk_mtiles, u0 = pos - col * p.sk_mtiles;        // sk_mtiles: units per column
+    int run = p.sk_mtiles - u0;
+    if (run > end - pos) run = end - pos;
+    const int u = sk_tile_units(run);
+    s->lead_row0 = u0 * 256;
+    s->mb_cap = u;
+    s->z = col / p.sk_gx;
+    s->y = col - s->z * p.sk_gx;
+    s->i0 = 0;
+    s->n = p.sk_its;
+    pos += u;
+    return true;
+  }
+  const int t = pos / p.sk_its;
+  s->i0 = pos - t * p.sk_its;
+  const int left = end - pos, room = p.sk_its - s->i0;
+  s->n = left < room ? left : room;
+  const int r = t / p.sk_mtiles;                                            // sk_mtiles: 1024-row tiles per column
+  s->lead_row0 = (t - r * p.sk_mtiles) * 1024;
+  s->mb_cap = 4;
+  s->z = r / p.sk_gx;
+  s->y = r - s->z * p.sk_gx;
+  pos += s->n;
+  return true;
+}
+
+template <bool kDgrad, int kMode>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTma, 1)
+contract_pair_sk_kernel(const __grid_constant__ TmaContractParams p) {
+  constexpr bool kConv = kMode == 1;
+  constexpr int kSigns = kMode == 2 ? 1 : 0;
+  constexpr int MB = 4;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  long long w_mma_w = 0, w_mma_a = 0, w_mma_t = 0, w_gen = 0, w_tma = 0, w_epi = 0;
+  (void)w_mma_w; (void)w_mma_a; (void)w_mma_t; (void)w_gen; (void)w_tma; (void)w_epi;
+#ifdef BNN_PROFILE_WAITS
+  const long long t_kernel0 = clock64();
+  if (threadIdx.x == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    atomicMin(&g_stage_cycles[6], g);
+  }
+#endif
+  const SkPipe pipe = carve_sk(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) mbar_init(pipe.full_a + i, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(pipe.full_w + i, 2 * kGroupWarps); mbar_init(pipe.empty_w + i, 1); }
+    mbar_init(pipe.accum_full, 1);
+    mbar_init(pipe.tmem_empty, 2 * (kEpiThreads / 32));
+    fence_mbar_init();
+  }
+  if (warp == kTmaWarp && lane == 0) tma_prefetch_desc(&p.map_l);
+  if (warp == kMmaWarpT) tmem_alloc_pair(pipe.tmem_slot, 512);
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(pipe.tmem_slot);
+#ifdef BNN_PROFILE_WAITS
+  if (threadIdx.x == 0) { BNN_STAGE(0, t_kernel0); atomicAdd(&g_stage_cycles[5], 1ull); }
+#endif
+
+  const int slot = static_cast<int>(blockIdx.x >> 1);
+  const int range_a = static_cast<int>(static_cast<long long>(p.sk_total) * slot / p.sk_slots);
+  const int range_b = static_cast<int>(static_cast<long long>(p.sk_total) * (slot + 1) / p.sk_slots);
+  const int n_cols = kDgrad ? p.K : p.N;
+  const int n_red = kDgrad ? p.N : p.K;
+  const int red_blocks = (n_red + kBK - 1) / kBK;
+
+  if (warp < kGenWarps) {
+    // ------------------------------------------------------------------ weight generators (half tile per CTA, four groups)
+    const int group = warp / kGroupWarps, tid = threadIdx.x - group * kGroupThreads;
+    const RngKey key = resolve_rng(p.rng_w);
+    const uint32_t lead_full_w = mapa_u32(smem_u32(pipe.full_w + group), 0);
+    const uint32_t tile = pipe.ring_w + group * kHalfTileBytes;
+    int pos = range_a, gi0 = 0;
+    SkSeg sg;
+    while (sk_next(p, pos, range_b, &sg)) {
+      const int half0 = sg.y * 128 + static_cast<int>(rank) * 64;
+      for (int j = (group - gi0) & 3; j < sg.n; j += kGenGroups) {       // iterations gi = gi0 + j with gi % 4 == group
+        const int gi = gi0 + j, it = sg.i0 + j;
+        const int ds = it / red_blocks, rb = it - ds * red_blocks;
+        EpsSrc eps;
+        eps.inj = p.eps_w ? p.eps_w + static_cast<int64_t>(sg.z + ds) * p.w_numel : nullptr;
+        eps.key = key;
+        eps.sample = p.sample_begin + sg.z + ds;
+        { BNN_T0(); mbar_wait(pipe.empty_w + group, ((gi >> 2) & 1) ^ 1); BNN_ACC(w_gen); }
+        if (!kDgrad)
+          gen_w_tile<64, false, kSigns>(tile, p.mu_w, p.sigma_w, eps, half0, p.N, rb * kBK, p.K, tid, p.K, 0);
+        else if (!kConv)
+          gen_w_tile<64, true, kSigns>(tile, p.mu_w, p.sigma_w, eps, rb * kBK, p.N, half0, p.K, tid, p.K, 0);
+        else {
+          const int tapf = rb / p.conv.cblocks, o0 = (rb - tapf * p.conv.cblocks) * kBK;
+          gen_w_tile<64, true, kSigns>(tile, p.mu_w, p.sigma_w, eps, o0, p.conv.w_rows, half0, p.K, tid,
+                               static_cast<int64_t>(p.conv.taps) * p.K, static_cast<int64_t>(p.conv.taps - 1 - tapf) * p.K);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_full_w);
+      }
+      gi0 += sg.n;
+    }
+  } else if (warp == kTmaWarp) {
+    // ------------------------------------------------------------------ TMA issuer (own rows; bytes counted by the leader)
+    if (lane == 0) {
+      const uint32_t lead_full_a = mapa_u32(smem_u32(pipe.full_a), 0);
+      int pos = range_a, gi = 0;
+      SkSeg sg;
+      while (sk_next(p, pos, range_b, &sg)) {
+        const int row0 = sg.lead_row0 + static_cast<int>(rank) * (sg.mb_cap * 128);
+        int mb_pair = (p.M - sg.lead_row0 + 127) / 128;
+        if (mb_pair > sg.mb_cap) mb_pair = sg.mb_cap;
+        int ds = sg.i0 / red_blocks, rb = sg.i0 - ds * red_blocks;
+        int smp = p.shared_l ? 0 : sg.z + ds;
+        int cw[MB], ch[MB], cn[MB];
+        int tap = 0, cb = 0;
+        if (kConv) {
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) conv_pixel(p.conv, row0 + mb * 128, smp, &cw[mb], &ch[mb], &cn[mb]);
+          tap = rb / p.conv.cblocks;
+          cb = rb - tap * p.conv.cblocks;
+        }
+        for (int j = 0; j < sg.n; ++j, ++gi) {
+          const int g = gi & 1;
+          if (gi >= 2) { BNN_T0(); mbar_wait(pipe.empty_w + ((gi - 2) & 3), ((gi - 2) >> 2) & 1); BNN_ACC(w_tma); }
+          if (rank == 0) mbar_arrive_expect_tx(pipe.full_a + g, 2 * mb_pair * kTileBytes);
+          if (!kConv) {
+            for (int mb = 0; mb < mb_pair; ++mb)
+              tma_load_3d_pair(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, rb * kBK, row0 + mb * 128, smp,
+                               lead_full_a + g * 8);
+          } else {
+            const int kh = tap / p.conv.KW, kw = tap - kh * p.conv.KW;
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+              if (mb < mb_pair)
+                tma_load_im2col_4d_pair(pipe.ring_a + (g * MB + mb) * kTileBytes, &p.map_l, cb * kBK, cw[mb], ch[mb], cn[mb],
+                                        static_cast<uint16_t>(kw * p.conv.dw), static_cast<uint16_t>(kh * p.conv.dh),
+                                        lead_full_a + g * 8);
+            if (++cb == p.conv.cblocks) { cb = 0; ++tap; }
+          }
+          if (++rb == red_blocks) {                  // next sample of a summed tile
+            rb = 0; ++ds; tap = 0; cb = 0;
+            if (!p.shared_l) {
+              smp = sg.z + ds;
+              if (kConv) {
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) cn[mb] += p.conv.imgs;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarpT) {
+    // ------------------------------------------------------------------ MMA issuer (leader only)
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(256, 128, false, kDgrad);
+      const uint64_t desc_a0 = make_smem_desc(pipe.ring_a);
+      const uint64_t desc_w0 = kDgrad ? make_smem_desc_mn(pipe.ring_w, kMnLbo, kMnSbo) : make_smem_desc(pipe.ring_w);
+      int pos = range_a, gi = 0, seg = 0;
+      SkSeg sg;
+      while (sk_next(p, pos, range_b, &sg)) {
+        int mb_pair = (p.M - sg.lead_row0 + 127) / 128;
+        if (mb_pair > sg.mb_cap) mb_pair = sg.mb_cap;
+        if (seg > 0) {                                 // the epilogue warps of both CTAs have drained the last segment
+          { BNN_T0(); mbar_wait_cluster(pipe.tmem_empty, (seg - 1) & 1); BNN_ACC(w_mma_t); }
+          tc_fence_after_sync();
+        }
+        for (int j = 0; j < sg.n; ++j, ++gi) {
+          const int wslot = gi & 3, g = gi & 1;
+          { BNN_T0(); mbar_wait_cluster(pipe.full_w + wslot, (gi >> 2) & 1); BNN_ACC(w_mma_w); }
+          { BNN_T0(); mbar_wait_cluster(pipe.full_a + g, (gi >> 1) & 1); BNN_ACC(w_mma_a); }
+          tc_fence_after_sync();
+          const uint64_t da0 = desc_advance(desc_a0, static_cast<uint32_t>(g * MB) * (kTileBytes >> 4));
+          const uint64_t db0 = desc_advance(desc_w0, static_cast<uint32_t>(wslot) * (kHalfTileBytes >> 4));
+          for (int mb = 0; mb < mb_pair; ++mb) {
+#pragma unroll
+            for (int ks = 0; ks < kBK / 8; ++ks)
+              mma_tf32_pair(tmem + mb * 128, desc_advance(da0, mb * (kTileBytes >> 4) + ks * 2),
+                            desc_advance(db0, ks * ((kDgrad ? kMnKStep : 32u) >> 4)), idesc, j > 0 || ks > 0);
+          }
+          mma_commit_pair(pipe.empty_w + wslot, 3);
+        }
+        mma_commit_pair(pipe.accum_full, 3);
+        ++seg;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (own TMEM, own rows)
+    const int et = threadIdx.x - kEpiWarp0T * 32;   // 0..127
+    const int quad = warp & 3;
+    const uint32_t lead_tmem_empty = mapa_u32(smem_u32(pipe.tmem_empty), 0);
+    int pos = range_a, seg = 0;
+    SkSeg sg;
+    while (sk_next(p, pos, range_b, &sg)) {
+      const int col0 = sg.y * 128;
+      const int row0 = sg.lead_row0 + static_cast<int>(rank) * (sg.mb_cap * 128);
+      int mb_pair = (p.M - sg.lead_row0 + 127) / 128;
+      if (mb_pair > sg.mb_cap) mb_pair = sg.mb_cap;
+      const bool add = p.atomic_out != 0;              // summed tiles: every segment adds into the zeroed output
+      float* aux = pipe.aux + (seg & 1) * 128;
+      if (!kDgrad) {
+        float b = 0.f;
+        const int n = col0 + et;
+        if (p.mu_b != nullptr && n < p.N) {
+          const float e = p.eps_b ? __ldg(p.eps_b + static_cast<int64_t>(sg.z) * p.N + n)
+                                  : eps1(resolve_rng(p.rng_b), p.sample_begin + sg.z, static_cast<uint64_t>(n));
+          b = fmaf(__ldg(p.sigma_b + n), e, __ldg(p.mu_b + n));
+        }
+        aux[et] = b;
+        named_bar_sync(kEpiBarrier, kEpiThreads);
+      }
+      mbar_wait(pipe.accum_full, seg & 1);
+      tc_fence_after_sync();
+#ifdef BNN_PROFILE_WAITS
+      const long long t_epi0 = clock64();
+#endif
+      View out = p.out;
+      out.base += (p.sum_samples ? 0 : static_cast<int64_t>(sg.z) * p.out_sample_stride);
+      const int cols_here = n_cols - col0 < 128 ? n_cols - col0 : 128;
+      const bool staged = stage_eligible(out, p.vec_out != 0, cols_here) && (out.P == 1 || (p.M & 3) == 0);
+      for (int mb = 0; mb < mb_pair; ++mb) {
+        const int m = row0 + mb * 128 + quad * 32 + lane;
+        if (row0 + mb * 128 >= p.M) break;               // uniform per CTA
+        if (staged) {
+          drain_block_staged<!kDgrad>(tmem + (static_cast<uint32_t>(quad * 32) << 16) + mb * 128,
+                                      pipe.stage + quad * kStageWarpBytes, aux, out, row0 + mb * 128 + quad * 32,
+                                      p.M, col0, cols_here, lane, add);
+          continue;
+        }
+        for (int c = 0; c * 16 < cols_here; ++c) {
+          float v[16];
+          tmem_ld16(tmem + (static_cast<uint32_t>(quad * 32) << 16) + mb * 128 + c * 16, v);
+          if (!kDgrad) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += aux[c * 16 + j];
+          }
+          if (m < p.M) {
+            if (add) add_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+            else store_chunk(out, m, col0 + c * 16, n_cols, v, p.vec_out != 0);
+          }
+        }
+      }
+      tc_fence_before_sync();                            // all tcgen05.ld of this segment have completed (wait::ld)
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_tmem_empty);
+#ifdef BNN_PROFILE_WAITS
+      w_epi += clock64() - t_epi0;
+#endif
+      ++seg;
+    }
+  }
+#ifdef BNN_PROFILE_WAITS
+  if (threadIdx.x == kEpiWarp0T * 32) BNN_STAGE(3, t_kernel0);
+  if (threadIdx.x == 0) BNN_STAGE(1, t_kernel0);
+  if (lane == 0) {      // [0] kernel [1] MMA: weights [2] MMA: activations [3] generator warp 0 [4] TMA [5] CTAs [6] MMA: TMEM drain [7] epilogue busy
+    if (warp == 0) { atomicAdd(&g_wait_cycles[3], (unsigned long long)w_gen); atomicAdd(&g_wait_cycles[0], (unsigned long long)(clock64() - t_kernel0)); atomicAdd(&g_wait_cycles[5], 1ull); }
+    if (w_mma_w | w_mma_a | w_mma_t) { atomicAdd(&g_wait_cycles[1], (unsigned long long)w_mma_w); atomicAdd(&g_wait_cycles[2], (unsigned long long)w_mma_a); atomicAdd(&g_wait_cycles[6], (unsigned long long)w_mma_t); }
+    if (w_tma) atomicAdd(&g_wait_cycles[4], (unsigned long long)w_tma);
+    if (warp == kEpiWarp0T) atomicAdd(&g_wait_cycles[7], (unsigned long long)w_epi);
+  }
+#endif
+  tc_fence_before_sync();
+  cluster_sync_all();                                // nobody leaves while the partner may still signal or read
+  if (warp == kMmaWarpT) {
+    tc_fence_after_sync();
+    tmem_dealloc_pair(tmem, 512);
+  }
+#ifdef BNN_PROFILE_WAITS
+  if (threadIdx.x == 0) {
+    BNN_STAGE(4, t_kernel0);
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    atomicMax(&g_stage_cycles[7], g);
+  }
+#endif
+}
+
+template <bool kDgrad, int kMode>
+int launch_pair_sk_v(const TmaContractParams& p, cudaStream_t st) {
+  static SmemOptIn opt_in;
+  const int rc = allow_dynamic_smem(contract_pair_sk_kernel<kDgrad, kMode>, kPairSkSmem, &opt_in);
+  if (rc != BNN_OK) return rc;
+  contract_pair_sk_kernel<kDgrad, kMode><<<dim3(2 * p.sk_slots, 1, 1), kThreadsTma, kPairSkSmem, st>>>(p);
+  BNN_CUDA_OK(cudaGetLastError());
+  return BNN_OK;
+}
+template <bool kDgrad>
+int launch_pair_sk(const TmaContractParams& p, cudaStream_t st) {
+  if (p.conv.on) return launch_pair_sk_v<kDgrad, 1>(p, st);
+  if (p.rng_w.row_sign != nullptr) return launch_pair_sk_v<kDgrad, 2>(p, st);
+  return launch_pair_sk_v<kDgrad, 0>(p, st);
+}
+
 bool pair_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -757,7 +1307,8 @@ bool pair_enabled() {
 
 // Test aid: force one kernel variant (0 = pair, 1 / 2 / 4 = rows blocks per CTA, -1 = cost model) so that small test
 // shapes reach every variant.  Set through bnn_debug_force_contract_variant (tests) — the environment variable
-// BNN_CONTRACT_VARIANT = pair | mb4 | mb2 | mb1 only provides the initial value, read once.
+// BNN_CONTRACT_VARIANT = pair | balanced | mb4 | mb2 | mb1 only provides the initial value, read once.  8 = the CTA-pair
+// kernel's balanced schedule (contract_pair_sk_kernel) whenever the pair kernel is eligible.
 std::atomic<int> g_forced_variant{-2};
 int forced_variant() {
   int v = g_forced_variant.load(std::memory_order_relaxed);
@@ -765,6 +1316,7 @@ int forced_variant() {
   v = -1;
   const char* e = getenv("BNN_CONTRACT_VARIANT");
   if (e != nullptr && e[0] == 'p') v = 0;
+  else if (e != nullptr && e[0] == 'b') v = 8;                  // "balanced"
   else if (e != nullptr && e[0] == 'm' && e[1] == 'b') v = e[2] == '4' ? 4 : (e[2] == '2' ? 2 : (e[2] == '1' ? 1 : -1));
   g_forced_variant.store(v, std::memory_order_relaxed);
   return v;
@@ -830,6 +1382,125 @@ bool solve_pair_tiles(TilePlan* plan, int m_blocks, int S, int slots) {
   return true;
 }
 
+// ---- balanced schedule, host side
+std::atomic<int> g_sk_slot_cap{0};              // test aid: fewer slots than the machine has (0 = no cap)
+std::atomic<int> g_sk_launches{0};              // launches that took the balanced schedule (tests, bench)
+std::atomic<int> g_sk_on{-1};                   // -1: not decided yet (off unless BNN_BALANCED=1 is in the environment)
+bool sk_enabled() {                             // opt-in (bnn_contract_set_balanced / BNN_BALANCED=1): measured slower on B200, DESIGN §4
+  int v = g_sk_on.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("BNN_BALANCED");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    g_sk_on.store(v, std::memory_order_relaxed);
+  }
+  return v == 1;
+}
+// clusters of contract_pair_sk_kernel that are resident at the same time on the current device (cached per device);
+// the schedule does not depend on co-residency (slots never wait for each other), it only sizes the grid
+int sk_max_slots() {
+  static std::mutex mu;
+  static int cached[64];
+  static bool known[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!known[dev]) {
+    known[dev] = true;
+    cached[dev] = 0;
+    static SmemOptIn opt_in;
+    if (allow_dynamic_smem(contract_pair_sk_kernel<false, 0>, kPairSkSmem, &opt_in) == BNN_OK) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(static_cast<unsigned>(sm_count() & ~1), 1, 1);
+      cfg.blockDim = dim3(kThreadsTma, 1, 1);
+      cfg.dynamicSmemBytes = kPairSkSmem;
+      cudaLaunchAttribute attr{};
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, contract_pair_sk_kernel<false, 0>, &cfg) == cudaSuccess) cached[dev] = n;
+      else (void)cudaGetLastError();
+    }
+  }
+  return cached[dev];
+}
+
+// k-block cost of a tile of u units (one row block per CTA each), in cycles (CTA timeline of a profiling build at the C3
+// conv shape: the leader issues a 256 x 128 x 8 MMA per ~117 cycles, a CTA generates its half tile in ~1200)
+inline double sk_kblock_cycles(int u) {
+  const double mma = 117.0 * 4 * u + 130.0;
+  return mma > 1250.0 ? mma : 1250.0;
+}
+
+template <bool kDgrad>
+bool plan_sk(TmaContractParams& p, int gx, int m_blocks, int uniform_pairs, bool forced) {
+  p.sk_slots = 0;
+  if (!forced && !sk_enabled()) return false;
+  if (p.sum_samples && p.out.P != 1) return false;
+  const int slots = sk_max_slots();
+  if (slots < 2) return false;
+  const int red_blocks = ((kDgrad ? p.N : p.K) + kBK - 1) / kBK;
+  const int cap = g_sk_slot_cap.load(std::memory_order_relaxed);
+  const double fixed = 6000.0, epilogue = 3500.0;         // launch + prologue + pipeline fill; per row block of a tile
+  const double waves = static_cast<double>((uniform_pairs + slots - 1) / slots);
+  if (p.sum_samples) {
+    // items = k-block iterations of the 1024-row tiles over ALL samples; every segment adds
+    const int m_tiles = (m_blocks + 7) / 8;
+    const int64_t n_tiles = static_cast<int64_t>(gx) * m_tiles;
+    const int64_t its = static_cast<int64_t>(red_blocks) * p.S;
+    const int64_t total = n_tiles * its;
+    if (total <= 0 || total > (int64_t(1) << 30)) return false;
+    int64_t q = slots;
+    if (q > total / 8) q = total / 8;           // at least eight k-blocks per slot
+    if (cap > 0 && q > cap) q = cap;
+    if (q < 1) return false;
+    if (!forced) {
+      const double per_slot = static_cast<double>((total + q - 1) / q);
+      const double segs = per_slot / static_cast<double>(its) + 1.0;
+      const double sk_cost = fixed + per_slot * sk_kblock_cycles(4) + segs * 4 * epilogue * 1.4;
+      const double uniform_cost = waves * (fixed + static_cast<double>(red_blocks) * p.z_per * sk_kblock_cycles(4) + 4 * epilogue * 1.4);
+      if (sk_cost > 0.95 * uniform_cost) return false;
+    }
+    p.sk_msplit = 0;
+    p.sk_slots = static_cast<int>(q);
+    p.sk_mtiles = m_tiles;
+    p.sk_gx = gx;
+    p.sk_its = static_cast<int>(its);
+    p.sk_total = static_cast<int>(total);
+  } else {
+    // items = 256-row units of the (sample, column tile) columns; a segment = a tile of 1..4 units, whole reduction
+    const int m_units = (m_blocks + 1) / 2;
+    const int64_t total = static_cast<int64_t>(gx) * p.S * m_units;
+    if (total <= 0 || total > (int64_t(1) << 30)) return false;
+    int64_t q = slots;
+    if (q > total) q = total;
+    if (cap > 0 && q > cap) q = cap;
+    if (q < 1) return false;
+    if (!forced) {
+      // the busiest slot: ceil(total / q) units cut by sk_tile_units (ranges that straddle a column cost one more cut)
+      int left = static_cast<int>((total + q - 1) / q);
+      double sk_cost = fixed;
+      while (left > 0) {
+        const int u = sk_tile_units(left < m_units ? left : m_units);
+        sk_cost += red_blocks * sk_kblock_cycles(u) + u * epilogue;
+        left -= u;
+      }
+      const int u_uniform = m_units < 4 ? m_units : 4;
+      const double uniform_cost = waves * (fixed + red_blocks * sk_kblock_cycles(u_uniform) + u_uniform * epilogue);
+      if (sk_cost > 0.95 * uniform_cost) return false;
+    }
+    p.sk_msplit = 1;
+    p.sk_slots = static_cast<int>(q);
+    p.sk_mtiles = m_units;
+    p.sk_gx = gx;
+    p.sk_its = red_blocks;
+    p.sk_total = static_cast<int>(total);
+  }
+  p.plan.on = 0;
+  return true;
+}
+
 template <bool kDgrad>
 int dispatch_tma_contract(TmaContractParams& p, int n_cols, cudaStream_t st) {
   const int m_blocks = (p.M + 127) / 128;
@@ -881,9 +1552,20 @@ int dispatch_tma_contract(TmaContractParams& p, int n_cols, cudaStream_t st) {
   }
   if (m_blocks > 4 && pair_enabled() && cost_pair() < 0.9 * best_cost) best = 0;       // a clear win only: the model is coarse
   const int forced = forced_variant();
-  if (forced > 0 || (forced == 0 && m_blocks > 4)) best = forced;
+  const bool force_sk = forced == 8 && m_blocks > 4;
+  if (force_sk) best = 0;
+  else if ((forced > 0 && forced != 8) || (forced == 0 && m_blocks > 4)) best = forced;
   if (best == 0) {                                                // two CTAs (one cluster) per 1024 rows
     const int pairs = (m_blocks + 7) / 8;
+    if ((forced < 0 || force_sk) && plan_sk<kDgrad>(p, gx, m_blocks, pairs * gx * gz, force_sk)) {
+      if (p.sum_samples && !p.atomic_out) {                       // every segment adds: the output starts from zero
+        p.atomic_out = 1;
+        BNN_CUDA_OK(cudaMemset2DAsync(p.out.base, static_cast<size_t>(p.out.bs) * 4, 0, static_cast<size_t>(n_cols) * 4,
+                                      static_cast<size_t>(p.M), st));
+      }
+      g_sk_launches.fetch_add(1, std::memory_order_relaxed);
+      return launch_pair_sk<kDgrad>(p, st);
+    }
     if (plan_pair_tiles(&p.plan, m_blocks, p.S, gx, gz, p.sum_samples != 0, sms / 2))
       return launch_pair_contract<4, kDgrad>(p, dim3(2 * (p.plan.n_a + p.plan.s1 * p.plan.b1 + (p.S - p.plan.s1) * p.plan.b2), 1, 1), st);
     return launch_pair_contract<4, kDgrad>(p, dim3(2 * pairs, gx, gz), st);
@@ -1454,6 +2136,20 @@ int tma_wait_counters(unsigned long long* out8, int reset) {
 #endif
 }
 
+int tma_stage_counters(unsigned long long* out8, int reset) {
+#ifdef BNN_PROFILE_WAITS
+  BNN_CUDA_OK(cudaMemcpyFromSymbol(out8, g_stage_cycles, 8 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, ~0ull, 0};
+    BNN_CUDA_OK(cudaMemcpyToSymbol(g_stage_cycles, z, sizeof(z)));
+  }
+  return BNN_OK;
+#else
+  (void)out8; (void)reset;
+  return kNotEligible;
+#endif
+}
+
 int tma_pair_tile_plan(int m_blocks, int S, int slots, int32_t* out7) {      // host only: the plan the launcher would use
   TilePlan plan{};
   solve_pair_tiles(&plan, m_blocks, S, slots);
@@ -1462,7 +2158,19 @@ int tma_pair_tile_plan(int m_blocks, int S, int slots, int32_t* out7) {      // 
 }
 
 int tma_force_variant(int variant) {
-  g_forced_variant.store(variant < -1 || variant > 4 || variant == 3 ? -1 : variant, std::memory_order_relaxed);
+  const bool ok = variant == -1 || variant == 0 || variant == 1 || variant == 2 || variant == 4 || variant == 8;
+  g_forced_variant.store(ok ? variant : -1, std::memory_order_relaxed);
+  return BNN_OK;
+}
+
+int contract_set_balanced(int on) {
+  g_sk_on.store(on ? 1 : 0, std::memory_order_relaxed);
+  return BNN_OK;
+}
+int contract_balanced_state(int slot_cap, int* launches_out, int* slots_out) {
+  if (slot_cap >= 0) g_sk_slot_cap.store(slot_cap, std::memory_order_relaxed);
+  if (launches_out) *launches_out = g_sk_launches.load(std::memory_order_relaxed);
+  if (slots_out) *slots_out = sk_max_slots();
   return BNN_OK;
 }
 

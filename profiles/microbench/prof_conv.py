@@ -1,5 +1,5 @@
 """Profiling driver: the C3 (default) or C2 Bayesian conv layer through the implicit-GEMM path — forward, input gradient,
-weight gradient — with CUDA-event times per call.  `python profiles/microbench/prof_conv.py [c3|c2] [shared|per]`.
+weight gradient — with CUDA-event times per call.  `python profiles/microbench/prof_conv.py [c3|c2] [shared|per] [nchw]`.
 Under ncu: `-k regex:"contract_|wgrad_tma"`."""
 import sys
 
@@ -29,8 +29,12 @@ rw, rb = C.make_rng(1, 0, 1), C.make_rng(1, 0, 2)
 xss = 0 if shared else B * HW * HW * Cn
 
 
+nchw = len(sys.argv) > 3 and sys.argv[3] == "nchw"        # the layers' default output layout (view P = OH*OW)
+y_view = C.make_view(y.data_ptr(), Cn * OH * OH, OH * OH) if nchw else C.make_view(y.data_ptr(), Cn, 1)
+
+
 def fwd():
-    C.sampled_conv2d_fwd(x, xss, wl[0], wl[1], mub, sigb, None, None, C.make_view(y.data_ptr(), Cn, 1), M * Cn, geom, S, 0, rw, rb)
+    C.sampled_conv2d_fwd(x, xss, wl[0], wl[1], mub, sigb, None, None, y_view, M * Cn, geom, S, 0, rw, rb)
 
 
 def dgrad():
@@ -42,6 +46,11 @@ def wgrad():
     C.sampled_conv2d_wgrad(dy, x, xss, wl[2], None, gr[0], gr[1], geom, S, 0, rw)
 
 
+import os  # noqa: E402
+if os.environ.get("BNN_SK_CAP"):          # cap the pair slots of the balanced schedule (scaling experiments)
+    C.balanced_schedule_state(slot_cap=int(os.environ["BNN_SK_CAP"]))
+if os.environ.get("BNN_FORCE_VARIANT"):
+    C.force_contract_variant(os.environ["BNN_FORCE_VARIANT"])
 for _ in range(3):
     fwd(), dgrad(), wgrad()
 torch.cuda.synchronize()
@@ -53,7 +62,8 @@ for name, fn in (("fwd", fwd), ("dgrad", dgrad), ("wgrad", wgrad)):
         a.record(); fn(); b.record()
         torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b))
-    print(f"{which} {'shared' if shared else 'per-sample'} {name}: {best * 1e3:.1f} us  {flops / best / 1e9:.1f} TFLOP/s")
+    print(f"{which} {'shared' if shared else 'per-sample'} {name}: {best * 1e3:.1f} us  {flops / best / 1e9:.1f} TFLOP/s"
+          f"  (balanced launches so far: {C.balanced_schedule_state()[0]})")
 
 # profiling builds only (BNN_EXTRA_NVCC_FLAGS=-DBNN_PROFILE_WAITS): wait cycles of the contraction kernels' roles
 import ctypes  # noqa: E402
@@ -63,12 +73,24 @@ try:
     f.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
     buf = (ctypes.c_ulonglong * 8)()
     f(buf, 1)
+    f2 = C.lib().bnn_debug_stage_counters
+    f2.restype = ctypes.c_int
+    f2.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
+    st = (ctypes.c_ulonglong * 8)()
+    f2(st, 1)
     for name, fn in (("fwd", fwd), ("dgrad", dgrad)):
         fn()
         torch.cuda.synchronize()
+        if f2(st, 1) == 0 and st[5]:
+            n = st[5]
+            span = (st[7] - st[6]) * 1e-3
+            print(f"{name}: CTA timeline (cycles since CTA start, mean of {n} CTAs): prologue {st[0] / n:.0f} | generators done {st[1] / n:.0f} | "
+                  f"accumulator complete {st[2] / n:.0f} | epilogue done {st[3] / n:.0f} | CTA end {st[4] / n:.0f} | "
+                  f"first CTA start -> last CTA end {span:.1f} us")
         if f(buf, 1) == 0 and buf[5]:
             n = buf[5]
             print(f"{name}: CTAs {n}  kernel {buf[0] / n:.0f} cycles/CTA | MMA thread waits: weights {buf[1] / n * 2:.0f} (leader only) "
-                  f"activations {buf[2] / n * 2:.0f} | generators wait for a free slot {buf[3] / n:.0f} | TMA thread waits {buf[4] / n:.0f}")
+                  f"activations {buf[2] / n * 2:.0f} | generators wait for a free slot {buf[3] / n:.0f} | TMA thread waits {buf[4] / n:.0f}"
+                  f" | balanced schedule: MMA waits for the TMEM drain {buf[6] / n * 2:.0f} (leader only), epilogue busy {buf[7] / n:.0f}")
 except AttributeError:
     pass
