@@ -11,8 +11,13 @@ signs are per example (conv.py:154-161).
   sample-and-contract kernels (bnn_rng.row_sign / col_sign: the generator warps read the two sign vectors instead of
   drawing Philox normals), where the reference runs two GEMMs and two elementwise passes; the backward kernels form
   d mean and d scale with the same eps.  R / S are still drawn by torch and kept as attributes (`sampled`).
-* The conv layers' signs differ per example, which makes the perturbed filter example specific: those stay torch
-  composites (two cuDNN convolutions with unsampled weights).  CPU tensors take the composite everywhere.
+* The conv layers' signs differ per example, which makes the perturbed filter example specific: there is no common
+  sampled weight, the layer really is TWO convolutions with unsampled weights, conv(x, mean) + conv(x * S, stddev) * R.
+  FlipOutNormalConv1d / 2d (CUDA, groups == 1, in_channels % 32 == 0) run both through the library's implicit-GEMM
+  contraction kernels (the sample-and-contract kernels with injected eps = 0, i.e. W = the given tensor; TMA im2col
+  operand, tcgen05 MMAs; forward, input gradient and weight gradients), with the sign products and d stddev / d scale
+  left to torch element-wise ops; everything else (3-d, grouped, odd channel counts, CPU tensors) evaluates the
+  reference's composite with torch's convolutions.
 Their variational tensor is a WeightNormal, hence KLDivergence and PruneNormal treat them like every other Bayesian layer
 (the fused KL / prune kernels).
 """
@@ -21,6 +26,7 @@ import torch.nn.functional as F
 from torch.distributions.normal import Normal
 
 from .. import runtime
+from ..functional import conv_implicit_eligible
 from ..utils.traversal import _pair, _single, _triple
 from .layers import NormalConvNd, NormalLinear
 
@@ -30,11 +36,17 @@ def _signs(*shape, device):
 
 
 _FUSED_LINEAR = {"on": True}
+_KERNEL_CONV = {"on": True}
 
 
 def set_fused_flipout_linear(flag=True):
     """False: FlipoutNormalLinear evaluates the reference's two-contraction composite on CUDA too (A/B comparisons)."""
     _FUSED_LINEAR["on"] = bool(flag)
+
+
+def set_flipout_conv_kernels(flag=True):
+    """False: FlipOutNormalConv1d / 2d evaluate the reference's composite with torch's convolutions on CUDA too."""
+    _KERNEL_CONV["on"] = bool(flag)
 
 
 class FlipoutNormalLinear(NormalLinear):
@@ -118,10 +130,41 @@ class FlipOutNormalConvNd(NormalConvNd):
     def sampled(self):
         return (self.R, self.S)
 
+    def _kernel_path(self, x, nd):
+        return (_KERNEL_CONV["on"] and nd <= 2 and x.is_cuda and x.dtype == torch.float32 and x.dim() == nd + 2
+                and not self.transposed and conv_implicit_eligible(self.in_channels, self.groups))
+
+    def _contract(self, x4, w4, geometry):
+        """conv2d(x4, w4) through the implicit-GEMM contraction kernels: the sample-and-contract path with ONE sample and
+        injected eps = 0 (W = w4 exactly); autograd returns d x4 and d w4 from the library's input- / weight-gradient
+        kernels."""
+        from ..functional import DrawSpec, SampledConv2dImplicit
+        zero = getattr(self, "_zero_eps", None)
+        if zero is None or zero.device != w4.device or zero.numel() != w4.numel():
+            zero = torch.zeros(1, w4.numel(), device=w4.device, dtype=torch.float32)
+            self._zero_eps = zero
+        spec = DrawSpec(0, 0, 0, eps=zero)
+        return SampledConv2dImplicit.apply(x4, w4, self.weight.scale.detach().view(w4.shape), None, None, 1, True, spec,
+                                           None, runtime.precision(), *geometry)
+
     def _flipout(self, x, nd, sample):
         _, x, _ = runtime.mc_expand_rows(x)
         if sample:
             self.sample(x.size(0), (1,) * nd)
+        if self._kernel_path(x, nd):
+            xs = x * self.S.expand_as(x)
+            mean, stddev = self.weight.mean, self.weight.stddev
+            if nd == 1:            # a 2-d convolution with a height of one
+                shape4 = (mean.shape[0], mean.shape[1], 1, mean.shape[2])
+                geometry = ((1, tuple(self.stride)[0]), (0, tuple(self.padding)[0]), (1, tuple(self.dilation)[0]))
+                x, xs, mean, stddev = x.unsqueeze(2), xs.unsqueeze(2), mean.view(shape4), stddev.view(shape4)
+            else:
+                geometry = (tuple(self.stride), tuple(self.padding), tuple(self.dilation))
+            out = self._contract(x, mean, geometry)
+            pert = self._contract(xs, stddev, geometry)
+            if nd == 1:
+                out, pert = out.squeeze(2), pert.squeeze(2)
+            return out + pert * self.R.expand_as(out)
         op = type(self)._op
         args = (self.stride, self.padding, self.dilation, self.groups)
         out = op(x, self.weight.mean, self.bias, *args)

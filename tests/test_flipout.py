@@ -226,3 +226,56 @@ def test_fused_flipout_linear_equals_the_two_contraction_composite(shape, prec, 
     finally:
         bnn.set_precision("fp32")
         flipout.set_fused_flipout_linear(True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", 2e-3)])
+@pytest.mark.parametrize("case", [
+    # cls, in, out, kernel, stride, padding, dilation, spatial, batch
+    (FlipOutNormalConv2d, 64, 64, 3, 2, 1, 1, (6, 6), 48),       # the FashionMNIST example layer's geometry
+    (FlipOutNormalConv2d, 32, 40, 3, 1, 1, 2, (9, 7), 10),       # dilation, ragged channel count
+    (FlipOutNormalConv1d, 32, 16, 5, 1, 2, 1, (33,), 12),        # 1-d as a height-1 2-d convolution
+])
+def test_flipout_conv_runs_on_the_contraction_kernels(case, prec, tol):
+    """FlipOutNormalConv1d / 2d on CUDA (groups == 1, in_channels % 32 == 0): conv(x, mean) + conv(x * S, stddev) * R
+    (conv.py:207-221) with both convolutions on the library's implicit-GEMM contraction kernels (injected eps = 0):
+    output and the gradients of x, mean and scale against the same formula evaluated by torch in fp64 with the same
+    per-example signs; sample=False reuses the signs; the torch composite gives the same numbers; the library was
+    actually called (launch counter)."""
+    import bayesianneuralnetworks_b200 as bnn
+    from bayesianneuralnetworks_b200 import _C
+    from bayesianneuralnetworks_b200.nn import flipout
+    cls, cin, cout, k, stride, padding, dilation, spatial, B = case
+    op = torch.nn.functional.conv2d if len(spatial) == 2 else torch.nn.functional.conv1d
+    torch.manual_seed(8)
+    bnn.set_precision(prec)
+    try:
+        layer = cls(cin, cout, k, stride, padding, dilation).cuda()
+        x = torch.randn(B, cin, *spatial, device="cuda", requires_grad=True)
+        before = _C.launch_count
+        y = layer(x)
+        assert _C.launch_count > before, "the contraction kernels were not launched"
+        dy = torch.randn(y.shape, device="cuda")
+        y.backward(dy)
+        R, S = layer.R.double(), layer.S.double()
+        assert R.shape[:2] == (B, cout) and S.shape[:2] == (B, cin)            # per example (conv.py:154-161)
+        xd = x.detach().double().requires_grad_(True)
+        mu = layer.weight.mean.detach().double().requires_grad_(True)
+        rho = layer.weight.scale.detach().double().requires_grad_(True)
+        sigma = 1e-10 + torch.nn.functional.softplus(rho)
+        ref = op(xd, mu, None, stride, padding, dilation)
+        ref = ref + op(xd * S, sigma, None, stride, padding, dilation) * R
+        ref.backward(dy.double())
+
+        def close(a, b):
+            return float((a.double() - b).abs().max()) <= tol * float(b.abs().max()) + 1e-12
+        assert y.shape == ref.shape
+        assert close(y, ref) and close(x.grad, xd.grad)
+        assert close(layer.weight.mean.grad, mu.grad) and close(layer.weight.scale.grad, rho.grad)
+        assert torch.equal(layer(x, sample=False), y)
+        flipout.set_flipout_conv_kernels(False)            # torch's composite (cuDNN, TF32 by default): same signs, same result
+        comp = layer(x, sample=False)
+        assert float((comp.double() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+    finally:
+        bnn.set_precision("fp32")
+        flipout.set_flipout_conv_kernels(True)
