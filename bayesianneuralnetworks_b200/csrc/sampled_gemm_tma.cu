@@ -649,14 +649,19 @@ int launch_tma_contract(const TmaContractParams& p, dim3 grid, cudaStream_t st) 
 // barrier), the generator warps of the peer arrive on the leader's barrier through the cluster address space, the
 // leader's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256) and frees the slots of BOTH CTAs with
 // multicast commits.  Epilogue: every CTA drains its own TMEM.
-constexpr int kPairWSlots = 4;               // 8 KiB half-tiles (the k-block bookkeeping assumes 4)
+constexpr int kPairWSlots = 4;               // 8 KiB half-tiles: slot = k-block % kPairWSlots (a power of two, a multiple of
+constexpr int kPairWShift = 2;               // the four generator groups).  Eight slots were measured: the generators wait
+                                             // less (19 k instead of 26 k cycles per C3 tile), the MMA thread's 8.8 k cycles of
+                                             // waiting for weights do not move — they are the cold start of a tile (first
+                                             // mu / sigma loads, instruction cache), not a lack of slack in the ring
+constexpr int kSkWSlots = 4;                 // balanced schedule: four slots (its epilogue staging needs the space)
 constexpr int kHalfTileBytes = kTileBytes / 2;
 constexpr size_t kPairSmem = kSmemAux + 1024 + static_cast<size_t>(kASlots) * kTileBytes + kPairWSlots * kHalfTileBytes;
 
 struct PairPipe {
   uint64_t* full_a;      // [2]  leader: 1 arrival (expect_tx) + the bytes of both CTAs' tiles of one k-block group
-  uint64_t* full_w;      // [4]  leader: one arrival per warp of the owning generator group of both CTAs
-  uint64_t* empty_w;     // [4]  both CTAs: "k-block consumed", one multicast tcgen05.commit per k-block
+  uint64_t* full_w;      // [kPairWSlots]  leader: one arrival per warp of the owning generator group of both CTAs
+  uint64_t* empty_w;     // [kPairWSlots]  both CTAs: "k-block consumed", one multicast tcgen05.commit per k-block
   uint64_t* accum_full;  // both CTAs
   uint32_t* tmem_slot;
   float* aux;
@@ -702,7 +707,7 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
     // weight tile j (one arrival per generator warp of both CTAs); both CTAs: empty_w[j] = "k-block consumed", ONE
     // multicast tcgen05.commit per k-block (frees weight slot j, and activation group j & 1 two k-blocks later)
     for (int i = 0; i < 2; ++i) mbar_init(pipe.full_a + i, 1);
-    for (int i = 0; i < 4; ++i) { mbar_init(pipe.full_w + i, 2 * kGroupWarps); mbar_init(pipe.empty_w + i, 1); }
+    for (int i = 0; i < kPairWSlots; ++i) { mbar_init(pipe.full_w + i, 2 * kGroupWarps); mbar_init(pipe.empty_w + i, 1); }
     mbar_init(pipe.accum_full, 1);
     fence_mbar_init();
   }
@@ -761,15 +766,16 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
     const RngKey key = resolve_rng(p.rng_w);
     const int half0 = col0 + static_cast<int>(rank) * 64;
     const int total = red_blocks * (s_end - s_begin);
-    const uint32_t lead_full_w = mapa_u32(smem_u32(pipe.full_w + group), 0);
+    const uint32_t lead_full_w0 = mapa_u32(smem_u32(pipe.full_w), 0);
     for (int it = group; it < total; it += kGenGroups) {
+      const int wslot = it & (kPairWSlots - 1);
       const int s = s_begin + it / red_blocks, rb = it - (it / red_blocks) * red_blocks;
       EpsSrc eps;
       eps.inj = p.eps_w ? p.eps_w + static_cast<int64_t>(s) * p.w_numel : nullptr;
       eps.key = key;
       eps.sample = p.sample_begin + s;
-      { BNN_T0(); mbar_wait(pipe.empty_w + group, ((it >> 2) & 1) ^ 1); BNN_ACC(w_gen); }
-      const uint32_t tile = pipe.ring_w + group * kHalfTileBytes;
+      { BNN_T0(); mbar_wait(pipe.empty_w + wslot, ((it >> kPairWShift) & 1) ^ 1); BNN_ACC(w_gen); }
+      const uint32_t tile = pipe.ring_w + wslot * kHalfTileBytes;
       if (!kDgrad)
         gen_w_tile<64, false, kSigns>(tile, p.mu_w, p.sigma_w, eps, half0, p.N, rb * kBK, p.K, tid, p.K, 0);
       else if (!kConv)
@@ -781,7 +787,7 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(lead_full_w);
+      if (lane == 0) mbar_arrive_cluster(lead_full_w0 + wslot * 8);
     }
     if (staged && (warp >> 2) < kDrainPerQuad - 1) {     // join the drain (TMEM lane quarter = warp % 4)
       if (!kDgrad) named_bar_sync(kDrainBarrier, kDrainThreads);          // the bias row is in shared memory
@@ -805,7 +811,7 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
         int tap = 0, cb = 0;
         for (int rb = 0; rb < red_blocks; ++rb, ++it) {
           const int g = it & 1;
-          if (it >= 2) { BNN_T0(); mbar_wait(pipe.empty_w + ((it - 2) & 3), ((it - 2) >> 2) & 1); BNN_ACC(w_tma); }
+          if (it >= 2) { BNN_T0(); mbar_wait(pipe.empty_w + ((it - 2) & (kPairWSlots - 1)), ((it - 2) >> kPairWShift) & 1); BNN_ACC(w_tma); }
           if (rank == 0) mbar_arrive_expect_tx(pipe.full_a + g, 2 * mb_pair * kTileBytes);
           if (!kConv) {
             for (int mb = 0; mb < mb_pair; ++mb)
@@ -835,8 +841,12 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
       int it = 0;
       for (int s = s_begin; s < s_end; ++s) {
         for (int rb = 0; rb < red_blocks; ++rb, ++it) {
-          const int wslot = it & 3, g = it & 1;
-          { BNN_T0(); mbar_wait_cluster(pipe.full_w + wslot, (it >> 2) & 1); BNN_ACC(w_mma_w); }
+          const int wslot = it & (kPairWSlots - 1), g = it & 1;
+          { BNN_T0(); mbar_wait_cluster(pipe.full_w + wslot, (it >> kPairWShift) & 1); BNN_ACC(w_mma_w); }
+#ifdef BNN_PROFILE_WAITS
+          if (it == 0) atomicAdd(&g_wait_cycles[6], (unsigned long long)(clock64() - t_kernel0));    // first weight tile ready
+          if (it == 4) atomicAdd(&g_wait_cycles[7], (unsigned long long)w_mma_w);                    // weight waits of k-blocks 0..4
+#endif
           { BNN_T0(); mbar_wait_cluster(pipe.full_a + g, (it >> 1) & 1); BNN_ACC(w_mma_a); }
           tc_fence_after_sync();
           const uint64_t da0 = desc_advance(desc_a0, static_cast<uint32_t>(g * MB) * (kTileBytes >> 4));
@@ -969,20 +979,21 @@ struct SkPipe {
   uint32_t ring_a, ring_w;
   uint32_t stage;        // four staging buffers of the epilogue warps (the rings stay live across segments)
 };
-constexpr size_t kPairSkSmem = kPairSmem + 4 * static_cast<size_t>(kStageWarpBytes);
+constexpr size_t kPairSkSmem = kSmemAux + 1024 + static_cast<size_t>(kASlots) * kTileBytes + kSkWSlots * kHalfTileBytes +
+                               4 * static_cast<size_t>(kStageWarpBytes);
 __device__ __forceinline__ SkPipe carve_sk(uint8_t* smem_raw) {
   SkPipe p;
   p.full_a = reinterpret_cast<uint64_t*>(smem_raw);
   p.full_w = p.full_a + 2;
-  p.empty_w = p.full_w + kPairWSlots;
-  p.accum_full = p.empty_w + kPairWSlots;
+  p.empty_w = p.full_w + kSkWSlots;
+  p.accum_full = p.empty_w + kSkWSlots;
   p.tmem_empty = p.accum_full + 1;
   p.tmem_slot = reinterpret_cast<uint32_t*>(p.tmem_empty + 1);
   p.aux = reinterpret_cast<float*>(smem_raw + 512);
   const uint32_t base = smem_u32(smem_raw) + kSmemAux;
   p.ring_a = (base + 1023u) & ~1023u;
   p.ring_w = p.ring_a + kASlots * kTileBytes;
-  p.stage = p.ring_w + kPairWSlots * kHalfTileBytes;
+  p.stage = p.ring_w + kSkWSlots * kHalfTileBytes;
   return p;
 }
 struct SkSeg {

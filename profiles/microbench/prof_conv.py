@@ -91,6 +91,7 @@ try:
             n = buf[5]
             print(f"{name}: CTAs {n}  kernel {buf[0] / n:.0f} cycles/CTA | MMA thread waits: weights {buf[1] / n * 2:.0f} (leader only) "
                   f"activations {buf[2] / n * 2:.0f} | generators wait for a free slot {buf[3] / n:.0f} | TMA thread waits {buf[4] / n:.0f}"
-                  f" | balanced schedule: MMA waits for the TMEM drain {buf[6] / n * 2:.0f} (leader only), epilogue busy {buf[7] / n:.0f}")
+                  f" | uniform grid: first weight tile ready at {buf[6] / n * 2:.0f}, weight waits of k-blocks 0..4 {buf[7] / n * 2:.0f}"
+                  f" (balanced schedule: MMA waits for the TMEM drain / epilogue busy)")
 except AttributeError:
     pass
