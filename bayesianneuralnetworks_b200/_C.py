@@ -164,6 +164,7 @@ _SIGNATURES = {
     "bnn_debug_pair_tile_plan": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                 ctypes.POINTER(ctypes.c_int32)]),
     "bnn_contract_set_balanced": (ctypes.c_int, [ctypes.c_int32]),
+    "bnn_debug_balanced_plan": (ctypes.c_int, [ctypes.c_int32] * 7 + [ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]),
     "bnn_debug_balanced_schedule": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
                                                    ctypes.POINTER(ctypes.c_int32)]),
     "bnn_selftest_umma": (ctypes.c_int, [_c_f32p, ctypes.c_void_p]),
@@ -337,6 +338,21 @@ def set_balanced_schedule(flag=True):
     model prefers it (bnn_contract_set_balanced).  Off by default — measured slower on B200; BNN_BALANCED=1 in
     the environment starts the process with it on."""
     _check(lib().bnn_contract_set_balanced(1 if flag else 0), "bnn_contract_set_balanced")
+
+
+def balanced_plan(m_blocks, samples, column_tiles, red_blocks, sum_samples, slots, slot):
+    """Host-side test aid: [(leader's first row, row blocks per CTA, column tile, sample, first k-block, k-blocks)] that
+    `slot` walks in the balanced schedule (no device needed)."""
+    cap = 64
+    while True:
+        buf = (ctypes.c_int32 * (6 * cap))()
+        n = lib().bnn_debug_balanced_plan(m_blocks, samples, column_tiles, red_blocks, 1 if sum_samples else 0, slots, slot,
+                                          buf, cap)
+        if n < 0:
+            _check(-n, "bnn_debug_balanced_plan")
+        if n <= cap:
+            return [tuple(buf[6 * i:6 * i + 6]) for i in range(n)]
+        cap = n
 
 
 def balanced_schedule_state(slot_cap=-1, device=None):

@@ -1007,7 +1007,7 @@ __host__ __device__ __forceinline__ int sk_tile_units(int run) {
   return (run >= 8 || run <= 4) ? (run < 4 ? run : 4) : (run + 1) / 2;
 }
 // next segment of the range [pos, end); advances pos
-__device__ __forceinline__ bool sk_next(const TmaContractParams& p, int& pos, int end, SkSeg* s) {
+__host__ __device__ __forceinline__ bool sk_next(const TmaContractParams& p, int& pos, int end, SkSeg* s) {
   if (pos >= end) return false;
   if (p.sk_msplit) {
     const int col = pos / p.sk_mtiles, u0 = pos - col * p.sk_mtiles;        // sk_mtiles: units per column
@@ -2159,6 +2159,33 @@ int tma_stage_counters(unsigned long long* out8, int reset) {
   (void)out8; (void)reset;
   return kNotEligible;
 #endif
+}
+
+// host only: the segments contract_pair_sk_kernel's slot `slot` of `slots` would walk (the kernel's own sk_next), six ints
+// each: {first row of the leader, row blocks per CTA, column tile, sample, first k-block iteration, iterations}
+int tma_balanced_plan(int m_blocks, int S, int gx, int red_blocks, int sum_samples, int slots, int slot, int32_t* out,
+                      int max_segments) {
+  TmaContractParams p{};
+  if (sum_samples) {
+    p.sk_msplit = 0; p.sk_mtiles = (m_blocks + 7) / 8; p.sk_its = red_blocks * S;
+    p.sk_total = gx * p.sk_mtiles * p.sk_its;
+  } else {
+    p.sk_msplit = 1; p.sk_mtiles = (m_blocks + 1) / 2; p.sk_its = red_blocks;
+    p.sk_total = gx * S * p.sk_mtiles;
+  }
+  p.sk_gx = gx; p.sk_slots = slots;
+  int pos = static_cast<int>(static_cast<long long>(p.sk_total) * slot / slots);
+  const int end = static_cast<int>(static_cast<long long>(p.sk_total) * (slot + 1) / slots);
+  SkSeg sg;
+  int n = 0;
+  while (sk_next(p, pos, end, &sg)) {
+    if (n < max_segments) {
+      int32_t* o = out + 6 * n;
+      o[0] = sg.lead_row0; o[1] = sg.mb_cap; o[2] = sg.y; o[3] = sg.z; o[4] = sg.i0; o[5] = sg.n;
+    }
+    ++n;
+  }
+  return n;
 }
 
 int tma_pair_tile_plan(int m_blocks, int S, int slots, int32_t* out7) {      // host only: the plan the launcher would use

@@ -418,6 +418,13 @@ int bnn_debug_force_contract_variant(int32_t variant);
  * *slots_out = co-resident clusters on the current device (either may be NULL).  Variant 8 of
  * bnn_debug_force_contract_variant forces the schedule wherever the CTA-pair kernel is eligible. */
 int bnn_debug_balanced_schedule(int32_t slot_cap, int32_t* launches_out, int32_t* slots_out);
+/* test aid, host arithmetic only: the segments that slot `slot` of `slots` walks in the balanced schedule for `samples`
+ * samples of `m_blocks` 128-row blocks x `column_tiles` 128-column tiles with `red_blocks` 32-wide k-blocks (sum_samples:
+ * the summed data gradient).  Six ints per segment: {first row of the leader CTA, row blocks per CTA, column tile, sample,
+ * first k-block iteration of the tile, iterations}.  Returns the number of segments (may exceed max_segments; only
+ * max_segments are written) or a negative bnn_status. */
+int bnn_debug_balanced_plan(int32_t m_blocks, int32_t samples, int32_t column_tiles, int32_t red_blocks, int32_t sum_samples,
+                            int32_t slots, int32_t slot, int32_t* out, int32_t max_segments);
 /* test aid, host arithmetic only: the heterogeneous tile list of the CTA-pair kernel for `samples` samples of `m_blocks`
  * 128-row blocks on `pair_slots` SM pairs (narrow layers: one column tile).  out7 = {on, n_a, s1, a1, b1, a2, b2}: samples
  * [0, s1) are cut into a1 tiles of 8 row blocks followed by b1 tiles of 6, the others into a2 / b2; n_a = number of
