@@ -776,6 +776,10 @@ contract_pair_kernel(const __grid_constant__ TmaContractParams p) {
       eps.sample = p.sample_begin + s;
       { BNN_T0(); mbar_wait(pipe.empty_w + wslot, ((it >> kPairWShift) & 1) ^ 1); BNN_ACC(w_gen); }
       const uint32_t tile = pipe.ring_w + wslot * kHalfTileBytes;
+#ifdef BNN_PROFILE_WAITS
+      if (p.exp_flags & 2) eps.inj = p.sigma_w;   // elimination run: eps read from memory (any valid array): loads and stores, no Philox
+      if (p.exp_flags & 1) { /* elimination run: barrier traffic only, no generation */ } else
+#endif
       if (!kDgrad)
         gen_w_tile<64, false, kSigns>(tile, p.mu_w, p.sigma_w, eps, half0, p.N, rb * kBK, p.K, tid, p.K, 0);
       else if (!kConv)
@@ -2073,6 +2077,9 @@ int tma_conv_fwd(const float* x, int64_t x_sample_stride, const float* mu_w, con
   p.rng_w = *rng_w; p.rng_b = rng_b ? *rng_b : *rng_w;
   p.shared_l = shared ? 1 : 0;
   p.sum_samples = 0;
+#ifdef BNN_PROFILE_WAITS
+  { const char* e = getenv("BNN_EXP_FLAGS"); p.exp_flags = e ? atoi(e) : 0; }
+#endif
   p.vec_out = (y.P == 1) && (y.batch_stride % 4 == 0) && (y_sample_stride % 4 == 0) && aligned16(y.base);
   return dispatch_tma_contract<false>(p, p.N, st);
 }
